@@ -1,0 +1,151 @@
+"""GraphSAGE-pool forward/backward, loss and Adam -- oracle only (torch CPU).
+
+Layer formula = DGL SAGEConv(in, out, 'pool') as imported at
+train/graphsage/pytorch/graphsage_dgl.py:3 and unrolled by the reference itself at
+inference_optimized.py:135-139,258-260,273-276:
+
+    h_self = x[:n_dst];  hp = relu(fc_pool(x));  neigh[d] = max_{e: dst(e)=d} hp[src(e)] (0 if none)
+    out = fc_self(h_self) + fc_neigh(neigh);  relu unless last layer
+
+Model = GraphSAGE(F, H, C, n_layers=depth-1, relu, dropout, 'pool')
+(graphsage_dgl.py:10-59; `pool_feats`/`edge_feats` are ignored there, so fc_pool is in->in).
+Loss = CrossEntropyLoss(mean | none) on labels.flatten(), Adam(lr=1e-3)
+(pytorch/model.py:20-25,103-107).  PARITY UNPINNED against DGL (absent); the argmax tie
+rule (lowest edge slot wins) is this repo's specification.
+
+``quant='bf16'`` models the product's bf16 tensor-core path: every GEMM operand
+(activations, weights, activation gradients) is rounded to bf16 exactly where the
+product stores it, accumulation stays fp32/fp64.
+"""
+import math
+import torch
+
+
+def xavier_params(in_feats, n_hidden, n_classes, n_layers, seed, dtype=torch.float32):
+    """Parameters with DGL SAGEConv.reset_parameters() semantics [recalled]: Xavier-uniform
+    weights with gain=sqrt(2) (calculate_gain('relu')), nn.Linear default biases.
+    Key names follow the reference state_dict (inference_optimized.py:135-139)."""
+    g = torch.Generator().manual_seed(seed)
+    dims = [(in_feats, n_hidden)] + [(n_hidden, n_hidden)] * (n_layers - 1) + [(n_hidden, n_classes)]
+    p = {}
+    for i, (fi, fo) in enumerate(dims):
+        for name, (o, k) in (("fc_pool", (fi, fi)), ("fc_self", (fo, fi)), ("fc_neigh", (fo, fi))):
+            a = math.sqrt(2.0) * math.sqrt(6.0 / (o + k))
+            p[f"layers.{i}.{name}.weight"] = ((torch.rand(o, k, generator=g, dtype=torch.float64) * 2 - 1) * a).to(dtype)
+            b = 1.0 / math.sqrt(k)
+            p[f"layers.{i}.{name}.bias"] = ((torch.rand(o, generator=g, dtype=torch.float64) * 2 - 1) * b).to(dtype)
+    return p
+
+
+class _Q(torch.autograd.Function):
+    """Round to bf16 in forward AND round the incoming gradient to bf16 in backward
+    (the product stores activation gradients once, in bf16)."""
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _Qf(torch.autograd.Function):
+    """Round forward only (weights / leaves: their gradients stay full precision)."""
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _Qb(torch.autograd.Function):
+    """Identity forward, round the gradient (models a stored bf16 activation gradient)."""
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def segment_max(hp, edge_src, n_dst, fanout):
+    """neigh[d, f] = max_j hp[edge_src[d*fanout+j], f]; empty slots (-1) ignored; rows with
+    no edge give 0.  Returns (neigh, argslot[int64 n_dst x F], -1 where no edge).  Gradient
+    flows only to the FIRST slot attaining the max."""
+    F_ = hp.shape[1]
+    es = edge_src.view(n_dst, fanout)
+    valid = es >= 0
+    vals = hp[es.clamp(min=0)]                                  # [n_dst, fanout, F]
+    neg = torch.full((), -float("inf"), dtype=hp.dtype)
+    vals = torch.where(valid[:, :, None], vals, neg)
+    mx = vals.max(dim=1).values
+    first = (vals == mx[:, None, :]).to(torch.int8).argmax(dim=1)   # first slot attaining the max
+    picked = torch.gather(vals, 1, first[:, None, :]).squeeze(1)
+    has = valid.any(dim=1)
+    neigh = torch.where(has[:, None], picked, torch.zeros((), dtype=hp.dtype))
+    arg = torch.where(has[:, None].expand(-1, F_), first, torch.full((), -1, dtype=torch.int64))
+    return neigh, arg
+
+
+def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, quant=None):
+    q = _Q.apply if quant == "bf16" else (lambda t: t)
+    qf = _Qf.apply if quant == "bf16" else (lambda t: t)
+    hp = q(torch.relu(x @ qf(Wp).t() + bp))
+    neigh, arg = segment_max(hp, edge_src, n_dst, fanout)
+    if quant == "bf16":
+        neigh = _Qb.apply(neigh)
+    out = x[:n_dst] @ qf(Ws).t() + neigh @ qf(Wn).t() + (bs + bn)
+    if relu_out:
+        out = q(torch.relu(out))
+    return out, dict(hp=hp, neigh=neigh, arg=arg)
+
+
+def forward(params, x_in, blocks, quant=None):
+    """blocks: list (input layer first) of dict(n_dst, edge_src[int64], fanout).  x_in: features
+    of blocks[0]'s src nodes.  Returns (logits, per-layer intermediates)."""
+    h = _Qf.apply(x_in) if quant == "bf16" else x_in
+    inter = []
+    L = len(blocks)
+    for i, b in enumerate(blocks):
+        g = lambda n: params[f"layers.{i}.{n}"]
+        h, it = sage_layer(h, b["n_dst"], b["edge_src"], b["fanout"],
+                           g("fc_pool.weight"), g("fc_pool.bias"), g("fc_self.weight"), g("fc_self.bias"),
+                           g("fc_neigh.weight"), g("fc_neigh.bias"), relu_out=(i < L - 1), quant=quant)
+        it["out"] = h
+        inter.append(it)
+    return h, inter
+
+
+def xent(logits, labels, reduction="mean", quant=None):
+    if quant == "bf16":
+        logits = _Qb.apply(logits)
+    return torch.nn.functional.cross_entropy(logits, labels.flatten(), reduction=reduction)
+
+
+def loss_and_grads(params, x_in, blocks, labels, quant=None, dtype=torch.float32):
+    """One fwd+bwd.  Returns (loss_mean, per_vertex_loss, logits, grads dict, intermediates)."""
+    p = {k: v.detach().to(dtype).requires_grad_(True) for k, v in params.items()}
+    logits, inter = forward(p, x_in.to(dtype), blocks, quant=quant)
+    per = xent(logits, labels, "none", quant=quant)
+    loss = per.mean()
+    loss.backward()
+    return loss.detach(), per.detach(), logits.detach(), {k: v.grad for k, v in p.items()}, inter
+
+
+def adam_step(params, grads, state, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam defaults (pytorch/model.py:25), single step, in place."""
+    state["t"] = state.get("t", 0) + 1
+    t = state["t"]
+    for k, p in params.items():
+        g = grads[k].to(p.dtype)
+        m = state.setdefault("m." + k, torch.zeros_like(p))
+        v = state.setdefault("v." + k, torch.zeros_like(p))
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+        denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+        p.addcdiv_(m, denom, value=-(lr / bc1))
+    return params
