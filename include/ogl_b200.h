@@ -1,0 +1,192 @@
+/*
+ * ogl_b200.h -- C ABI of the B200-native streaming GraphSAGE hot path.
+ *
+ * Drop-in boundary for MassimoPerini/online-gnn-learning's `--backend pytorch --cuda`
+ * path.  The reference has no FFI of its own (it is pure Python over DGL + PyTorch), so
+ * every entry point below cites the reference call site (file:line under
+ * /root/reference) whose DGL / PyTorch / Python work it replaces.  INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  `*_dev` pointers are device
+ *     memory, `*_host` pointers are host memory (pinned for async copies).
+ *   - every call returns 0 on success, <0 on error; ogl_last_error() returns the message
+ *     of the last failing call on this thread.  No C++ exception crosses the boundary.
+ *   - all work is ordered on the caller's `stream` (a cudaStream_t passed as void*);
+ *     one host thread per GPU; the library starts no host threads.
+ *   - persistent device memory lives only inside the opaque handles created/destroyed
+ *     here.  There is NO CPU fallback: every entry point fails if no sm_100 device is
+ *     present.
+ */
+#ifndef OGL_B200_H_
+#define OGL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+typedef struct ogl_graph ogl_graph;       /* streaming in-edge CSR (slack rows + snapshot tails) */
+typedef struct ogl_features ogl_features; /* device feature / label store (padded rows) */
+typedef struct ogl_plan ogl_plan;         /* sampler + GraphSAGE-pool model + optimiser workspace */
+typedef struct ogl_sumtree ogl_sumtree;   /* fp64 sum-tree for PBR */
+
+enum { OGL_F32 = 0, OGL_BF16 = 1 };      /* arithmetic mode of the dense path */
+enum { OGL_OK = 0, OGL_ERR_CUDA = -1, OGL_ERR_ARG = -2, OGL_ERR_CAPACITY = -3, OGL_ERR_NODEVICE = -4 };
+
+const char* ogl_last_error(void);
+int ogl_version(void);
+/* number of kernels launched by this library since process start (bench.py: gpu_launches) */
+int64_t ogl_kernel_launches(void);
+
+/* ------------------------------------------------------------------ graph ----------
+ * Replaces dgl.graph([]) + add_nodes / add_edges / subgraph as driven by
+ *   train/graph/dynamic_graph_edge.py:27,61-72 (build), :190-218 (evolve)
+ *   train/graph/dynamic_graph_vertex.py:82-94 (build), :132-141 (evolve)
+ * Canonical content: in-neighbour list of v = sources of edges with dst == v in
+ * ascending edge id (edge id = insertion order).
+ */
+int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_directed);
+int ogl_graph_destroy(ogl_graph* g);
+/* add_nodes(n): ids [V, V+n) become valid rows */
+int ogl_graph_insert_vertices(ogl_graph* g, int64_t n, void* stream);
+/* add_edges(src,dst) [then add_edges(dst,src) if symmetric]; device or host int64 ids.
+ * Edge ids continue the insertion order: forward edges first, then the reverse edges
+ * (dynamic_graph_edge.py:214-215). */
+int ogl_graph_insert_edges(ogl_graph* g, const int64_t* src_dev, const int64_t* dst_dev, int64_t n,
+                           int symmetric, void* stream);
+int ogl_graph_insert_edges_host(ogl_graph* g, const int64_t* src_host, const int64_t* dst_host, int64_t n,
+                                int symmetric, void* stream);
+/* vertex streams: load the parent graph once (ids already relabelled to arrival rank,
+ * in-CSR in parent edge-id order), then activate a prefix; rebuilds the induced CSR the
+ * way graph.subgraph(evolving_vertices) does at dynamic_graph_vertex.py:85,140 */
+int ogl_graph_load_parent(ogl_graph* g, const int64_t* indptr_dev, const int64_t* indices_dev,
+                          const int64_t* eids_dev, int64_t n_vertices, void* stream);
+int ogl_graph_set_active_prefix(ogl_graph* g, int64_t n_active, void* stream);
+int ogl_graph_num_vertices(ogl_graph* g, int64_t* out);
+int ogl_graph_num_edges(ogl_graph* g, int64_t* out);          /* directed */
+int ogl_graph_degrees(ogl_graph* g, int64_t* out_dev, void* stream);
+/* canonical compact CSR (indptr[V+1], indices[E], eids[E]); eids_dev may be NULL */
+int ogl_graph_export_csr(ogl_graph* g, int64_t* indptr_dev, int64_t* indices_dev, int64_t* eids_dev, void* stream);
+/* squeeze relocation garbage out of the adjacency pool (also run automatically when full) */
+int ogl_graph_compact(ogl_graph* g, void* stream);
+/* pool statistics: {pool_used, pool_cap, relocations, compactions} */
+int ogl_graph_stats(ogl_graph* g, int64_t out[4]);
+
+/* ------------------------------------------------------------------ features --------
+ * Replaces graph.ndata['feat'] / ['target'] storage + the per-batch CPU gather and H2D
+ * copy at train/graphsage/pytorch/model.py:88-99; rows are appended by add_nodes
+ * (dynamic_graph_edge.py:64-65,206-207).  Rows are stored padded, in the arithmetic mode.
+ */
+int ogl_features_create(ogl_features** out, int64_t v_cap, int n_feats, int mode);
+int ogl_features_destroy(ogl_features* f);
+/* rows [row0, row0+n) <- fp32 feats[n, n_feats] and int64 labels[n]; dev or host source */
+int ogl_features_write(ogl_features* f, int64_t row0, int64_t n, const float* feats, const int64_t* labels,
+                       int src_is_host, void* stream);
+/* rows[i] <- fp32 feats[src_rows[i]] (device table gather; vertex-stream relabelling) */
+int ogl_features_write_permuted(ogl_features* f, int64_t n, const float* feats_dev, const int64_t* labels_dev,
+                                const int64_t* src_rows_dev, void* stream);
+
+/* ------------------------------------------------------------------ plan ------------
+ * One plan = the sampler, the L-layer GraphSAGE('pool') model and Adam, with all
+ * workspaces sized for max_seeds.  Replaces, per minibatch,
+ *   dgl.sampling.MultiLayerNeighborSampler + NodeDataLoader   pytorch/model.py:44-47,128-131
+ *   GraphSAGE.forward over DGL SAGEConv('pool')              graphsage_dgl.py:48-59
+ *   CrossEntropyLoss / backward / Adam.step                  pytorch/model.py:20-25,103-107
+ */
+typedef struct {
+  int n_layers;          /* = number of hops/blocks (reference: always 2) */
+  int dims[8];           /* dims[0]=F, dims[1..L-1]=hidden, dims[L]=classes */
+  int fanouts[8];        /* fanouts[0] at the seeds hop, [1] next hop out, ... */
+  int max_seeds;
+  int64_t v_cap;
+  int mode;              /* OGL_F32 | OGL_BF16 */
+  int gemm_impl;         /* 0 = default for mode (tcgen05 for bf16), 1 = force SIMT (tests) */
+  uint64_t seed;         /* Philox key */
+  float lr, beta1, beta2, eps;
+} ogl_plan_config;
+
+int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg);
+int ogl_plan_destroy(ogl_plan* p);
+/* flat fp32 parameter / gradient buffers (caller-owned device memory, e.g. a torch
+ * tensor): per layer i, in order fc_pool.weight [in,in], fc_pool.bias [in],
+ * fc_self.weight [out,in], fc_self.bias [out], fc_neigh.weight [out,in], fc_neigh.bias [out] */
+int64_t ogl_plan_param_count(const ogl_plan* p);
+int ogl_plan_bind_params(ogl_plan* p, float* params_dev, float* grads_dev, void* stream);
+/* call after params were changed outside the library (load_state_dict) */
+int ogl_plan_refresh_params(ogl_plan* p, void* stream);
+int ogl_plan_set_step(ogl_plan* p, uint32_t step, void* stream);
+
+/* sample the L-hop minibatch for `seeds` (device int64, n_seeds <= max_seeds) */
+int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_dev, int n_seeds, void* stream);
+/* forward over the sampled minibatch; logits_dev (fp32 [n_seeds, classes]) may be NULL */
+int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev, void* stream);
+/* loss + backward; grads land in the bound gradient buffer (overwritten).
+ * loss_scale multiplies dlogits (1/global_batch for the 'mean' reduction);
+ * per_vertex_loss_dev (fp32 [n_seeds]) may be NULL */
+int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev,
+                           float* loss_sum_dev, void* stream);
+/* autograd-compat path (GraphSAGE.forward(blocks, x) + loss.backward() driven from Python):
+ * supply the input rows x [n_rows, F] fp32 for the outermost level instead of gathering them
+ * (then call ogl_plan_forward with f == NULL), and back-propagate a caller-computed
+ * dlogits [n_seeds, classes] fp32 into the bound gradient buffer */
+int ogl_plan_set_input(ogl_plan* p, const float* x_dev, int n_rows, void* stream);
+int ogl_plan_backward(ogl_plan* p, const float* dlogits_dev, void* stream);
+int ogl_plan_adam_step(ogl_plan* p, void* stream);
+/* fused: sample + forward + loss + backward (+ Adam if do_step) for host or device seeds */
+int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds,
+                        int seeds_on_host, float loss_scale, int do_step, float* per_vertex_loss_dev,
+                        float* loss_sum_dev, void* stream);
+/* eval: sample + forward + per-vertex CE loss (PBR recompute_priorities, pytorch/model.py:210-254) */
+int ogl_plan_eval_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds,
+                       int seeds_on_host, float* logits_dev, float* per_vertex_loss_dev, void* stream);
+
+/* introspection for parity tests: device pointers into the plan's workspaces.
+ * level 0 = seeds, level l+1 = src nodes of hop l.  block(hop) = dst level hop. */
+int ogl_plan_level_nodes(ogl_plan* p, int level, const int32_t** nodes_dev, const int32_t** count_dev, int* max_count);
+int ogl_plan_block_edges(ogl_plan* p, int hop, const int32_t** edge_src_local_dev, const int32_t** edge_src_global_dev,
+                         const int64_t** edge_eid_dev, int* fanout);
+/* named tensors: "hp<l>", "neigh<l>", "arg<l>", "out<l>" for layer l; returns pointer, rows(max), pitch, elem bytes */
+int ogl_plan_tensor(ogl_plan* p, const char* name, const void** ptr_dev, int* rows_max, int* pitch, int* elem_bytes);
+
+/* standalone sampler (config 5 sweep + tests): picks into caller buffers.
+ * out_src_dev int32 [n*fanout] (-1 for empty rows), out_eid_dev int64 or NULL */
+int ogl_sample_neighbors(ogl_graph* g, const int64_t* dst_dev, int64_t n, int fanout, uint64_t seed,
+                         uint32_t step, uint32_t hop, int32_t* out_src_dev, int64_t* out_eid_dev, void* stream);
+
+/* ------------------------------------------------------------------ replay ----------
+ * RBR: uniform n-subset of a population of size n_pop (train/graph/train_test_graph.py:210-216;
+ * counter-RNG replacement of the in-place random.shuffle).  out_idx_dev int64 [n].
+ * PBR: fp64 sum-tree (train/prioritized_replay/segment_tree.py:69-79,94-125) and the
+ * stratified proportional draw (replay_buffer.py:164-203).
+ */
+int ogl_draw_uniform(int64_t n_pop, int64_t n, uint64_t seed, uint32_t counter, int64_t* out_idx_dev, void* stream);
+
+int ogl_sumtree_create(ogl_sumtree** out, int64_t capacity_pow2);
+int ogl_sumtree_destroy(ogl_sumtree* t);
+int ogl_sumtree_set(ogl_sumtree* t, const int64_t* idx_dev, const double* val_dev, int64_t n, void* stream);
+/* leaf[idx] = transform(loss): clip -> log -> running min/max normalise -> +eps -> pow(alpha)
+ * (replay_buffer.py:110-130,219-244).  minmax_io_dev = {min_val,max_val,min_log,max_log} running state */
+int ogl_sumtree_set_from_loss(ogl_sumtree* t, const int64_t* idx_dev, const float* loss_dev, int64_t n,
+                              double clip_lo, double clip_hi, double eps, double alpha, double* minmax_io_dev, void* stream);
+/* sum over leaves [lo, hi) with the reference's association order */
+int ogl_sumtree_sum(ogl_sumtree* t, int64_t lo, int64_t hi, double* out_dev, void* stream);
+/* out_idx[i] = find_prefixsum_idx(mass[i]) */
+int ogl_sumtree_find(ogl_sumtree* t, const double* mass_dev, int64_t n, int64_t* out_idx_dev, void* stream);
+/* stratified draw: mass_i = u[i]*(p_total/n) + i*(p_total/n), p_total = sum(0, n_items-1) */
+int ogl_sumtree_sample_stratified(ogl_sumtree* t, const double* uniforms_dev, int64_t n, int64_t n_items,
+                                  int64_t* out_idx_dev, void* stream);
+int ogl_sumtree_values(ogl_sumtree* t, const double** value_dev, int64_t* capacity);
+
+/* ------------------------------------------------------------------ dense GEMM (tests / bench) */
+/* C[M,N] (fp32, ldc) = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb), tcgen05 path */
+int ogl_gemm_bf16_nt(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc,
+                     int m, int n, int k, void* stream);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGL_B200_H_ */

@@ -1,0 +1,344 @@
+"""Thin object layer over the C ABI: device memory stays in torch tensors, every call is
+ordered on torch's current CUDA stream.  Nothing here computes: it only marshals pointers."""
+import ctypes as C
+import numpy as np
+import torch
+
+from ._lib import lib, check, PlanConfig, OGL_F32, OGL_BF16, kernel_launches  # noqa: F401
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_contiguous(), "ogl_b200: tensors crossing the C ABI must be contiguous"
+    return C.c_void_p(t.data_ptr())
+
+
+def _dev(t, dtype):
+    """torch CUDA tensor of `dtype` from a tensor / ndarray / list (H2D copy if needed)."""
+    if isinstance(t, torch.Tensor):
+        return t.to(device="cuda", dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(t), dtype=dtype).cuda()
+
+
+class _CAI:
+    def __init__(self, ptr, shape, typestr, strides):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2,
+                                             strides=strides)
+
+
+_TYPESTR = {torch.float32: ("<f4", 4), torch.int32: ("<i4", 4), torch.int64: ("<i8", 8), torch.uint8: ("|u1", 1),
+            torch.float64: ("<f8", 8), torch.bfloat16: ("<i2", 2)}
+
+
+def wrap_device(ptr, shape, dtype, pitch=None):
+    """Zero-copy torch view of library-owned device memory ([rows, cols] with row pitch in elements)."""
+    ts, es = _TYPESTR[dtype]
+    if len(shape) == 2 and pitch is not None and pitch != shape[1]:
+        strides = (pitch * es, es)
+    else:
+        strides = None
+    if any(int(s) == 0 for s in shape):
+        return torch.empty(tuple(shape), dtype=dtype, device="cuda")
+    t = torch.as_tensor(_CAI(ptr, shape, ts, strides), device="cuda")
+    return t.view(torch.bfloat16) if dtype == torch.bfloat16 else t
+
+
+class Graph:
+    """ogl_graph handle: streaming in-edge CSR."""
+
+    def __init__(self, v_cap, e_cap_directed):
+        self._h = C.c_void_p()
+        check(lib.ogl_graph_create(C.byref(self._h), int(v_cap), int(e_cap_directed)))
+        self.v_cap = int(v_cap)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.ogl_graph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def insert_vertices(self, n):
+        check(lib.ogl_graph_insert_vertices(self._h, int(n), _stream()))
+
+    def insert_edges(self, src, dst, symmetric=True):
+        """src/dst: CUDA int64 tensors (device path) or host arrays / CPU tensors (host path: the
+        H2D copy happens inside the call)."""
+        if isinstance(src, torch.Tensor) and src.is_cuda:
+            s, d = src.to(torch.int64).contiguous(), dst.to(torch.int64).contiguous()
+            check(lib.ogl_graph_insert_edges(self._h, _ptr(s), _ptr(d), s.numel(), int(symmetric), _stream()))
+            return
+        if isinstance(src, torch.Tensor):
+            s, d = src.to(torch.int64).contiguous(), dst.to(torch.int64).contiguous()
+            ps, pd, n = C.c_void_p(s.data_ptr()), C.c_void_p(d.data_ptr()), s.numel()
+        else:
+            s = np.ascontiguousarray(src, dtype=np.int64)
+            d = np.ascontiguousarray(dst, dtype=np.int64)
+            ps, pd, n = C.c_void_p(s.ctypes.data), C.c_void_p(d.ctypes.data), s.size
+        check(lib.ogl_graph_insert_edges_host(self._h, ps, pd, int(n), int(symmetric), _stream()))
+        torch.cuda.current_stream().synchronize()   # host buffers may be released by the caller
+
+    def load_parent(self, indptr, indices, eids):
+        ip, ix, ei = _dev(indptr, torch.int64), _dev(indices, torch.int64), _dev(eids, torch.int64)
+        check(lib.ogl_graph_load_parent(self._h, _ptr(ip), _ptr(ix), _ptr(ei), ip.numel() - 1, _stream()))
+        torch.cuda.current_stream().synchronize()
+
+    def set_active_prefix(self, n_active):
+        check(lib.ogl_graph_set_active_prefix(self._h, int(n_active), _stream()))
+
+    @property
+    def num_vertices(self):
+        v = C.c_int64()
+        check(lib.ogl_graph_num_vertices(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def num_edges(self):
+        v = C.c_int64()
+        check(lib.ogl_graph_num_edges(self._h, C.byref(v)))
+        return v.value
+
+    def degrees(self):
+        out = torch.empty(self.num_vertices, dtype=torch.int64, device="cuda")
+        check(lib.ogl_graph_degrees(self._h, _ptr(out), _stream()))
+        return out
+
+    def export_csr(self, with_eids=True):
+        V, E = self.num_vertices, self.num_edges
+        indptr = torch.empty(V + 1, dtype=torch.int64, device="cuda")
+        indices = torch.empty(E, dtype=torch.int64, device="cuda")
+        eids = torch.empty(E, dtype=torch.int64, device="cuda") if with_eids else None
+        check(lib.ogl_graph_export_csr(self._h, _ptr(indptr), _ptr(indices), _ptr(eids), _stream()))
+        return indptr, indices, eids
+
+    def compact(self):
+        check(lib.ogl_graph_compact(self._h, _stream()))
+
+    def stats(self):
+        a = (C.c_int64 * 4)()
+        check(lib.ogl_graph_stats(self._h, C.byref(a)))
+        return dict(pool_used=a[0], pool_cap=a[1], relocations=a[2], compactions=a[3])
+
+
+class Features:
+    """ogl_features handle: padded feature rows in the arithmetic mode + int32 labels."""
+
+    def __init__(self, v_cap, n_feats, mode):
+        self._h = C.c_void_p()
+        check(lib.ogl_features_create(C.byref(self._h), int(v_cap), int(n_feats), int(mode)))
+        self.v_cap, self.n_feats, self.mode = int(v_cap), int(n_feats), int(mode)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.ogl_features_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def write(self, row0, feats, labels):
+        """feats fp32 [n, F], labels int64 [n] (or [n,1]); CUDA tensors or host tensors/arrays."""
+        on_host = not (isinstance(feats if feats is not None else labels, torch.Tensor) and
+                       (feats if feats is not None else labels).is_cuda)
+        if on_host:
+            f = None if feats is None else torch.as_tensor(feats, dtype=torch.float32).contiguous()
+            l = None if labels is None else torch.as_tensor(labels, dtype=torch.int64).reshape(-1).contiguous()
+        else:
+            f = None if feats is None else feats.to(torch.float32).contiguous()
+            l = None if labels is None else labels.to(torch.int64).reshape(-1).contiguous()
+        n = f.shape[0] if f is not None else l.numel()
+        check(lib.ogl_features_write(self._h, int(row0), int(n), _ptr(f), _ptr(l), int(on_host), _stream()))
+        if on_host:
+            torch.cuda.current_stream().synchronize()
+
+    def write_permuted(self, feats_dev, labels_dev, src_rows_dev):
+        f = feats_dev.to(torch.float32).contiguous()
+        l = labels_dev.to(torch.int64).reshape(-1).contiguous()
+        r = src_rows_dev.to(torch.int64).contiguous()
+        check(lib.ogl_features_write_permuted(self._h, r.numel(), _ptr(f), _ptr(l), _ptr(r), _stream()))
+
+
+class Plan:
+    """ogl_plan handle: sampler + L-layer GraphSAGE-pool + Adam over one workspace."""
+
+    def __init__(self, dims, fanouts, max_seeds, v_cap, mode=OGL_BF16, seed=0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 gemm_impl=0):
+        L = len(fanouts)
+        assert len(dims) == L + 1
+        cfg = PlanConfig()
+        cfg.n_layers = L
+        for i, d in enumerate(dims):
+            cfg.dims[i] = int(d)
+        for i, f in enumerate(fanouts):
+            cfg.fanouts[i] = int(f)
+        cfg.max_seeds, cfg.v_cap, cfg.mode, cfg.gemm_impl, cfg.seed = int(max_seeds), int(v_cap), int(mode), int(gemm_impl), int(seed)
+        cfg.lr, cfg.beta1, cfg.beta2, cfg.eps = lr, betas[0], betas[1], eps
+        self._h = C.c_void_p()
+        check(lib.ogl_plan_create(C.byref(self._h), C.byref(cfg)))
+        self.dims, self.fanouts, self.L = list(dims), list(fanouts), L
+        self.max_seeds, self.v_cap, self.mode = int(max_seeds), int(v_cap), int(mode)
+        self.dtype = torch.bfloat16 if mode == OGL_BF16 else torch.float32
+        self.n_params = int(lib.ogl_plan_param_count(self._h))
+        self._params = self._grads = None
+        self.n_seeds = 0
+        self._stamp = 0
+        self._version = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.ogl_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    # -- parameters ---------------------------------------------------------------------------
+    def bind_params(self, flat_params, flat_grads):
+        assert flat_params.is_cuda and flat_params.dtype == torch.float32 and flat_params.numel() == self.n_params
+        assert flat_grads.is_cuda and flat_grads.dtype == torch.float32 and flat_grads.numel() == self.n_params
+        self._params, self._grads = flat_params, flat_grads      # keep alive
+        check(lib.ogl_plan_bind_params(self._h, _ptr(flat_params), _ptr(flat_grads), _stream()))
+
+    def refresh_params(self):
+        check(lib.ogl_plan_refresh_params(self._h, _stream()))
+
+    def set_step(self, step):
+        check(lib.ogl_plan_set_step(self._h, int(step) & 0xFFFFFFFF, _stream()))
+
+    # -- minibatch ----------------------------------------------------------------------------
+    def sample(self, graph, seeds_dev):
+        s = seeds_dev.to(device="cuda", dtype=torch.int64).contiguous()
+        check(lib.ogl_plan_sample(self._h, graph._h, _ptr(s), s.numel(), _stream()))
+        self.n_seeds = s.numel()
+        self._stamp += 1
+
+    def forward(self, features, want_logits=True):
+        out = torch.empty(self.n_seeds, self.dims[-1], dtype=torch.float32, device="cuda") if want_logits else None
+        check(lib.ogl_plan_forward(self._h, features._h if features is not None else None, _ptr(out), _stream()))
+        return out
+
+    def set_input(self, x):
+        x = x.to(device="cuda", dtype=torch.float32).contiguous()
+        check(lib.ogl_plan_set_input(self._h, _ptr(x), x.shape[0], _stream()))
+
+    def loss_backward(self, features, loss_scale, want_per_vertex=True):
+        per = torch.empty(self.n_seeds, dtype=torch.float32, device="cuda") if want_per_vertex else None
+        tot = torch.empty(1, dtype=torch.float32, device="cuda")
+        check(lib.ogl_plan_loss_backward(self._h, features._h, float(loss_scale), _ptr(per), _ptr(tot), _stream()))
+        return per, tot
+
+    def backward(self, dlogits):
+        d = dlogits.to(device="cuda", dtype=torch.float32).contiguous()
+        check(lib.ogl_plan_backward(self._h, _ptr(d), _stream()))
+
+    def adam_step(self):
+        check(lib.ogl_plan_adam_step(self._h, _stream()))
+
+    def train_step(self, graph, features, seeds, loss_scale=None, do_step=True, per_vertex_out=None, loss_sum_out=None):
+        """seeds: CUDA int64 tensor (device path) or pinned/pageable CPU int64 tensor (host path)."""
+        n = seeds.numel()
+        on_host = not seeds.is_cuda
+        assert seeds.dtype == torch.int64 and seeds.is_contiguous()
+        if loss_scale is None:
+            loss_scale = 1.0 / n
+        check(lib.ogl_plan_train_step(self._h, graph._h, features._h, C.c_void_p(seeds.data_ptr()), n, int(on_host),
+                                      float(loss_scale), int(do_step), _ptr(per_vertex_out), _ptr(loss_sum_out), _stream()))
+        self.n_seeds = n
+        self._stamp += 1
+
+    def eval_step(self, graph, features, seeds, logits_out=None, per_vertex_out=None):
+        n = seeds.numel()
+        on_host = not seeds.is_cuda
+        assert seeds.dtype == torch.int64 and seeds.is_contiguous()
+        check(lib.ogl_plan_eval_step(self._h, graph._h, features._h, C.c_void_p(seeds.data_ptr()), n, int(on_host),
+                                     _ptr(logits_out), _ptr(per_vertex_out), _stream()))
+        self.n_seeds = n
+        self._stamp += 1
+
+    # -- introspection (parity tests, DGL-style block objects) ---------------------------------
+    def level_nodes(self, level):
+        p, c, m = C.c_void_p(), C.c_void_p(), C.c_int()
+        check(lib.ogl_plan_level_nodes(self._h, level, C.byref(p), C.byref(c), C.byref(m)))
+        n = int(wrap_device(c.value, (1,), torch.int32).item())
+        return wrap_device(p.value, (n,), torch.int32)
+
+    def block_edges(self, hop):
+        a, b, e, f = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+        check(lib.ogl_plan_block_edges(self._h, hop, C.byref(a), C.byref(b), C.byref(e), C.byref(f)))
+        n_dst = self.level_nodes(hop).numel()
+        ne = n_dst * f.value
+        return (wrap_device(a.value, (ne,), torch.int32), wrap_device(b.value, (ne,), torch.int32),
+                wrap_device(e.value, (ne,), torch.int64), f.value)
+
+    def tensor(self, name, rows=None):
+        p, r, pt, eb = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.ogl_plan_tensor(self._h, name.encode(), C.byref(p), C.byref(r), C.byref(pt), C.byref(eb)))
+        dt = {1: torch.uint8, 2: torch.bfloat16, 4: torch.float32}[eb.value]
+        return wrap_device(p.value, (rows if rows is not None else r.value, pt.value), dt)
+
+
+class SumTree:
+    """ogl_sumtree handle: fp64 sum tree."""
+
+    def __init__(self, capacity):
+        self._h = C.c_void_p()
+        check(lib.ogl_sumtree_create(C.byref(self._h), int(capacity)))
+        self.capacity = int(capacity)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.ogl_sumtree_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def set(self, idx, val):
+        i, v = _dev(idx, torch.int64), _dev(val, torch.float64)
+        check(lib.ogl_sumtree_set(self._h, _ptr(i), _ptr(v), i.numel(), _stream()))
+
+    def set_from_loss(self, idx, loss, clip_lo, clip_hi, eps, alpha, minmax_state):
+        i, l = _dev(idx, torch.int64), _dev(loss, torch.float32)
+        check(lib.ogl_sumtree_set_from_loss(self._h, _ptr(i), _ptr(l), i.numel(), clip_lo, clip_hi, eps, alpha,
+                                            _ptr(minmax_state), _stream()))
+
+    def sum(self, lo=0, hi=None):
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        check(lib.ogl_sumtree_sum(self._h, int(lo), int(self.capacity if hi is None else hi), _ptr(out), _stream()))
+        return out
+
+    def find(self, mass):
+        m = _dev(mass, torch.float64)
+        out = torch.empty(m.numel(), dtype=torch.int64, device="cuda")
+        check(lib.ogl_sumtree_find(self._h, _ptr(m), m.numel(), _ptr(out), _stream()))
+        return out
+
+    def sample_stratified(self, uniforms, n_items):
+        u = _dev(uniforms, torch.float64)
+        out = torch.empty(u.numel(), dtype=torch.int64, device="cuda")
+        check(lib.ogl_sumtree_sample_stratified(self._h, _ptr(u), u.numel(), int(n_items), _ptr(out), _stream()))
+        return out
+
+    def values(self):
+        p, c = C.c_void_p(), C.c_int64()
+        check(lib.ogl_sumtree_values(self._h, C.byref(p), C.byref(c)))
+        return wrap_device(p.value, (2 * c.value,), torch.float64)
+
+
+def draw_uniform(n_pop, n, seed, counter):
+    out = torch.empty(int(n), dtype=torch.int64, device="cuda")
+    check(lib.ogl_draw_uniform(int(n_pop), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(counter) & 0xFFFFFFFF, _ptr(out), _stream()))
+    return out
+
+
+def sample_neighbors(graph, dst, fanout, seed, step, hop, want_eids=True):
+    d = _dev(dst, torch.int64)
+    src = torch.empty(d.numel() * fanout, dtype=torch.int32, device="cuda")
+    eid = torch.empty(d.numel() * fanout, dtype=torch.int64, device="cuda") if want_eids else None
+    check(lib.ogl_sample_neighbors(graph._h, _ptr(d), d.numel(), int(fanout), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step), int(hop),
+                                   _ptr(src), _ptr(eid), _stream()))
+    return src, eid
+
+
+def gemm_bf16_nt(a, b):
+    """C[M,N] fp32 = A[M,K] bf16 @ B[N,K]^T bf16 on the tcgen05 path (tests / bench)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+    a, b = a.contiguous(), b.contiguous()
+    c = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device="cuda")
+    check(lib.ogl_gemm_bf16_nt(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), c.shape[1], a.shape[0], b.shape[0], a.shape[1],
+                               _stream()))
+    return c

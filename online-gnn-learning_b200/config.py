@@ -1,0 +1,39 @@
+"""Process-wide settings of the B200 backend."""
+from ._lib import OGL_F32, OGL_BF16
+
+_STATE = {"precision": "bf16", "seed": 1, "faithful": True}
+
+
+def set_precision(name):
+    """'bf16' (tcgen05 tensor-core path, rtol 1e-3 vs the bf16-operand oracle) or
+    'fp32' (SIMT FFMA path, rtol 1e-5 vs the fp32 oracle)."""
+    assert name in ("bf16", "fp32")
+    _STATE["precision"] = name
+
+
+def precision():
+    return _STATE["precision"]
+
+
+def mode():
+    return OGL_BF16 if _STATE["precision"] == "bf16" else OGL_F32
+
+
+def set_seed(seed):
+    """Philox key of the neighbour sampler / RBR draws (the reference never seeds DGL)."""
+    _STATE["seed"] = int(seed)
+
+
+def seed():
+    return _STATE["seed"]
+
+
+def set_faithful(flag):
+    """faithful=True reproduces the reference's vertex choosers literally (Python `random`
+    shuffles, numpy train/test split, PBR falling back to uniform draws: SURVEY 8(a) a10/a11);
+    faithful=False uses the on-GPU counter-RNG draws and real proportional PBR sampling."""
+    _STATE["faithful"] = bool(flag)
+
+
+def faithful():
+    return _STATE["faithful"]

@@ -1,0 +1,56 @@
+// Dense GEMM entry points of the GraphSAGE-pool path (SIMT fp32-accumulate + tcgen05 bf16).
+#pragma once
+#include "common.cuh"
+
+namespace ogl {
+
+// C[m, n] = act( sum_seg sum_k A_seg[m, k] * B_seg[n, k] + bias[n] ) , optional relu / mask.
+// A, B row-major with the contraction index contiguous ("NT").  Up to two (A, B, K) segments
+// accumulate into the same output (used for [h_self | neigh] x [W_self | W_neigh]^T).
+struct GemmNT {
+  const void* a[2] = {nullptr, nullptr};   // element type = in_bf16 ? bf16 : f32
+  int lda[2] = {0, 0};
+  const void* b[2] = {nullptr, nullptr};
+  int ldb[2] = {0, 0};
+  int k[2] = {0, 0};
+  int n_seg = 1;
+  const int32_t* a_rows_dev[2] = {nullptr, nullptr};  // rows of segment s valid for m < *a_rows_dev[s] (nullptr: all)
+  const float* bias = nullptr;     // [n] fp32 (nullable)
+  const float* bias2 = nullptr;    // second bias added too (fc_self.bias + fc_neigh.bias)
+  int relu = 0;
+  const void* mask = nullptr;      // same shape/type as A-typed [m, ldmask]: out = mask>0 ? out : 0
+  int ldmask = 0;
+  void* c = nullptr;               // out_bf16 ? bf16 : f32
+  int ldc = 0;
+  int m_max = 0;                   // static row bound (grid size)
+  const int32_t* m_dev = nullptr;  // dynamic row count on device (nullptr: m_max)
+  int n = 0;
+  int in_bf16 = 0, out_bf16 = 0;
+  int zero_tail = 1;               // write zeros to rows [m, round_up(m, 128)) (contraction padding for later TN GEMMs)
+};
+
+// C[n, k] = sum_{m < *m_dev} A[m, n] * B[m, k]   (fp32 out; weight gradients)
+struct GemmTN {
+  const void* a = nullptr;   // [m, lda], n contiguous
+  int lda = 0;
+  const void* b = nullptr;   // [m, ldb], k contiguous
+  int ldb = 0;
+  float* c = nullptr;        // [n, ldc]
+  int ldc = 0;
+  int n = 0, k = 0;
+  int m_max = 0;
+  const int32_t* m_dev = nullptr;
+  int in_bf16 = 0;
+  float* partial = nullptr;  // split workspace [splits, n, k]
+  int64_t partial_elems = 0;
+};
+
+int gemm_nt_simt(const GemmNT& g, cudaStream_t s);
+int gemm_tn_simt(const GemmTN& g, cudaStream_t s);
+
+// tcgen05 / TMA / TMEM versions (bf16 in, fp32 accumulate); same contracts
+int gemm_nt_tc(const GemmNT& g, cudaStream_t s);
+int gemm_tn_tc(const GemmTN& g, cudaStream_t s);
+bool gemm_tc_available();
+
+}  // namespace ogl

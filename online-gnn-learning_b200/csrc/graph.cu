@@ -1,0 +1,558 @@
+// Streaming in-edge CSR on the GPU.
+//
+// Layout in HBM (all arrays device-resident):
+//   row_start[v] int64, deg[v] int32, cap[v] int32      -- one slack row per vertex
+//   adj_src[pool] int32, adj_eid[pool] uint32            -- adjacency pool, rows = [row_start, row_start+cap)
+// A snapshot's edges are appended into each touched row's tail (the per-snapshot delta
+// region [deg_old, deg_new)); rows that run out of slack are relocated to the pool top with
+// doubled capacity (bump allocation), so an insert costs O(batch) amortised instead of the
+// reference's O(E_total) COO concat + CSC rebuild (dynamic_graph_edge.py:214-215, DGL
+// add_edges).  Slots inside a batch are claimed with atomics and every tail is then put
+// into ascending-edge-id order, so the row contents are canonical (bit-exact with the
+// oracle's stable COO->CSC conversion).
+#include "graph.cuh"
+
+namespace ogl {
+
+constexpr int kBlock = 256;
+constexpr int kLargeTail = 2048;   // tails longer than this are ordered by a whole CTA
+
+__device__ __forceinline__ int32_t grow_cap(int32_t need) {
+  if (need <= 0) return 0;
+  int64_t c = (int64_t)need * 2;
+  if (c < 4) c = 4;
+  c = (c + 3) & ~3LL;
+  return (int32_t)(c > 0x7fffffffLL ? 0x7fffffff : c);
+}
+
+// -- batch edge accessor: i in [0, n) forward (src->dst), [n, 2n) reverse (dst->src) ------
+struct BatchEdges {
+  const int64_t* src;
+  const int64_t* dst;
+  int64_t n;
+  int symmetric;
+  __device__ __forceinline__ int64_t total() const { return symmetric ? 2 * n : n; }
+  __device__ __forceinline__ void get(int64_t i, int64_t& s, int64_t& d) const {
+    if (i < n) { s = src[i]; d = dst[i]; } else { s = dst[i - n]; d = src[i - n]; }
+  }
+};
+
+__global__ void __launch_bounds__(kBlock) k_count(BatchEdges b, int32_t* __restrict__ add, int32_t* __restrict__ touched,
+                                                  GraphCtl* ctl, int64_t n_vertices) {
+  const int64_t tot = b.total();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s, d;
+    b.get(i, s, d);
+    if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) { ctl->bad_id = 1; continue; }
+    int old = atomicAdd(&add[d], 1);
+    if (old == 0) touched[atomicAdd(&ctl->n_touched, 1)] = (int32_t)d;
+  }
+}
+
+// slots this batch must take from the pool top
+__global__ void __launch_bounds__(kBlock) k_need(const int32_t* __restrict__ touched, const int32_t* __restrict__ add,
+                                                 const int32_t* __restrict__ deg, const int32_t* __restrict__ cap, GraphCtl* ctl) {
+  const int nt = ctl->n_touched;
+  unsigned long long local = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    int v = touched[t];
+    int need = deg[v] + add[v];
+    if (need > cap[v]) local += (unsigned long long)grow_cap(need);
+  }
+  // warp reduce then one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&ctl->need, local);
+}
+
+// relocate rows without enough slack: one warp per touched row
+__global__ void __launch_bounds__(kBlock) k_reserve(const int32_t* __restrict__ touched, const int32_t* __restrict__ add,
+                                                    int64_t* __restrict__ row_start, const int32_t* __restrict__ deg,
+                                                    int32_t* __restrict__ cap, int32_t* __restrict__ tail_len,
+                                                    int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid, GraphCtl* ctl) {
+  const int nt = ctl->n_touched;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nt; t += warps) {
+    const int v = touched[t];
+    const int a = add[v], d = deg[v];
+    if (lane == 0) tail_len[t] = a;
+    const int need = d + a;
+    if (need > cap[v]) {
+      const int nc = grow_cap(need);
+      unsigned long long off = 0;
+      if (lane == 0) {
+        off = atomicAdd(&ctl->pool_top, (unsigned long long)nc);
+        atomicAdd(&ctl->relocations, 1ULL);
+      }
+      off = __shfl_sync(0xffffffffu, off, 0);
+      const int64_t old = row_start[v];
+      for (int i = lane; i < d; i += 32) {
+        adj_src[off + i] = adj_src[old + i];
+        adj_eid[off + i] = adj_eid[old + i];
+      }
+      __syncwarp();
+      if (lane == 0) { row_start[v] = (int64_t)off; cap[v] = nc; }
+    }
+  }
+}
+
+// claim a slot in the row tail (arbitrary order inside the batch; fixed up by k_fix)
+__global__ void __launch_bounds__(kBlock) k_place(BatchEdges b, int32_t* __restrict__ add, const int64_t* __restrict__ row_start,
+                                                  const int32_t* __restrict__ deg, int32_t* __restrict__ adj_src,
+                                                  uint32_t* __restrict__ adj_eid, uint32_t eid_base, int64_t n_vertices) {
+  const int64_t tot = b.total();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s, d;
+    b.get(i, s, d);
+    if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) continue;
+    const int p = atomicSub(&add[d], 1) - 1;      // add[] returns to zero by the end of the kernel
+    const int64_t at = row_start[d] + deg[d] + p;
+    adj_src[at] = (int32_t)s;
+    adj_eid[at] = eid_base + (uint32_t)i;
+  }
+}
+
+// put every tail into ascending edge-id order; one warp per touched row
+__global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
+                                                const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
+                                                int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
+                                                int32_t* __restrict__ scr_src, uint32_t* __restrict__ scr_eid,
+                                                int32_t* __restrict__ large, GraphCtl* ctl) {
+  const int nt = ctl->n_touched;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nt; t += warps) {
+    const int v = touched[t];
+    const int L = tail_len[t];
+    const int64_t base = row_start[v] + deg[v];
+    if (L > kLargeTail) {
+      if (lane == 0) large[atomicAdd(&ctl->n_large, 1)] = t;
+      continue;
+    }
+    if (L >= 2 && L <= 32) {
+      uint32_t e = lane < L ? adj_eid[base + lane] : 0xffffffffu;
+      int32_t s = lane < L ? adj_src[base + lane] : 0;
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+        rank += (j < L && ej < e) ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane < L) { adj_eid[base + rank] = e; adj_src[base + rank] = s; }
+    } else if (L > 32) {
+      unsigned long long off = 0;
+      if (lane == 0) off = atomicAdd(&ctl->scratch_top, (unsigned long long)L);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      for (int i = lane; i < L; i += 32) { scr_eid[off + i] = adj_eid[base + i]; scr_src[off + i] = adj_src[base + i]; }
+      __syncwarp();
+      for (int i = lane; i < L; i += 32) {
+        const uint32_t e = scr_eid[off + i];
+        int rank = 0;
+        for (int j = 0; j < L; ++j) rank += scr_eid[off + j] < e ? 1 : 0;
+        adj_eid[base + rank] = e;
+        adj_src[base + rank] = scr_src[off + i];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) deg[v] += L;
+  }
+}
+
+// very long tails (hub rows in a big batch): a whole CTA ranks the tail
+__global__ void __launch_bounds__(1024) k_fix_large(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
+                                                    const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
+                                                    int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
+                                                    int32_t* __restrict__ scr_src, uint32_t* __restrict__ scr_eid,
+                                                    const int32_t* __restrict__ large, GraphCtl* ctl) {
+  __shared__ unsigned long long s_off;
+  const int nl = ctl->n_large;
+  for (int k = blockIdx.x; k < nl; k += gridDim.x) {
+    const int t = large[k];
+    const int v = touched[t];
+    const int L = tail_len[t];
+    const int64_t base = row_start[v] + deg[v];
+    if (threadIdx.x == 0) s_off = atomicAdd(&ctl->scratch_top, (unsigned long long)L);
+    __syncthreads();
+    const unsigned long long off = s_off;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) { scr_eid[off + i] = adj_eid[base + i]; scr_src[off + i] = adj_src[base + i]; }
+    __syncthreads();
+    // batch edge ids are dense in [lo, lo + span): rank by counting smaller ids in chunks held in registers
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+      const uint32_t e = scr_eid[off + i];
+      int rank = 0;
+      for (int j = 0; j < L; ++j) rank += scr_eid[off + j] < e ? 1 : 0;
+      adj_eid[base + rank] = e;
+      adj_src[base + rank] = scr_src[off + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) deg[v] += L;
+    __syncthreads();
+  }
+}
+
+// ---- compaction / growth: rewrite all rows into a fresh pool ---------------------------------
+__global__ void __launch_bounds__(kBlock) k_newcap(const int32_t* __restrict__ deg, const int32_t* __restrict__ add,
+                                                   int32_t* __restrict__ newcap, int64_t n) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+    newcap[v] = grow_cap(deg[v] + add[v]);
+}
+
+__global__ void __launch_bounds__(kBlock) k_move_rows(const int64_t* __restrict__ old_start, const int64_t* __restrict__ new_start,
+                                                      const int32_t* __restrict__ deg, const int32_t* __restrict__ old_src,
+                                                      const uint32_t* __restrict__ old_eid, int32_t* __restrict__ new_src,
+                                                      uint32_t* __restrict__ new_eid, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n; v += warps) {
+    const int d = deg[v];
+    const int64_t a = old_start[v], b = new_start[v];
+    for (int i = lane; i < d; i += 32) { new_src[b + i] = old_src[a + i]; new_eid[b + i] = old_eid[a + i]; }
+  }
+}
+
+// ---- export / degrees ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_deg64(const int32_t* __restrict__ deg, int64_t* __restrict__ out, int64_t n) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) out[v] = deg[v];
+}
+
+__global__ void __launch_bounds__(kBlock) k_export_rows(const int64_t* __restrict__ row_start, const int32_t* __restrict__ deg,
+                                                        const int32_t* __restrict__ adj_src, const uint32_t* __restrict__ adj_eid,
+                                                        const int64_t* __restrict__ indptr, int64_t* __restrict__ indices,
+                                                        int64_t* __restrict__ eids, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n; v += warps) {
+    const int d = deg[v];
+    const int64_t a = row_start[v], b = indptr[v];
+    for (int i = lane; i < d; i += 32) {
+      indices[b + i] = adj_src[a + i];
+      if (eids) eids[b + i] = adj_eid[a + i];
+    }
+  }
+}
+
+__global__ void k_set_last(int64_t* indptr, const int64_t* total, int64_t n) { indptr[n] = *total; }
+
+// ---- vertex streams: induced subgraph of the arrival-order prefix ------------------------------
+__global__ void __launch_bounds__(kBlock) k_convert_parent(const int64_t* __restrict__ indices, const int64_t* __restrict__ eids,
+                                                           int32_t* __restrict__ p_indices, uint32_t* __restrict__ p_eids, int64_t e) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+    p_indices[i] = (int32_t)indices[i];
+    p_eids[i] = (uint32_t)eids[i];
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_prefix_count(const int64_t* __restrict__ p_indptr, const int32_t* __restrict__ p_indices,
+                                                         int32_t* __restrict__ deg, int32_t* __restrict__ cap, int64_t n_active, int64_t v_all) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < v_all; v += warps) {
+    int c = 0;
+    if (v < n_active) {
+      const int64_t a = p_indptr[v], b = p_indptr[v + 1];
+      for (int64_t i = a + lane; i < b; i += 32) c += (p_indices[i] < n_active) ? 1 : 0;
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { deg[v] = c; cap[v] = c; }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_prefix_fill(const int64_t* __restrict__ p_indptr, const int32_t* __restrict__ p_indices,
+                                                        const uint32_t* __restrict__ p_eids, const int64_t* __restrict__ row_start,
+                                                        int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid, int64_t n_active) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n_active; v += warps) {
+    const int64_t a = p_indptr[v], b = p_indptr[v + 1];
+    int64_t out = row_start[v];
+    for (int64_t i0 = a; i0 < b; i0 += 32) {
+      const int64_t i = i0 + lane;
+      const int32_t u = i < b ? p_indices[i] : 0x7fffffff;
+      const bool keep = u < n_active;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int64_t at = out + __popc(m & ((1u << lane) - 1));
+        adj_src[at] = u;
+        adj_eid[at] = p_eids[i];
+      }
+      out += __popc(m);
+    }
+  }
+}
+
+}  // namespace ogl
+
+using namespace ogl;
+
+// ================================== host side ====================================================
+struct ogl_graph {
+  int64_t v_cap = 0, pool_cap = 0;
+  int64_t n_vertices = 0, n_edges = 0;
+  int64_t batch_cap = 0;   // stream edges per internal chunk
+  int64_t* row_start = nullptr;
+  int32_t *deg = nullptr, *cap = nullptr, *add = nullptr;
+  int32_t* adj_src = nullptr;
+  uint32_t* adj_eid = nullptr;
+  GraphCtl* ctl = nullptr;
+  GraphCtl* h_ctl = nullptr;     // pinned mirror
+  int32_t *touched = nullptr, *tail_len = nullptr, *large = nullptr;
+  int32_t* scr_src = nullptr;
+  uint32_t* scr_eid = nullptr;
+  int64_t *stage_src = nullptr, *stage_dst = nullptr;   // host-insert staging
+  int32_t* newcap = nullptr;
+  int64_t* scan_scratch = nullptr;
+  int64_t* total_dev = nullptr;
+  int64_t* new_start = nullptr;
+  // parent graph (vertex streams)
+  int64_t* p_indptr = nullptr;
+  int32_t* p_indices = nullptr;
+  uint32_t* p_eids = nullptr;
+  int64_t p_v = 0, p_e = 0;
+  int64_t pool_used_host = 0, relocations = 0, compactions = 0;
+};
+
+static int graph_alloc_pool(ogl_graph* g, int64_t cap) {
+  OGL_CUDA(cudaMalloc(&g->adj_src, sizeof(int32_t) * (size_t)cap));
+  OGL_CUDA(cudaMalloc(&g->adj_eid, sizeof(uint32_t) * (size_t)cap));
+  g->pool_cap = cap;
+  return OGL_OK;
+}
+
+extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_directed) {
+  OGL_TRY(require_device());
+  OGL_ARG(out && v_cap > 0 && e_cap_directed >= 0, "ogl_graph_create: bad arguments");
+  OGL_ARG(v_cap < 0x7fffffffLL, "ogl_graph_create: v_cap must fit int32");
+  ogl_graph* g = new ogl_graph();
+  g->v_cap = v_cap;
+  g->batch_cap = 1 << 21;
+  const int64_t pool = e_cap_directed * 3 + 1024;   // slack rows (x2) + relocation holes
+  int r = graph_alloc_pool(g, pool);
+  if (r != OGL_OK) { delete g; return r; }
+#define A(ptr, bytes) OGL_CUDA(cudaMalloc(&(ptr), (size_t)(bytes)))
+  A(g->row_start, sizeof(int64_t) * v_cap);
+  A(g->deg, sizeof(int32_t) * v_cap);
+  A(g->cap, sizeof(int32_t) * v_cap);
+  A(g->add, sizeof(int32_t) * v_cap);
+  A(g->newcap, sizeof(int32_t) * v_cap);
+  A(g->new_start, sizeof(int64_t) * (v_cap + 1));
+  A(g->ctl, sizeof(GraphCtl));
+  A(g->touched, sizeof(int32_t) * 2 * g->batch_cap);
+  A(g->tail_len, sizeof(int32_t) * 2 * g->batch_cap);
+  A(g->large, sizeof(int32_t) * 2 * g->batch_cap / kLargeTail + 64);
+  A(g->scr_src, sizeof(int32_t) * 2 * g->batch_cap);
+  A(g->scr_eid, sizeof(uint32_t) * 2 * g->batch_cap);
+  A(g->stage_src, sizeof(int64_t) * g->batch_cap);
+  A(g->stage_dst, sizeof(int64_t) * g->batch_cap);
+  A(g->scan_scratch, sizeof(int64_t) * scan_scratch_elems(v_cap + 1));
+  A(g->total_dev, sizeof(int64_t));
+#undef A
+  OGL_CUDA(cudaMallocHost(&g->h_ctl, sizeof(GraphCtl)));
+  OGL_CUDA(cudaMemset(g->row_start, 0, sizeof(int64_t) * v_cap));
+  OGL_CUDA(cudaMemset(g->deg, 0, sizeof(int32_t) * v_cap));
+  OGL_CUDA(cudaMemset(g->cap, 0, sizeof(int32_t) * v_cap));
+  OGL_CUDA(cudaMemset(g->add, 0, sizeof(int32_t) * v_cap));
+  OGL_CUDA(cudaMemset(g->ctl, 0, sizeof(GraphCtl)));
+  *out = g;
+  return OGL_OK;
+}
+
+extern "C" int ogl_graph_destroy(ogl_graph* g) {
+  if (!g) return OGL_OK;
+  void* ptrs[] = {g->row_start, g->deg, g->cap, g->add, g->adj_src, g->adj_eid, g->ctl, g->touched, g->tail_len, g->large,
+                  g->scr_src, g->scr_eid, g->stage_src, g->stage_dst, g->newcap, g->scan_scratch, g->total_dev, g->new_start,
+                  g->p_indptr, g->p_indices, g->p_eids};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (g->h_ctl) cudaFreeHost(g->h_ctl);
+  delete g;
+  return OGL_OK;
+}
+
+extern "C" int ogl_graph_insert_vertices(ogl_graph* g, int64_t n, void* stream) {
+  OGL_ARG(g && n >= 0, "ogl_graph_insert_vertices: bad arguments");
+  if (g->n_vertices + n > g->v_cap) {
+    set_error("ogl_graph_insert_vertices: %lld + %lld exceeds v_cap %lld", (long long)g->n_vertices, (long long)n, (long long)g->v_cap);
+    return OGL_ERR_CAPACITY;
+  }
+  g->n_vertices += n;
+  return OGL_OK;
+}
+
+// rewrite all rows into a pool of at least `min_cap` slots; caps become grow(deg + pending add)
+static int graph_rebuild_pool(ogl_graph* g, int64_t extra, cudaStream_t s) {
+  const int64_t V = g->n_vertices;
+  OGL_LAUNCH(k_newcap, grid_for(V, kBlock), kBlock, 0, s, g->deg, g->add, g->newcap, V);
+  OGL_TRY(exclusive_scan_i32_to_i64(g->newcap, g->new_start, V, g->scan_scratch, g->total_dev, s));
+  int64_t total = 0;
+  OGL_CUDA(cudaMemcpyAsync(&total, g->total_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  OGL_CUDA(cudaStreamSynchronize(s));
+  int64_t want = total + total / 2 + extra + 1024;
+  if (want < g->pool_cap) want = g->pool_cap;
+  int32_t* old_src = g->adj_src;
+  uint32_t* old_eid = g->adj_eid;
+  OGL_TRY(graph_alloc_pool(g, want));
+  OGL_LAUNCH(k_move_rows, grid_for(V * 32, kBlock), kBlock, 0, s, g->row_start, g->new_start, g->deg, old_src, old_eid,
+             g->adj_src, g->adj_eid, V);
+  OGL_CUDA(cudaMemcpyAsync(g->row_start, g->new_start, sizeof(int64_t) * V, cudaMemcpyDeviceToDevice, s));
+  OGL_CUDA(cudaMemcpyAsync(g->cap, g->newcap, sizeof(int32_t) * V, cudaMemcpyDeviceToDevice, s));
+  unsigned long long top = (unsigned long long)total;
+  OGL_CUDA(cudaMemcpyAsync(&g->ctl->pool_top, &top, sizeof(top), cudaMemcpyHostToDevice, s));
+  OGL_CUDA(cudaStreamSynchronize(s));
+  cudaFree(old_src);
+  cudaFree(old_eid);
+  g->pool_used_host = total;
+  g->compactions++;
+  return OGL_OK;
+}
+
+static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_t* dst_dev, int64_t n, int symmetric, cudaStream_t s) {
+  BatchEdges b{src_dev, dst_dev, n, symmetric};
+  const int64_t tot = symmetric ? 2 * n : n;
+  if (g->n_edges + tot > 0xffffffffLL) {
+    set_error("ogl_graph_insert_edges: edge ids exceed 32 bits");
+    return OGL_ERR_CAPACITY;
+  }
+  // reset the per-batch counters (pool_top / relocations persist)
+  OGL_CUDA(cudaMemsetAsync(&g->ctl->n_touched, 0, sizeof(GraphCtl) - offsetof(GraphCtl, n_touched), s));
+  OGL_LAUNCH(k_count, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->touched, g->ctl, g->n_vertices);
+  OGL_LAUNCH(k_need, grid_for(tot, kBlock), kBlock, 0, s, g->touched, g->add, g->deg, g->cap, g->ctl);
+  OGL_CUDA(cudaMemcpyAsync(g->h_ctl, g->ctl, sizeof(GraphCtl), cudaMemcpyDeviceToHost, s));
+  OGL_CUDA(cudaStreamSynchronize(s));
+  if (g->h_ctl->bad_id) {
+    // undo the counters so the graph stays usable
+    OGL_CUDA(cudaMemsetAsync(g->add, 0, sizeof(int32_t) * g->v_cap, s));
+    set_error("ogl_graph_insert_edges: vertex id out of range [0, %lld) (call insert_vertices first)", (long long)g->n_vertices);
+    return OGL_ERR_ARG;
+  }
+  if ((int64_t)(g->h_ctl->pool_top + g->h_ctl->need) > g->pool_cap) {
+    OGL_TRY(graph_rebuild_pool(g, tot, s));   // caps now cover the pending adds: nothing left to relocate
+  }
+  const int nt = g->h_ctl->n_touched;
+  const int wgrid = grid_for((int64_t)nt * 32, kBlock);
+  OGL_LAUNCH(k_reserve, wgrid, kBlock, 0, s, g->touched, g->add, g->row_start, g->deg, g->cap, g->tail_len, g->adj_src, g->adj_eid, g->ctl);
+  OGL_LAUNCH(k_place, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->row_start, g->deg, g->adj_src, g->adj_eid,
+             (uint32_t)g->n_edges, g->n_vertices);
+  OGL_LAUNCH(k_fix, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid, g->scr_src,
+             g->scr_eid, g->large, g->ctl);
+  OGL_LAUNCH(k_fix_large, 64, 1024, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid, g->scr_src,
+             g->scr_eid, g->large, g->ctl);
+  g->n_edges += tot;
+  return OGL_OK;
+}
+
+static int graph_insert(ogl_graph* g, const int64_t* src, const int64_t* dst, int64_t n, int symmetric, int on_host, void* stream) {
+  OGL_ARG(g && n >= 0 && (n == 0 || (src && dst)), "ogl_graph_insert_edges: bad arguments");
+  OGL_ARG(g->p_indptr == nullptr, "ogl_graph_insert_edges: graph is in vertex-stream (parent prefix) mode");
+  cudaStream_t s = (cudaStream_t)stream;
+  // edge ids inside one call are forward-then-reverse over the WHOLE call (dynamic_graph_edge.py:214-215), so a
+  // symmetric call that does not fit one chunk is issued as forward chunks followed by reverse chunks.
+  if (n == 0) return OGL_OK;
+  if (!symmetric || n <= g->batch_cap) {
+    for (int64_t o = 0; o < n; o += g->batch_cap) {
+      const int64_t m = (n - o < g->batch_cap) ? n - o : g->batch_cap;
+      const int64_t *ps = src + o, *pd = dst + o;
+      if (on_host) {
+        OGL_CUDA(cudaMemcpyAsync(g->stage_src, ps, sizeof(int64_t) * m, cudaMemcpyHostToDevice, s));
+        OGL_CUDA(cudaMemcpyAsync(g->stage_dst, pd, sizeof(int64_t) * m, cudaMemcpyHostToDevice, s));
+        ps = g->stage_src; pd = g->stage_dst;
+      }
+      OGL_TRY(graph_insert_chunk(g, ps, pd, m, symmetric, s));
+    }
+    return OGL_OK;
+  }
+  OGL_TRY(graph_insert(g, src, dst, n, 0, on_host, stream));
+  return graph_insert(g, dst, src, n, 0, on_host, stream);
+}
+
+extern "C" int ogl_graph_insert_edges(ogl_graph* g, const int64_t* src_dev, const int64_t* dst_dev, int64_t n, int symmetric, void* stream) {
+  return graph_insert(g, src_dev, dst_dev, n, symmetric, 0, stream);
+}
+extern "C" int ogl_graph_insert_edges_host(ogl_graph* g, const int64_t* src_host, const int64_t* dst_host, int64_t n, int symmetric, void* stream) {
+  return graph_insert(g, src_host, dst_host, n, symmetric, 1, stream);
+}
+
+extern "C" int ogl_graph_compact(ogl_graph* g, void* stream) {
+  OGL_ARG(g, "ogl_graph_compact: null graph");
+  if (g->p_indptr) return OGL_OK;
+  return graph_rebuild_pool(g, 0, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_graph_num_vertices(ogl_graph* g, int64_t* out) { OGL_ARG(g && out, "null"); *out = g->n_vertices; return OGL_OK; }
+extern "C" int ogl_graph_num_edges(ogl_graph* g, int64_t* out) { OGL_ARG(g && out, "null"); *out = g->n_edges; return OGL_OK; }
+
+extern "C" int ogl_graph_degrees(ogl_graph* g, int64_t* out_dev, void* stream) {
+  OGL_ARG(g && out_dev, "ogl_graph_degrees: null");
+  if (g->n_vertices == 0) return OGL_OK;
+  OGL_LAUNCH(k_deg64, grid_for(g->n_vertices, kBlock), kBlock, 0, stream, g->deg, out_dev, g->n_vertices);
+  return OGL_OK;
+}
+
+extern "C" int ogl_graph_export_csr(ogl_graph* g, int64_t* indptr_dev, int64_t* indices_dev, int64_t* eids_dev, void* stream) {
+  OGL_ARG(g && indptr_dev && (indices_dev || g->n_edges == 0), "ogl_graph_export_csr: null");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t V = g->n_vertices;
+  OGL_TRY(exclusive_scan_i32_to_i64(g->deg, indptr_dev, V, g->scan_scratch, g->total_dev, s));
+  OGL_LAUNCH(k_set_last, 1, 1, 0, s, indptr_dev, g->total_dev, V);
+  if (V > 0 && g->n_edges > 0)
+    OGL_LAUNCH(k_export_rows, grid_for(V * 32, kBlock), kBlock, 0, s, g->row_start, g->deg, g->adj_src, g->adj_eid, indptr_dev,
+               indices_dev, eids_dev, V);
+  return OGL_OK;
+}
+
+extern "C" int ogl_graph_stats(ogl_graph* g, int64_t out[4]) {
+  OGL_ARG(g && out, "null");
+  GraphCtl c;
+  OGL_CUDA(cudaMemcpy(&c, g->ctl, sizeof(c), cudaMemcpyDeviceToHost));
+  out[0] = (int64_t)c.pool_top; out[1] = g->pool_cap; out[2] = (int64_t)c.relocations; out[3] = g->compactions;
+  return OGL_OK;
+}
+
+extern "C" int ogl_graph_load_parent(ogl_graph* g, const int64_t* indptr_dev, const int64_t* indices_dev, const int64_t* eids_dev,
+                                     int64_t n_vertices, void* stream) {
+  OGL_ARG(g && indptr_dev && n_vertices > 0 && n_vertices <= g->v_cap, "ogl_graph_load_parent: bad arguments");
+  OGL_ARG(g->n_edges == 0 && g->p_indptr == nullptr, "ogl_graph_load_parent: graph not empty");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t e = 0;
+  OGL_CUDA(cudaMemcpyAsync(&e, indptr_dev + n_vertices, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  OGL_CUDA(cudaStreamSynchronize(s));
+  OGL_ARG(e >= 0 && e <= 0xffffffffLL, "ogl_graph_load_parent: bad edge count");
+  if (e > g->pool_cap) {
+    cudaFree(g->adj_src); cudaFree(g->adj_eid);
+    OGL_TRY(graph_alloc_pool(g, e + 1024));
+  }
+  OGL_CUDA(cudaMalloc(&g->p_indptr, sizeof(int64_t) * (n_vertices + 1)));
+  OGL_CUDA(cudaMalloc(&g->p_indices, sizeof(int32_t) * (e + 1)));
+  OGL_CUDA(cudaMalloc(&g->p_eids, sizeof(uint32_t) * (e + 1)));
+  OGL_CUDA(cudaMemcpyAsync(g->p_indptr, indptr_dev, sizeof(int64_t) * (n_vertices + 1), cudaMemcpyDeviceToDevice, s));
+  if (e > 0) OGL_LAUNCH(k_convert_parent, grid_for(e, kBlock), kBlock, 0, s, indices_dev, eids_dev, g->p_indices, g->p_eids, e);
+  g->p_v = n_vertices;
+  g->p_e = e;
+  g->n_vertices = 0;
+  return OGL_OK;
+}
+
+extern "C" int ogl_graph_set_active_prefix(ogl_graph* g, int64_t n_active, void* stream) {
+  OGL_ARG(g && g->p_indptr, "ogl_graph_set_active_prefix: no parent graph loaded");
+  OGL_ARG(n_active >= 0 && n_active <= g->p_v, "ogl_graph_set_active_prefix: n_active out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t V = g->p_v;
+  OGL_LAUNCH(k_prefix_count, grid_for(V * 32, kBlock), kBlock, 0, s, g->p_indptr, g->p_indices, g->deg, g->cap, n_active, V);
+  OGL_TRY(exclusive_scan_i32_to_i64(g->deg, g->row_start, V, g->scan_scratch, g->total_dev, s));
+  if (n_active > 0)
+    OGL_LAUNCH(k_prefix_fill, grid_for(n_active * 32, kBlock), kBlock, 0, s, g->p_indptr, g->p_indices, g->p_eids, g->row_start,
+               g->adj_src, g->adj_eid, n_active);
+  int64_t total = 0;
+  OGL_CUDA(cudaMemcpyAsync(&total, g->total_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  OGL_CUDA(cudaStreamSynchronize(s));
+  g->n_vertices = n_active;
+  g->n_edges = total;
+  return OGL_OK;
+}
+
+namespace ogl {
+GraphView graph_view(const ogl_graph* g) {
+  GraphView v;
+  v.row_start = g->row_start; v.deg = g->deg; v.adj_src = g->adj_src; v.adj_eid = g->adj_eid; v.n_vertices = g->n_vertices;
+  return v;
+}
+}  // namespace ogl

@@ -1,0 +1,32 @@
+// Device-side view of the streaming CSR shared by graph.cu / sample.cu / plan.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ogl {
+
+struct GraphCtl {
+  unsigned long long pool_top;      // persistent: next free adjacency slot
+  unsigned long long relocations;   // persistent: rows moved to the pool top so far
+  // ---- per-batch (zeroed before every chunk) ----
+  int n_touched;
+  int bad_id;
+  int n_large;
+  int pad_;
+  unsigned long long need;          // slots this batch takes from the pool top
+  unsigned long long scratch_top;   // bump pointer into the tail-ordering scratch
+};
+
+struct GraphView {
+  const int64_t* row_start;
+  const int32_t* deg;
+  const int32_t* adj_src;
+  const uint32_t* adj_eid;
+  int64_t n_vertices;
+};
+
+}  // namespace ogl
+
+struct ogl_graph;
+namespace ogl {
+GraphView graph_view(const ogl_graph* g);
+}

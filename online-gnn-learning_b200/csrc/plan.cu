@@ -1,0 +1,510 @@
+// Feature store + training plan: sampler -> L x SAGEConv('pool') -> CE loss -> backward -> Adam.
+//
+// One plan owns every workspace, sized once for max_seeds, and every kernel reads its row
+// counts from device memory, so a whole train step is a fixed launch sequence with no host
+// synchronisation (CUDA-graph capturable).  Replaces the per-minibatch body of
+// train/graphsage/pytorch/model.py:77-107 (train_step) and :39-71 (_run_custom_eval).
+#include "graph.cuh"
+#include "sample.cuh"
+#include "gemm.cuh"
+#include "sage_kernels.cuh"
+#include <vector>
+#include <string>
+
+using namespace ogl;
+
+static inline int pitch_of(int d) { return round_up(d, 8); }
+
+// ------------------------------------------------------------------ feature store ----------------
+struct ogl_features {
+  int64_t v_cap = 0;
+  int F = 0, pitch = 0, mode = 0;
+  void* table = nullptr;      // [v_cap, pitch] f32 | bf16
+  int32_t* labels = nullptr;  // [v_cap]
+  float* stage_f = nullptr;   // host-source staging
+  int64_t* stage_l = nullptr;
+  int64_t stage_rows = 0;
+};
+
+extern "C" int ogl_features_create(ogl_features** out, int64_t v_cap, int n_feats, int mode) {
+  OGL_TRY(require_device());
+  OGL_ARG(out && v_cap > 0 && n_feats > 0 && (mode == OGL_F32 || mode == OGL_BF16), "ogl_features_create: bad arguments");
+  ogl_features* f = new ogl_features();
+  f->v_cap = v_cap; f->F = n_feats; f->pitch = pitch_of(n_feats); f->mode = mode;
+  const size_t es = mode == OGL_BF16 ? 2 : 4;
+  OGL_CUDA(cudaMalloc(&f->table, es * (size_t)v_cap * f->pitch));
+  OGL_CUDA(cudaMemset(f->table, 0, es * (size_t)v_cap * f->pitch));
+  OGL_CUDA(cudaMalloc(&f->labels, sizeof(int32_t) * v_cap));
+  OGL_CUDA(cudaMemset(f->labels, 0, sizeof(int32_t) * v_cap));
+  *out = f;
+  return OGL_OK;
+}
+
+extern "C" int ogl_features_destroy(ogl_features* f) {
+  if (!f) return OGL_OK;
+  cudaFree(f->table); cudaFree(f->labels); cudaFree(f->stage_f); cudaFree(f->stage_l);
+  delete f;
+  return OGL_OK;
+}
+
+extern "C" int ogl_features_write(ogl_features* f, int64_t row0, int64_t n, const float* feats, const int64_t* labels, int src_is_host,
+                                  void* stream) {
+  OGL_ARG(f && row0 >= 0 && n >= 0 && row0 + n <= f->v_cap, "ogl_features_write: rows [%lld, %lld) out of range", (long long)row0, (long long)(row0 + n));
+  if (n == 0) return OGL_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (src_is_host) {
+    // chunked H2D through a device staging buffer (fp32 rows are converted/padded on the GPU)
+    const int64_t chunk = 1 << 16;
+    if (f->stage_rows < chunk) {
+      OGL_CUDA(cudaMalloc(&f->stage_f, sizeof(float) * chunk * f->F));
+      OGL_CUDA(cudaMalloc(&f->stage_l, sizeof(int64_t) * chunk));
+      f->stage_rows = chunk;
+    }
+    for (int64_t o = 0; o < n; o += chunk) {
+      const int64_t m = n - o < chunk ? n - o : chunk;
+      if (feats) {
+        OGL_CUDA(cudaMemcpyAsync(f->stage_f, feats + o * f->F, sizeof(float) * m * f->F, cudaMemcpyHostToDevice, s));
+        OGL_TRY(feat_write(f->mode == OGL_BF16, f->stage_f, nullptr, m, f->F, f->table, f->pitch, row0 + o, s));
+      }
+      if (labels) {
+        OGL_CUDA(cudaMemcpyAsync(f->stage_l, labels + o, sizeof(int64_t) * m, cudaMemcpyHostToDevice, s));
+        OGL_TRY(label_write(f->stage_l, nullptr, m, f->labels, row0 + o, s));
+      }
+    }
+    return OGL_OK;
+  }
+  if (feats) OGL_TRY(feat_write(f->mode == OGL_BF16, feats, nullptr, n, f->F, f->table, f->pitch, row0, s));
+  if (labels) OGL_TRY(label_write(labels, nullptr, n, f->labels, row0, s));
+  return OGL_OK;
+}
+
+extern "C" int ogl_features_write_permuted(ogl_features* f, int64_t n, const float* feats_dev, const int64_t* labels_dev,
+                                           const int64_t* src_rows_dev, void* stream) {
+  OGL_ARG(f && n >= 0 && n <= f->v_cap && src_rows_dev, "ogl_features_write_permuted: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (feats_dev) OGL_TRY(feat_write(f->mode == OGL_BF16, feats_dev, src_rows_dev, n, f->F, f->table, f->pitch, 0, s));
+  if (labels_dev) OGL_TRY(label_write(labels_dev, src_rows_dev, n, f->labels, 0, s));
+  return OGL_OK;
+}
+
+// ------------------------------------------------------------------ plan --------------------------
+struct LayerBuf {
+  int in = 0, out = 0, pin = 0, pout = 0;
+  // offsets into the flat fp32 parameter / gradient buffers
+  int64_t o_wp = 0, o_bp = 0, o_ws = 0, o_bs = 0, o_wn = 0, o_bn = 0;
+  // shadows in the arithmetic type
+  void *wp = nullptr, *wpT = nullptr, *ws = nullptr, *wsT = nullptr, *wn = nullptr, *wnT = nullptr;
+  // activations
+  void* hp = nullptr;       // [nmax[src], pin]
+  void* neigh = nullptr;    // [nmax[dst], pin]
+  uint8_t* arg = nullptr;   // [nmax[dst], pin]
+  void* dpre = nullptr;     // [nmax[dst], pout]   gradient wrt this layer's pre-activation output
+};
+
+struct ogl_plan {
+  ogl_plan_config cfg;
+  int L = 0;
+  int bf16 = 0;
+  size_t es = 4;
+  std::vector<int> nmax;                 // [L+1]
+  std::vector<int32_t*> nodes;           // [L+1]
+  int32_t* counts = nullptr;             // [L+1] device
+  std::vector<int32_t*> edge_lid, edge_gsrc;   // [L]
+  std::vector<int64_t*> edge_eid;
+  std::vector<void*> act;                // [L+1]; act[0] = logits (fp32)
+  std::vector<LayerBuf> layer;
+  ToBlockWs tb;
+  int64_t* seeds_stage = nullptr;
+  uint32_t* ctl = nullptr;               // [0]=philox step, [1]=adam t
+  int n_seeds = 0;
+  // backward scratch
+  float* dhp32 = nullptr;
+  void* dhp = nullptr;
+  void* dng = nullptr;
+  float* tn_partial = nullptr;
+  int64_t tn_partial_elems = 0;
+  float* colsum_partial = nullptr;
+  float* per_loss = nullptr;
+  float* loss_sum = nullptr;
+  // parameters
+  int64_t n_params = 0;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+};
+
+static int gemm_nt(const ogl_plan* p, const GemmNT& g, cudaStream_t s) {
+  if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_nt_tc(g, s);
+  return gemm_nt_simt(g, s);
+}
+static int gemm_tn(const ogl_plan* p, const GemmTN& g, cudaStream_t s) {
+  if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_tn_tc(g, s);
+  return gemm_tn_simt(g, s);
+}
+
+static int dmalloc0(void** ptr, size_t bytes) {
+  OGL_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
+  OGL_CUDA(cudaMemset(*ptr, 0, bytes ? bytes : 16));
+  return OGL_OK;
+}
+#define DM0(ptr, bytes) OGL_TRY(dmalloc0((void**)&(ptr), (size_t)(bytes)))
+
+extern "C" int64_t ogl_plan_param_count(const ogl_plan* p) { return p ? p->n_params : 0; }
+
+extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
+  OGL_TRY(require_device());
+  OGL_ARG(out && cfg, "ogl_plan_create: null");
+  OGL_ARG(cfg->n_layers >= 1 && cfg->n_layers <= 7, "ogl_plan_create: n_layers must be in [1,7]");
+  OGL_ARG(cfg->max_seeds > 0 && cfg->v_cap > 0, "ogl_plan_create: max_seeds / v_cap must be positive");
+  OGL_ARG(cfg->mode == OGL_F32 || cfg->mode == OGL_BF16, "ogl_plan_create: bad mode");
+  for (int i = 0; i <= cfg->n_layers; ++i) OGL_ARG(cfg->dims[i] > 0, "ogl_plan_create: dims[%d] must be positive", i);
+  for (int i = 0; i < cfg->n_layers; ++i) OGL_ARG(cfg->fanouts[i] > 0 && cfg->fanouts[i] < 255, "ogl_plan_create: fanouts[%d] must be in [1,254]", i);
+  ogl_plan* p = new ogl_plan();
+  p->cfg = *cfg;
+  const int L = p->L = cfg->n_layers;
+  p->bf16 = cfg->mode == OGL_BF16;
+  p->es = p->bf16 ? 2 : 4;
+  p->nmax.resize(L + 1);
+  p->nmax[0] = cfg->max_seeds;
+  for (int h = 0; h < L; ++h) {
+    int64_t n = (int64_t)p->nmax[h] * (1 + cfg->fanouts[h]);
+    if (n > cfg->v_cap) n = cfg->v_cap;
+    p->nmax[h + 1] = (int)n;
+  }
+  p->nodes.resize(L + 1); p->act.resize(L + 1);
+  p->edge_lid.resize(L); p->edge_gsrc.resize(L); p->edge_eid.resize(L); p->layer.resize(L);
+  DM0(p->counts, sizeof(int32_t) * (L + 1));
+  DM0(p->ctl, sizeof(uint32_t) * 4);
+  DM0(p->seeds_stage, sizeof(int64_t) * cfg->max_seeds);
+  int64_t ne_max = 0;
+  for (int lv = 0; lv <= L; ++lv) DM0(p->nodes[lv], sizeof(int32_t) * p->nmax[lv]);
+  for (int h = 0; h < L; ++h) {
+    const int64_t ne = (int64_t)p->nmax[h] * cfg->fanouts[h];
+    if (ne > ne_max) ne_max = ne;
+    DM0(p->edge_lid[h], sizeof(int32_t) * ne);
+    DM0(p->edge_gsrc[h], sizeof(int32_t) * ne);
+    DM0(p->edge_eid[h], sizeof(int64_t) * ne);
+  }
+  OGL_TRY(to_block_init(&p->tb, cfg->v_cap, ne_max));
+  // activations (row counts padded to 128 for the zero-tail rule)
+  auto rows = [](int n) { return (size_t)round_up(n, 128); };
+  DM0(p->act[L], p->es * rows(p->nmax[L]) * pitch_of(cfg->dims[0]));
+  int64_t off = 0, max_src_elems = 0, max_dst_in_elems = 0, max_nk = 0, max_colsum = 0;
+  for (int l = 0; l < L; ++l) {
+    LayerBuf& lb = p->layer[l];
+    const int h = L - 1 - l, s = h + 1, d = h;
+    lb.in = cfg->dims[l]; lb.out = cfg->dims[l + 1]; lb.pin = pitch_of(lb.in); lb.pout = pitch_of(lb.out);
+    lb.o_wp = off; off += (int64_t)lb.in * lb.in;
+    lb.o_bp = off; off += lb.in;
+    lb.o_ws = off; off += (int64_t)lb.out * lb.in;
+    lb.o_bs = off; off += lb.out;
+    lb.o_wn = off; off += (int64_t)lb.out * lb.in;
+    lb.o_bn = off; off += lb.out;
+    DM0(lb.wp, p->es * (size_t)lb.in * lb.pin);
+    DM0(lb.wpT, p->es * (size_t)lb.in * lb.pin);
+    DM0(lb.ws, p->es * (size_t)lb.out * lb.pin);
+    DM0(lb.wsT, p->es * (size_t)lb.in * lb.pout);
+    DM0(lb.wn, p->es * (size_t)lb.out * lb.pin);
+    DM0(lb.wnT, p->es * (size_t)lb.in * lb.pout);
+    DM0(lb.hp, p->es * rows(p->nmax[s]) * lb.pin);
+    DM0(lb.neigh, p->es * rows(p->nmax[d]) * lb.pin);
+    DM0(lb.arg, rows(p->nmax[d]) * lb.pin);
+    DM0(lb.dpre, p->es * rows(p->nmax[d]) * lb.pout);
+    // layer output: logits are always fp32
+    const size_t oes = (l == L - 1) ? 4 : p->es;
+    DM0(p->act[d], oes * rows(p->nmax[d]) * lb.pout);
+    max_src_elems = std::max<int64_t>(max_src_elems, (int64_t)rows(p->nmax[s]) * lb.pin);
+    max_dst_in_elems = std::max<int64_t>(max_dst_in_elems, (int64_t)rows(p->nmax[d]) * lb.pin);
+    max_nk = std::max<int64_t>(max_nk, (int64_t)std::max(lb.in, lb.out) * lb.in);
+    max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[s], lb.pin));
+    max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[d], lb.pout));
+  }
+  p->n_params = off;
+  DM0(p->dhp32, sizeof(float) * max_src_elems);
+  DM0(p->dhp, p->es * max_src_elems);
+  DM0(p->dng, p->es * max_dst_in_elems);
+  p->tn_partial_elems = max_nk * 32;
+  DM0(p->tn_partial, sizeof(float) * p->tn_partial_elems);
+  DM0(p->colsum_partial, sizeof(float) * max_colsum);
+  DM0(p->per_loss, sizeof(float) * cfg->max_seeds);
+  DM0(p->loss_sum, sizeof(float) * 4);
+  DM0(p->adam_m, sizeof(float) * p->n_params);
+  DM0(p->adam_v, sizeof(float) * p->n_params);
+  *out = p;
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_destroy(ogl_plan* p) {
+  if (!p) return OGL_OK;
+  for (auto x : p->nodes) cudaFree(x);
+  for (auto x : p->edge_lid) cudaFree(x);
+  for (auto x : p->edge_gsrc) cudaFree(x);
+  for (auto x : p->edge_eid) cudaFree(x);
+  for (auto x : p->act) cudaFree(x);
+  for (auto& lb : p->layer) {
+    void* ptrs[] = {lb.wp, lb.wpT, lb.ws, lb.wsT, lb.wn, lb.wnT, lb.hp, lb.neigh, lb.arg, lb.dpre};
+    for (void* q : ptrs) cudaFree(q);
+  }
+  to_block_free(&p->tb);
+  void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dhp32, p->dhp, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
+                  p->loss_sum, p->adam_m, p->adam_v};
+  for (void* q : ptrs) cudaFree(q);
+  delete p;
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_refresh_params(ogl_plan* p, void* stream) {
+  OGL_ARG(p && p->params, "ogl_plan_refresh_params: parameters not bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (auto& lb : p->layer) {
+    OGL_TRY(weight_shadow(p->bf16, p->params + lb.o_wp, lb.in, lb.in, lb.wp, lb.pin, lb.wpT, lb.pin, s));
+    OGL_TRY(weight_shadow(p->bf16, p->params + lb.o_ws, lb.out, lb.in, lb.ws, lb.pin, lb.wsT, lb.pout, s));
+    OGL_TRY(weight_shadow(p->bf16, p->params + lb.o_wn, lb.out, lb.in, lb.wn, lb.pin, lb.wnT, lb.pout, s));
+  }
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_bind_params(ogl_plan* p, float* params_dev, float* grads_dev, void* stream) {
+  OGL_ARG(p && params_dev && grads_dev, "ogl_plan_bind_params: null");
+  p->params = params_dev;
+  p->grads = grads_dev;
+  return ogl_plan_refresh_params(p, stream);
+}
+
+extern "C" int ogl_plan_set_step(ogl_plan* p, uint32_t step, void* stream) {
+  OGL_ARG(p, "null");
+  OGL_CUDA(cudaMemcpyAsync(p->ctl, &step, sizeof(uint32_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  OGL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return OGL_OK;
+}
+
+__global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
+
+extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_dev, int n_seeds, void* stream) {
+  OGL_ARG(p && g && seeds_dev, "ogl_plan_sample: null");
+  OGL_ARG(n_seeds > 0 && n_seeds <= p->cfg.max_seeds, "ogl_plan_sample: n_seeds %d not in [1, %d]", n_seeds, p->cfg.max_seeds);
+  cudaStream_t s = (cudaStream_t)stream;
+  const GraphView gv = graph_view(g);
+  OGL_ARG(gv.n_vertices <= p->cfg.v_cap, "ogl_plan_sample: graph has more vertices than the plan's v_cap");
+  p->n_seeds = n_seeds;
+  OGL_TRY(cast_nodes(seeds_dev, p->nodes[0], n_seeds, s));
+  OGL_LAUNCH(k_set_i32, 1, 1, 0, s, p->counts, n_seeds);
+  for (int h = 0; h < p->L; ++h) {
+    OGL_TRY(sample_hop(gv, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->cfg.seed, p->ctl, 0, (uint32_t)h,
+                       p->edge_gsrc[h], p->edge_eid[h], s));
+    OGL_TRY(to_block(&p->tb, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->edge_gsrc[h], p->nodes[h + 1],
+                     p->counts + h + 1, p->nmax[h + 1], p->edge_lid[h], s));
+  }
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev, void* stream) {
+  OGL_ARG(p && p->params, "ogl_plan_forward: null / parameters not bound");
+  OGL_ARG(!f || (f->mode == p->cfg.mode && f->F == p->cfg.dims[0]), "ogl_plan_forward: feature store does not match the plan (mode/F)");
+  OGL_ARG(p->n_seeds > 0, "ogl_plan_forward: no minibatch sampled");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int L = p->L;
+  // f == NULL: the input rows were supplied by ogl_plan_set_input
+  if (f) OGL_TRY(gather_rows(p->bf16, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
+  for (int l = 0; l < L; ++l) {
+    LayerBuf& lb = p->layer[l];
+    const int h = L - 1 - l, sl = h + 1, dl = h;
+    GemmNT g1;
+    g1.a[0] = p->act[sl]; g1.lda[0] = lb.pin; g1.b[0] = lb.wp; g1.ldb[0] = lb.pin; g1.k[0] = lb.in; g1.n_seg = 1;
+    g1.bias = p->params + lb.o_bp; g1.relu = 1;
+    g1.c = lb.hp; g1.ldc = lb.pin; g1.m_max = p->nmax[sl]; g1.m_dev = p->counts + sl; g1.n = lb.in;
+    g1.in_bf16 = p->bf16; g1.out_bf16 = p->bf16;
+    OGL_TRY(gemm_nt(p, g1, s));
+    OGL_TRY(segmax_fwd(p->bf16, lb.hp, lb.pin, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], lb.neigh, lb.arg, s));
+    GemmNT g2;
+    g2.a[0] = p->act[sl]; g2.lda[0] = lb.pin; g2.b[0] = lb.ws; g2.ldb[0] = lb.pin; g2.k[0] = lb.in;
+    g2.a[1] = lb.neigh; g2.lda[1] = lb.pin; g2.b[1] = lb.wn; g2.ldb[1] = lb.pin; g2.k[1] = lb.in; g2.n_seg = 2;
+    g2.bias = p->params + lb.o_bs; g2.bias2 = p->params + lb.o_bn; g2.relu = (l < L - 1);
+    g2.c = p->act[dl]; g2.ldc = lb.pout; g2.m_max = p->nmax[dl]; g2.m_dev = p->counts + dl; g2.n = lb.out;
+    g2.in_bf16 = p->bf16; g2.out_bf16 = (l < L - 1) ? p->bf16 : 0;
+    OGL_TRY(gemm_nt(p, g2, s));
+  }
+  if (logits_dev)
+    OGL_TRY(unpad_copy((const float*)p->act[0], p->layer[L - 1].pout, p->nmax[0], p->counts, p->cfg.dims[L], logits_dev, s));
+  return OGL_OK;
+}
+
+static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
+  const int L = p->L;
+  LayerBuf& last = p->layer[L - 1];
+  float* per = per_vertex_loss_dev ? per_vertex_loss_dev : p->per_loss;
+  OGL_TRY(xent(p->bf16, (const float*)p->act[0], last.pout, p->cfg.dims[L], f->labels, p->nodes[0], p->counts, p->nmax[0],
+               round_up(p->nmax[0], 128), scale, per, last.dpre, last.pout, want_grad, s));
+  if (loss_sum_dev) OGL_TRY(sum_f32(per, p->counts, p->nmax[0], loss_sum_dev, s));
+  return OGL_OK;
+}
+
+static int plan_backward_layers(ogl_plan* p, cudaStream_t s);
+
+extern "C" int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
+                                      void* stream) {
+  OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_loss_backward: plan not ready");
+  cudaStream_t s = (cudaStream_t)stream;
+  OGL_TRY(plan_loss(p, f, loss_scale, 1, per_vertex_loss_dev, loss_sum_dev, s));
+  return plan_backward_layers(p, s);
+}
+
+static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
+  const int L = p->L;
+  for (int l = L - 1; l >= 0; --l) {
+    LayerBuf& lb = p->layer[l];
+    const int h = L - 1 - l, sl = h + 1, dl = h;
+    float* G = p->grads;
+    // dWs = dpre^T act[src][:n_d] ; dWn = dpre^T neigh
+    GemmTN t;
+    t.a = lb.dpre; t.lda = lb.pout; t.n = lb.out; t.b = p->act[sl]; t.ldb = lb.pin; t.k = lb.in;
+    t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16;
+    t.partial = p->tn_partial; t.partial_elems = p->tn_partial_elems;
+    OGL_TRY(gemm_tn(p, t, s));
+    t.b = lb.neigh; t.c = G + lb.o_wn;
+    OGL_TRY(gemm_tn(p, t, s));
+    OGL_TRY(colsum(p->bf16, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl], p->colsum_partial, G + lb.o_bs, G + lb.o_bn, s));
+    // dneigh = dpre Wn
+    GemmNT n1;
+    n1.a[0] = lb.dpre; n1.lda[0] = lb.pout; n1.b[0] = lb.wnT; n1.ldb[0] = lb.pout; n1.k[0] = lb.out; n1.n_seg = 1;
+    n1.c = p->dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
+    n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.zero_tail = 0;
+    OGL_TRY(gemm_nt(p, n1, s));
+    // scatter through the argmax, relu mask
+    OGL_TRY(segmax_bwd(p->bf16, p->dng, lb.pin, lb.in, lb.arg, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], p->dhp32, s));
+    OGL_TRY(mask_convert(p->bf16, p->dhp32, lb.hp, lb.pin, p->counts + sl, p->nmax[sl], p->dhp, s));
+    // dWp = dhp^T act[src]
+    GemmTN tp;
+    tp.a = p->dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
+    tp.c = G + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16;
+    tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
+    OGL_TRY(gemm_tn(p, tp, s));
+    OGL_TRY(colsum(p->bf16, p->dhp, lb.pin, lb.in, p->counts + sl, p->nmax[sl], p->colsum_partial, G + lb.o_bp, nullptr, s));
+    if (l > 0) {
+      // dpre[l-1] = relu'(act[src]) * ( dhp Wp + [dpre Ws on the first n_d rows] )
+      LayerBuf& prev = p->layer[l - 1];
+      GemmNT d;
+      d.a[0] = p->dhp; d.lda[0] = lb.pin; d.b[0] = lb.wpT; d.ldb[0] = lb.pin; d.k[0] = lb.in;
+      d.a[1] = lb.dpre; d.lda[1] = lb.pout; d.b[1] = lb.wsT; d.ldb[1] = lb.pout; d.k[1] = lb.out; d.a_rows_dev[1] = p->counts + dl;
+      d.n_seg = 2;
+      d.mask = p->act[sl]; d.ldmask = lb.pin;
+      d.c = prev.dpre; d.ldc = prev.pout; d.m_max = p->nmax[sl]; d.m_dev = p->counts + sl; d.n = lb.in;
+      d.in_bf16 = p->bf16; d.out_bf16 = p->bf16;
+      OGL_TRY(gemm_nt(p, d, s));
+    }
+  }
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_set_input(ogl_plan* p, const float* x_dev, int n_rows, void* stream) {
+  OGL_ARG(p && x_dev && n_rows > 0 && n_rows <= p->nmax[p->L], "ogl_plan_set_input: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int L = p->L, F = p->cfg.dims[0], pt = pitch_of(F);
+  OGL_TRY(feat_write(p->bf16, x_dev, nullptr, n_rows, F, p->act[L], pt, 0, s));
+  const int np = std::min(round_up(n_rows, 128), round_up(p->nmax[L], 128));
+  if (np > n_rows) OGL_CUDA(cudaMemsetAsync((char*)p->act[L] + p->es * (size_t)n_rows * pt, 0, p->es * (size_t)(np - n_rows) * pt, s));
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_backward(ogl_plan* p, const float* dlogits_dev, void* stream) {
+  OGL_ARG(p && dlogits_dev && p->params && p->n_seeds > 0, "ogl_plan_backward: plan not ready");
+  cudaStream_t s = (cudaStream_t)stream;
+  LayerBuf& last = p->layer[p->L - 1];
+  const int n = p->n_seeds;
+  OGL_TRY(feat_write(p->bf16, dlogits_dev, nullptr, n, last.out, last.dpre, last.pout, 0, s));
+  const int np = round_up(n, 128);
+  if (np > n) OGL_CUDA(cudaMemsetAsync((char*)last.dpre + p->es * (size_t)n * last.pout, 0, p->es * (size_t)(np - n) * last.pout, s));
+  return plan_backward_layers(p, s);
+}
+
+extern "C" int ogl_plan_adam_step(ogl_plan* p, void* stream) {
+  OGL_ARG(p && p->params, "ogl_plan_adam_step: parameters not bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  OGL_TRY(adam(p->params, p->grads, p->adam_m, p->adam_v, p->n_params, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps, p->ctl + 1, s));
+  OGL_TRY(bump(nullptr, p->ctl + 1, s));
+  return ogl_plan_refresh_params(p, stream);
+}
+
+static int stage_seeds(ogl_plan* p, const int64_t* seeds, int n_seeds, int on_host, const int64_t** out, cudaStream_t s) {
+  OGL_ARG(n_seeds > 0 && n_seeds <= p->cfg.max_seeds, "n_seeds %d not in [1, %d]", n_seeds, p->cfg.max_seeds);
+  if (on_host) {
+    OGL_CUDA(cudaMemcpyAsync(p->seeds_stage, seeds, sizeof(int64_t) * n_seeds, cudaMemcpyHostToDevice, s));
+    *out = p->seeds_stage;
+  } else {
+    *out = seeds;
+  }
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
+                                   float loss_scale, int do_step, float* per_vertex_loss_dev, float* loss_sum_dev, void* stream) {
+  OGL_ARG(p && g && f && seeds, "ogl_plan_train_step: null");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t* sd = nullptr;
+  OGL_TRY(stage_seeds(p, seeds, n_seeds, seeds_on_host, &sd, s));
+  OGL_TRY(ogl_plan_sample(p, g, sd, n_seeds, stream));
+  OGL_TRY(ogl_plan_forward(p, f, nullptr, stream));
+  OGL_TRY(ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, stream));
+  if (do_step) OGL_TRY(ogl_plan_adam_step(p, stream));
+  OGL_TRY(bump(p->ctl, nullptr, s));
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_eval_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
+                                  float* logits_dev, float* per_vertex_loss_dev, void* stream) {
+  OGL_ARG(p && g && f && seeds, "ogl_plan_eval_step: null");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t* sd = nullptr;
+  OGL_TRY(stage_seeds(p, seeds, n_seeds, seeds_on_host, &sd, s));
+  OGL_TRY(ogl_plan_sample(p, g, sd, n_seeds, stream));
+  OGL_TRY(ogl_plan_forward(p, f, logits_dev, stream));
+  if (per_vertex_loss_dev) OGL_TRY(plan_loss(p, f, 1.f, 0, per_vertex_loss_dev, nullptr, s));
+  OGL_TRY(bump(p->ctl, nullptr, s));
+  return OGL_OK;
+}
+
+// ------------------------------------------------------------------ introspection ------------------
+extern "C" int ogl_plan_level_nodes(ogl_plan* p, int level, const int32_t** nodes_dev, const int32_t** count_dev, int* max_count) {
+  OGL_ARG(p && level >= 0 && level <= p->L, "ogl_plan_level_nodes: bad level");
+  if (nodes_dev) *nodes_dev = p->nodes[level];
+  if (count_dev) *count_dev = p->counts + level;
+  if (max_count) *max_count = p->nmax[level];
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_block_edges(ogl_plan* p, int hop, const int32_t** edge_src_local_dev, const int32_t** edge_src_global_dev,
+                                    const int64_t** edge_eid_dev, int* fanout) {
+  OGL_ARG(p && hop >= 0 && hop < p->L, "ogl_plan_block_edges: bad hop");
+  if (edge_src_local_dev) *edge_src_local_dev = p->edge_lid[hop];
+  if (edge_src_global_dev) *edge_src_global_dev = p->edge_gsrc[hop];
+  if (edge_eid_dev) *edge_eid_dev = p->edge_eid[hop];
+  if (fanout) *fanout = p->cfg.fanouts[hop];
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_tensor(ogl_plan* p, const char* name, const void** ptr_dev, int* rows_max, int* pitch, int* elem_bytes) {
+  OGL_ARG(p && name && ptr_dev, "ogl_plan_tensor: null");
+  const std::string n(name);
+  const int L = p->L;
+  auto ret = [&](const void* ptr, int r, int pt, int eb) {
+    *ptr_dev = ptr;
+    if (rows_max) *rows_max = r;
+    if (pitch) *pitch = pt;
+    if (elem_bytes) *elem_bytes = eb;
+    return OGL_OK;
+  };
+  if (n == "x") return ret(p->act[L], p->nmax[L], pitch_of(p->cfg.dims[0]), (int)p->es);
+  if (n.size() >= 2) {
+    const int l = n.back() - '0';
+    const std::string base = n.substr(0, n.size() - 1);
+    if (l >= 0 && l < L) {
+      LayerBuf& lb = p->layer[l];
+      const int h = L - 1 - l;
+      if (base == "hp") return ret(lb.hp, p->nmax[h + 1], lb.pin, (int)p->es);
+      if (base == "neigh") return ret(lb.neigh, p->nmax[h], lb.pin, (int)p->es);
+      if (base == "arg") return ret(lb.arg, p->nmax[h], lb.pin, 1);
+      if (base == "out") return ret(p->act[h], p->nmax[h], lb.pout, l == L - 1 ? 4 : (int)p->es);
+      if (base == "dpre") return ret(lb.dpre, p->nmax[h], lb.pout, (int)p->es);
+    }
+  }
+  set_error("ogl_plan_tensor: unknown tensor '%s'", name);
+  return OGL_ERR_ARG;
+}

@@ -1,0 +1,341 @@
+// Memory-bound kernels of the GraphSAGE-pool layer: feature gather, segment max with argmax
+// capture, argmax gradient scatter, bias-gradient column sums, cross-entropy, Adam.
+// All are HBM-bound: 128-bit coalesced row accesses, device-side row counts (no host sync),
+// grids sized from the SM count.
+#include "sage_kernels.cuh"
+
+namespace ogl {
+
+constexpr int kBlock = 256;
+
+template <typename T> struct Vec;           // 16-byte vector of T
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
+
+__device__ __forceinline__ int dyn_count(const int32_t* n_dev, int n_max) { return n_dev ? min(*n_dev, n_max) : n_max; }
+__device__ __forceinline__ int pad128(int n, int n_max) { return min((n + 127) / 128 * 128, n_max); }
+
+// ---- feature store -------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_feat_write(const float* __restrict__ src, const int64_t* __restrict__ src_rows, int64_t n, int F,
+                                                       T* __restrict__ dst, int pitch, int64_t row0) {
+  // one warp per row; fp32 -> T, zero the pad columns
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const float* s = src + (src_rows ? src_rows[r] : r) * (int64_t)F;
+    T* d = dst + (row0 + r) * (int64_t)pitch;
+    for (int c = lane; c < pitch; c += 32) d[c] = from_f32<T>(c < F ? s[c] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_label_write(const int64_t* __restrict__ src, const int64_t* __restrict__ src_rows, int64_t n,
+                                                        int32_t* __restrict__ dst, int64_t row0) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[row0 + i] = (int32_t)src[src_rows ? src_rows[i] : i];
+}
+
+// out[r, :] = table[nodes[r], :] for r < n; zero rows [n, pad128(n))
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_gather_rows(const T* __restrict__ table, int pitch, const int32_t* __restrict__ nodes,
+                                                        const int32_t* __restrict__ n_dev, int n_max, T* __restrict__ out) {
+  const int n = dyn_count(n_dev, n_max);
+  const int np = pad128(n, n_max);
+  const int vpr = pitch / Vec<T>::N;            // 16-byte vectors per row
+  const int64_t total = (int64_t)np * vpr;
+  const uint4* tb = reinterpret_cast<const uint4*>(table);
+  uint4* ob = reinterpret_cast<uint4*>(out);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / vpr), c = (int)(t % vpr);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < n) v = __ldg(tb + (int64_t)nodes[r] * vpr + c);
+    ob[t] = v;
+  }
+}
+
+// ---- segment max over the fixed-fanout block (ELL layout), first-slot-wins argmax -----------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_segmax_fwd(const T* __restrict__ hp, int pitch, const int32_t* __restrict__ edge_lid, int fanout,
+                                                       const int32_t* __restrict__ n_dst_dev, int n_dst_max, T* __restrict__ ng,
+                                                       uint8_t* __restrict__ arg) {
+  constexpr int NV = Vec<T>::N;
+  const int n = dyn_count(n_dst_dev, n_dst_max);
+  const int np = pad128(n, n_dst_max);
+  const int vpr = pitch / NV;
+  const int64_t total = (int64_t)np * vpr;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(t / vpr), c = (int)(t % vpr);
+    float best[NV];
+    uint8_t slot[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { best[i] = 0.f; slot[i] = 255; }
+    if (d < n) {
+      bool any = false;
+      const int32_t* el = edge_lid + (int64_t)d * fanout;
+      for (int j = 0; j < fanout; ++j) {
+        const int lid = el[j];
+        if (lid < 0) continue;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(hp + (int64_t)lid * pitch) + c);
+        const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float x = to_f32<T>(v[i]);
+          if (!any || x > best[i]) { best[i] = x; slot[i] = (uint8_t)j; }
+        }
+        any = true;
+      }
+    }
+    T o[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) o[i] = from_f32<T>(best[i]);
+    *reinterpret_cast<uint4*>(ng + (int64_t)d * pitch + c * NV) = *reinterpret_cast<const uint4*>(o);
+    if (d < n) {
+      if (NV == 8) *reinterpret_cast<uint2*>(arg + (int64_t)d * pitch + c * NV) = *reinterpret_cast<const uint2*>(slot);
+      else *reinterpret_cast<uint32_t*>(arg + (int64_t)d * pitch + c * NV) = *reinterpret_cast<const uint32_t*>(slot);
+    }
+  }
+}
+
+// dhp32[src(argslot), f] += dng[d, f]
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_segmax_bwd(const T* __restrict__ dng, int pitch, int feat, const uint8_t* __restrict__ arg,
+                                                       const int32_t* __restrict__ edge_lid, int fanout, const int32_t* __restrict__ n_dst_dev,
+                                                       int n_dst_max, float* __restrict__ dhp32) {
+  const int n = dyn_count(n_dst_dev, n_dst_max);
+  const int64_t total = (int64_t)n * pitch;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(t / pitch), f = (int)(t % pitch);
+    if (f >= feat) continue;
+    const int sl = arg[t];
+    if (sl == 255) continue;
+    const float g = to_f32<T>(dng[t]);
+    if (g == 0.f) continue;
+    const int lid = edge_lid[(int64_t)d * fanout + sl];
+    atomicAdd(&dhp32[(int64_t)lid * pitch + f], g);
+  }
+}
+
+// dhp[r, f] = hp[r, f] > 0 ? dhp32[r, f] : 0 ; dhp32 is zeroed again; rows [n, pad128) zero
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_mask_convert(float* __restrict__ dhp32, const T* __restrict__ hp, int pitch,
+                                                         const int32_t* __restrict__ n_dev, int n_max, T* __restrict__ dhp) {
+  const int n = dyn_count(n_dev, n_max);
+  const int np = pad128(n, n_max);
+  const int64_t total = (int64_t)np * pitch / 4;
+  float4* g4 = reinterpret_cast<float4*>(dhp32);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = t * 4;
+    const int r = (int)(e / pitch);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < n) {
+      const float4 g = g4[t];
+      const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = to_f32<T>(hp[e + i]) > 0.f ? gv[i] : 0.f;
+      g4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dhp[e + i] = from_f32<T>(o[i]);
+  }
+}
+
+// ---- bias gradient: deterministic two-phase column sum -------------------------------------------
+constexpr int kColRows = 128;
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_colsum_partial(const T* __restrict__ x, int pitch, int cols, const int32_t* __restrict__ n_dev,
+                                                           int n_max, float* __restrict__ partial) {
+  const int n = dyn_count(n_dev, n_max);
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * kColRows, r1 = min(r0 + kColRows, n);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(int64_t)r * pitch + c]);
+    partial[(int64_t)chunk * cols + c] = s;
+  }
+}
+__global__ void __launch_bounds__(kBlock) k_colsum_final(const float* __restrict__ partial, int cols, const int32_t* __restrict__ n_dev,
+                                                         int n_max, float* __restrict__ out, float* __restrict__ out2) {
+  const int n = dyn_count(n_dev, n_max);
+  const int chunks = (n + kColRows - 1) / kColRows;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += partial[(int64_t)k * cols + c];
+    out[c] = s;
+    if (out2) out2[c] = s;
+  }
+}
+
+// ---- cross entropy: per-vertex loss + dlogits (rows >= n zeroed up to the padded count) -----------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_xent(const float* __restrict__ logits, int ldl, int C, const int32_t* __restrict__ labels,
+                                                 const int32_t* __restrict__ nodes, const int32_t* __restrict__ n_dev, int n_max,
+                                                 int rows_buf, float scale,
+                                                 float* __restrict__ per_loss, T* __restrict__ dlogits, int ldd, int want_grad) {
+  const int n = dyn_count(n_dev, n_max);
+  const int nz = want_grad ? pad128(n, rows_buf) : n;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < max(n, nz); r += gridDim.x * blockDim.x) {
+    if (r < n) {
+      const float* l = logits + (int64_t)r * ldl;
+      float mx = -INFINITY;
+      for (int c = 0; c < C; ++c) mx = fmaxf(mx, l[c]);
+      float se = 0.f;
+      for (int c = 0; c < C; ++c) se += expf(l[c] - mx);
+      const float lse = mx + logf(se);
+      const int y = labels[nodes[r]];
+      if (per_loss) per_loss[r] = lse - l[y];
+      if (want_grad) {
+        T* d = dlogits + (int64_t)r * ldd;
+        for (int c = 0; c < ldd; ++c) {
+          float g = 0.f;
+          if (c < C) g = (expf(l[c] - lse) - (c == y ? 1.f : 0.f)) * scale;
+          d[c] = from_f32<T>(g);
+        }
+      }
+    } else if (want_grad) {
+      T* d = dlogits + (int64_t)r * ldd;
+      for (int c = 0; c < ldd; ++c) d[c] = from_f32<T>(0.f);
+    }
+  }
+}
+
+// single CTA, fixed order: deterministic sum of the per-vertex losses
+__global__ void __launch_bounds__(1024) k_sum_f32(const float* __restrict__ x, const int32_t* __restrict__ n_dev, int n_max, float* __restrict__ out) {
+  __shared__ float s[32];
+  const int n = dyn_count(n_dev, n_max);
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += x[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = s[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) *out = a;
+  }
+}
+
+// ---- Adam (torch.optim.Adam defaults, pytorch/model.py:25) on the flat fp32 buffers ---------------
+__global__ void __launch_bounds__(kBlock) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                 int64_t n, float lr, float b1, float b2, float eps, uint32_t* __restrict__ t_dev) {
+  const uint32_t t = *t_dev + 1;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  const float step = lr / bc1, isq = rsqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) * isq + eps);
+  }
+}
+__global__ void k_bump(uint32_t* a, uint32_t* b) {
+  if (a) *a += 1;
+  if (b) *b += 1;
+}
+
+// weight shadows in the arithmetic type: W [out, pitch(in)] and W^T [in, pitch(out)]
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_weight_shadow(const float* __restrict__ w, int out, int in, T* __restrict__ ws, int pitch_in,
+                                                          T* __restrict__ wt, int pitch_out) {
+  const int64_t total = (int64_t)out * pitch_in;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(t / pitch_in), i = (int)(t % pitch_in);
+    const float x = i < in ? w[(int64_t)o * in + i] : 0.f;
+    ws[t] = from_f32<T>(x);
+    if (wt && i < in) wt[(int64_t)i * pitch_out + o] = from_f32<T>(x);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_unpad_copy(const float* __restrict__ src, int lds, int n_rows_max, const int32_t* n_dev, int cols, float* __restrict__ dst) {
+  const int n = dyn_count(n_dev, n_rows_max);
+  const int64_t total = (int64_t)n * cols;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+    dst[t] = src[(t / cols) * lds + (t % cols)];
+}
+
+// ================================ host wrappers ====================================================
+#define L2(K, grid, s, ...)                                              \
+  do {                                                                   \
+    if (bf16) OGL_LAUNCH((K<__nv_bfloat16>), grid, kBlock, 0, s, __VA_ARGS__); \
+    else OGL_LAUNCH((K<float>), grid, kBlock, 0, s, __VA_ARGS__);        \
+  } while (0)
+
+int feat_write(int bf16, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s) {
+  if (n <= 0) return OGL_OK;
+  const int grid = grid_for(n * 32, kBlock);
+  if (bf16) OGL_LAUNCH((k_feat_write<__nv_bfloat16>), grid, kBlock, 0, s, src, src_rows, n, F, (__nv_bfloat16*)dst, pitch, row0);
+  else OGL_LAUNCH((k_feat_write<float>), grid, kBlock, 0, s, src, src_rows, n, F, (float*)dst, pitch, row0);
+  return OGL_OK;
+}
+int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t* dst, int64_t row0, cudaStream_t s) {
+  if (n <= 0) return OGL_OK;
+  OGL_LAUNCH(k_label_write, grid_for(n, kBlock), kBlock, 0, s, src, src_rows, n, dst, row0);
+  return OGL_OK;
+}
+int gather_rows(int bf16, const void* table, int pitch, const int32_t* nodes, const int32_t* n_dev, int n_max, void* out, cudaStream_t s) {
+  const int grid = grid_for((int64_t)n_max * pitch / 8, kBlock, 16);
+  if (bf16) OGL_LAUNCH((k_gather_rows<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)table, pitch, nodes, n_dev, n_max, (__nv_bfloat16*)out);
+  else OGL_LAUNCH((k_gather_rows<float>), grid, kBlock, 0, s, (const float*)table, pitch, nodes, n_dev, n_max, (float*)out);
+  return OGL_OK;
+}
+int segmax_fwd(int bf16, const void* hp, int pitch, const int32_t* edge_lid, int fanout, const int32_t* n_dst_dev, int n_dst_max, void* ng,
+               uint8_t* arg, cudaStream_t s) {
+  const int grid = grid_for((int64_t)n_dst_max * pitch / 8, kBlock, 16);
+  if (bf16) OGL_LAUNCH((k_segmax_fwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)hp, pitch, edge_lid, fanout, n_dst_dev, n_dst_max, (__nv_bfloat16*)ng, arg);
+  else OGL_LAUNCH((k_segmax_fwd<float>), grid, kBlock, 0, s, (const float*)hp, pitch, edge_lid, fanout, n_dst_dev, n_dst_max, (float*)ng, arg);
+  return OGL_OK;
+}
+int segmax_bwd(int bf16, const void* dng, int pitch, int feat, const uint8_t* arg, const int32_t* edge_lid, int fanout,
+               const int32_t* n_dst_dev, int n_dst_max, float* dhp32, cudaStream_t s) {
+  const int grid = grid_for((int64_t)n_dst_max * pitch, kBlock, 16);
+  if (bf16) OGL_LAUNCH((k_segmax_bwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)dng, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
+  else OGL_LAUNCH((k_segmax_bwd<float>), grid, kBlock, 0, s, (const float*)dng, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
+  return OGL_OK;
+}
+int mask_convert(int bf16, float* dhp32, const void* hp, int pitch, const int32_t* n_dev, int n_max, void* dhp, cudaStream_t s) {
+  const int grid = grid_for((int64_t)n_max * pitch / 4, kBlock, 16);
+  if (bf16) OGL_LAUNCH((k_mask_convert<__nv_bfloat16>), grid, kBlock, 0, s, dhp32, (const __nv_bfloat16*)hp, pitch, n_dev, n_max, (__nv_bfloat16*)dhp);
+  else OGL_LAUNCH((k_mask_convert<float>), grid, kBlock, 0, s, dhp32, (const float*)hp, pitch, n_dev, n_max, (float*)dhp);
+  return OGL_OK;
+}
+int64_t colsum_partial_elems(int n_max, int cols) { return ceil_div(n_max, kColRows) * (int64_t)cols; }
+int colsum(int bf16, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s) {
+  dim3 grid((unsigned)ceil_div(cols, kBlock), (unsigned)ceil_div(n_max, kColRows));
+  if (bf16) OGL_LAUNCH((k_colsum_partial<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)x, pitch, cols, n_dev, n_max, partial);
+  else OGL_LAUNCH((k_colsum_partial<float>), grid, kBlock, 0, s, (const float*)x, pitch, cols, n_dev, n_max, partial);
+  OGL_LAUNCH(k_colsum_final, (unsigned)ceil_div(cols, kBlock), kBlock, 0, s, partial, cols, n_dev, n_max, out, out2);
+  return OGL_OK;
+}
+int xent(int bf16, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,
+         int rows_buf, float scale, float* per_loss, void* dlogits, int ldd, int want_grad, cudaStream_t s) {
+  const int grid = grid_for(rows_buf > n_max ? rows_buf : n_max, kBlock);
+  if (bf16) OGL_LAUNCH((k_xent<__nv_bfloat16>), grid, kBlock, 0, s, logits, ldl, C, labels, nodes, n_dev, n_max, rows_buf, scale, per_loss, (__nv_bfloat16*)dlogits, ldd, want_grad);
+  else OGL_LAUNCH((k_xent<float>), grid, kBlock, 0, s, logits, ldl, C, labels, nodes, n_dev, n_max, rows_buf, scale, per_loss, (float*)dlogits, ldd, want_grad);
+  return OGL_OK;
+}
+int sum_f32(const float* x, const int32_t* n_dev, int n_max, float* out, cudaStream_t s) {
+  OGL_LAUNCH(k_sum_f32, 1, 1024, 0, s, x, n_dev, n_max, out);
+  return OGL_OK;
+}
+int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, uint32_t* t_dev, cudaStream_t s) {
+  OGL_LAUNCH(k_adam, grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev);
+  return OGL_OK;
+}
+int bump(uint32_t* a, uint32_t* b, cudaStream_t s) {
+  OGL_LAUNCH(k_bump, 1, 1, 0, s, a, b);
+  return OGL_OK;
+}
+int weight_shadow(int bf16, const float* w, int out, int in, void* ws, int pitch_in, void* wt, int pitch_out, cudaStream_t s) {
+  const int grid = grid_for((int64_t)out * pitch_in, kBlock);
+  if (bf16) OGL_LAUNCH((k_weight_shadow<__nv_bfloat16>), grid, kBlock, 0, s, w, out, in, (__nv_bfloat16*)ws, pitch_in, (__nv_bfloat16*)wt, pitch_out);
+  else OGL_LAUNCH((k_weight_shadow<float>), grid, kBlock, 0, s, w, out, in, (float*)ws, pitch_in, (float*)wt, pitch_out);
+  return OGL_OK;
+}
+int unpad_copy(const float* src, int lds, int n_rows_max, const int32_t* n_dev, int cols, float* dst, cudaStream_t s) {
+  OGL_LAUNCH((k_unpad_copy<float>), grid_for((int64_t)n_rows_max * cols, kBlock), kBlock, 0, s, src, lds, n_rows_max, n_dev, cols, dst);
+  return OGL_OK;
+}
+
+}  // namespace ogl

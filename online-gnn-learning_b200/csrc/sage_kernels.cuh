@@ -1,0 +1,26 @@
+// Host wrappers of the memory-bound GraphSAGE-pool kernels (see sage_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ogl {
+
+int feat_write(int bf16, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s);
+int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t* dst, int64_t row0, cudaStream_t s);
+int gather_rows(int bf16, const void* table, int pitch, const int32_t* nodes, const int32_t* n_dev, int n_max, void* out, cudaStream_t s);
+int segmax_fwd(int bf16, const void* hp, int pitch, const int32_t* edge_lid, int fanout, const int32_t* n_dst_dev, int n_dst_max, void* ng,
+               uint8_t* arg, cudaStream_t s);
+int segmax_bwd(int bf16, const void* dng, int pitch, int feat, const uint8_t* arg, const int32_t* edge_lid, int fanout,
+               const int32_t* n_dst_dev, int n_dst_max, float* dhp32, cudaStream_t s);
+int mask_convert(int bf16, float* dhp32, const void* hp, int pitch, const int32_t* n_dev, int n_max, void* dhp, cudaStream_t s);
+int64_t colsum_partial_elems(int n_max, int cols);
+int colsum(int bf16, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s);
+int xent(int bf16, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,
+         int rows_buf, float scale, float* per_loss, void* dlogits, int ldd, int want_grad, cudaStream_t s);
+int sum_f32(const float* x, const int32_t* n_dev, int n_max, float* out, cudaStream_t s);
+int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, uint32_t* t_dev, cudaStream_t s);
+int bump(uint32_t* a, uint32_t* b, cudaStream_t s);
+int weight_shadow(int bf16, const float* w, int out, int in, void* ws, int pitch_in, void* wt, int pitch_out, cudaStream_t s);
+int unpad_copy(const float* src, int lds, int n_rows_max, const int32_t* n_dev, int cols, float* dst, cudaStream_t s);
+int reduce_splits(const float* partial, int splits, int n, int k, float* c, int ldc, cudaStream_t s);
+
+}  // namespace ogl

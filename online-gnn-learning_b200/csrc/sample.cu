@@ -1,0 +1,246 @@
+// Uniform k-neighbour sampler (Philox) + to_block frontier compaction + RBR subset draw.
+//
+// Replaces dgl.sampling.MultiLayerNeighborSampler([s]*2, replace=True, return_eids=True) and
+// NodeDataLoader's to_block as driven from train/graphsage/pytorch/model.py:44-47,128-131.
+// Device twin of oracle/sampler.py (bit-exact index lists under the same Philox stream).
+#include "sample.cuh"
+
+namespace ogl {
+
+constexpr int kBlock = 256;
+
+// one thread per (row, quad of picks): 1 Philox call -> 4 picks
+__global__ void __launch_bounds__(kBlock) k_sample(GraphView g, const int32_t* __restrict__ dst_nodes, const int32_t* __restrict__ n_dst_dev,
+                                                   int n_dst_max, int fanout, uint2 key, const uint32_t* __restrict__ step_dev,
+                                                   uint32_t step_imm, uint32_t hop, int32_t* __restrict__ out_src,
+                                                   int64_t* __restrict__ out_eid) {
+  const int Q = (fanout + 3) >> 2;
+  const int n_dst = n_dst_dev ? min(*n_dst_dev, n_dst_max) : n_dst_max;
+  const uint32_t step = step_dev ? *step_dev : step_imm;
+  const int64_t total = (int64_t)n_dst * Q;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(t / Q), q = (int)(t % Q);
+    const int v = dst_nodes[row];
+    const int deg = g.deg[v];
+    const int64_t start = g.row_start[v];
+    const uint4 w = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)row, hop, step), key);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = q * 4 + i;
+      if (j < fanout) {
+        const int64_t o = (int64_t)row * fanout + j;
+        if (deg > 0) {
+          const uint32_t r = __umulhi(pick4(w, i), (uint32_t)deg);
+          out_src[o] = g.adj_src[start + r];
+          if (out_eid) out_eid[o] = (int64_t)g.adj_eid[start + r];
+        } else {
+          out_src[o] = -1;
+          if (out_eid) out_eid[o] = -1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_cast_nodes(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
+// ---- to_block: direct-address first-appearance table ----------------------------------------
+// first[g] = min over appearances of (position in dst list | n_dst + edge position)
+__global__ void __launch_bounds__(kBlock) k_tb_mark(const int32_t* __restrict__ dst_nodes, const int32_t* __restrict__ n_dst_dev,
+                                                    int n_dst_max, int fanout, const int32_t* __restrict__ picked, int32_t* __restrict__ first) {
+  const int n_dst = min(*n_dst_dev, n_dst_max);
+  const int64_t ne = (int64_t)n_dst * fanout;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_dst + ne; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < n_dst) {
+      atomicMin(&first[dst_nodes[t]], (int32_t)t);
+    } else {
+      const int g = picked[t - n_dst];
+      if (g >= 0) atomicMin(&first[g], (int32_t)t);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_tb_flags(const int32_t* __restrict__ n_dst_dev, int n_dst_max, int fanout,
+                                                     const int32_t* __restrict__ picked, const int32_t* __restrict__ first,
+                                                     int32_t* __restrict__ flags, int64_t ne_max) {
+  const int n_dst = min(*n_dst_dev, n_dst_max);
+  const int64_t ne = (int64_t)n_dst * fanout;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ne_max; p += (int64_t)gridDim.x * blockDim.x) {
+    int f = 0;
+    if (p < ne) {
+      const int g = picked[p];
+      f = (g >= 0 && first[g] == (int32_t)(n_dst + p)) ? 1 : 0;
+    }
+    flags[p] = f;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_tb_emit(const int32_t* __restrict__ dst_nodes, const int32_t* __restrict__ n_dst_dev,
+                                                    int n_dst_max, int fanout, const int32_t* __restrict__ picked,
+                                                    const int32_t* __restrict__ first, const int32_t* __restrict__ flags,
+                                                    const int32_t* __restrict__ pos, const int32_t* __restrict__ n_new_dev,
+                                                    int32_t* __restrict__ src_nodes, int32_t* __restrict__ n_src_dev,
+                                                    int32_t* __restrict__ edge_lid, int64_t ne_max) {
+  const int n_dst = min(*n_dst_dev, n_dst_max);
+  const int64_t ne = (int64_t)n_dst * fanout;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_src_dev = n_dst + *n_new_dev;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_dst_max + ne_max; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < n_dst_max) {
+      if (t < n_dst) src_nodes[t] = dst_nodes[t];
+    } else {
+      const int64_t p = t - n_dst_max;
+      if (p < ne) {
+        const int g = picked[p];
+        int lid = -1;
+        if (g >= 0) {
+          const int m = first[g];
+          lid = m < n_dst ? m : n_dst + pos[m - n_dst];
+          if (flags[p]) src_nodes[n_dst + pos[p]] = g;
+        }
+        edge_lid[p] = lid;
+      } else {
+        edge_lid[p] = -1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_tb_reset(const int32_t* __restrict__ src_nodes, const int32_t* __restrict__ n_src_dev,
+                                                     int n_src_max, int32_t* __restrict__ first) {
+  const int n = min(*n_src_dev, n_src_max);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) first[src_nodes[t]] = 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(kBlock) k_fill_i32(int32_t* p, int32_t v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int sample_hop(const GraphView& g, const int32_t* dst_nodes, const int32_t* n_dst_dev, int n_dst_max, int fanout, uint64_t seed,
+               const uint32_t* step_dev, uint32_t step_imm, uint32_t hop, int32_t* out_src, int64_t* out_eid, cudaStream_t s) {
+  const int Q = (fanout + 3) / 4;
+  const uint2 key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  OGL_LAUNCH(k_sample, grid_for((int64_t)n_dst_max * Q, kBlock), kBlock, 0, s, g, dst_nodes, n_dst_dev, n_dst_max, fanout, key,
+             step_dev, step_imm, hop, out_src, out_eid);
+  return OGL_OK;
+}
+
+int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max) {
+  ws->v_cap = v_cap;
+  ws->ne_max = ne_max;
+  OGL_CUDA(cudaMalloc(&ws->first, sizeof(int32_t) * v_cap));
+  OGL_CUDA(cudaMalloc(&ws->flags, sizeof(int32_t) * (ne_max + 1)));
+  OGL_CUDA(cudaMalloc(&ws->pos, sizeof(int32_t) * (ne_max + 1)));
+  OGL_CUDA(cudaMalloc(&ws->scan_scratch, sizeof(int32_t) * scan_scratch_elems(ne_max + 1)));
+  OGL_CUDA(cudaMalloc(&ws->n_new, sizeof(int32_t)));
+  OGL_LAUNCH(k_fill_i32, grid_for(v_cap, kBlock), kBlock, 0, 0, ws->first, 0x7fffffff, v_cap);
+  OGL_CUDA(cudaDeviceSynchronize());
+  return OGL_OK;
+}
+
+void to_block_free(ToBlockWs* ws) {
+  cudaFree(ws->first); cudaFree(ws->flags); cudaFree(ws->pos); cudaFree(ws->scan_scratch); cudaFree(ws->n_new);
+  *ws = ToBlockWs();
+}
+
+int to_block(ToBlockWs* ws, const int32_t* dst_nodes, const int32_t* n_dst_dev, int n_dst_max, int fanout, const int32_t* picked,
+             int32_t* src_nodes, int32_t* n_src_dev, int n_src_max, int32_t* edge_lid, cudaStream_t s) {
+  const int64_t ne_max = (int64_t)n_dst_max * fanout;
+  OGL_ARG(ne_max <= ws->ne_max, "to_block: workspace too small");
+  OGL_LAUNCH(k_tb_mark, grid_for(n_dst_max + ne_max, kBlock), kBlock, 0, s, dst_nodes, n_dst_dev, n_dst_max, fanout, picked, ws->first);
+  OGL_LAUNCH(k_tb_flags, grid_for(ne_max, kBlock), kBlock, 0, s, n_dst_dev, n_dst_max, fanout, picked, ws->first, ws->flags, ne_max);
+  OGL_TRY(exclusive_scan_i32(ws->flags, ws->pos, ne_max, ws->scan_scratch, ws->n_new, s));
+  OGL_LAUNCH(k_tb_emit, grid_for(n_dst_max + ne_max, kBlock), kBlock, 0, s, dst_nodes, n_dst_dev, n_dst_max, fanout, picked, ws->first,
+             ws->flags, ws->pos, ws->n_new, src_nodes, n_src_dev, edge_lid, ne_max);
+  OGL_LAUNCH(k_tb_reset, grid_for(n_src_max, kBlock), kBlock, 0, s, src_nodes, n_src_dev, n_src_max, ws->first);
+  return OGL_OK;
+}
+
+int cast_nodes(const int64_t* in, int32_t* out, int64_t n, cudaStream_t s) {
+  if (n > 0) OGL_LAUNCH(k_cast_nodes, grid_for(n, kBlock), kBlock, 0, s, in, out, n);
+  return OGL_OK;
+}
+
+// ---- RBR: keyed Feistel permutation, first n hits below n_pop (oracle/sampler.py:draw_uniform_subset) ----
+__device__ __forceinline__ uint32_t feistel(uint32_t x, int bits, uint2 key, uint32_t counter) {
+  const int half = bits >> 1;
+  const uint32_t mask = (1u << half) - 1u;
+  uint32_t l = x >> half, r = x & mask;
+#pragma unroll
+  for (uint32_t rnd = 0; rnd < 4; ++rnd) {
+    const uint32_t f = philox4x32_10(make_uint4(r, rnd, counter, 0x5EEDu), key).x & mask;
+    const uint32_t nl = r;
+    r = l ^ f;
+    l = nl;
+  }
+  return (l << half) | r;
+}
+
+// single CTA: candidates i = 0,1,2,... in rounds of blockDim.x; ordered compaction of hits
+__global__ void __launch_bounds__(1024) k_draw_uniform(int64_t n_pop, int64_t n, int bits, uint2 key, uint32_t counter, int64_t* __restrict__ out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t have = 0;
+  const uint64_t domain = 1ull << bits;
+  for (uint64_t base = 0; have < n && base < domain; base += blockDim.x) {
+    const uint64_t i = base + threadIdx.x;
+    uint32_t c = 0;
+    bool hit = false;
+    if (i < domain) {
+      c = feistel((uint32_t)i, bits, key, counter);
+      hit = (int64_t)c < n_pop;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane];
+      int inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      s_warp[lane] = inc - v;
+      if (lane == 31) s_total = inc;
+    }
+    __syncthreads();
+    if (hit) {
+      const int64_t at = have + s_warp[warp] + __popc(m & ((1u << lane) - 1));
+      if (at < n) out[at] = (int64_t)c;
+    }
+    have += s_total;
+    __syncthreads();
+  }
+}
+
+}  // namespace ogl
+
+using namespace ogl;
+
+extern "C" int ogl_draw_uniform(int64_t n_pop, int64_t n, uint64_t seed, uint32_t counter, int64_t* out_idx_dev, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(n_pop >= 0 && n >= 0 && n <= n_pop && out_idx_dev && n_pop < (1LL << 31), "ogl_draw_uniform: bad arguments");
+  if (n == 0) return OGL_OK;
+  int bits = 2;
+  while ((1LL << bits) < n_pop) ++bits;
+  bits += bits & 1;
+  const uint2 key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  OGL_LAUNCH(k_draw_uniform, 1, 1024, 0, stream, n_pop, n, bits, key, counter, out_idx_dev);
+  return OGL_OK;
+}
+
+extern "C" int ogl_sample_neighbors(ogl_graph* g, const int64_t* dst_dev, int64_t n, int fanout, uint64_t seed, uint32_t step,
+                                    uint32_t hop, int32_t* out_src_dev, int64_t* out_eid_dev, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(g && dst_dev && out_src_dev && n >= 0 && n < (1LL << 31) && fanout > 0, "ogl_sample_neighbors: bad arguments");
+  if (n == 0) return OGL_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* tmp = nullptr;
+  OGL_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * n, s));
+  int r = cast_nodes(dst_dev, tmp, n, s);
+  if (r == OGL_OK) r = sample_hop(graph_view(g), tmp, nullptr, (int)n, fanout, seed, nullptr, step, hop, out_src_dev, out_eid_dev, s);
+  cudaFreeAsync(tmp, s);
+  return r;
+}

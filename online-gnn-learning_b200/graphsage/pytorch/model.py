@@ -1,0 +1,232 @@
+"""The four training policies on the B200 path (mirror of train/graphsage/pytorch/model.py:12-323).
+
+Where the reference builds a DGL sampler + DataLoader per call, gathers features on the CPU, copies
+them over PCIe and runs DGL/cuBLAS kernels (:77-107), every minibatch here is ONE C call
+(`ogl_plan_train_step`): seeds go host->device (8 bytes each), everything else -- sampling, to_block,
+feature gather, the GraphSAGE-pool forward/backward, CE loss, Adam -- stays on the GPU with no host
+synchronisation.  Per-vertex losses for PBR come back only in faithful mode.
+"""
+import numpy as np
+import torch
+
+from ... import config, utils
+from ...sampling import MultiLayerNeighborSampler, NodeDataLoader
+from ..model import SupervisedGraphSage
+
+
+class _FusedAdam:
+    """`trainer.optimizer` look-alike: Adam(lr=1e-3) state lives in the training plan (pytorch/model.py:25)."""
+
+    def __init__(self, trainer):
+        self._t = trainer
+
+    def zero_grad(self):
+        pass
+
+    def step(self):
+        plan = self._t._last_plan
+        plan.adam_step()
+        self._t.graphsage_model.mark_updated(plan)
+
+
+class PytorchSupervisedGraphSage(SupervisedGraphSage):
+    def __init__(self, graphsage_model, batch_per_timestep, batch_size, labels, samples, reduction="mean", n_workers=1,
+                 cuda=False, batch_full=512, fanouts=None):
+        if not cuda:
+            raise RuntimeError("ogl_b200 trainers are the `--cuda` path; there is no CPU fallback")
+        super().__init__(graphsage_model, batch_per_timestep, batch_size, labels, samples, n_workers, cuda, batch_full)
+        self.reduction = reduction
+        n_layers = len(graphsage_model.layers)
+        # the reference samples [samples]*2 (one int for both hops); per-hop fan-outs are an opt-in extension
+        self.hop_fanouts = list(fanouts) if fanouts is not None else [samples] * n_layers
+        self.optimizer = None
+        self._last_plan = None
+        self._pin = None
+
+    def build_optimizer(self):
+        self.optimizer = _FusedAdam(self)
+
+    def get_model(self):
+        return "base_model"
+
+    # ---- plans / staging ---------------------------------------------------------------------------
+    def _train_plan(self, graph):
+        return self.graphsage_model.plan_for(graph, self.hop_fanouts, max(self.batch_size, 1))
+
+    def _eval_plan(self, graph):
+        return self.graphsage_model.plan_for(graph, self.hop_fanouts, max(self.batch_full, 1))
+
+    def _host_seeds(self, vertices):
+        """pinned int64 staging buffer for the seed ids (the only per-step host->device payload)"""
+        if isinstance(vertices, torch.Tensor) and vertices.is_cuda:
+            return vertices.to(torch.int64).contiguous()
+        v = torch.as_tensor(np.asarray(vertices, dtype=np.int64))
+        if self._pin is None or self._pin.numel() < v.numel():
+            self._pin = torch.empty(max(v.numel(), 1024), dtype=torch.int64).pin_memory()
+        self._pin[:v.numel()].copy_(v)
+        return self._pin[:v.numel()]
+
+    # ---- evaluation (reference :39-71) -------------------------------------------------------------
+    def _run_custom_eval(self, graph, subgraph_to_id, id_to_subgraph, test_vertices):
+        self.graphsage_model.eval()
+        seeds = self._host_seeds(test_vertices)
+        n = seeds.numel()
+        if n == 0:
+            return []
+        plan = self._eval_plan(graph)
+        C = self.graphsage_model.dims[-1]
+        out = torch.empty(n, C, dtype=torch.float32, device="cuda")
+        for i in range(0, n, self.batch_full):
+            chunk = seeds[i:i + self.batch_full]
+            plan.eval_step(graph.native, graph.features, chunk, logits_out=out[i:i + chunk.numel()])
+        host = out.cpu().numpy()
+        return [host[i:i + self.batch_full] for i in range(0, n, self.batch_full)]
+
+    # ---- one minibatch -----------------------------------------------------------------------------
+    def _fused_step(self, graph, seeds, per_vertex_out=None, loss_sum_out=None):
+        plan = self._train_plan(graph)
+        plan.train_step(graph.native, graph.features, seeds, loss_scale=1.0 / seeds.numel(), do_step=True,
+                        per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
+        self.graphsage_model.mark_updated(plan)
+        self._last_plan = plan
+
+    def train_step(self, graph, blocks, input_nodes, seeds, subgraph_to_id):
+        """DGL-style signature of the reference (:77-107).  The blocks only identify the minibatch: the fused
+        kernels re-derive it from the same Philox counters, so this is one fused step on `seeds`."""
+        self._fused_step(graph, seeds.to("cuda", torch.int64).contiguous())
+
+    def _batches(self, vertices, batch):
+        seeds = self._host_seeds(vertices)
+        batch = max(int(batch), 1)
+        return [seeds[i:i + batch] for i in range(0, seeds.numel(), batch)]
+
+
+class RandomPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
+    """RBR: rehearsal on uniformly drawn train vertices (reference :110-138)."""
+
+    def __init__(self, model, batch_per_timestep, batch_size, labels, samples, cuda=False, batch_full=512, n_workers=0, fanouts=None):
+        super().__init__(model, batch_per_timestep, batch_size, labels, samples, n_workers=n_workers, cuda=cuda,
+                         batch_full=batch_full, fanouts=fanouts)
+
+    def choose_vertices(self, graph_util):
+        draws = [graph_util.draw_random_train_nodes(self.batch_size) for _ in range(self.batch_per_timestep)]
+        if draws and isinstance(draws[0], torch.Tensor):
+            return torch.cat(draws)
+        return [v for d in draws for v in d]
+
+    def _run_custom_train(self, graph, subgraph_to_id, id_to_subgraph, train_vertices, graph_util):
+        self.graphsage_model.train()
+        n = len(train_vertices)
+        if n == 0:
+            return
+        for seeds in self._batches(train_vertices, n // self.batch_per_timestep):
+            self._fused_step(graph, seeds)
+
+    def get_model(self):
+        return "random"
+
+
+class PrioritizedPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
+    """PBR: loss-prioritised rehearsal (reference :141-257)."""
+
+    def __init__(self, model, batch_per_timestep, batch_size, labels, samples, priority_strategy, full_pass=2, cuda=False,
+                 batch_full=512, n_workers=0, fanouts=None):
+        super().__init__(model, batch_per_timestep, batch_size, labels, samples, reduction="none", n_workers=n_workers,
+                         cuda=cuda, batch_full=batch_full, fanouts=fanouts)
+        self.time_step = 0
+        self.pass_var = 0
+        self.full_pass = full_pass
+        self.priority_strategy = priority_strategy
+
+    def choose_vertices(self, graph_util):
+        if self.time_step % self.full_pass == 0:
+            self.pass_var += 1
+            self.recompute_priorities(graph_util, graph_util.get_train_set())
+        elif len(graph_util.get_new_train_nodes()) > 1:
+            self.recompute_priorities(graph_util, graph_util.get_new_train_nodes())
+        draws = [graph_util.draw_priority_train_nodes(self.batch_size) for _ in range(self.batch_per_timestep)]
+        return [v for d in draws for v in d]
+
+    def _push_priorities(self, graph_util, nodes, losses_dev):
+        if config.faithful():
+            pri = self.priority_strategy.get_priorities(nodes, losses_dev.cpu().numpy())
+            graph_util.update_priorities(dict(zip(nodes, pri)))
+        else:
+            graph_util.update_priorities_device(list(nodes), losses_dev)
+
+    def _run_custom_train(self, graph, subgraph_to_id, id_to_subgraph, train_vertices, graph_util):
+        self.graphsage_model.train()
+        n = len(train_vertices)
+        if n:
+            for seeds in self._batches(train_vertices, n // self.batch_per_timestep):
+                per = torch.empty(seeds.numel(), dtype=torch.float32, device="cuda")
+                self._fused_step(graph, seeds, per_vertex_out=per)
+                nodes = subgraph_to_id[seeds.cpu().numpy()]
+                self._push_priorities(graph_util, np.asarray(nodes).tolist(), per)
+        self.time_step += 1
+
+    def recompute_priorities(self, graph_util, train_set):
+        """eval-mode forward over `train_set` in batch_full chunks; per-vertex CE loss -> priorities (reference :210-254)"""
+        self.graphsage_model.eval()
+        id_to_subgraph = graph_util.get_original_to_subgraph_map()
+        graph = graph_util.get_graph()
+        sub = np.asarray(id_to_subgraph[train_set], dtype=np.int64)
+        n = len(sub)
+        if n == 0:
+            return
+        seeds = self._host_seeds(sub)
+        plan = self._eval_plan(graph)
+        losses = torch.empty(n, dtype=torch.float32, device="cuda")
+        for i in range(0, n, self.batch_full):
+            chunk = seeds[i:i + self.batch_full]
+            plan.eval_step(graph.native, graph.features, chunk, per_vertex_out=losses[i:i + chunk.numel()])
+        self._push_priorities(graph_util, list(train_set), losses)
+
+    def get_model(self):
+        return "prioritized"
+
+
+class FullPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
+    """offline baseline: `batch_per_timestep` epochs over the whole train set (reference :260-290)."""
+
+    def __init__(self, model, batch_per_timestep, batch_size, labels, samples, cuda=False, batch_full=512, n_workers=0, fanouts=None):
+        super().__init__(model, batch_per_timestep, batch_size, labels, samples, n_workers=n_workers, cuda=cuda,
+                         batch_full=batch_full, fanouts=fanouts)
+
+    def choose_vertices(self, graph_util):
+        return list(graph_util.get_train_set())
+
+    def _run_custom_train(self, graph, subgraph_to_id, id_to_subgraph, batch_nodes, graph_util):
+        self.graphsage_model.train()
+        train_set = torch.as_tensor(np.asarray(batch_nodes, dtype=np.int64))
+        for _ in range(self.batch_per_timestep):
+            train_set = train_set[torch.randperm(train_set.numel())]
+            for seeds in self._batches(train_set, self.batch_size):
+                self._fused_step(graph, seeds)
+
+    def get_model(self):
+        return "offline"
+
+
+class NoRehPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
+    """no rehearsal: train on the newest vertices only (reference :293-323)."""
+
+    def __init__(self, model, batch_per_timestep, batch_size, labels, samples, cuda=False, batch_full=512, n_workers=0, fanouts=None):
+        super().__init__(model, batch_per_timestep, batch_size, labels, samples, n_workers=n_workers, cuda=cuda,
+                         batch_full=batch_full, fanouts=fanouts)
+
+    def choose_vertices(self, graph_util):
+        return []
+
+    def _run_custom_train(self, graph, subgraph_to_id, id_to_subgraph, batch_nodes, graph_util):
+        self.graphsage_model.train()
+        for _ in range(self.batch_per_timestep):
+            idxs = graph_util.get_new_train_nodes(self.batch_size)
+            if len(idxs) < 2:
+                return
+            sub = torch.as_tensor(np.asarray(id_to_subgraph[idxs], dtype=np.int64))
+            sub = sub[torch.randperm(sub.numel())]          # NodeDataLoader(shuffle=True) of the reference
+            self._fused_step(graph, self._host_seeds(sub))
+
+    def get_model(self):
+        return "no_rehersal"
