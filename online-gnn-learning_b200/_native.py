@@ -334,11 +334,25 @@ def sample_neighbors(graph, dst, fanout, seed, step, hop, want_eids=True):
     return src, eid
 
 
-def gemm_bf16_nt(a, b):
-    """C[M,N] fp32 = A[M,K] bf16 @ B[N,K]^T bf16 on the tcgen05 path (tests / bench)."""
+def gemm_bf16_nt(a, b, k=None):
+    """C[M,N] fp32 = A[M,:k] bf16 @ B[N,:k]^T bf16 on the tcgen05 path (tests / bench); row pitches = shape[1]."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
     a, b = a.contiguous(), b.contiguous()
-    c = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device="cuda")
-    check(lib.ogl_gemm_bf16_nt(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), c.shape[1], a.shape[0], b.shape[0], a.shape[1],
-                               _stream()))
+    k = a.shape[1] if k is None else int(k)
+    ldc = (b.shape[0] + 7) // 8 * 8
+    c = torch.empty(a.shape[0], ldc, dtype=torch.float32, device="cuda")
+    check(lib.ogl_gemm_bf16_nt(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), ldc, a.shape[0], b.shape[0], k, _stream()))
+    return c[:, :b.shape[0]]
+
+
+def gemm_bf16_tn(a, b, n=None, k=None, workspace_elems=1 << 24):
+    """C[N,K] fp32 = A[M,:n]^T bf16 @ B[M,:k] bf16 on the tcgen05 path (tests / bench); row pitches = shape[1]."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda and a.shape[0] == b.shape[0]
+    a, b = a.contiguous(), b.contiguous()
+    n = a.shape[1] if n is None else int(n)
+    k = b.shape[1] if k is None else int(k)
+    c = torch.empty(n, k, dtype=torch.float32, device="cuda")
+    ws = torch.empty(workspace_elems, dtype=torch.float32, device="cuda") if workspace_elems else None
+    check(lib.ogl_gemm_bf16_tn(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), k, a.shape[0], n, k,
+                               _ptr(ws), int(workspace_elems), _stream()))
     return c

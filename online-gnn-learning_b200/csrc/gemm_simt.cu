@@ -140,6 +140,24 @@ __global__ void __launch_bounds__(256) k_reduce_splits(const float* __restrict__
   }
 }
 
+// partials with a padded row pitch ldp (tcgen05 TN kernel)
+__global__ void __launch_bounds__(256) k_reduce_splits_ld(const float* __restrict__ partial, int splits, int n, int k, int ldp,
+                                                          float* __restrict__ c, int ldc) {
+  const int64_t total = (int64_t)n * k;
+  const int64_t stride = (int64_t)n * ldp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k, col = i % k;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * stride + r * ldp + col];
+    c[r * ldc + col] = s;
+  }
+}
+
+int reduce_splits_ld(const float* partial, int splits, int n, int k, int ldp, float* c, int ldc, cudaStream_t s) {
+  OGL_LAUNCH(k_reduce_splits_ld, grid_for((int64_t)n * k, 256), 256, 0, s, partial, splits, n, k, ldp, c, ldc);
+  return OGL_OK;
+}
+
 int reduce_splits(const float* partial, int splits, int n, int k, float* c, int ldc, cudaStream_t s) {
   OGL_LAUNCH(k_reduce_splits, grid_for((int64_t)n * k, 256), 256, 0, s, partial, splits, n, k, c, ldc);
   return OGL_OK;

