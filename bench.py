@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""Benchmark of the streaming GraphSAGE-pool hot path (BASELINE.json metric: train target-vertices/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit|elliptic|arxiv|pubmed]
+
+A "step" is one training minibatch of the workload: sample the 2-hop neighbourhood of B target vertices from the
+streaming CSR (Philox, with replacement), compact the frontiers, gather the input feature rows, GraphSAGE-pool
+forward, cross-entropy, backward, Adam.  `value` times K such steps with the seeds already in HBM; `e2e` times
+the same K steps through the host API (pinned host seeds -> H2D inside the call, loss read back D2H every step).
+Default workload = the Reddit-shaped synthetic graph north_star quotes its targets on (232,965 vertices,
+~114.6 M directed edges, 602 features, 41 classes, hidden 600, B = 1024, fan-outs 25/10): it fits one B200
+(~6 GB resident), so it is also the N = 1 workload; with N > 1 every rank holds a replica and trains its own
+B-vertex shard of a global batch of N*B, gradients all-reduced over NCCL (weak scaling).
+
+`--impl reference` times the CPU restatement of the reference's path (oracle/: numpy Philox sampler + to_block,
+torch-CPU SAGEConv('pool') fwd/bwd + Adam) on the box's host cores: the reference itself cannot run here
+(DGL is un-vendored, un-pinned and absent -- SURVEY 8(c)).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: V, stream edges, F, C, H, B, fanouts (seeds hop first), zipf exponent of the degree weights
+    "reddit": dict(V=232965, E=57300000, F=602, C=41, H=600, B=1024, fanouts=[25, 10]),
+    "elliptic": dict(V=203769, E=234355, F=166, C=2, H=256, B=32, fanouts=[45, 45]),
+    "arxiv": dict(V=169343, E=1166243, F=128, C=40, H=32, B=32, fanouts=[40, 40]),
+    "pubmed": dict(V=19717, E=44338, F=500, C=3, H=32, B=32, fanouts=[10, 10]),
+}
+NAMES = ("fc_pool.weight", "fc_pool.bias", "fc_self.weight", "fc_self.bias", "fc_neigh.weight", "fc_neigh.bias")
+
+
+# ----------------------------------------------------------------------------------------- synthetic data
+def gen_edges(w, device, seed=1):
+    """Chung-Lu style power-law stream: endpoints drawn with probability ~ (rank + 50)^-0.83 (degree exponent
+    ~2.2), vertex ranks scattered by a fixed permutation.  Returns int64 (src, dst) of length E on `device`."""
+    V, E = w["V"], w["E"]
+    g = torch.Generator(device=device).manual_seed(seed)
+    wt = (torch.arange(V, device=device, dtype=torch.float64) + 50.0) ** -0.83
+    cdf = torch.cumsum(wt / wt.sum(), 0).float()
+    perm = torch.randperm(V, generator=g, device=device)
+    out = []
+    for _ in range(2):
+        parts = []
+        for a in range(0, E, 1 << 24):
+            n = min(1 << 24, E - a)
+            u = torch.rand(n, generator=g, device=device)
+            parts.append(perm[torch.searchsorted(cdf, u).clamp_(max=V - 1)])
+        out.append(torch.cat(parts))
+    return out[0], out[1]
+
+
+def gen_features(w, device, seed=2):
+    g = torch.Generator(device=device).manual_seed(seed)
+    feats = torch.randn(w["V"], w["F"], generator=g, device=device, dtype=torch.float32)
+    g3 = torch.Generator(device=device).manual_seed(seed + 1)
+    labels = torch.randint(0, w["C"], (w["V"],), generator=g3, device=device, dtype=torch.int64)
+    return feats, labels
+
+
+def init_params(w, seed=0):
+    from oracle.sage import xavier_params          # parameter init only (same init for both arms)
+    return xavier_params(w["F"], w["H"], w["C"], 1, seed=seed)
+
+
+def seed_batches(w, n_batches, rank, world, seed=4):
+    """target-vertex minibatches: uniform B-subsets of the 85 % train split (RBR draw), one per step per rank"""
+    rng = np.random.default_rng(seed)
+    train = rng.permutation(w["V"])[: int(0.85 * w["V"])]
+    out = []
+    for _ in range(n_batches):
+        glob = rng.choice(train, size=w["B"] * world, replace=False)
+        out.append(np.ascontiguousarray(glob[rank * w["B"]:(rank + 1) * w["B"]], dtype=np.int64))
+    return out
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, smax, reasons = [], 0, set()
+        for t, line in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0]))
+                smax = max(smax, float(p[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ----------------------------------------------------------------------------------------- CPU path (oracle)
+class CpuPath:
+    """The reference's CPU path restated (oracle/): DGL-style sampling + to_block in numpy, SAGEConv('pool') +
+    CrossEntropy + Adam in torch-CPU fp32 (train/graphsage/pytorch/model.py:77-107 with cuda=False)."""
+
+    def __init__(self, w, indptr, indices, feats, labels, params, seed=11):
+        from oracle import sampler, sage
+        self.w, self.sampler, self.sage = w, sampler, sage
+        self.indptr, self.indices = indptr, indices
+        self.feats, self.labels = feats, labels
+        self.params = {k: v.clone().float().requires_grad_(True) for k, v in params.items()}
+        self.opt = torch.optim.Adam(list(self.params.values()), lr=1e-3)
+        self.seed, self.step_no = seed, 0
+
+    def step(self, seeds):
+        w = self.w
+        input_nodes, blocks = self.sampler.sample_blocks(self.indptr, self.indices, self.indices, seeds, w["fanouts"], self.seed,
+                                                         self.step_no, fast=True)
+        self.step_no += 1
+        ob = [dict(n_dst=len(b["dst_nodes"]), edge_src=torch.from_numpy(b["edge_src"]), fanout=b["fanout"]) for b in blocks]
+        x = self.feats[torch.from_numpy(input_nodes)]
+        self.opt.zero_grad()
+        logits, _ = self.sage.forward(self.params, x, ob)
+        loss = torch.nn.functional.cross_entropy(logits, self.labels[torch.from_numpy(seeds)])
+        loss.backward()
+        self.opt.step()
+        return float(loss.item())
+
+
+def cpu_csr(src, dst, V):
+    """in-edge CSR (indptr, indices) of the symmetrised stream on the host (torch CPU stable sort)"""
+    es = torch.cat([src, dst])
+    ed = torch.cat([dst, src])
+    order = torch.sort(ed, stable=True).indices
+    deg = torch.bincount(ed, minlength=V)
+    indptr = torch.zeros(V + 1, dtype=torch.int64)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    return indptr.numpy(), es[order].numpy()
+
+
+def time_cpu(path, batches, warmup):
+    for b in batches[:warmup]:
+        path.step(b)
+    t0 = time.perf_counter()
+    for b in batches[warmup:]:
+        path.step(b)
+    return time.perf_counter() - t0
+
+
+# ----------------------------------------------------------------------------------------- roofline helpers
+def stage_flops(stage, w, lv):
+    """algorithmic FLOPs of one GEMM stage for per-step mean level counts lv = [B, N1, N0]"""
+    F, H, C = w["F"], w["H"], w["C"]
+    B, N1, N0 = lv
+    dims = [F, H, C]
+    l = int(stage[1])
+    fin, fout = dims[l], dims[l + 1]
+    n_src, n_dst = (N0, N1) if l == 0 else (N1, B)
+    kind = stage.split(".", 1)[1]
+    return {"pool_gemm": 2.0 * n_src * fin * fin, "out_gemm": 4.0 * n_dst * fin * fout, "dW_self": 2.0 * n_dst * fin * fout,
+            "dW_neigh": 2.0 * n_dst * fin * fout, "dneigh_gemm": 2.0 * n_dst * fin * fout, "dW_pool": 2.0 * n_src * fin * fin,
+            "dx_gemm": 2.0 * n_src * fin * fin + 2.0 * n_dst * fin * fout}.get(kind)
+
+
+def stage_bytes(stage, w, lv, es=2):
+    """algorithmic HBM bytes of the memory-bound stages; es = bytes per stored feature element"""
+    F, H = w["F"], w["H"]
+    B, N1, N0 = lv
+    f0, f1 = w["fanouts"]
+    if stage == "gather":
+        return 2.0 * N0 * F * es + 4.0 * N0
+    if stage.startswith("sample.h"):
+        h = int(stage[-1])
+        D, s = (B, f0) if h == 0 else (N1, f1)
+        return D * (4 + 8 + 4) + D * s * (4 + 4) + D * s * (4 + 8)          # row meta + (src,eid) reads + (src,eid) writes
+    if stage.endswith(".segmax"):
+        l = int(stage[1])
+        E, fin, nd = (N1 * f1, F, N1) if l == 0 else (B * f0, H, B)
+        return E * fin * es + nd * fin * (es + 1) + E * 4
+    return None
+
+
+# ----------------------------------------------------------------------------------------- main arms
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    torch.manual_seed(0)
+    t_setup = time.time()
+    src, dst = gen_edges(w, "cpu")
+    indptr, indices = cpu_csr(src, dst, w["V"])
+    del src, dst
+    feats, labels = gen_features(w, "cpu")
+    path = CpuPath(w, indptr, indices, feats, labels, init_params(w))
+    batches = seed_batches(w, args.steps + args.warmup, 0, 1)
+    setup_s = time.time() - t_setup
+    el = time_cpu(path, batches, args.warmup)
+    value = w["B"] * args.steps / el
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "graphsage_train_vertices_per_s", "value": value, "unit": "vertices/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, args.workload, 1),
+            "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": cores, "kind": "port",
+                             "sample": "%d full train steps (B=%d) of the same workload on %d host threads (os.cpu_count=%d); setup %.0f s untimed"
+                                       % (args.steps, w["B"], cores, os.cpu_count(), setup_s)},
+            "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, name, world):
+    return {"workload": "%s-shaped synthetic graph: V=%d, %d stream edges (%d directed), F=%d, C=%d, hidden %d, B=%d per GPU, fan-outs %s, "
+                        "2-layer GraphSAGE-pool, Adam" % (name, w["V"], w["E"], 2 * w["E"], w["F"], w["C"], w["H"], w["B"], w["fanouts"]),
+            "global_batch": w["B"] * world, "parallelism": "dp%d (replicated graph+features, NCCL grad all-reduce)" % world if world > 1 else "single GPU",
+            "l2": "inputs larger than L2: feature table %.0f MB + CSR %.0f MB resident, random row gathers; no explicit flush"
+                  % (w["V"] * ((w["F"] + 7) // 8 * 8) * 2 / 1e6, 2 * w["E"] * 8 * 1.5 / 1e6)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import ogl_b200
+    from ogl_b200 import native
+    w = WORKLOADS[args.workload]
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+
+    # ---- build the streaming graph by inserting the edge stream in snapshot batches (timed: edge inserts/s)
+    src, dst = gen_edges(w, dev)
+    V, E = w["V"], w["E"]
+    g = native.Graph(V, 2 * E)
+    g.insert_vertices(V)
+    chunk = max(1 << 14, min(1 << 21, E // 16))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ogl_b200.kernel_launches()
+    e0.record()
+    for a in range(0, E, chunk):
+        g.insert_edges(src[a:a + chunk], dst[a:a + chunk], symmetric=True)
+    e1.record()
+    torch.cuda.synchronize()
+    insert_ms = e0.elapsed_time(e1)
+    insert_launches = ogl_b200.kernel_launches() - launches0
+    assert g.num_edges == 2 * E
+    feats, labels = gen_features(w, dev)
+    mode = ogl_b200.OGL_BF16
+    fs = native.Features(V, w["F"], mode)
+    fs.write(0, feats, labels)
+    host_csr = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ip, ix, _ = g.export_csr(with_eids=False)
+        host_csr = (ip.cpu().numpy(), ix.cpu().numpy())
+        del ip, ix
+        feats_host, labels_host = feats.cpu(), labels.cpu()
+    del feats, src, dst
+    torch.cuda.empty_cache()
+
+    params = init_params(w)
+    flat = torch.cat([params[f"layers.{i}.{n}"].reshape(-1).float() for i in range(2) for n in NAMES]).to(dev)
+    grad = torch.zeros_like(flat)
+    plan = native.Plan([w["F"], w["H"], w["C"]], w["fanouts"], w["B"], V, mode=mode, seed=11)
+    plan.bind_params(flat, grad)
+    B = w["B"]
+    K, W = args.steps, args.warmup
+    batches = seed_batches(w, K + W, rank, world)
+    dev_batches = [torch.as_tensor(b).to(dev) for b in batches]
+    pin = [torch.as_tensor(b).pin_memory() for b in batches]
+    loss_dev = torch.zeros(1, device=dev)
+    loss_scale = 1.0 / (B * world)
+
+    def step(seeds):
+        if world == 1:
+            plan.train_step(g, fs, seeds, loss_scale=loss_scale, do_step=True, loss_sum_out=loss_dev)
+        else:
+            plan.train_step(g, fs, seeds, loss_scale=loss_scale, do_step=False, loss_sum_out=loss_dev)
+            dist.all_reduce(grad)
+            plan.adam_step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(inputs, read_back):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events, max over ranks"""
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        wall0 = time.time()
+        t0.record()
+        losses = []
+        for s in inputs:
+            step(s)
+            if read_back:
+                losses.append(float(loss_dev.item()))          # D2H read of the step's loss (synchronises)
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall0, time.time(), losses
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    for s in dev_batches[:W]:
+        step(s)
+    # ---- value: inputs resident in HBM, stage events on
+    plan.profile(True)
+    l0 = ogl_b200.kernel_launches()
+    ms_dev, wall0, wall1, _ = timed(dev_batches[W:], read_back=False)
+    launches = ogl_b200.kernel_launches() - l0
+    stages, level_sums, n_prof = plan.profile_read()
+    plan.profile(False)
+    # ---- e2e: pinned host seeds -> H2D inside the call, loss D2H every step
+    for s in pin[:W]:
+        step(s)
+    ms_e2e, _, _, losses = timed(pin[W:], read_back=True)
+    clk = clocks.window(wall0, wall1) if clocks else None
+    if clocks:
+        clocks.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = B * world * K / (ms_dev / 1e3)
+    e2e = B * world * K / (ms_e2e / 1e3)
+    lv = [x / max(n_prof, 1) for x in level_sums]                 # mean [B, N1, N0] per step
+    per = {k: v[0] / max(n_prof, 1) for k, v in stages.items()}   # ms per step per stage
+    total_stage_ms = sum(per.values())
+    # dominant kernel = the stage with the largest share of the step
+    top = max(per, key=per.get)
+    is_layer = lambda k: len(k) > 3 and k[0] == "l" and k[1].isdigit() and k[2] == "."
+    fl = stage_flops(top, w, lv) if is_layer(top) else None
+    by = stage_bytes(top, w, lv)
+    if fl:
+        ach = fl / (per[top] * 1e-3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
+                "traffic": None, "peak_source": peak_src + ", sustained bf16", "flops_per_launch": fl, "ms_per_launch": per[top]}
+    elif by:
+        ach = by / (per[top] * 1e-3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": by, "ms_per_launch": per[top]}
+    else:
+        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None}
+    stage_table = {}
+    for k in sorted(per, key=per.get, reverse=True):
+        ent = {"ms": round(per[k], 4), "share": round(per[k] / total_stage_ms, 4)}
+        f_, b_ = (stage_flops(k, w, lv) if is_layer(k) else None), stage_bytes(k, w, lv)
+        if f_:
+            ent["tflops"] = round(f_ / (per[k] * 1e-3) / 1e12, 1)
+        if b_:
+            ent["gbs"] = round(b_ / (per[k] * 1e-3) / 1e9, 1)
+        stage_table[k] = ent
+
+    cpu = None
+    if host_csr is not None:
+        path = CpuPath(w, host_csr[0], host_csr[1], feats_host, labels_host, params)
+        cb = seed_batches(w, args.cpu_steps + 1, 0, 1, seed=5)
+        el = time_cpu(path, cb, 1)
+        cpu = {"value": B * args.cpu_steps / el, "unit": "vertices/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d full train steps (B=%d) of the same workload, oracle port (numpy sampler + torch-CPU fp32 SAGE-pool + Adam), %.1f s"
+                         % (args.cpu_steps, B, el)}
+    line = {"metric": "graphsage_train_vertices_per_s", "value": value, "unit": "vertices/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(w, args.workload, world),
+            "e2e": {"value": e2e, "unit": "vertices/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
+                    "api": "ogl_plan_train_step(host seeds) + loss read-back", "last_loss": losses[-1] / (B * world) if losses else None},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "mean_level_counts": {"B": lv[0], "N1": lv[1], "N0": lv[2]}, "stages": stage_table,
+            "edge_insert": {"stream_edges_per_s": E / (insert_ms / 1e3), "ms": insert_ms, "batch_stream_edges": chunk, "launches": insert_launches,
+                            "algorithmic_gbs": 2 * E * (16 + 8 + 8) / (insert_ms / 1e3) / 1e9}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200: the product path has no CPU fallback")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

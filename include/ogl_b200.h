@@ -143,6 +143,14 @@ int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_
 int ogl_plan_eval_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds,
                        int seeds_on_host, float* logits_dev, float* per_vertex_loss_dev, void* stream);
 
+/* stage profiling for bench.py's roofline: CUDA events recorded around every stage of the plan's calls on the
+ * caller's stream (off by default).  enable=1 (re)starts a collection.  _read synchronises the device and returns,
+ * per stage, the summed milliseconds and kernel launches, plus the per-level node counts summed over the
+ * profiled train steps (level 0 = seeds ... level L = input nodes). names are '\n'-separated. */
+int ogl_plan_profile(ogl_plan* p, int enable);
+int ogl_plan_profile_read(ogl_plan* p, char* names_buf, int names_len, float* ms_out, int64_t* launches_out, int max_stages,
+                          int* n_stages, int64_t* level_count_sums, int* n_steps);
+
 /* introspection for parity tests: device pointers into the plan's workspaces.
  * level 0 = seeds, level l+1 = src nodes of hop l.  block(hop) = dst level hop. */
 int ogl_plan_level_nodes(ogl_plan* p, int level, const int32_t** nodes_dev, const int32_t** count_dev, int* max_count);

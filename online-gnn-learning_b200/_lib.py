@@ -72,6 +72,8 @@ SIGNATURES = {
     "ogl_plan_adam_step": (_i, [_vp, _vp]),
     "ogl_plan_train_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     "ogl_plan_eval_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "ogl_plan_profile": (_i, [_vp, _i]),
+    "ogl_plan_profile_read": (_i, [_vp, C.c_char_p, _i, _vp, _vp, _i, C.POINTER(_i), _vp, C.POINTER(_i)]),
     "ogl_plan_level_nodes": (_i, [_vp, _i, _pp, _pp, C.POINTER(_i)]),
     "ogl_plan_block_edges": (_i, [_vp, _i, _pp, _pp, _pp, C.POINTER(_i)]),
     "ogl_plan_tensor": (_i, [_vp, C.c_char_p, _pp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

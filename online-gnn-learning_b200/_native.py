@@ -252,6 +252,22 @@ class Plan:
         self.n_seeds = n
         self._stamp += 1
 
+    # -- stage profiling (bench.py) ---------------------------------------------------------------
+    def profile(self, enable=True):
+        check(lib.ogl_plan_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        """-> (dict stage -> (ms_total, launches_total), level_count_sums[L+1], n_steps)"""
+        names = C.create_string_buffer(8192)
+        ms = (C.c_float * 256)()
+        ln = (C.c_int64 * 256)()
+        n, steps = C.c_int(), C.c_int()
+        sums = (C.c_int64 * 8)()
+        check(lib.ogl_plan_profile_read(self._h, names, 8192, C.cast(ms, C.c_void_p), C.cast(ln, C.c_void_p), 256, C.byref(n),
+                                        C.cast(sums, C.c_void_p), C.byref(steps)))
+        keys = names.value.decode().split("\n")[:n.value]
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(keys)}, [int(sums[i]) for i in range(self.L + 1)], steps.value
+
     # -- introspection (parity tests, DGL-style block objects) ---------------------------------
     def level_nodes(self, level):
         p, c, m = C.c_void_p(), C.c_void_p(), C.c_int()

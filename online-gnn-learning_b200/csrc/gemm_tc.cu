@@ -28,7 +28,12 @@ constexpr int BN_MAX = 256;      // UMMA N upper bound
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
 constexpr int B_STAGE_BYTES = BN_MAX * BK * 2;    // 32 KB
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);   // 192 KB
+constexpr int STORE_BOX_BYTES = 32 * 128;                              // one TMA-store box: 32 rows x 128 B
+constexpr int STORE_BYTES = 4 /*warps*/ * 2 /*buffers*/ * STORE_BOX_BYTES;   // 32 KB epilogue staging
+constexpr int BIAS_BYTES = 2 * BN_MAX * 4;                              // per-accumulator bias slice
+constexpr int SMEM_BYTES = RING_BYTES + STORE_BYTES + BIAS_BYTES + 128 /*barriers + tmem slot*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 // ------------------------------------------------------------------ PTX wrappers ----------------
@@ -62,6 +67,21 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -118,18 +138,24 @@ struct SmemLayout {
   uint8_t* b0;
   __device__ __forceinline__ uint8_t* a(int i) const { return a0 + i * A_STAGE_BYTES; }
   __device__ __forceinline__ uint8_t* b(int i) const { return b0 + i * B_STAGE_BYTES; }
+  uint8_t* store;        // [4 warps][2][STORE_BOX_BYTES] epilogue staging for TMA stores
+  float* bias;           // [2][BN_MAX]
   uint64_t* full;        // [STAGES]
   uint64_t* empty;       // [STAGES]
   uint64_t* acc_full;    // [2]
   uint64_t* acc_empty;   // [2]
   uint32_t* tmem_slot;
 };
-__device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
+__device__ __forceinline__ SmemLayout carve(uint8_t* base) {
+  // the dynamic shared window of a kernel without static __shared__ starts 1024-byte aligned (SWIZZLE_128B atoms
+  // need it); checked at run time instead of paying 1 KB of slack
+  if ((smem_u32(base) & 1023u) != 0) __trap();
   SmemLayout s;
-  uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   s.a0 = base;
   s.b0 = base + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(base + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  s.store = base + RING_BYTES;
+  s.bias = (float*)(base + RING_BYTES + STORE_BYTES);
+  uint64_t* bars = (uint64_t*)(base + RING_BYTES + STORE_BYTES + BIAS_BYTES);
   s.full = bars;
   s.empty = bars + STAGES;
   s.acc_full = bars + 2 * STAGES;
@@ -146,6 +172,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // ------------------------------------------------------------------ NT kernel --------------------
 struct NtParams {
   CUtensorMap ta[2], tb[2];
+  CUtensorMap tc;               // bf16 output [m_max, ldc], box 64 x 32 (TMA store); unused for fp32 output
   int k[2];
   int n_seg;
   const int32_t* a_rows_dev[2];
@@ -164,7 +191,7 @@ struct NtParams {
 };
 
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemLayout s = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -250,68 +277,113 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
     }
     __syncwarp();
   } else {
-    // ===== epilogue: TMEM -> registers -> bias / ReLU / mask -> global =====
+    // ===== epilogue: TMEM -> registers -> bias / ReLU / mask -> swizzled smem box -> TMA store =====
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
+    const int epi_tid = (warp - 2) * 32 + lane;
+    uint8_t* const stage_buf = s.store + (warp - 2) * 2 * STORE_BOX_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t boxes_issued = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mb = t / p.n_tiles, nb = t % p.n_tiles;
       const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
       const int gm = mb * BM + quarter * 32 + lane;
       const bool row_store = gm < m_pad;
       const bool row_live = gm < m_dyn;
+      // bias slice of this tile -> shared (broadcast reads below); double-buffered with the accumulator
+      float* bias_s = s.bias + acc * BN_MAX;
+      for (int j = epi_tid; j < bn_tile; j += 128) {
+        const int gn = nb * BN_MAX + j;
+        float bv = 0.f;
+        if (gn < p.n) {
+          if (p.bias) bv += __ldg(p.bias + gn);
+          if (p.bias2) bv += __ldg(p.bias2 + gn);
+        }
+        bias_s[j] = bv;
+      }
+      epi_barrier();
       mbar_wait(&s.acc_full[acc], acc_phase);
       tc_fence_after();
-      for (int c0 = 0; c0 < bn_tile; c0 += 32) {
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + c0), r);
-        const int gn0 = nb * BN_MAX + c0;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int gn = gn0 + j;
-          float x = 0.f;
-          if (row_live && gn < p.n) {
-            x = __uint_as_float(r[j]);
-            if (p.bias) x += __ldg(p.bias + gn);
-            if (p.bias2) x += __ldg(p.bias2 + gn);
-            if (p.relu) x = fmaxf(x, 0.f);
+      if (p.out_bf16) {
+        for (int c0 = 0; c0 < bn_tile; c0 += 64) {
+          uint8_t* buf = stage_buf + (boxes_issued & 1) * STORE_BOX_BYTES;
+          if (boxes_issued >= 2) {                 // the store issued two boxes ago has finished reading this buffer
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
           }
-          v[j] = x;
-        }
-        if (p.mask && row_live) {
-          const __nv_bfloat16* mrow = p.mask + (int64_t)gm * p.ldmask + gn0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (gn0 + q * 8 < p.ldmask) {
-              const uint4 raw = __ldg(reinterpret_cast<const uint4*>(mrow) + q);
-              const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+          for (int half = 0; half < 2; ++half) {
+            const int cc = c0 + half * 32;
+            if (cc >= bn_tile) break;              // columns >= bn_tile >= ldc are clipped by the TMA store
+            uint32_t r[32];
+            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + cc), r);
+            const int gn0 = nb * BN_MAX + cc;
+            float v[32];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (!(__bfloat162float(mv[j]) > 0.f)) v[q * 8 + j] = 0.f;
+            for (int j = 0; j < 32; ++j) {
+              float x = 0.f;
+              if (row_live && gn0 + j < p.n) {
+                x = __uint_as_float(r[j]) + bias_s[cc + j];
+                if (p.relu) x = fmaxf(x, 0.f);
+              }
+              v[j] = x;
             }
-          }
-        }
-        if (row_store) {
-          if (p.out_bf16) {
-            __nv_bfloat16* crow = (__nv_bfloat16*)p.c + (int64_t)gm * p.ldc + gn0;
+            if (p.mask && row_live) {
+              const __nv_bfloat16* mrow = p.mask + (int64_t)gm * p.ldmask + gn0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (gn0 + q * 8 < p.ldc) {
-                uint4 o;
-                o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-                o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-                o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-                o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-                reinterpret_cast<uint4*>(crow)[q] = o;
+              for (int q = 0; q < 4; ++q) {
+                if (gn0 + q * 8 < p.ldmask) {
+                  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(mrow) + q);
+                  const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (!(__bfloat162float(mv[j]) > 0.f)) v[q * 8 + j] = 0.f;
+                }
               }
             }
-          } else {
+            // row `lane` of the box, 16-byte chunk (half*4 + q) XOR-swizzled like TMA's SWIZZLE_128B
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = o;
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          // rows >= m_pad of the tile receive zeros (never read: consumers stop at the padded count); rows >= m_max
+          // and columns >= ldc are clipped by the tensor map
+          if (lane == 0) {
+            tma_store_2d(&p.tc, buf, nb * BN_MAX + c0, mb * BM + quarter * 32);
+            tma_store_commit();
+          }
+          ++boxes_issued;
+        }
+      } else {
+        for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + c0), r);
+          const int gn0 = nb * BN_MAX + c0;
+          if (row_store) {
             float* crow = (float*)p.c + (int64_t)gm * p.ldc + gn0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              if (gn0 + q * 4 < p.ldc)
-                reinterpret_cast<float4*>(crow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              if (gn0 + q * 4 < p.ldc) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float x = 0.f;
+                  if (row_live && gn0 + q * 4 + j < p.n) {
+                    x = __uint_as_float(r[q * 4 + j]) + bias_s[c0 + q * 4 + j];
+                    if (p.relu) x = fmaxf(x, 0.f);
+                  }
+                  v[j] = x;
+                }
+                reinterpret_cast<float4*>(crow)[q] = make_float4(v[0], v[1], v[2], v[3]);
+              }
             }
           }
         }
@@ -321,6 +393,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
       if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();          // shared memory must stay valid until the last store has read it
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -333,6 +407,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
 // ------------------------------------------------------------------ TN kernel --------------------
 struct TnParams {
   CUtensorMap ta, tb;            // boxes of 64 (inner, n / k index) x 64 (rows m)
+  CUtensorMap tout;              // fp32 partials [splits][n][k] (pitch ldo), box 32 x 32 x 1 (TMA store)
+  int use_tma_store;
   const int32_t* m_dev;
   int m_max;
   int n, k;                      // output [n, k]
@@ -343,7 +419,7 @@ struct TnParams {
 };
 
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant__ TnParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemLayout s = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -417,20 +493,52 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       mbar_wait(&s.acc_full[0], 0);
       tc_fence_after();
     }
-    float* orow = p.out + (int64_t)z * p.split_stride + (int64_t)gn * p.ldo;
-    for (int c0 = 0; c0 < bn_tile; c0 += 32) {
-      uint32_t r[32];
-      if (have) {
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-      } else {
+    if (p.use_tma_store) {
+      uint8_t* const stage_buf = s.store + (warp - 2) * 2 * STORE_BOX_BYTES;
+      uint32_t boxes_issued = 0;
+      for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+        if (kt * BN_MAX + c0 >= p.k) break;                  // whole box clipped
+        uint8_t* buf = stage_buf + (boxes_issued & 1) * STORE_BOX_BYTES;
+        if (boxes_issued >= 2) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
+        uint32_t r[32];
+        if (have) {
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&p.tout, buf, kt * BN_MAX + c0, nb * BM + quarter * 32, z);   // rows >= n / cols >= k clipped
+          tma_store_commit();
+        }
+        ++boxes_issued;
       }
-      if (gn < p.n) {
-        const int gk0 = kt * BN_MAX + c0;
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
+    } else {
+      float* orow = p.out + (int64_t)z * p.split_stride + (int64_t)gn * p.ldo;
+      for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+        uint32_t r[32];
+        if (have) {
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (gk0 + j < p.k) orow[gk0 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (gn < p.n) {
+          const int gk0 = kt * BN_MAX + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gk0 + j < p.k) orow[gk0 + j] = __uint_as_float(r[j]);
+        }
       }
     }
   }
@@ -488,6 +596,23 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
   return OGL_OK;
 }
 
+// fp32 [d2][d1][d0] tensor (pitch ld0 elements, plane stride d1*ld0), box 32 x 32 x 1, 128-byte swizzle
+int make_map_f32_3d(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t ld0) {
+  OGL_ARG(((uintptr_t)ptr & 15) == 0 && (ld0 * 4) % 16 == 0, "gemm_tc: fp32 output not 16-byte aligned");
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld0 * 4, (cuuint64_t)ld0 * 4 * (cuuint64_t)d1};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled (fp32 3-D) failed (%d)", (int)r);
+    return OGL_ERR_CUDA;
+  }
+  return OGL_OK;
+}
+
 }  // namespace
 
 bool gemm_tc_available() { return tc_init() == 1; }
@@ -519,6 +644,8 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.ldc = g.ldc;
   p.out_bf16 = g.out_bf16;
   p.zero_tail = g.zero_tail;
+  OGL_ARG(!(g.mask && !g.out_bf16), "gemm_nt_tc: the mask epilogue is implemented for bf16 output only");
+  if (g.out_bf16) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 64, 32));
   OGL_ARG(g.ldc % 8 == 0 && ((uintptr_t)g.c & 15) == 0, "gemm_nt_tc: output pitch must be a multiple of 8 elements");
   OGL_ARG(!g.mask || (g.ldmask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0), "gemm_nt_tc: mask pitch must be a multiple of 8 elements");
   const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
@@ -549,17 +676,22 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
   if ((int64_t)splits * per > g.partial_elems) splits = (int)(g.partial_elems / per);
   if (splits < 1) splits = 1;
   p.splits = splits;
-  if (splits == 1) {
+  const bool staged = g.partial != nullptr && per <= g.partial_elems;   // partials (pitch % 4 == 0) take TMA stores
+  if (!staged) {
+    OGL_ARG(splits == 1, "gemm_tn_tc: internal: split without workspace");
     p.out = g.c;
     p.ldo = g.ldc;
     p.split_stride = 0;
+    p.use_tma_store = 0;
   } else {
     p.out = g.partial;
     p.ldo = ldo;
     p.split_stride = per;
+    p.use_tma_store = 1;
+    OGL_TRY(make_map_f32_3d(&p.tout, g.partial, g.k, g.n, splits, ldo));
   }
   OGL_LAUNCH(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_BYTES, s, p);
-  if (splits > 1) return reduce_splits_ld(g.partial, splits, g.n, g.k, ldo, g.c, g.ldc, s);
+  if (staged) return reduce_splits_ld(g.partial, splits, g.n, g.k, ldo, g.c, g.ldc, s);
   return OGL_OK;
 }
 

@@ -129,7 +129,52 @@ struct ogl_plan {
   // parameters
   int64_t n_params = 0;
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  // stage profiling (bench.py roofline): CUDA events around every stage, on the caller's stream
+  int prof_on = 0;
+  std::vector<std::string> prof_names;
+  struct ProfRec { int stage; cudaEvent_t e0, e1; long long launches; };
+  std::vector<ProfRec> prof_recs;
+  size_t prof_used = 0;
+  int32_t* prof_counts_host = nullptr;   // pinned [kProfSteps][8]
+  int prof_steps = 0;
 };
+constexpr int kProfSteps = 4096;
+
+static void prof_begin(ogl_plan* p, const char* name, cudaStream_t s) {
+  if (!p->prof_on) return;
+  int stage = -1;
+  for (size_t i = 0; i < p->prof_names.size(); ++i)
+    if (p->prof_names[i] == name) { stage = (int)i; break; }
+  if (stage < 0) { p->prof_names.push_back(name); stage = (int)p->prof_names.size() - 1; }
+  if (p->prof_used == p->prof_recs.size()) {
+    ogl_plan::ProfRec r;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    p->prof_recs.push_back(r);
+  }
+  ogl_plan::ProfRec& r = p->prof_recs[p->prof_used];
+  r.stage = stage;
+  r.launches = g_launches.load();
+  cudaEventRecord(r.e0, s);
+}
+static void prof_end(ogl_plan* p, cudaStream_t s) {
+  if (!p->prof_on) return;
+  ogl_plan::ProfRec& r = p->prof_recs[p->prof_used++];
+  r.launches = g_launches.load() - r.launches;
+  cudaEventRecord(r.e1, s);
+}
+#define STAGE(name, call)            \
+  do {                               \
+    prof_begin(p, name, s);          \
+    int _sr = (call);                \
+    prof_end(p, s);                  \
+    if (_sr != OGL_OK) return _sr;   \
+  } while (0)
+static std::string nm(const char* fmt, int i) {
+  char b[64];
+  snprintf(b, sizeof(b), fmt, i);
+  return b;
+}
 
 static int gemm_nt(const ogl_plan* p, const GemmNT& g, cudaStream_t s) {
   if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_nt_tc(g, s);
@@ -214,7 +259,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     max_src_elems = std::max<int64_t>(max_src_elems, (int64_t)rows(p->nmax[s]) * lb.pin);
     max_dst_in_elems = std::max<int64_t>(max_dst_in_elems, (int64_t)rows(p->nmax[d]) * lb.pin);
     max_nk = std::max<int64_t>(max_nk, (int64_t)std::max(lb.in, lb.out) * lb.in);
-    max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[s], lb.pin));
+    max_colsum = std::max<int64_t>(max_colsum, dhp_convert_partial_elems(p->nmax[s], lb.pin));
     max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[d], lb.pout));
   }
   p->n_params = off;
@@ -247,6 +292,8 @@ extern "C" int ogl_plan_destroy(ogl_plan* p) {
   void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dhp32, p->dhp, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
                   p->loss_sum, p->adam_m, p->adam_v};
   for (void* q : ptrs) cudaFree(q);
+  for (auto& r : p->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  if (p->prof_counts_host) cudaFreeHost(p->prof_counts_host);
   delete p;
   return OGL_OK;
 }
@@ -288,10 +335,10 @@ extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_d
   OGL_TRY(cast_nodes(seeds_dev, p->nodes[0], n_seeds, s));
   OGL_LAUNCH(k_set_i32, 1, 1, 0, s, p->counts, n_seeds);
   for (int h = 0; h < p->L; ++h) {
-    OGL_TRY(sample_hop(gv, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->cfg.seed, p->ctl, 0, (uint32_t)h,
-                       p->edge_gsrc[h], p->edge_eid[h], s));
-    OGL_TRY(to_block(&p->tb, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->edge_gsrc[h], p->nodes[h + 1],
-                     p->counts + h + 1, p->nmax[h + 1], p->edge_lid[h], s));
+    STAGE(nm("sample.h%d", h).c_str(), sample_hop(gv, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->cfg.seed, p->ctl, 0,
+                                                  (uint32_t)h, p->edge_gsrc[h], p->edge_eid[h], s));
+    STAGE(nm("to_block.h%d", h).c_str(), to_block(&p->tb, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->edge_gsrc[h],
+                                                  p->nodes[h + 1], p->counts + h + 1, p->nmax[h + 1], p->edge_lid[h], s));
   }
   return OGL_OK;
 }
@@ -303,7 +350,7 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
   cudaStream_t s = (cudaStream_t)stream;
   const int L = p->L;
   // f == NULL: the input rows were supplied by ogl_plan_set_input
-  if (f) OGL_TRY(gather_rows(p->bf16, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
+  if (f) STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
   for (int l = 0; l < L; ++l) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, sl = h + 1, dl = h;
@@ -312,15 +359,16 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
     g1.bias = p->params + lb.o_bp; g1.relu = 1;
     g1.c = lb.hp; g1.ldc = lb.pin; g1.m_max = p->nmax[sl]; g1.m_dev = p->counts + sl; g1.n = lb.in;
     g1.in_bf16 = p->bf16; g1.out_bf16 = p->bf16;
-    OGL_TRY(gemm_nt(p, g1, s));
-    OGL_TRY(segmax_fwd(p->bf16, lb.hp, lb.pin, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], lb.neigh, lb.arg, s));
+    STAGE(nm("l%d.pool_gemm", l).c_str(), gemm_nt(p, g1, s));
+    STAGE(nm("l%d.segmax", l).c_str(),
+          segmax_fwd(p->bf16, lb.hp, lb.pin, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], lb.neigh, lb.arg, s));
     GemmNT g2;
     g2.a[0] = p->act[sl]; g2.lda[0] = lb.pin; g2.b[0] = lb.ws; g2.ldb[0] = lb.pin; g2.k[0] = lb.in;
     g2.a[1] = lb.neigh; g2.lda[1] = lb.pin; g2.b[1] = lb.wn; g2.ldb[1] = lb.pin; g2.k[1] = lb.in; g2.n_seg = 2;
     g2.bias = p->params + lb.o_bs; g2.bias2 = p->params + lb.o_bn; g2.relu = (l < L - 1);
     g2.c = p->act[dl]; g2.ldc = lb.pout; g2.m_max = p->nmax[dl]; g2.m_dev = p->counts + dl; g2.n = lb.out;
     g2.in_bf16 = p->bf16; g2.out_bf16 = (l < L - 1) ? p->bf16 : 0;
-    OGL_TRY(gemm_nt(p, g2, s));
+    STAGE(nm("l%d.out_gemm", l).c_str(), gemm_nt(p, g2, s));
   }
   if (logits_dev)
     OGL_TRY(unpad_copy((const float*)p->act[0], p->layer[L - 1].pout, p->nmax[0], p->counts, p->cfg.dims[L], logits_dev, s));
@@ -331,9 +379,9 @@ static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, f
   const int L = p->L;
   LayerBuf& last = p->layer[L - 1];
   float* per = per_vertex_loss_dev ? per_vertex_loss_dev : p->per_loss;
-  OGL_TRY(xent(p->bf16, (const float*)p->act[0], last.pout, p->cfg.dims[L], f->labels, p->nodes[0], p->counts, p->nmax[0],
-               round_up(p->nmax[0], 128), scale, per, last.dpre, last.pout, want_grad, s));
-  if (loss_sum_dev) OGL_TRY(sum_f32(per, p->counts, p->nmax[0], loss_sum_dev, s));
+  STAGE("xent", xent(p->bf16, (const float*)p->act[0], last.pout, p->cfg.dims[L], f->labels, p->nodes[0], p->counts, p->nmax[0],
+                     round_up(p->nmax[0], 128), scale, per, last.dpre, last.pout, want_grad, s));
+  if (loss_sum_dev) STAGE("loss_sum", sum_f32(per, p->counts, p->nmax[0], loss_sum_dev, s));
   return OGL_OK;
 }
 
@@ -358,26 +406,29 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     t.a = lb.dpre; t.lda = lb.pout; t.n = lb.out; t.b = p->act[sl]; t.ldb = lb.pin; t.k = lb.in;
     t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16;
     t.partial = p->tn_partial; t.partial_elems = p->tn_partial_elems;
-    OGL_TRY(gemm_tn(p, t, s));
+    STAGE(nm("l%d.dW_self", l).c_str(), gemm_tn(p, t, s));
     t.b = lb.neigh; t.c = G + lb.o_wn;
-    OGL_TRY(gemm_tn(p, t, s));
-    OGL_TRY(colsum(p->bf16, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl], p->colsum_partial, G + lb.o_bs, G + lb.o_bn, s));
+    STAGE(nm("l%d.dW_neigh", l).c_str(), gemm_tn(p, t, s));
+    STAGE(nm("l%d.db_out", l).c_str(),
+          colsum(p->bf16, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl], p->colsum_partial, G + lb.o_bs, G + lb.o_bn, s));
     // dneigh = dpre Wn
     GemmNT n1;
     n1.a[0] = lb.dpre; n1.lda[0] = lb.pout; n1.b[0] = lb.wnT; n1.ldb[0] = lb.pout; n1.k[0] = lb.out; n1.n_seg = 1;
     n1.c = p->dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
     n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.zero_tail = 0;
-    OGL_TRY(gemm_nt(p, n1, s));
+    STAGE(nm("l%d.dneigh_gemm", l).c_str(), gemm_nt(p, n1, s));
     // scatter through the argmax, relu mask
-    OGL_TRY(segmax_bwd(p->bf16, p->dng, lb.pin, lb.in, lb.arg, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], p->dhp32, s));
-    OGL_TRY(mask_convert(p->bf16, p->dhp32, lb.hp, lb.pin, p->counts + sl, p->nmax[sl], p->dhp, s));
+    STAGE(nm("l%d.segmax_bwd", l).c_str(), segmax_bwd(p->bf16, p->dng, lb.neigh, lb.pin, lb.in, lb.arg, p->edge_lid[h], p->cfg.fanouts[h],
+                                                      p->counts + dl, p->nmax[dl], p->dhp32, s));
+    // fp32 scatter buffer -> arithmetic type (+ re-zero) and the fc_pool bias gradient in one pass
+    STAGE(nm("l%d.dhp_convert", l).c_str(),
+          dhp_convert(p->bf16, p->dhp32, lb.pin, lb.in, p->counts + sl, p->nmax[sl], p->dhp, p->colsum_partial, G + lb.o_bp, s));
     // dWp = dhp^T act[src]
     GemmTN tp;
     tp.a = p->dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
     tp.c = G + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16;
     tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
-    OGL_TRY(gemm_tn(p, tp, s));
-    OGL_TRY(colsum(p->bf16, p->dhp, lb.pin, lb.in, p->counts + sl, p->nmax[sl], p->colsum_partial, G + lb.o_bp, nullptr, s));
+    STAGE(nm("l%d.dW_pool", l).c_str(), gemm_tn(p, tp, s));
     if (l > 0) {
       // dpre[l-1] = relu'(act[src]) * ( dhp Wp + [dpre Ws on the first n_d rows] )
       LayerBuf& prev = p->layer[l - 1];
@@ -388,7 +439,7 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       d.mask = p->act[sl]; d.ldmask = lb.pin;
       d.c = prev.dpre; d.ldc = prev.pout; d.m_max = p->nmax[sl]; d.m_dev = p->counts + sl; d.n = lb.in;
       d.in_bf16 = p->bf16; d.out_bf16 = p->bf16;
-      OGL_TRY(gemm_nt(p, d, s));
+      STAGE(nm("l%d.dx_gemm", l).c_str(), gemm_nt(p, d, s));
     }
   }
   return OGL_OK;
@@ -418,9 +469,10 @@ extern "C" int ogl_plan_backward(ogl_plan* p, const float* dlogits_dev, void* st
 extern "C" int ogl_plan_adam_step(ogl_plan* p, void* stream) {
   OGL_ARG(p && p->params, "ogl_plan_adam_step: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  OGL_TRY(adam(p->params, p->grads, p->adam_m, p->adam_v, p->n_params, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps, p->ctl + 1, s));
+  STAGE("adam", adam(p->params, p->grads, p->adam_m, p->adam_v, p->n_params, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps, p->ctl + 1, s));
   OGL_TRY(bump(nullptr, p->ctl + 1, s));
-  return ogl_plan_refresh_params(p, stream);
+  STAGE("weight_shadow", ogl_plan_refresh_params(p, stream));
+  return OGL_OK;
 }
 
 static int stage_seeds(ogl_plan* p, const int64_t* seeds, int n_seeds, int on_host, const int64_t** out, cudaStream_t s) {
@@ -445,6 +497,46 @@ extern "C" int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, c
   OGL_TRY(ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, stream));
   if (do_step) OGL_TRY(ogl_plan_adam_step(p, stream));
   OGL_TRY(bump(p->ctl, nullptr, s));
+  if (p->prof_on && p->prof_steps < kProfSteps) {
+    OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
+    p->prof_steps++;
+  }
+  return OGL_OK;
+}
+
+// ------------------------------------------------------------------ stage profiling -----------------
+extern "C" int ogl_plan_profile(ogl_plan* p, int enable) {
+  OGL_ARG(p, "ogl_plan_profile: null");
+  if (enable && !p->prof_counts_host) OGL_CUDA(cudaMallocHost(&p->prof_counts_host, sizeof(int32_t) * 8 * kProfSteps));
+  p->prof_on = enable ? 1 : 0;
+  p->prof_used = 0;          // (re)start: event pairs are reused
+  p->prof_steps = 0;
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_profile_read(ogl_plan* p, char* names_buf, int names_len, float* ms_out, int64_t* launches_out, int max_stages,
+                                     int* n_stages, int64_t* level_count_sums /*[8]*/, int* n_steps) {
+  OGL_ARG(p && names_buf && ms_out && launches_out && n_stages, "ogl_plan_profile_read: null");
+  OGL_CUDA(cudaDeviceSynchronize());
+  const int ns = (int)p->prof_names.size();
+  OGL_ARG(ns <= max_stages, "ogl_plan_profile_read: %d stages, room for %d", ns, max_stages);
+  std::string joined;
+  for (int i = 0; i < ns; ++i) { ms_out[i] = 0.f; launches_out[i] = 0; joined += p->prof_names[i]; joined += '\n'; }
+  OGL_ARG((int)joined.size() < names_len, "ogl_plan_profile_read: name buffer too small");
+  memcpy(names_buf, joined.c_str(), joined.size() + 1);
+  for (size_t i = 0; i < p->prof_used; ++i) {
+    float ms = 0.f;
+    OGL_CUDA(cudaEventElapsedTime(&ms, p->prof_recs[i].e0, p->prof_recs[i].e1));
+    ms_out[p->prof_recs[i].stage] += ms;
+    launches_out[p->prof_recs[i].stage] += p->prof_recs[i].launches;
+  }
+  *n_stages = ns;
+  if (level_count_sums) {
+    for (int l = 0; l < 8; ++l) level_count_sums[l] = 0;
+    for (int st = 0; st < p->prof_steps; ++st)
+      for (int l = 0; l <= p->L; ++l) level_count_sums[l] += p->prof_counts_host[8 * st + l];
+  }
+  if (n_steps) *n_steps = p->prof_steps;
   return OGL_OK;
 }
 

@@ -96,61 +96,126 @@ __global__ void __launch_bounds__(kBlock) k_segmax_fwd(const T* __restrict__ hp,
   }
 }
 
-// dhp32[src(argslot), f] += dng[d, f]
+// dhp32[src(argslot), f] += relu'(hp) * dng[d, f].  The ReLU mask of the pooled activation is applied HERE, on the
+// destination side: neigh[d, f] is exactly hp[src(argslot), f], so hp > 0 <=> neigh > 0 and no pass over the (much
+// larger) source-side matrix is needed for it.  16-byte loads of dng / neigh, 8-byte loads of the slots.
 template <typename T>
-__global__ void __launch_bounds__(kBlock) k_segmax_bwd(const T* __restrict__ dng, int pitch, int feat, const uint8_t* __restrict__ arg,
-                                                       const int32_t* __restrict__ edge_lid, int fanout, const int32_t* __restrict__ n_dst_dev,
-                                                       int n_dst_max, float* __restrict__ dhp32) {
+__global__ void __launch_bounds__(kBlock) k_segmax_bwd(const T* __restrict__ dng, const T* __restrict__ neigh, int pitch, int feat,
+                                                       const uint8_t* __restrict__ arg, const int32_t* __restrict__ edge_lid, int fanout,
+                                                       const int32_t* __restrict__ n_dst_dev, int n_dst_max, float* __restrict__ dhp32) {
+  constexpr int NV = Vec<T>::N;
   const int n = dyn_count(n_dst_dev, n_dst_max);
-  const int64_t total = (int64_t)n * pitch;
+  const int vpr = pitch / NV;
+  const int64_t total = (int64_t)n * vpr;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(t / pitch), f = (int)(t % pitch);
-    if (f >= feat) continue;
-    const int sl = arg[t];
-    if (sl == 255) continue;
-    const float g = to_f32<T>(dng[t]);
-    if (g == 0.f) continue;
-    const int lid = edge_lid[(int64_t)d * fanout + sl];
-    atomicAdd(&dhp32[(int64_t)lid * pitch + f], g);
+    const int d = (int)(t / vpr), c = (int)(t % vpr);
+    const int64_t e0 = (int64_t)d * pitch + c * NV;
+    const uint4 graw = __ldg(reinterpret_cast<const uint4*>(dng + e0));
+    const uint4 nraw = __ldg(reinterpret_cast<const uint4*>(neigh + e0));
+    const T* gv = reinterpret_cast<const T*>(&graw);
+    const T* nv = reinterpret_cast<const T*>(&nraw);
+    uint8_t sl[NV];
+    if (NV == 8) *reinterpret_cast<uint2*>(sl) = __ldg(reinterpret_cast<const uint2*>(arg + e0));
+    else *reinterpret_cast<uint32_t*>(sl) = __ldg(reinterpret_cast<const uint32_t*>(arg + e0));
+    const int32_t* el = edge_lid + (int64_t)d * fanout;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int f = c * NV + i;
+      if (f >= feat || sl[i] == 255) continue;
+      const float g = to_f32<T>(gv[i]);
+      if (g == 0.f || !(to_f32<T>(nv[i]) > 0.f)) continue;
+      atomicAdd(&dhp32[(int64_t)__ldg(el + sl[i]) * pitch + f], g);
+    }
   }
 }
 
-// dhp[r, f] = hp[r, f] > 0 ? dhp32[r, f] : 0 ; dhp32 is zeroed again; rows [n, pad128) zero
+// dhp[r, :] = T(dhp32[r, :]); dhp32 is zeroed again (it is the scatter target of the next layer / step); rows
+// [n, pad128) of dhp are zero; and the bias gradient db[c] = sum_r dhp[r, c] comes out of the same pass:
+// blockDim.x threads own one float4 column strip each, a block walks kCvtRows rows, so every thread keeps its 4
+// column sums in registers (no atomics, no shared memory) and writes one partial per (block, column); the
+// partials are summed in block order by k_colsum_final -> deterministic.  Fully coalesced 16-byte accesses.
+constexpr int kCvtRows = 64;
 template <typename T>
-__global__ void __launch_bounds__(kBlock) k_mask_convert(float* __restrict__ dhp32, const T* __restrict__ hp, int pitch,
-                                                         const int32_t* __restrict__ n_dev, int n_max, T* __restrict__ dhp) {
+__global__ void k_dhp_convert(float* __restrict__ dhp32, int pitch, const int32_t* __restrict__ n_dev, int n_max, T* __restrict__ dhp,
+                              float* __restrict__ partial) {
   const int n = dyn_count(n_dev, n_max);
   const int np = pad128(n, n_max);
-  const int64_t total = (int64_t)np * pitch / 4;
-  float4* g4 = reinterpret_cast<float4*>(dhp32);
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = t * 4;
-    const int r = (int)(e / pitch);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r < n) {
-      const float4 g = g4[t];
-      const float gv[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = to_f32<T>(hp[e + i]) > 0.f ? gv[i] : 0.f;
-      g4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int strips = pitch >> 2;
+  const int c4 = threadIdx.x;
+  const int r0 = blockIdx.x * kCvtRows;
+  if (r0 >= np) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < strips) {
+    const int r1 = min(r0 + kCvtRows, np);
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      float4* src = reinterpret_cast<float4*>(dhp32 + (int64_t)r * pitch) + c4;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < n) {
+        g = *src;
+        *src = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      T o[4] = {from_f32<T>(g.x), from_f32<T>(g.y), from_f32<T>(g.z), from_f32<T>(g.w)};
+      // the bias gradient sums the values as stored (rounded), like the column sum of the stored matrix did
+      acc.x += to_f32<T>(o[0]); acc.y += to_f32<T>(o[1]); acc.z += to_f32<T>(o[2]); acc.w += to_f32<T>(o[3]);
+      T* dst = dhp + (int64_t)r * pitch + c4 * 4;
+      if (sizeof(T) == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
+      else *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(o);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dhp[e + i] = from_f32<T>(o[i]);
+    reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * pitch)[c4] = acc;
+  }
+}
+// db[c] = sum over the blocks that held live rows, ascending
+__global__ void __launch_bounds__(kBlock) k_cvt_colsum_final(const float* __restrict__ partial, int pitch, int cols, const int32_t* __restrict__ n_dev,
+                                                             int n_max, float* __restrict__ out) {
+  const int n = dyn_count(n_dev, n_max);
+  const int blocks = (n + kCvtRows - 1) / kCvtRows;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < blocks; ++k) s += partial[(int64_t)k * pitch + c];
+    out[c] = s;
   }
 }
 
 // ---- bias gradient: deterministic two-phase column sum -------------------------------------------
-constexpr int kColRows = 128;
+// phase 1: a block covers 32 16-byte column strips x kColRows rows; warp w takes rows w, w+8, ...; the 8 warps are
+// combined in shared memory in a fixed order.  phase 2 sums the per-chunk partials in ascending chunk order.
+constexpr int kColRows = 256;
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_colsum_partial(const T* __restrict__ x, int pitch, int cols, const int32_t* __restrict__ n_dev,
                                                            int n_max, float* __restrict__ partial) {
+  constexpr int NV = Vec<T>::N;
+  __shared__ float sm[8][32][NV + 1];
   const int n = dyn_count(n_dev, n_max);
   const int chunk = blockIdx.y;
   const int r0 = chunk * kColRows, r1 = min(r0 + kColRows, n);
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += to_f32<T>(x[(int64_t)r * pitch + c]);
-    partial[(int64_t)chunk * cols + c] = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int strip = blockIdx.x * 32 + lane;
+  const int vpr = pitch / NV;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  if (strip < vpr) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)r * pitch) + strip);
+      const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += to_f32<T>(v[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sm[warp][lane][i] = acc[i];
+  __syncthreads();
+  // 32 strips x NV columns = up to 256 outputs: one per thread
+  const int o_strip = threadIdx.x / NV, o_i = threadIdx.x % NV;
+  if (o_strip < 32) {
+    const int c = (blockIdx.x * 32 + o_strip) * NV + o_i;
+    if (c < cols) {
+      float s_ = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s_ += sm[w][o_strip][o_i];
+      partial[(int64_t)chunk * cols + c] = s_;
+    }
   }
 }
 __global__ void __launch_bounds__(kBlock) k_colsum_final(const float* __restrict__ partial, int cols, const int32_t* __restrict__ n_dev,
@@ -287,22 +352,27 @@ int segmax_fwd(int bf16, const void* hp, int pitch, const int32_t* edge_lid, int
   else OGL_LAUNCH((k_segmax_fwd<float>), grid, kBlock, 0, s, (const float*)hp, pitch, edge_lid, fanout, n_dst_dev, n_dst_max, (float*)ng, arg);
   return OGL_OK;
 }
-int segmax_bwd(int bf16, const void* dng, int pitch, int feat, const uint8_t* arg, const int32_t* edge_lid, int fanout,
+int segmax_bwd(int bf16, const void* dng, const void* neigh, int pitch, int feat, const uint8_t* arg, const int32_t* edge_lid, int fanout,
                const int32_t* n_dst_dev, int n_dst_max, float* dhp32, cudaStream_t s) {
-  const int grid = grid_for((int64_t)n_dst_max * pitch, kBlock, 16);
-  if (bf16) OGL_LAUNCH((k_segmax_bwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)dng, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
-  else OGL_LAUNCH((k_segmax_bwd<float>), grid, kBlock, 0, s, (const float*)dng, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
+  const int grid = grid_for((int64_t)n_dst_max * pitch / (bf16 ? 8 : 4), kBlock, 16);
+  if (bf16) OGL_LAUNCH((k_segmax_bwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)dng, (const __nv_bfloat16*)neigh, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
+  else OGL_LAUNCH((k_segmax_bwd<float>), grid, kBlock, 0, s, (const float*)dng, (const float*)neigh, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
   return OGL_OK;
 }
-int mask_convert(int bf16, float* dhp32, const void* hp, int pitch, const int32_t* n_dev, int n_max, void* dhp, cudaStream_t s) {
-  const int grid = grid_for((int64_t)n_max * pitch / 4, kBlock, 16);
-  if (bf16) OGL_LAUNCH((k_mask_convert<__nv_bfloat16>), grid, kBlock, 0, s, dhp32, (const __nv_bfloat16*)hp, pitch, n_dev, n_max, (__nv_bfloat16*)dhp);
-  else OGL_LAUNCH((k_mask_convert<float>), grid, kBlock, 0, s, dhp32, (const float*)hp, pitch, n_dev, n_max, (float*)dhp);
+int64_t dhp_convert_partial_elems(int n_max, int pitch) { return ceil_div(round_up(n_max, 128), kCvtRows) * (int64_t)pitch; }
+int dhp_convert(int bf16, float* dhp32, int pitch, int cols, const int32_t* n_dev, int n_max, void* dhp, float* partial, float* db,
+                cudaStream_t s) {
+  const int threads = round_up(pitch / 4, 32);
+  OGL_ARG(threads <= 1024 && pitch % 4 == 0, "dhp_convert: row pitch %d unsupported", pitch);
+  const int grid = (int)ceil_div(round_up(n_max, 128), kCvtRows);
+  if (bf16) OGL_LAUNCH((k_dhp_convert<__nv_bfloat16>), grid, threads, 0, s, dhp32, pitch, n_dev, n_max, (__nv_bfloat16*)dhp, partial);
+  else OGL_LAUNCH((k_dhp_convert<float>), grid, threads, 0, s, dhp32, pitch, n_dev, n_max, (float*)dhp, partial);
+  OGL_LAUNCH(k_cvt_colsum_final, (unsigned)ceil_div(cols, kBlock), kBlock, 0, s, partial, pitch, cols, n_dev, n_max, db);
   return OGL_OK;
 }
 int64_t colsum_partial_elems(int n_max, int cols) { return ceil_div(n_max, kColRows) * (int64_t)cols; }
 int colsum(int bf16, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s) {
-  dim3 grid((unsigned)ceil_div(cols, kBlock), (unsigned)ceil_div(n_max, kColRows));
+  dim3 grid((unsigned)ceil_div(pitch / (bf16 ? 8 : 4), 32), (unsigned)ceil_div(n_max, kColRows));
   if (bf16) OGL_LAUNCH((k_colsum_partial<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)x, pitch, cols, n_dev, n_max, partial);
   else OGL_LAUNCH((k_colsum_partial<float>), grid, kBlock, 0, s, (const float*)x, pitch, cols, n_dev, n_max, partial);
   OGL_LAUNCH(k_colsum_final, (unsigned)ceil_div(cols, kBlock), kBlock, 0, s, partial, cols, n_dev, n_max, out, out2);

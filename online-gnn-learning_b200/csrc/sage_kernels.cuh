@@ -9,9 +9,11 @@ int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t*
 int gather_rows(int bf16, const void* table, int pitch, const int32_t* nodes, const int32_t* n_dev, int n_max, void* out, cudaStream_t s);
 int segmax_fwd(int bf16, const void* hp, int pitch, const int32_t* edge_lid, int fanout, const int32_t* n_dst_dev, int n_dst_max, void* ng,
                uint8_t* arg, cudaStream_t s);
-int segmax_bwd(int bf16, const void* dng, int pitch, int feat, const uint8_t* arg, const int32_t* edge_lid, int fanout,
+int segmax_bwd(int bf16, const void* dng, const void* neigh, int pitch, int feat, const uint8_t* arg, const int32_t* edge_lid, int fanout,
                const int32_t* n_dst_dev, int n_dst_max, float* dhp32, cudaStream_t s);
-int mask_convert(int bf16, float* dhp32, const void* hp, int pitch, const int32_t* n_dev, int n_max, void* dhp, cudaStream_t s);
+int64_t dhp_convert_partial_elems(int n_max, int pitch);
+int dhp_convert(int bf16, float* dhp32, int pitch, int cols, const int32_t* n_dev, int n_max, void* dhp, float* partial, float* db,
+                cudaStream_t s);
 int64_t colsum_partial_elems(int n_max, int cols);
 int colsum(int bf16, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s);
 int xent(int bf16, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,

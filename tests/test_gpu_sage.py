@@ -119,6 +119,60 @@ def test_forward_backward_parity_simt(mode, rtol, rtol_store, dims, fanouts):
             close(got[k], v, rtol * (3 if mode == "bf16" else 1), "grad " + k)
 
 
+@pytest.mark.parametrize("dims,fanouts,n_seeds", [((50, 24, 5), (6, 4), 96), ((166, 256, 2), (9, 9), 64), ((602, 600, 41), (10, 5), 300),
+                                                  ((33, 7), (5,), 40), ((128, 32, 32, 40), (4, 3, 2), 50)])
+def test_forward_backward_parity_tcgen05(dims, fanouts, n_seeds):
+    """the default bf16 path: every GEMM on the tcgen05 kernels (gemm_impl=0), vs the bf16-operand oracle AND vs
+    the SIMT implementation of the same arithmetic"""
+    c = Case(V=3000, E=20000, dims=dims, fanouts=fanouts, n_seeds=n_seeds, mode="bf16", gemm_impl=0)
+    seeds_dev = torch.as_tensor(c.seeds).cuda()
+    c.plan.sample(c.g, seeds_dev)
+    logits = c.plan.forward(c.f)
+    per, tot = c.plan.loss_backward(c.f, 1.0 / len(c.seeds))
+    L = c.L
+    # pass 1: free-running oracle -> forward tensors; the device's argmax slots must attain the oracle's max
+    _, per_ref, logits_ref, _, inter = c.run_oracle()
+    close(logits, logits_ref, 1e-3, "logits")
+    close(per, per_ref, 1e-3, "per-vertex loss")
+    x_in, blocks = c.oracle_blocks()
+    for l in range(L):
+        h = L - 1 - l
+        n_src, n_dst = c.plan.level_nodes(h + 1).numel(), c.plan.level_nodes(h).numel()
+        close(c.plan.tensor(f"hp{l}", rows=n_src)[:, :dims[l]].float(), inter[l]["hp"], 2 ** -8, f"hp{l}")
+        close(c.plan.tensor(f"neigh{l}", rows=n_dst)[:, :dims[l]].float(), inter[l]["neigh"], 2 ** -8, f"neigh{l}")
+        arg = c.plan.tensor(f"arg{l}", rows=n_dst)[:, :dims[l]].long().cpu()
+        arg[arg == 255] = -1
+        assert torch.equal(arg < 0, inter[l]["arg"] < 0)
+        es = blocks[l]["edge_src"].view(n_dst, fanouts[h])
+        src_row = torch.gather(es, 1, arg.clamp(min=0))                      # [n_dst, F] local src row of the device's slot
+        assert bool((src_row[arg >= 0] >= 0).all()), "device argmax points at an empty slot"
+        hp_o = inter[l]["hp"].detach()
+        picked = hp_o[src_row.clamp(min=0), torch.arange(dims[l])[None, :].expand_as(src_row)]
+        mx = inter[l]["neigh"].detach()
+        # one bf16 ulp of the value + the fp32 accumulation-order noise of a cancelling dot product (relative to the scale)
+        # (same tolerance as the comparison of the stored hp itself: layer >= 1 inherits bf16 rounding flips of its input)
+        ok = (picked >= mx - 2 ** -7 * mx.abs() - 2 ** -8 * hp_o.abs().max()) | (arg < 0)
+        assert bool(ok.all()), "device argmax slot is not a maximum within one bf16 ulp: %d bad" % int((~ok).sum())
+        blocks[l]["arg"] = arg
+    # pass 2: gradients with the device's routing through the max-pool
+    labels = c.labels[torch.as_tensor(c.seeds)]
+    _, _, _, grads_ref, _ = osage.loss_and_grads(c.params, x_in, blocks, labels, quant="bf16", dtype=torch.float64)
+    got = dict_from_flat(c.grad, dims)
+    for k, v in grads_ref.items():
+        if k in got:
+            close(got[k], v, 3e-3, "grad " + k)
+    # same arithmetic on the SIMT kernels: same minibatch (same Philox step), tighter agreement
+    g_tc = c.grad.clone()
+    simt = c.ogl.native.Plan(c.dims, c.fanouts, max(n_seeds, 8), c.V, mode=c.mode, seed=11, gemm_impl=1)
+    g2 = torch.zeros_like(c.flat)
+    simt.bind_params(c.flat, g2)
+    simt.sample(c.g, seeds_dev)
+    logits2 = simt.forward(c.f)
+    simt.loss_backward(c.f, 1.0 / len(c.seeds))
+    close(logits, logits2, 1e-3, "tc vs simt logits")
+    close(g_tc, g2, 3e-3, "tc vs simt grads")
+
+
 def test_zero_degree_rows_and_tail_padding():
     """all seeds isolated: neigh = 0 everywhere, out = fc_self(h) + biases; nothing leaks from stale workspace rows"""
     c = Case(dims=(12, 8, 3), fanouts=(4, 4), n_seeds=8, mode="fp32", isolated=40)
