@@ -139,6 +139,11 @@ int ogl_plan_adam_step(ogl_plan* p, void* stream);
 int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds,
                         int seeds_on_host, float loss_scale, int do_step, float* per_vertex_loss_dev,
                         float* loss_sum_dev, void* stream);
+/* options: "cuda_graph" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence
+ * (re-captured when the graph pool, the handles, n_seeds or the output pointers change) */
+int ogl_plan_set_option(ogl_plan* p, const char* name, int value);
+/* out = {graphs captured, graph replays} */
+int ogl_plan_graph_stats(ogl_plan* p, int64_t out[2]);
 /* eval: sample + forward + per-vertex CE loss (PBR recompute_priorities, pytorch/model.py:210-254) */
 int ogl_plan_eval_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds,
                        int seeds_on_host, float* logits_dev, float* per_vertex_loss_dev, void* stream);

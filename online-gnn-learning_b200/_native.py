@@ -252,6 +252,14 @@ class Plan:
         self.n_seeds = n
         self._stamp += 1
 
+    def set_option(self, name, value):
+        check(lib.ogl_plan_set_option(self._h, name.encode(), int(value)))
+
+    def graph_stats(self):
+        a = (C.c_int64 * 2)()
+        check(lib.ogl_plan_graph_stats(self._h, C.byref(a)))
+        return dict(captures=a[0], replays=a[1])
+
     # -- stage profiling (bench.py) ---------------------------------------------------------------
     def profile(self, enable=True):
         check(lib.ogl_plan_profile(self._h, int(bool(enable))))

@@ -310,9 +310,11 @@ struct ogl_graph {
   uint32_t* p_eids = nullptr;
   int64_t p_v = 0, p_e = 0;
   int64_t pool_used_host = 0, relocations = 0, compactions = 0;
+  uint64_t generation = 1;
 };
 
 static int graph_alloc_pool(ogl_graph* g, int64_t cap) {
+  g->generation++;
   OGL_CUDA(cudaMalloc(&g->adj_src, sizeof(int32_t) * (size_t)cap));
   OGL_CUDA(cudaMalloc(&g->adj_eid, sizeof(uint32_t) * (size_t)cap));
   g->pool_cap = cap;
@@ -550,6 +552,7 @@ extern "C" int ogl_graph_set_active_prefix(ogl_graph* g, int64_t n_active, void*
 }
 
 namespace ogl {
+uint64_t graph_generation(const ogl_graph* g) { return g->generation; }
 GraphView graph_view(const ogl_graph* g) {
   GraphView v;
   v.row_start = g->row_start; v.deg = g->deg; v.adj_src = g->adj_src; v.adj_eid = g->adj_eid; v.n_vertices = g->n_vertices;

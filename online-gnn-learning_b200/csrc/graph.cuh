@@ -29,4 +29,6 @@ struct GraphView {
 struct ogl_graph;
 namespace ogl {
 GraphView graph_view(const ogl_graph* g);
+// changes whenever a device pointer of the view changes (pool rebuild): invalidates captured CUDA graphs
+uint64_t graph_generation(const ogl_graph* g);
 }

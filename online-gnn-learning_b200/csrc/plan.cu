@@ -110,6 +110,7 @@ struct ogl_plan {
   std::vector<int32_t*> nodes;           // [L+1]
   int32_t* counts = nullptr;             // [L+1] device
   std::vector<int32_t*> edge_lid, edge_gsrc;   // [L]
+  std::vector<int32_t*> rev_ptr, rev_edge;     // [L] reverse edge lists per hop (source row -> picking slots)
   std::vector<int64_t*> edge_eid;
   std::vector<void*> act;                // [L+1]; act[0] = logits (fp32)
   std::vector<LayerBuf> layer;
@@ -118,7 +119,6 @@ struct ogl_plan {
   uint32_t* ctl = nullptr;               // [0]=philox step, [1]=adam t
   int n_seeds = 0;
   // backward scratch
-  float* dhp32 = nullptr;
   void* dhp = nullptr;
   void* dng = nullptr;
   float* tn_partial = nullptr;
@@ -129,6 +129,25 @@ struct ogl_plan {
   // parameters
   int64_t n_params = 0;
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  ShadowSeg* shadow_segs = nullptr;      // device table for the fused Adam + shadow refresh
+  int n_shadow_segs = 0;
+  // CUDA-graph replay of the train step (fixed launch sequence, all sizes read from device memory)
+  int use_graph = 1;
+  struct StepKey {
+    const void *g, *f, *per, *loss;
+    uint64_t g_gen;
+    int n_seeds, do_step;
+    float loss_scale;
+    bool operator==(const StepKey& o) const {
+      return g == o.g && f == o.f && per == o.per && loss == o.loss && g_gen == o.g_gen && n_seeds == o.n_seeds && do_step == o.do_step &&
+             loss_scale == o.loss_scale;
+    }
+  };
+  struct StepGraph { StepKey key; cudaGraphExec_t exec; uint64_t last_use; };
+  std::vector<StepGraph> step_graphs;    // small LRU
+  uint64_t graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  long long graph_replays = 0, graph_captures = 0;
   // stage profiling (bench.py roofline): CUDA events around every stage, on the caller's stream
   int prof_on = 0;
   std::vector<std::string> prof_names;
@@ -216,6 +235,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   }
   p->nodes.resize(L + 1); p->act.resize(L + 1);
   p->edge_lid.resize(L); p->edge_gsrc.resize(L); p->edge_eid.resize(L); p->layer.resize(L);
+  p->rev_ptr.resize(L); p->rev_edge.resize(L);
   DM0(p->counts, sizeof(int32_t) * (L + 1));
   DM0(p->ctl, sizeof(uint32_t) * 4);
   DM0(p->seeds_stage, sizeof(int64_t) * cfg->max_seeds);
@@ -227,6 +247,8 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     DM0(p->edge_lid[h], sizeof(int32_t) * ne);
     DM0(p->edge_gsrc[h], sizeof(int32_t) * ne);
     DM0(p->edge_eid[h], sizeof(int64_t) * ne);
+    DM0(p->rev_ptr[h], sizeof(int32_t) * ((size_t)p->nmax[h + 1] + 2));
+    DM0(p->rev_edge[h], sizeof(int32_t) * ne);
   }
   OGL_TRY(to_block_init(&p->tb, cfg->v_cap, ne_max));
   // activations (row counts padded to 128 for the zero-tail rule)
@@ -259,11 +281,21 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     max_src_elems = std::max<int64_t>(max_src_elems, (int64_t)rows(p->nmax[s]) * lb.pin);
     max_dst_in_elems = std::max<int64_t>(max_dst_in_elems, (int64_t)rows(p->nmax[d]) * lb.pin);
     max_nk = std::max<int64_t>(max_nk, (int64_t)std::max(lb.in, lb.out) * lb.in);
-    max_colsum = std::max<int64_t>(max_colsum, dhp_convert_partial_elems(p->nmax[s], lb.pin));
+    max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[d], lb.pin));
     max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[d], lb.pout));
   }
   p->n_params = off;
-  DM0(p->dhp32, sizeof(float) * max_src_elems);
+  {
+    std::vector<ShadowSeg> segs;
+    for (auto& lb : p->layer) {
+      segs.push_back({lb.o_wp, lb.o_wp + (int64_t)lb.in * lb.in, lb.in, lb.in, lb.pin, lb.pin, lb.wp, lb.wpT});
+      segs.push_back({lb.o_ws, lb.o_ws + (int64_t)lb.out * lb.in, lb.out, lb.in, lb.pin, lb.pout, lb.ws, lb.wsT});
+      segs.push_back({lb.o_wn, lb.o_wn + (int64_t)lb.out * lb.in, lb.out, lb.in, lb.pin, lb.pout, lb.wn, lb.wnT});
+    }
+    p->n_shadow_segs = (int)segs.size();
+    DM0(p->shadow_segs, sizeof(ShadowSeg) * segs.size());
+    OGL_CUDA(cudaMemcpy(p->shadow_segs, segs.data(), sizeof(ShadowSeg) * segs.size(), cudaMemcpyHostToDevice));
+  }
   DM0(p->dhp, p->es * max_src_elems);
   DM0(p->dng, p->es * max_dst_in_elems);
   p->tn_partial_elems = max_nk * 32;
@@ -283,16 +315,20 @@ extern "C" int ogl_plan_destroy(ogl_plan* p) {
   for (auto x : p->edge_lid) cudaFree(x);
   for (auto x : p->edge_gsrc) cudaFree(x);
   for (auto x : p->edge_eid) cudaFree(x);
+  for (auto x : p->rev_ptr) cudaFree(x);
+  for (auto x : p->rev_edge) cudaFree(x);
   for (auto x : p->act) cudaFree(x);
   for (auto& lb : p->layer) {
     void* ptrs[] = {lb.wp, lb.wpT, lb.ws, lb.wsT, lb.wn, lb.wnT, lb.hp, lb.neigh, lb.arg, lb.dpre};
     for (void* q : ptrs) cudaFree(q);
   }
   to_block_free(&p->tb);
-  void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dhp32, p->dhp, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
-                  p->loss_sum, p->adam_m, p->adam_v};
+  void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dhp, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
+                  p->loss_sum, p->adam_m, p->adam_v, p->shadow_segs};
   for (void* q : ptrs) cudaFree(q);
   for (auto& r : p->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto& sg : p->step_graphs) cudaGraphExecDestroy(sg.exec);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->prof_counts_host) cudaFreeHost(p->prof_counts_host);
   delete p;
   return OGL_OK;
@@ -339,6 +375,8 @@ extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_d
                                                   (uint32_t)h, p->edge_gsrc[h], p->edge_eid[h], s));
     STAGE(nm("to_block.h%d", h).c_str(), to_block(&p->tb, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->edge_gsrc[h],
                                                   p->nodes[h + 1], p->counts + h + 1, p->nmax[h + 1], p->edge_lid[h], s));
+    STAGE(nm("rev_edges.h%d", h).c_str(), reverse_edges(&p->tb, p->edge_lid[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->nmax[h + 1],
+                                                        p->rev_ptr[h], p->rev_edge[h], s));
   }
   return OGL_OK;
 }
@@ -416,13 +454,14 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     n1.a[0] = lb.dpre; n1.lda[0] = lb.pout; n1.b[0] = lb.wnT; n1.ldb[0] = lb.pout; n1.k[0] = lb.out; n1.n_seg = 1;
     n1.c = p->dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
     n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.zero_tail = 0;
+    n1.mask = lb.neigh; n1.ldmask = lb.pin;        // relu'(hp) at the argmax: neigh[d, f] == hp[src(arg), f]
     STAGE(nm("l%d.dneigh_gemm", l).c_str(), gemm_nt(p, n1, s));
-    // scatter through the argmax, relu mask
-    STAGE(nm("l%d.segmax_bwd", l).c_str(), segmax_bwd(p->bf16, p->dng, lb.neigh, lb.pin, lb.in, lb.arg, p->edge_lid[h], p->cfg.fanouts[h],
-                                                      p->counts + dl, p->nmax[dl], p->dhp32, s));
-    // fp32 scatter buffer -> arithmetic type (+ re-zero) and the fc_pool bias gradient in one pass
-    STAGE(nm("l%d.dhp_convert", l).c_str(),
-          dhp_convert(p->bf16, p->dhp32, lb.pin, lb.in, p->counts + sl, p->nmax[sl], p->dhp, p->colsum_partial, G + lb.o_bp, s));
+    // fc_pool bias gradient: every dng[d, f] lands in exactly one source row, so colsum(dhp) == colsum(dng)
+    STAGE(nm("l%d.db_pool", l).c_str(),
+          colsum(p->bf16, p->dng, lb.pin, lb.in, p->counts + dl, p->nmax[dl], p->colsum_partial, G + lb.o_bp, nullptr, s));
+    // max-pool backward as a gather over the reverse edge lists
+    STAGE(nm("l%d.pool_bwd", l).c_str(), pool_bwd(p->bf16, p->dng, lb.pin, lb.arg, p->rev_ptr[h], p->rev_edge[h], p->cfg.fanouts[h],
+                                                  p->counts + sl, p->nmax[sl], p->dhp, s));
     // dWp = dhp^T act[src]
     GemmTN tp;
     tp.a = p->dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
@@ -469,9 +508,9 @@ extern "C" int ogl_plan_backward(ogl_plan* p, const float* dlogits_dev, void* st
 extern "C" int ogl_plan_adam_step(ogl_plan* p, void* stream) {
   OGL_ARG(p && p->params, "ogl_plan_adam_step: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  STAGE("adam", adam(p->params, p->grads, p->adam_m, p->adam_v, p->n_params, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps, p->ctl + 1, s));
+  STAGE("adam", adam_shadow(p->bf16, p->params, p->grads, p->adam_m, p->adam_v, p->n_params, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps,
+                            p->ctl + 1, p->shadow_segs, p->n_shadow_segs, s));
   OGL_TRY(bump(nullptr, p->ctl + 1, s));
-  STAGE("weight_shadow", ogl_plan_refresh_params(p, stream));
   return OGL_OK;
 }
 
@@ -486,21 +525,91 @@ static int stage_seeds(ogl_plan* p, const int64_t* seeds, int n_seeds, int on_ho
   return OGL_OK;
 }
 
+// the fixed launch sequence of one train step over the seeds already staged in p->seeds_stage
+static int train_step_body(ogl_plan* p, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step, float* per_vertex_loss_dev,
+                           float* loss_sum_dev, cudaStream_t s) {
+  OGL_TRY(ogl_plan_sample(p, g, p->seeds_stage, n_seeds, s));
+  OGL_TRY(ogl_plan_forward(p, f, nullptr, s));
+  OGL_TRY(ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s));
+  if (do_step) OGL_TRY(ogl_plan_adam_step(p, s));
+  OGL_TRY(bump(p->ctl, nullptr, s));
+  return OGL_OK;
+}
+
 extern "C" int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
                                    float loss_scale, int do_step, float* per_vertex_loss_dev, float* loss_sum_dev, void* stream) {
   OGL_ARG(p && g && f && seeds, "ogl_plan_train_step: null");
+  OGL_ARG(n_seeds > 0 && n_seeds <= p->cfg.max_seeds, "n_seeds %d not in [1, %d]", n_seeds, p->cfg.max_seeds);
+  OGL_ARG(p->params, "ogl_plan_train_step: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t* sd = nullptr;
-  OGL_TRY(stage_seeds(p, seeds, n_seeds, seeds_on_host, &sd, s));
-  OGL_TRY(ogl_plan_sample(p, g, sd, n_seeds, stream));
-  OGL_TRY(ogl_plan_forward(p, f, nullptr, stream));
-  OGL_TRY(ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, stream));
-  if (do_step) OGL_TRY(ogl_plan_adam_step(p, stream));
-  OGL_TRY(bump(p->ctl, nullptr, s));
+  // seeds always go through the plan's staging buffer so that the captured graph is independent of the caller's pointer
+  OGL_CUDA(cudaMemcpyAsync(p->seeds_stage, seeds, sizeof(int64_t) * n_seeds, seeds_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  if (!p->use_graph || p->prof_on) {
+    OGL_TRY(train_step_body(p, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s));
+  } else {
+    const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, graph_generation(g), n_seeds, do_step, loss_scale};
+    ogl_plan::StepGraph* hit = nullptr;
+    for (auto& sg : p->step_graphs)
+      if (sg.key == key) { hit = &sg; break; }
+    if (!hit) {
+      if (!p->cap_stream) OGL_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+      OGL_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int r = train_step_body(p, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, p->cap_stream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
+      if (r != OGL_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      OGL_CUDA(e);
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      OGL_CUDA(ei);
+      if (p->step_graphs.size() >= 8) {          // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < p->step_graphs.size(); ++i)
+          if (p->step_graphs[i].last_use < p->step_graphs[lru].last_use) lru = i;
+        cudaGraphExecDestroy(p->step_graphs[lru].exec);
+        p->step_graphs.erase(p->step_graphs.begin() + lru);
+      }
+      p->step_graphs.push_back({key, exec, 0});
+      hit = &p->step_graphs.back();
+      p->graph_captures++;
+    }
+    hit->last_use = ++p->graph_clock;
+    OGL_CUDA(cudaGraphLaunch(hit->exec, s));
+    p->graph_replays++;
+    p->n_seeds = n_seeds;
+  }
   if (p->prof_on && p->prof_steps < kProfSteps) {
     OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
     p->prof_steps++;
   }
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_set_option(ogl_plan* p, const char* name, int value) {
+  OGL_ARG(p && name, "ogl_plan_set_option: null");
+  if (strcmp(name, "cuda_graph") == 0) { p->use_graph = value ? 1 : 0; return OGL_OK; }
+  set_error("ogl_plan_set_option: unknown option '%s'", name);
+  return OGL_ERR_ARG;
+}
+
+extern "C" int ogl_plan_graph_stats(ogl_plan* p, int64_t out[2]) {
+  OGL_ARG(p && out, "ogl_plan_graph_stats: null");
+  out[0] = p->graph_captures;
+  out[1] = p->graph_replays;
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_eval_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
+                                  float* logits_dev, float* per_vertex_loss_dev, void* stream) {
+  OGL_ARG(p && g && f && seeds, "ogl_plan_eval_step: null");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t* sd = nullptr;
+  OGL_TRY(stage_seeds(p, seeds, n_seeds, seeds_on_host, &sd, s));
+  OGL_TRY(ogl_plan_sample(p, g, sd, n_seeds, stream));
+  OGL_TRY(ogl_plan_forward(p, f, logits_dev, stream));
+  if (per_vertex_loss_dev) OGL_TRY(plan_loss(p, f, 1.f, 0, per_vertex_loss_dev, nullptr, s));
+  OGL_TRY(bump(p->ctl, nullptr, s));
   return OGL_OK;
 }
 
@@ -537,19 +646,6 @@ extern "C" int ogl_plan_profile_read(ogl_plan* p, char* names_buf, int names_len
       for (int l = 0; l <= p->L; ++l) level_count_sums[l] += p->prof_counts_host[8 * st + l];
   }
   if (n_steps) *n_steps = p->prof_steps;
-  return OGL_OK;
-}
-
-extern "C" int ogl_plan_eval_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
-                                  float* logits_dev, float* per_vertex_loss_dev, void* stream) {
-  OGL_ARG(p && g && f && seeds, "ogl_plan_eval_step: null");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t* sd = nullptr;
-  OGL_TRY(stage_seeds(p, seeds, n_seeds, seeds_on_host, &sd, s));
-  OGL_TRY(ogl_plan_sample(p, g, sd, n_seeds, stream));
-  OGL_TRY(ogl_plan_forward(p, f, logits_dev, stream));
-  if (per_vertex_loss_dev) OGL_TRY(plan_loss(p, f, 1.f, 0, per_vertex_loss_dev, nullptr, s));
-  OGL_TRY(bump(p->ctl, nullptr, s));
   return OGL_OK;
 }
 

@@ -96,84 +96,48 @@ __global__ void __launch_bounds__(kBlock) k_segmax_fwd(const T* __restrict__ hp,
   }
 }
 
-// dhp32[src(argslot), f] += relu'(hp) * dng[d, f].  The ReLU mask of the pooled activation is applied HERE, on the
-// destination side: neigh[d, f] is exactly hp[src(argslot), f], so hp > 0 <=> neigh > 0 and no pass over the (much
-// larger) source-side matrix is needed for it.  16-byte loads of dng / neigh, 8-byte loads of the slots.
+// Backward of the max-pool, source side:  dhp[s, f] = sum over sampled edges e = (d, slot j) with src(e) = s of
+// (arg[d, f] == j) * dng[d, f].   The ReLU mask of hp is already folded into dng (dneigh GEMM epilogue, mask =
+// neigh: neigh[d, f] is exactly hp[src(arg), f]).  Instead of scattering with atomics into an fp32 buffer and
+// converting afterwards, every source row GATHERS over its reverse edge list (built at sampling time): dhp is
+// written once, in the arithmetic type, with no atomics.  One thread per (row, 16-byte column strip); the dng /
+// arg rows it re-reads (each destination row is visited once per slot) stay L2-resident.  Rows [n, pad128) = 0.
+// (The fc_pool bias gradient needs no pass over dhp at all: every dng[d, f] lands in exactly one source row, so
+// colsum(dhp) == colsum(dng).)
 template <typename T>
-__global__ void __launch_bounds__(kBlock) k_segmax_bwd(const T* __restrict__ dng, const T* __restrict__ neigh, int pitch, int feat,
-                                                       const uint8_t* __restrict__ arg, const int32_t* __restrict__ edge_lid, int fanout,
-                                                       const int32_t* __restrict__ n_dst_dev, int n_dst_max, float* __restrict__ dhp32) {
+__global__ void __launch_bounds__(kBlock) k_pool_bwd(const T* __restrict__ dng, int pitch, const uint8_t* __restrict__ arg,
+                                                     const int32_t* __restrict__ rev_ptr, const int32_t* __restrict__ rev_edge, int fanout,
+                                                     const int32_t* __restrict__ n_src_dev, int n_src_max, T* __restrict__ dhp) {
   constexpr int NV = Vec<T>::N;
-  const int n = dyn_count(n_dst_dev, n_dst_max);
+  const int n = dyn_count(n_src_dev, n_src_max);
+  const int np = pad128(n, n_src_max);
   const int vpr = pitch / NV;
-  const int64_t total = (int64_t)n * vpr;
+  const int64_t total = (int64_t)np * vpr;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(t / vpr), c = (int)(t % vpr);
-    const int64_t e0 = (int64_t)d * pitch + c * NV;
-    const uint4 graw = __ldg(reinterpret_cast<const uint4*>(dng + e0));
-    const uint4 nraw = __ldg(reinterpret_cast<const uint4*>(neigh + e0));
-    const T* gv = reinterpret_cast<const T*>(&graw);
-    const T* nv = reinterpret_cast<const T*>(&nraw);
-    uint8_t sl[NV];
-    if (NV == 8) *reinterpret_cast<uint2*>(sl) = __ldg(reinterpret_cast<const uint2*>(arg + e0));
-    else *reinterpret_cast<uint32_t*>(sl) = __ldg(reinterpret_cast<const uint32_t*>(arg + e0));
-    const int32_t* el = edge_lid + (int64_t)d * fanout;
+    const int r = (int)(t / vpr), strip = (int)(t % vpr);
+    float sum[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int f = c * NV + i;
-      if (f >= feat || sl[i] == 255) continue;
-      const float g = to_f32<T>(gv[i]);
-      if (g == 0.f || !(to_f32<T>(nv[i]) > 0.f)) continue;
-      atomicAdd(&dhp32[(int64_t)__ldg(el + sl[i]) * pitch + f], g);
-    }
-  }
-}
-
-// dhp[r, :] = T(dhp32[r, :]); dhp32 is zeroed again (it is the scatter target of the next layer / step); rows
-// [n, pad128) of dhp are zero; and the bias gradient db[c] = sum_r dhp[r, c] comes out of the same pass:
-// blockDim.x threads own one float4 column strip each, a block walks kCvtRows rows, so every thread keeps its 4
-// column sums in registers (no atomics, no shared memory) and writes one partial per (block, column); the
-// partials are summed in block order by k_colsum_final -> deterministic.  Fully coalesced 16-byte accesses.
-constexpr int kCvtRows = 64;
-template <typename T>
-__global__ void k_dhp_convert(float* __restrict__ dhp32, int pitch, const int32_t* __restrict__ n_dev, int n_max, T* __restrict__ dhp,
-                              float* __restrict__ partial) {
-  const int n = dyn_count(n_dev, n_max);
-  const int np = pad128(n, n_max);
-  const int strips = pitch >> 2;
-  const int c4 = threadIdx.x;
-  const int r0 = blockIdx.x * kCvtRows;
-  if (r0 >= np) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c4 < strips) {
-    const int r1 = min(r0 + kCvtRows, np);
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) {
-      float4* src = reinterpret_cast<float4*>(dhp32 + (int64_t)r * pitch) + c4;
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < n) {
-        g = *src;
-        *src = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV; ++i) sum[i] = 0.f;
+    if (r < n) {
+      const int e0 = __ldg(rev_ptr + r), e1 = __ldg(rev_ptr + r + 1);
+      for (int k = e0; k < e1; ++k) {
+        const int e = __ldg(rev_edge + k);
+        const int d = e / fanout, j = e - d * fanout;
+        const int64_t at = (int64_t)d * pitch + strip * NV;
+        const uint4 graw = __ldg(reinterpret_cast<const uint4*>(dng + at));
+        const T* gv = reinterpret_cast<const T*>(&graw);
+        uint8_t sl[NV];
+        if (NV == 8) *reinterpret_cast<uint2*>(sl) = __ldg(reinterpret_cast<const uint2*>(arg + at));
+        else *reinterpret_cast<uint32_t*>(sl) = __ldg(reinterpret_cast<const uint32_t*>(arg + at));
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (sl[i] == j) sum[i] += to_f32<T>(gv[i]);
       }
-      T o[4] = {from_f32<T>(g.x), from_f32<T>(g.y), from_f32<T>(g.z), from_f32<T>(g.w)};
-      // the bias gradient sums the values as stored (rounded), like the column sum of the stored matrix did
-      acc.x += to_f32<T>(o[0]); acc.y += to_f32<T>(o[1]); acc.z += to_f32<T>(o[2]); acc.w += to_f32<T>(o[3]);
-      T* dst = dhp + (int64_t)r * pitch + c4 * 4;
-      if (sizeof(T) == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
-      else *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(o);
     }
-    reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * pitch)[c4] = acc;
-  }
-}
-// db[c] = sum over the blocks that held live rows, ascending
-__global__ void __launch_bounds__(kBlock) k_cvt_colsum_final(const float* __restrict__ partial, int pitch, int cols, const int32_t* __restrict__ n_dev,
-                                                             int n_max, float* __restrict__ out) {
-  const int n = dyn_count(n_dev, n_max);
-  const int blocks = (n + kCvtRows - 1) / kCvtRows;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < blocks; ++k) s += partial[(int64_t)k * pitch + c];
-    out[c] = s;
+    T o[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) o[i] = from_f32<T>(sum[i]);
+    *reinterpret_cast<uint4*>(dhp + t * NV) = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -218,15 +182,24 @@ __global__ void __launch_bounds__(kBlock) k_colsum_partial(const T* __restrict__
     }
   }
 }
-__global__ void __launch_bounds__(kBlock) k_colsum_final(const float* __restrict__ partial, int cols, const int32_t* __restrict__ n_dev,
-                                                         int n_max, float* __restrict__ out, float* __restrict__ out2) {
+__global__ void __launch_bounds__(1024) k_colsum_final(const float* __restrict__ partial, int cols, const int32_t* __restrict__ n_dev,
+                                                       int n_max, float* __restrict__ out, float* __restrict__ out2) {
+  __shared__ float sm[32][33];
   const int n = dyn_count(n_dev, n_max);
   const int chunks = (n + kColRows - 1) / kColRows;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += partial[(int64_t)k * cols + c];
-    out[c] = s;
-    if (out2) out2[c] = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < cols)
+    for (int k = warp; k < chunks; k += 32) s += partial[(int64_t)k * cols + c];
+  sm[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += sm[w][lane];
+    out[c] = t;
+    if (out2) out2[c] = t;
   }
 }
 
@@ -294,6 +267,37 @@ __global__ void __launch_bounds__(kBlock) k_adam(float* __restrict__ p, const fl
     p[i] -= step * mi / (sqrtf(vi) * isq + eps);
   }
 }
+// Adam + refresh of the arithmetic-type weight shadows (W [out, pitch(in)] and W^T [in, pitch(out)]) in one pass over
+// the flat parameter buffer: the updated value is written to its shadow slots straight from the register.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_adam_shadow(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                        const uint32_t* __restrict__ t_dev, const ShadowSeg* __restrict__ segs, int n_segs) {
+  __shared__ ShadowSeg ss[48];
+  for (int i = threadIdx.x; i < n_segs; i += blockDim.x) ss[i] = segs[i];
+  __syncthreads();
+  const uint32_t t = *t_dev + 1;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  const float step = lr / bc1, isq = rsqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float pi = p[i] - step * mi / (sqrtf(vi) * isq + eps);
+    p[i] = pi;
+    int sg = 0;
+    while (sg < n_segs && i >= ss[sg].end) ++sg;
+    if (sg < n_segs && i >= ss[sg].begin) {
+      const ShadowSeg& q = ss[sg];
+      const int64_t r = i - q.begin;
+      const int o = (int)(r / q.in), c = (int)(r % q.in);
+      ((T*)q.ws)[(int64_t)o * q.pitch_in + c] = from_f32<T>(pi);
+      ((T*)q.wt)[(int64_t)c * q.pitch_out + o] = from_f32<T>(pi);
+    }
+  }
+}
 __global__ void k_bump(uint32_t* a, uint32_t* b) {
   if (a) *a += 1;
   if (b) *b += 1;
@@ -352,22 +356,11 @@ int segmax_fwd(int bf16, const void* hp, int pitch, const int32_t* edge_lid, int
   else OGL_LAUNCH((k_segmax_fwd<float>), grid, kBlock, 0, s, (const float*)hp, pitch, edge_lid, fanout, n_dst_dev, n_dst_max, (float*)ng, arg);
   return OGL_OK;
 }
-int segmax_bwd(int bf16, const void* dng, const void* neigh, int pitch, int feat, const uint8_t* arg, const int32_t* edge_lid, int fanout,
-               const int32_t* n_dst_dev, int n_dst_max, float* dhp32, cudaStream_t s) {
-  const int grid = grid_for((int64_t)n_dst_max * pitch / (bf16 ? 8 : 4), kBlock, 16);
-  if (bf16) OGL_LAUNCH((k_segmax_bwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)dng, (const __nv_bfloat16*)neigh, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
-  else OGL_LAUNCH((k_segmax_bwd<float>), grid, kBlock, 0, s, (const float*)dng, (const float*)neigh, pitch, feat, arg, edge_lid, fanout, n_dst_dev, n_dst_max, dhp32);
-  return OGL_OK;
-}
-int64_t dhp_convert_partial_elems(int n_max, int pitch) { return ceil_div(round_up(n_max, 128), kCvtRows) * (int64_t)pitch; }
-int dhp_convert(int bf16, float* dhp32, int pitch, int cols, const int32_t* n_dev, int n_max, void* dhp, float* partial, float* db,
-                cudaStream_t s) {
-  const int threads = round_up(pitch / 4, 32);
-  OGL_ARG(threads <= 1024 && pitch % 4 == 0, "dhp_convert: row pitch %d unsupported", pitch);
-  const int grid = (int)ceil_div(round_up(n_max, 128), kCvtRows);
-  if (bf16) OGL_LAUNCH((k_dhp_convert<__nv_bfloat16>), grid, threads, 0, s, dhp32, pitch, n_dev, n_max, (__nv_bfloat16*)dhp, partial);
-  else OGL_LAUNCH((k_dhp_convert<float>), grid, threads, 0, s, dhp32, pitch, n_dev, n_max, (float*)dhp, partial);
-  OGL_LAUNCH(k_cvt_colsum_final, (unsigned)ceil_div(cols, kBlock), kBlock, 0, s, partial, pitch, cols, n_dev, n_max, db);
+int pool_bwd(int bf16, const void* dng, int pitch, const uint8_t* arg, const int32_t* rev_ptr, const int32_t* rev_edge, int fanout,
+             const int32_t* n_src_dev, int n_src_max, void* dhp, cudaStream_t s) {
+  const int grid = grid_for((int64_t)round_up(n_src_max, 128) * pitch / (bf16 ? 8 : 4), kBlock, 32);
+  if (bf16) OGL_LAUNCH((k_pool_bwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)dng, pitch, arg, rev_ptr, rev_edge, fanout, n_src_dev, n_src_max, (__nv_bfloat16*)dhp);
+  else OGL_LAUNCH((k_pool_bwd<float>), grid, kBlock, 0, s, (const float*)dng, pitch, arg, rev_ptr, rev_edge, fanout, n_src_dev, n_src_max, (float*)dhp);
   return OGL_OK;
 }
 int64_t colsum_partial_elems(int n_max, int cols) { return ceil_div(n_max, kColRows) * (int64_t)cols; }
@@ -375,7 +368,7 @@ int colsum(int bf16, const void* x, int pitch, int cols, const int32_t* n_dev, i
   dim3 grid((unsigned)ceil_div(pitch / (bf16 ? 8 : 4), 32), (unsigned)ceil_div(n_max, kColRows));
   if (bf16) OGL_LAUNCH((k_colsum_partial<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)x, pitch, cols, n_dev, n_max, partial);
   else OGL_LAUNCH((k_colsum_partial<float>), grid, kBlock, 0, s, (const float*)x, pitch, cols, n_dev, n_max, partial);
-  OGL_LAUNCH(k_colsum_final, (unsigned)ceil_div(cols, kBlock), kBlock, 0, s, partial, cols, n_dev, n_max, out, out2);
+  OGL_LAUNCH(k_colsum_final, (unsigned)ceil_div(cols, 32), 1024, 0, s, partial, cols, n_dev, n_max, out, out2);
   return OGL_OK;
 }
 int xent(int bf16, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,
@@ -391,6 +384,13 @@ int sum_f32(const float* x, const int32_t* n_dev, int n_max, float* out, cudaStr
 }
 int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, uint32_t* t_dev, cudaStream_t s) {
   OGL_LAUNCH(k_adam, grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev);
+  return OGL_OK;
+}
+int adam_shadow(int bf16, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, uint32_t* t_dev,
+                const ShadowSeg* segs_dev, int n_segs, cudaStream_t s) {
+  OGL_ARG(n_segs <= 48, "adam_shadow: too many weight segments");
+  if (bf16) OGL_LAUNCH((k_adam_shadow<__nv_bfloat16>), grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
+  else OGL_LAUNCH((k_adam_shadow<float>), grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
   return OGL_OK;
 }
 int bump(uint32_t* a, uint32_t* b, cudaStream_t s) {

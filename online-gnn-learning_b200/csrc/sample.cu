@@ -117,6 +117,37 @@ __global__ void __launch_bounds__(kBlock) k_fill_i32(int32_t* p, int32_t v, int6
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// ---- reverse edge lists of a sampled block: for every source row the slots (d * fanout + j) that picked it -------
+__global__ void __launch_bounds__(kBlock) k_rev_count(const int32_t* __restrict__ edge_lid, const int32_t* __restrict__ n_dst_dev, int n_dst_max,
+                                                      int fanout, int32_t* __restrict__ cnt) {
+  const int64_t ne = (int64_t)min(*n_dst_dev, n_dst_max) * fanout;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ne; p += (int64_t)gridDim.x * blockDim.x) {
+    const int lid = edge_lid[p];
+    if (lid >= 0) atomicAdd(&cnt[lid], 1);
+  }
+}
+__global__ void __launch_bounds__(kBlock) k_rev_fill(const int32_t* __restrict__ edge_lid, const int32_t* __restrict__ n_dst_dev, int n_dst_max,
+                                                     int fanout, const int32_t* __restrict__ rev_ptr, int32_t* __restrict__ cursor,
+                                                     int32_t* __restrict__ rev_edge) {
+  const int64_t ne = (int64_t)min(*n_dst_dev, n_dst_max) * fanout;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ne; p += (int64_t)gridDim.x * blockDim.x) {
+    const int lid = edge_lid[p];
+    if (lid >= 0) rev_edge[rev_ptr[lid] + atomicAdd(&cursor[lid], 1)] = (int32_t)p;
+  }
+}
+
+int reverse_edges(ToBlockWs* ws, const int32_t* edge_lid, const int32_t* n_dst_dev, int n_dst_max, int fanout, int n_src_max,
+                  int32_t* rev_ptr, int32_t* rev_edge, cudaStream_t s) {
+  const int64_t ne_max = (int64_t)n_dst_max * fanout;
+  OGL_ARG(n_src_max + 1 <= ws->rev_cap, "reverse_edges: workspace too small");
+  OGL_CUDA(cudaMemsetAsync(ws->rev_cnt, 0, sizeof(int32_t) * 2 * (size_t)ws->rev_cap, s));     // counters + cursors
+  OGL_LAUNCH(k_rev_count, grid_for(ne_max, kBlock), kBlock, 0, s, edge_lid, n_dst_dev, n_dst_max, fanout, ws->rev_cnt);
+  OGL_TRY(exclusive_scan_i32(ws->rev_cnt, rev_ptr, (int64_t)n_src_max + 1, ws->scan_scratch, nullptr, s));
+  OGL_LAUNCH(k_rev_fill, grid_for(ne_max, kBlock), kBlock, 0, s, edge_lid, n_dst_dev, n_dst_max, fanout, rev_ptr, ws->rev_cnt + ws->rev_cap,
+             rev_edge);
+  return OGL_OK;
+}
+
 int sample_hop(const GraphView& g, const int32_t* dst_nodes, const int32_t* n_dst_dev, int n_dst_max, int fanout, uint64_t seed,
                const uint32_t* step_dev, uint32_t step_imm, uint32_t hop, int32_t* out_src, int64_t* out_eid, cudaStream_t s) {
   const int Q = (fanout + 3) / 4;
@@ -132,7 +163,10 @@ int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max) {
   OGL_CUDA(cudaMalloc(&ws->first, sizeof(int32_t) * v_cap));
   OGL_CUDA(cudaMalloc(&ws->flags, sizeof(int32_t) * (ne_max + 1)));
   OGL_CUDA(cudaMalloc(&ws->pos, sizeof(int32_t) * (ne_max + 1)));
-  OGL_CUDA(cudaMalloc(&ws->scan_scratch, sizeof(int32_t) * scan_scratch_elems(ne_max + 1)));
+  const int64_t scan_n = (ne_max > v_cap ? ne_max : v_cap) + 2;
+  OGL_CUDA(cudaMalloc(&ws->scan_scratch, sizeof(int32_t) * scan_scratch_elems(scan_n)));
+  ws->rev_cap = v_cap + 1;
+  OGL_CUDA(cudaMalloc(&ws->rev_cnt, sizeof(int32_t) * 2 * (size_t)ws->rev_cap));
   OGL_CUDA(cudaMalloc(&ws->n_new, sizeof(int32_t)));
   OGL_LAUNCH(k_fill_i32, grid_for(v_cap, kBlock), kBlock, 0, 0, ws->first, 0x7fffffff, v_cap);
   OGL_CUDA(cudaDeviceSynchronize());
@@ -140,7 +174,7 @@ int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max) {
 }
 
 void to_block_free(ToBlockWs* ws) {
-  cudaFree(ws->first); cudaFree(ws->flags); cudaFree(ws->pos); cudaFree(ws->scan_scratch); cudaFree(ws->n_new);
+  cudaFree(ws->first); cudaFree(ws->flags); cudaFree(ws->pos); cudaFree(ws->scan_scratch); cudaFree(ws->n_new); cudaFree(ws->rev_cnt);
   *ws = ToBlockWs();
 }
 

@@ -10,6 +10,8 @@ struct ToBlockWs {
   int32_t* pos = nullptr;           // [ne_max]
   int32_t* scan_scratch = nullptr;
   int32_t* n_new = nullptr;
+  int32_t* rev_cnt = nullptr;       // [2 * rev_cap]: per-source counters, then fill cursors
+  int64_t rev_cap = 0;
   int64_t v_cap = 0, ne_max = 0;
 };
 
@@ -23,6 +25,10 @@ int sample_hop(const GraphView& g, const int32_t* dst_nodes, const int32_t* n_ds
 // src_nodes = dst_nodes ++ first-appearance-ordered new sources; edge_lid[p] = local id of picked[p] (-1 if empty)
 int to_block(ToBlockWs* ws, const int32_t* dst_nodes, const int32_t* n_dst_dev, int n_dst_max, int fanout, const int32_t* picked,
              int32_t* src_nodes, int32_t* n_src_dev, int n_src_max, int32_t* edge_lid, cudaStream_t s);
+
+// reverse edge lists of a sampled block: rev_ptr[n_src_max + 1] (exclusive offsets), rev_edge[p] = slot index d * fanout + j
+int reverse_edges(ToBlockWs* ws, const int32_t* edge_lid, const int32_t* n_dst_dev, int n_dst_max, int fanout, int n_src_max,
+                  int32_t* rev_ptr, int32_t* rev_edge, cudaStream_t s);
 
 int cast_nodes(const int64_t* in, int32_t* out, int64_t n, cudaStream_t s);
 

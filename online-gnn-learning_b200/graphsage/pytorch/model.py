@@ -145,6 +145,7 @@ class PrioritizedPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
         super().__init__(model, batch_per_timestep, batch_size, labels, samples, reduction="none", n_workers=n_workers,
                          cuda=cuda, batch_full=batch_full, fanouts=fanouts)
         self.time_step = 0
+        self._per_buf = None
         self.pass_var = 0
         self.full_pass = full_pass
         self.priority_strategy = priority_strategy
@@ -170,7 +171,9 @@ class PrioritizedPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
         n = len(train_vertices)
         if n:
             for seeds in self._batches(train_vertices, n // self.batch_per_timestep):
-                per = torch.empty(seeds.numel(), dtype=torch.float32, device="cuda")
+                if self._per_buf is None or self._per_buf.numel() < seeds.numel():
+                    self._per_buf = torch.empty(max(seeds.numel(), self.batch_size), dtype=torch.float32, device="cuda")
+                per = self._per_buf[:seeds.numel()]       # persistent: keeps the captured CUDA graph of the step valid
                 self._fused_step(graph, seeds, per_vertex_out=per)
                 nodes = subgraph_to_id[seeds.cpu().numpy()]
                 self._push_priorities(graph_util, np.asarray(nodes).tolist(), per)
