@@ -304,15 +304,10 @@ def run_ours(args, rank, world, local_rank):
     dev_batches = [torch.as_tensor(b).to(dev) for b in batches]
     pin = [torch.as_tensor(b).pin_memory() for b in batches]
     loss_dev = torch.zeros(1, device=dev)
-    loss_scale = 1.0 / (B * world)
 
     def step(seeds):
-        if world == 1:
-            plan.train_step(g, fs, seeds, loss_scale=loss_scale, do_step=True, loss_sum_out=loss_dev)
-        else:
-            plan.train_step(g, fs, seeds, loss_scale=loss_scale, do_step=False, loss_sum_out=loss_dev)
-            dist.all_reduce(grad)
-            plan.adam_step()
+        # local sample / forward / backward -> (N > 1: one NCCL all-reduce of the flat gradient) -> fused Adam
+        ogl_b200.parallel.train_step(plan, g, fs, seeds, B * world, grad, loss_sum_out=loss_dev)
 
     def barrier():
         if world > 1:

@@ -668,7 +668,8 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
   p.n_tiles = (g.n + BM - 1) / BM;
   p.k_tiles = (g.k + BN_MAX - 1) / BN_MAX;
   const int tiles = p.n_tiles * p.k_tiles;
-  int splits = (int)ceil_div(sm_count(), tiles);
+  // one CTA per SM and exactly one wave: tiles * splits <= #SMs (150 CTAs on 148 SMs would run as two waves)
+  int splits = sm_count() / tiles;
   const int by_rows = (int)ceil_div(g.m_max, 4 * BK);          // at least 4 contraction blocks per split
   if (splits > by_rows) splits = by_rows;
   const int ldo = (g.k + 3) / 4 * 4;

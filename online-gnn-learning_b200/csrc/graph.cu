@@ -15,7 +15,6 @@
 namespace ogl {
 
 constexpr int kBlock = 256;
-constexpr int kLargeTail = 2048;   // tails longer than this are ordered by a whole CTA
 
 __device__ __forceinline__ int32_t grow_cap(int32_t need) {
   if (need <= 0) return 0;
@@ -64,11 +63,16 @@ __global__ void __launch_bounds__(kBlock) k_need(const int32_t* __restrict__ tou
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(&ctl->need, local);
 }
 
-// relocate rows without enough slack: one warp per touched row
+// relocate rows without enough slack: one warp per touched row claims the new space and copies short rows; long rows
+// are queued and copied by all CTAs of k_move_big together (a hub row of 10^5 entries must not hang on one warp)
+constexpr int kWarpCopyMax = 2048;
+struct MoveJob { long long from, to; int len; int pad; };
+
 __global__ void __launch_bounds__(kBlock) k_reserve(const int32_t* __restrict__ touched, const int32_t* __restrict__ add,
                                                     int64_t* __restrict__ row_start, const int32_t* __restrict__ deg,
                                                     int32_t* __restrict__ cap, int32_t* __restrict__ tail_len,
-                                                    int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid, GraphCtl* ctl) {
+                                                    int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid, MoveJob* __restrict__ jobs,
+                                                    int* __restrict__ n_jobs, GraphCtl* ctl) {
   const int nt = ctl->n_touched;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -86,12 +90,28 @@ __global__ void __launch_bounds__(kBlock) k_reserve(const int32_t* __restrict__ 
       }
       off = __shfl_sync(0xffffffffu, off, 0);
       const int64_t old = row_start[v];
-      for (int i = lane; i < d; i += 32) {
-        adj_src[off + i] = adj_src[old + i];
-        adj_eid[off + i] = adj_eid[old + i];
+      if (d <= kWarpCopyMax) {
+        for (int i = lane; i < d; i += 32) {
+          adj_src[off + i] = adj_src[old + i];
+          adj_eid[off + i] = adj_eid[old + i];
+        }
+      } else if (lane == 0) {
+        jobs[atomicAdd(n_jobs, 1)] = MoveJob{(long long)old, (long long)off, d, 0};
       }
       __syncwarp();
       if (lane == 0) { row_start[v] = (int64_t)off; cap[v] = nc; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_move_big(const MoveJob* __restrict__ jobs, const int* __restrict__ n_jobs,
+                                                     int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid) {
+  const int nj = *n_jobs;
+  for (int q = 0; q < nj; ++q) {
+    const MoveJob j = jobs[q];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < j.len; i += (int64_t)gridDim.x * blockDim.x) {
+      adj_src[j.to + i] = adj_src[j.from + i];
+      adj_eid[j.to + i] = adj_eid[j.from + i];
     }
   }
 }
@@ -112,12 +132,29 @@ __global__ void __launch_bounds__(kBlock) k_place(BatchEdges b, int32_t* __restr
   }
 }
 
-// put every tail into ascending edge-id order; one warp per touched row
+// ---- tail ordering -------------------------------------------------------------------------------
+// Slots inside a batch were claimed in arbitrary (atomic) order; every tail is put into ascending edge-id order so
+// that the row contents are canonical.  Three size classes:
+//   L <= 32        one warp, rank by shuffles, in registers                       (k_fix, inline)
+//   L <= kMedTail  one warp, bitonic sort of (eid << 32 | src) keys in shared     (k_fix_med)
+//   L <= kBigTail  one CTA, bitonic sort in dynamic shared memory                 (k_fix_big)
+//   larger         one CTA, rank-by-counting through a global scratch (rare: a hub taking > 8192 edges of one batch)
+constexpr int kMedTail = 512;
+constexpr int kBigTail = 8192;
+
+__device__ __forceinline__ void bitonic_step(unsigned long long* s, int i, int j, int k) {
+  const int ixj = i ^ j;
+  if (ixj > i) {
+    const unsigned long long a = s[i], b = s[ixj];
+    const bool up = (i & k) == 0;
+    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
                                                 const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
                                                 int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
-                                                int32_t* __restrict__ scr_src, uint32_t* __restrict__ scr_eid,
-                                                int32_t* __restrict__ large, GraphCtl* ctl) {
+                                                int32_t* __restrict__ med, int32_t* __restrict__ large, GraphCtl* ctl) {
   const int nt = ctl->n_touched;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -125,11 +162,14 @@ __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touc
     const int v = touched[t];
     const int L = tail_len[t];
     const int64_t base = row_start[v] + deg[v];
-    if (L > kLargeTail) {
-      if (lane == 0) large[atomicAdd(&ctl->n_large, 1)] = t;
+    if (L > 32) {
+      if (lane == 0) {
+        if (L <= kMedTail) med[atomicAdd(&ctl->n_med, 1)] = t;
+        else large[atomicAdd(&ctl->n_large, 1)] = t;
+      }
       continue;
     }
-    if (L >= 2 && L <= 32) {
+    if (L >= 2) {
       uint32_t e = lane < L ? adj_eid[base + lane] : 0xffffffffu;
       int32_t s = lane < L ? adj_src[base + lane] : 0;
       int rank = 0;
@@ -140,50 +180,87 @@ __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touc
       }
       __syncwarp();
       if (lane < L) { adj_eid[base + rank] = e; adj_src[base + rank] = s; }
-    } else if (L > 32) {
-      unsigned long long off = 0;
-      if (lane == 0) off = atomicAdd(&ctl->scratch_top, (unsigned long long)L);
-      off = __shfl_sync(0xffffffffu, off, 0);
-      for (int i = lane; i < L; i += 32) { scr_eid[off + i] = adj_eid[base + i]; scr_src[off + i] = adj_src[base + i]; }
-      __syncwarp();
-      for (int i = lane; i < L; i += 32) {
-        const uint32_t e = scr_eid[off + i];
-        int rank = 0;
-        for (int j = 0; j < L; ++j) rank += scr_eid[off + j] < e ? 1 : 0;
-        adj_eid[base + rank] = e;
-        adj_src[base + rank] = scr_src[off + i];
-      }
     }
     __syncwarp();
     if (lane == 0) deg[v] += L;
   }
 }
 
-// very long tails (hub rows in a big batch): a whole CTA ranks the tail
-__global__ void __launch_bounds__(1024) k_fix_large(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
+__global__ void __launch_bounds__(kBlock) k_fix_med(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
                                                     const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
                                                     int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
-                                                    int32_t* __restrict__ scr_src, uint32_t* __restrict__ scr_eid,
-                                                    const int32_t* __restrict__ large, GraphCtl* ctl) {
-  __shared__ unsigned long long s_off;
-  const int nl = ctl->n_large;
-  for (int k = blockIdx.x; k < nl; k += gridDim.x) {
-    const int t = large[k];
+                                                    const int32_t* __restrict__ med, GraphCtl* ctl) {
+  __shared__ unsigned long long keys[kBlock / 32][kMedTail];
+  const int nm = ctl->n_med;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long* s = keys[w];
+  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < nm; m += warps) {
+    const int t = med[m];
     const int v = touched[t];
     const int L = tail_len[t];
     const int64_t base = row_start[v] + deg[v];
-    if (threadIdx.x == 0) s_off = atomicAdd(&ctl->scratch_top, (unsigned long long)L);
-    __syncthreads();
-    const unsigned long long off = s_off;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) { scr_eid[off + i] = adj_eid[base + i]; scr_src[off + i] = adj_src[base + i]; }
-    __syncthreads();
-    // batch edge ids are dense in [lo, lo + span): rank by counting smaller ids in chunks held in registers
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-      const uint32_t e = scr_eid[off + i];
-      int rank = 0;
-      for (int j = 0; j < L; ++j) rank += scr_eid[off + j] < e ? 1 : 0;
-      adj_eid[base + rank] = e;
-      adj_src[base + rank] = scr_src[off + i];
+    int P = 64;
+    while (P < L) P <<= 1;
+    for (int i = lane; i < P; i += 32)
+      s[i] = i < L ? (((unsigned long long)adj_eid[base + i] << 32) | (uint32_t)adj_src[base + i]) : ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P; i += 32) bitonic_step(s, i, j, k);
+        __syncwarp();
+      }
+    for (int i = lane; i < L; i += 32) {
+      adj_eid[base + i] = (uint32_t)(s[i] >> 32);
+      adj_src[base + i] = (int32_t)(uint32_t)s[i];
+    }
+    __syncwarp();
+    if (lane == 0) deg[v] += L;
+  }
+}
+
+// long tails (hub rows in a big batch): a whole CTA orders the tail
+__global__ void __launch_bounds__(1024) k_fix_big(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
+                                                  const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
+                                                  int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
+                                                  int32_t* __restrict__ scr_src, uint32_t* __restrict__ scr_eid,
+                                                  const int32_t* __restrict__ large, GraphCtl* ctl) {
+  extern __shared__ unsigned long long bk[];      // kBigTail keys
+  __shared__ unsigned long long s_off;
+  const int nl = ctl->n_large;
+  for (int q = blockIdx.x; q < nl; q += gridDim.x) {
+    const int t = large[q];
+    const int v = touched[t];
+    const int L = tail_len[t];
+    const int64_t base = row_start[v] + deg[v];
+    if (L <= kBigTail) {
+      int P = 1024;
+      while (P < L) P <<= 1;
+      for (int i = threadIdx.x; i < P; i += blockDim.x)
+        bk[i] = i < L ? (((unsigned long long)adj_eid[base + i] << 32) | (uint32_t)adj_src[base + i]) : ~0ull;
+      __syncthreads();
+      for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = threadIdx.x; i < P; i += blockDim.x) bitonic_step(bk, i, j, k);
+          __syncthreads();
+        }
+      for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        adj_eid[base + i] = (uint32_t)(bk[i] >> 32);
+        adj_src[base + i] = (int32_t)(uint32_t)bk[i];
+      }
+    } else {
+      if (threadIdx.x == 0) s_off = atomicAdd(&ctl->scratch_top, (unsigned long long)L);
+      __syncthreads();
+      const unsigned long long off = s_off;
+      for (int i = threadIdx.x; i < L; i += blockDim.x) { scr_eid[off + i] = adj_eid[base + i]; scr_src[off + i] = adj_src[base + i]; }
+      __syncthreads();
+      for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const uint32_t e = scr_eid[off + i];
+        int rank = 0;
+        for (int j = 0; j < L; ++j) rank += scr_eid[off + j] < e ? 1 : 0;
+        adj_eid[base + rank] = e;
+        adj_src[base + rank] = scr_src[off + i];
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) deg[v] += L;
@@ -296,7 +373,9 @@ struct ogl_graph {
   uint32_t* adj_eid = nullptr;
   GraphCtl* ctl = nullptr;
   GraphCtl* h_ctl = nullptr;     // pinned mirror
-  int32_t *touched = nullptr, *tail_len = nullptr, *large = nullptr;
+  int32_t *touched = nullptr, *tail_len = nullptr, *large = nullptr, *med = nullptr;
+  ogl::MoveJob* jobs = nullptr;
+  int* n_jobs = nullptr;
   int32_t* scr_src = nullptr;
   uint32_t* scr_eid = nullptr;
   int64_t *stage_src = nullptr, *stage_dst = nullptr;   // host-insert staging
@@ -341,7 +420,10 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
   A(g->ctl, sizeof(GraphCtl));
   A(g->touched, sizeof(int32_t) * 2 * g->batch_cap);
   A(g->tail_len, sizeof(int32_t) * 2 * g->batch_cap);
-  A(g->large, sizeof(int32_t) * 2 * g->batch_cap / kLargeTail + 64);
+  A(g->large, sizeof(int32_t) * (2 * g->batch_cap / kMedTail + 64));
+  A(g->med, sizeof(int32_t) * (2 * g->batch_cap / 32 + 64));
+  A(g->jobs, sizeof(MoveJob) * ((v_cap < 2 * g->batch_cap ? v_cap : 2 * g->batch_cap) + 64));   // <= one job per touched row
+  A(g->n_jobs, sizeof(int));
   A(g->scr_src, sizeof(int32_t) * 2 * g->batch_cap);
   A(g->scr_eid, sizeof(uint32_t) * 2 * g->batch_cap);
   A(g->stage_src, sizeof(int64_t) * g->batch_cap);
@@ -350,6 +432,7 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
   A(g->total_dev, sizeof(int64_t));
 #undef A
   OGL_CUDA(cudaMallocHost(&g->h_ctl, sizeof(GraphCtl)));
+  OGL_CUDA(cudaFuncSetAttribute(k_fix_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBigTail * sizeof(unsigned long long))));
   OGL_CUDA(cudaMemset(g->row_start, 0, sizeof(int64_t) * v_cap));
   OGL_CUDA(cudaMemset(g->deg, 0, sizeof(int32_t) * v_cap));
   OGL_CUDA(cudaMemset(g->cap, 0, sizeof(int32_t) * v_cap));
@@ -361,7 +444,7 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
 
 extern "C" int ogl_graph_destroy(ogl_graph* g) {
   if (!g) return OGL_OK;
-  void* ptrs[] = {g->row_start, g->deg, g->cap, g->add, g->adj_src, g->adj_eid, g->ctl, g->touched, g->tail_len, g->large,
+  void* ptrs[] = {g->row_start, g->deg, g->cap, g->add, g->adj_src, g->adj_eid, g->ctl, g->touched, g->tail_len, g->large, g->med, g->jobs, g->n_jobs,
                   g->scr_src, g->scr_eid, g->stage_src, g->stage_dst, g->newcap, g->scan_scratch, g->total_dev, g->new_start,
                   g->p_indptr, g->p_indices, g->p_eids};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -431,13 +514,17 @@ static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_
   }
   const int nt = g->h_ctl->n_touched;
   const int wgrid = grid_for((int64_t)nt * 32, kBlock);
-  OGL_LAUNCH(k_reserve, wgrid, kBlock, 0, s, g->touched, g->add, g->row_start, g->deg, g->cap, g->tail_len, g->adj_src, g->adj_eid, g->ctl);
+  OGL_CUDA(cudaMemsetAsync(g->n_jobs, 0, sizeof(int), s));
+  OGL_LAUNCH(k_reserve, wgrid, kBlock, 0, s, g->touched, g->add, g->row_start, g->deg, g->cap, g->tail_len, g->adj_src, g->adj_eid, g->jobs,
+             g->n_jobs, g->ctl);
+  OGL_LAUNCH(k_move_big, sm_count() * 4, kBlock, 0, s, g->jobs, g->n_jobs, g->adj_src, g->adj_eid);
   OGL_LAUNCH(k_place, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->row_start, g->deg, g->adj_src, g->adj_eid,
              (uint32_t)g->n_edges, g->n_vertices);
-  OGL_LAUNCH(k_fix, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid, g->scr_src,
-             g->scr_eid, g->large, g->ctl);
-  OGL_LAUNCH(k_fix_large, 64, 1024, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid, g->scr_src,
-             g->scr_eid, g->large, g->ctl);
+  OGL_LAUNCH(k_fix, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid, g->med, g->large, g->ctl);
+  OGL_LAUNCH(k_fix_med, grid_for((int64_t)nt * 4, kBlock, 4), kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid,
+             g->med, g->ctl);
+  OGL_LAUNCH(k_fix_big, sm_count() * 2, 1024, kBigTail * sizeof(unsigned long long), s, g->touched, g->tail_len, g->row_start, g->deg,
+             g->adj_src, g->adj_eid, g->scr_src, g->scr_eid, g->large, g->ctl);
   g->n_edges += tot;
   return OGL_OK;
 }

@@ -10,8 +10,8 @@ struct GraphCtl {
   // ---- per-batch (zeroed before every chunk) ----
   int n_touched;
   int bad_id;
-  int n_large;
-  int pad_;
+  int n_large;                      // rows whose tail is ordered by a whole CTA
+  int n_med;                        // rows whose tail is ordered by one warp in shared memory
   unsigned long long need;          // slots this batch takes from the pool top
   unsigned long long scratch_top;   // bump pointer into the tail-ordering scratch
 };

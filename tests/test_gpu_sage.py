@@ -291,7 +291,7 @@ def test_cuda_graph_replay_equals_direct_launches():
         outs = []
         for step in range(5):
             if step == 3:      # grow the graph: forces a pool rebuild (new adjacency pointers)
-                extra = torch.randint(0, c.V - 40, (30000,), device="cuda")
+                extra = torch.randint(0, c.V - 40, (30000,), generator=torch.Generator().manual_seed(5)).cuda()
                 c.g.insert_edges(extra, extra.flip(0), symmetric=True)
             c.plan.train_step(c.g, c.f, seeds_dev, loss_scale=1.0 / len(c.seeds), do_step=True, per_vertex_out=per, loss_sum_out=tot)
             outs.append((per.clone(), tot.clone()))
@@ -302,7 +302,8 @@ def test_cuda_graph_replay_equals_direct_launches():
         else:
             assert st["replays"] == 0
         runs.append((c.flat.clone(), outs))
-    # (not bit-identical: the max-pool gradient scatter uses fp32 atomics whose order varies from run to run)
+    # the forward pass is deterministic; in the backward pass the reverse edge lists are filled in atomic order, so a
+    # source row's few bf16 contributions may be summed in a different order (almost always exact in fp32 anyway)
     close(runs[0][0], runs[1][0], 1e-4, "params graph vs direct")
     for (p0, t0), (p1, t1) in zip(runs[0][1], runs[1][1]):
         close(p0, p1, 1e-4, "per-vertex loss graph vs direct")
