@@ -311,6 +311,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
           }
+          if (p.mask) {
+            // the 32 x 64 mask box of this warp goes through the staging buffer first: 8 fully coalesced 512-byte
+            // warp loads (4 rows x 128 B each) instead of 32-sector row-per-thread loads; same XOR swizzle, and each
+            // thread later overwrites only the chunks of its own row that it has already consumed
+            const int rbase = mb * BM + quarter * 32, cbase = nb * BN_MAX + c0 + (lane & 7) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3);
+              uint4 mraw = make_uint4(0u, 0u, 0u, 0u);
+              if (rbase + r < m_dyn && cbase < p.ldmask)
+                mraw = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
+              *reinterpret_cast<uint4*>(buf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = mraw;
+            }
+            __syncwarp();
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int cc = c0 + half * 32;
@@ -328,17 +343,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
               }
               v[j] = x;
             }
-            if (p.mask && row_live) {
-              const __nv_bfloat16* mrow = p.mask + (int64_t)gm * p.ldmask + gn0;
+            if (p.mask) {                          // mask box staged in `buf` (coalesced loads, see above)
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                if (gn0 + q * 8 < p.ldmask) {
-                  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(mrow) + q);
-                  const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+                const uint4 raw = *reinterpret_cast<const uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4));
+                const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (!(__bfloat162float(mv[j]) > 0.f)) v[q * 8 + j] = 0.f;
-                }
+                for (int j = 0; j < 8; ++j)
+                  if (!(__bfloat162float(mv[j]) > 0.f)) v[q * 8 + j] = 0.f;
               }
             }
             // row `lane` of the box, 16-byte chunk (half*4 + q) XOR-swizzled like TMA's SWIZZLE_128B

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(1024) k_colsum_final(const float* __restrict__
   }
 }
 
-// ---- cross entropy: per-vertex loss + dlogits (rows >= n zeroed up to the padded count) -----------
+// ---- cross entropy: per-vertex loss + dlogits (rows >= n zeroed up to the padded count); one warp per row -------
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_xent(const float* __restrict__ logits, int ldl, int C, const int32_t* __restrict__ labels,
                                                  const int32_t* __restrict__ nodes, const int32_t* __restrict__ n_dev, int n_max,
@@ -211,19 +211,23 @@ __global__ void __launch_bounds__(kBlock) k_xent(const float* __restrict__ logit
                                                  float* __restrict__ per_loss, T* __restrict__ dlogits, int ldd, int want_grad) {
   const int n = dyn_count(n_dev, n_max);
   const int nz = want_grad ? pad128(n, rows_buf) : n;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < max(n, nz); r += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < max(n, nz); r += warps) {
     if (r < n) {
       const float* l = logits + (int64_t)r * ldl;
       float mx = -INFINITY;
-      for (int c = 0; c < C; ++c) mx = fmaxf(mx, l[c]);
+      for (int c = lane; c < C; c += 32) mx = fmaxf(mx, l[c]);
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       float se = 0.f;
-      for (int c = 0; c < C; ++c) se += expf(l[c] - mx);
+      for (int c = lane; c < C; c += 32) se += expf(l[c] - mx);
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
       const float lse = mx + logf(se);
       const int y = labels[nodes[r]];
-      if (per_loss) per_loss[r] = lse - l[y];
+      if (per_loss && lane == 0) per_loss[r] = lse - l[y];
       if (want_grad) {
         T* d = dlogits + (int64_t)r * ldd;
-        for (int c = 0; c < ldd; ++c) {
+        for (int c = lane; c < ldd; c += 32) {
           float g = 0.f;
           if (c < C) g = (expf(l[c] - lse) - (c == y ? 1.f : 0.f)) * scale;
           d[c] = from_f32<T>(g);
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(kBlock) k_xent(const float* __restrict__ logit
       }
     } else if (want_grad) {
       T* d = dlogits + (int64_t)r * ldd;
-      for (int c = 0; c < ldd; ++c) d[c] = from_f32<T>(0.f);
+      for (int c = lane; c < ldd; c += 32) d[c] = from_f32<T>(0.f);
     }
   }
 }
@@ -373,7 +377,7 @@ int colsum(int bf16, const void* x, int pitch, int cols, const int32_t* n_dev, i
 }
 int xent(int bf16, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,
          int rows_buf, float scale, float* per_loss, void* dlogits, int ldd, int want_grad, cudaStream_t s) {
-  const int grid = grid_for(rows_buf > n_max ? rows_buf : n_max, kBlock);
+  const int grid = grid_for((int64_t)(rows_buf > n_max ? rows_buf : n_max) * 32, kBlock);
   if (bf16) OGL_LAUNCH((k_xent<__nv_bfloat16>), grid, kBlock, 0, s, logits, ldl, C, labels, nodes, n_dev, n_max, rows_buf, scale, per_loss, (__nv_bfloat16*)dlogits, ldd, want_grad);
   else OGL_LAUNCH((k_xent<float>), grid, kBlock, 0, s, logits, ldl, C, labels, nodes, n_dev, n_max, rows_buf, scale, per_loss, (float*)dlogits, ldd, want_grad);
   return OGL_OK;
