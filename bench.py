@@ -200,6 +200,10 @@ def stage_bytes(stage, w, lv, es=2):
         h = int(stage[-1])
         D, s = (B, f0) if h == 0 else (N1, f1)
         return D * (4 + 8 + 4) + D * s * (4 + 4) + D * s * (4 + 8)          # row meta + (src,eid) reads + (src,eid) writes
+    if stage.endswith(".pool_bwd"):
+        l = int(stage[1])
+        E, fin, ns = (N1 * f1, F, N0) if l == 0 else (B * f0, H, N1)
+        return E * fin * (es + 1) + ns * fin * es + E * 4
     if stage.endswith(".segmax"):
         l = int(stage[1])
         E, fin, nd = (N1 * f1, F, N1) if l == 0 else (B * f0, H, B)
@@ -234,6 +238,94 @@ def run_reference(args, rank, world):
             "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def first_appearance_relabel(src, dst):
+    """dense vertex ids in first-appearance order (precondition of the reference's edge streams, reddit.py:101-113)"""
+    inter = np.empty(2 * len(src), dtype=np.int64)
+    inter[0::2], inter[1::2] = src, dst
+    uniq, first = np.unique(inter, return_index=True)
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+    lut = dict(zip(uniq.tolist(), rank.tolist())) if len(uniq) < 1000 else None
+    pos = np.searchsorted(uniq, inter)
+    out = rank[pos]
+    return out[0::2].copy(), out[1::2].copy(), uniq[np.argsort(first, kind="stable")]
+
+
+def aux_elliptic_pbr(n_snapshots=12, faithful=True):
+    """configs[1]: Elliptic-shaped edge stream through the drop-in Python API (DynamicGraphEdge + TrainTestGraph + the
+    PBR trainer with priority_forward = 2, settings/elliptic.json hyper-parameters): snapshot evolve, priority
+    recomputation, 60 minibatches of 32 per timestep.  Reports trained target vertices / s over whole timesteps
+    (choose_vertices + train + evolve), wall clock."""
+    import random
+    import ogl_b200
+    from ogl_b200 import config
+    from ogl_b200.graph import train_test_graph as ttg
+    w = WORKLOADS["elliptic"]
+    rng = np.random.default_rng(1)
+    src, dst = rng.integers(0, w["V"], w["E"]), rng.integers(0, w["V"], w["E"])
+    src, dst, order = first_appearance_relabel(src, dst)
+    V = len(order)
+    feats = rng.standard_normal((V, w["F"])).astype(np.float32)
+    targets = rng.integers(0, w["C"], (V, 1)).astype(np.int64)
+    config.set_faithful(faithful)
+    config.set_precision("bf16")
+    random.seed(1)
+    np.random.seed(1)
+    old = ttg.SIZE_BUFFER
+    ttg.SIZE_BUFFER = 1 << 18
+    try:
+        GraphSAGE, _, PrioT, _, _, act = ogl_b200.init(ogl_b200.Lib_supported.PYTORCH, True, -1)
+        dyn = ogl_b200.DynamicGraphEdge(1000, set(range(V)))
+        dyn.build(feats, targets, edge_timestamps={"src": src, "dst": dst}, keep_master=False)
+        gu = ttg.TrainTestGraph(dyn, split=0.15, start_prior_alpha=4, end_prior_alpha=50, scale=1, max_priority=10)
+        model = GraphSAGE(w["F"], w["H"], w["C"], 1, act, 0, "pool").cuda()
+        tr = PrioT(model, 60, 32, targets, 45, ogl_b200.LossPriority(), full_pass=2, cuda=True, batch_full=1024, n_workers=0)
+        tr.build_optimizer()
+        for _ in range(2):                       # warm-up timesteps (plan creation, graph capture)
+            tr.train_timestep(gu)
+            gu.evolve()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        trained = 0
+        for _ in range(n_snapshots):
+            tr.train_timestep(gu)
+            trained += min(60 * 32, 60 * len(gu.get_train_set()))
+            gu.evolve()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        return {"workload": "elliptic-shaped edge stream (V=%d, %d stream edges, F=%d, hidden %d, samples 45, batch 32 x 60 per timestep), "
+                            "PBR, priority_forward=2, through the Python drop-in API" % (V, w["E"], w["F"], w["H"]),
+                "timesteps": n_snapshots, "vertices_per_s": trained / el, "ms_per_timestep": 1e3 * el / n_snapshots,
+                "train_set": len(gu.get_train_set())}
+    finally:
+        ttg.SIZE_BUFFER = old
+        config.set_faithful(True)
+
+
+def aux_sampler_sweep(g, V, n_rows=1 << 20, fanout=25, iters=5):
+    """config 5 flavour: the standalone uniform k-neighbour sampler over the resident Reddit-shaped CSR, 2^20 random
+    destination rows x 25 picks per launch (indices + edge ids out)"""
+    from ogl_b200 import native
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    dst = torch.randint(0, V, (n_rows,), generator=gen, device="cuda", dtype=torch.int64)
+    for _ in range(2):
+        native.sample_neighbors(g, dst, fanout, seed=3, step=0, hop=0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        native.sample_neighbors(g, dst, fanout, seed=3, step=i + 1, hop=0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    picks = n_rows * fanout
+    alg = n_rows * (8 + 4 + 8) + picks * (4 + 4) + picks * (4 + 8)      # row meta + (src, eid) reads + (src, eid) writes
+    return {"rows": n_rows, "fanout": fanout, "ms": ms, "picks_per_s": picks / (ms * 1e-3), "algorithmic_gbs": alg / (ms * 1e-3) / 1e9,
+            "sector_gbs": (n_rows * 64 + picks * 64 + picks * 12) / (ms * 1e-3) / 1e9,
+            "note": "includes the int64->int32 cast of the row list and a stream-ordered scratch allocation per call; sector_gbs counts "
+                    "every random 4-byte read as the 32-byte DRAM sector it costs"}
 
 
 def workload_config(w, name, world):
@@ -353,8 +445,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e: pinned host seeds -> H2D inside the call, loss D2H every step
     for s in pin[:W]:
         step(s)
-    ms_e2e, _, _, losses = timed(pin[W:], read_back=True)
-    clk = clocks.window(wall0, wall1) if clocks else None
+    ms_e2e, _, wall2, losses = timed(pin[W:], read_back=True)
+    # clock samples (100 ms period) over the value + profiled + e2e regions: the same K steps back to back
+    clk = clocks.window(wall0, wall2) if clocks else None
     if clocks:
         clocks.stop()
 
@@ -367,21 +460,47 @@ def run_ours(args, rank, world, local_rank):
     lv = [x / max(n_prof, 1) for x in level_sums]                 # mean [B, N1, N0] per step
     per = {k: v[0] / max(n_prof, 1) for k, v in stages.items()}   # ms per step per stage
     total_stage_ms = sum(per.values())
-    # dominant kernel = the stage with the largest share of the step
-    top = max(per, key=per.get)
+    # dominant kernel = the kernel family with the largest total share of the step; the roofline is quoted on its
+    # largest launch (FLOPs / bytes of that launch from the per-step node counts, duration from the stage events)
     is_layer = lambda k: len(k) > 3 and k[0] == "l" and k[1].isdigit() and k[2] == "."
+    def family(k):
+        kind = k.split(".", 1)[1] if is_layer(k) else k.split(".")[0]
+        if kind in ("pool_gemm", "out_gemm", "dneigh_gemm", "dx_gemm"):
+            return "k_gemm_nt_tc"
+        if kind in ("dW_self", "dW_neigh", "dW_pool"):
+            return "k_gemm_tn_tc"
+        return {"pool_bwd": "k_pool_bwd", "segmax": "k_segmax_fwd", "gather": "k_gather_rows", "sample": "k_sample",
+                "to_block": "k_tb_*", "rev_edges": "k_rev_*", "db_out": "k_colsum_*", "db_pool": "k_colsum_*"}.get(kind, kind)
+    fam = {}
+    for k, v in per.items():
+        fam.setdefault(family(k), []).append(k)
+    fam_ms = {f: sum(per[k] for k in ks) for f, ks in fam.items()}
+    top_family = max(fam_ms, key=fam_ms.get)
+    top = max(fam[top_family], key=per.get)
     fl = stage_flops(top, w, lv) if is_layer(top) else None
     by = stage_bytes(top, w, lv)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+        if tr:
+            traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+    except Exception:
+        pass
+    common = {"kernel": top_family, "launch": top, "kernel_share_of_step": fam_ms[top_family] / total_stage_ms,
+              "kernel_ms_per_step": fam_ms[top_family], "kernel_launches_per_step": len(fam[top_family]), "traffic": traffic,
+              "ms_per_launch": per[top]}
     if fl:
         ach = fl / (per[top] * 1e-3) / 1e12
-        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
-                "traffic": None, "peak_source": peak_src + ", sustained bf16", "flops_per_launch": fl, "ms_per_launch": per[top]}
+        roof = dict(common, bound="tensor", achieved=ach, peak=tc_peak, unit="TFLOP/s", frac=ach / tc_peak,
+                    peak_source=peak_src + ", sustained bf16", flops_per_launch=fl)
+        fam_fl = sum(stage_flops(k, w, lv) or 0.0 for k in fam[top_family])
+        roof["kernel_avg_tflops"] = fam_fl / (fam_ms[top_family] * 1e-3) / 1e12
     elif by:
         ach = by / (per[top] * 1e-3) / 1e9
-        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                "peak_source": peak_src, "bytes_per_launch": by, "ms_per_launch": per[top]}
+        roof = dict(common, bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src,
+                    bytes_per_launch=by)
     else:
-        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None}
+        roof = dict(common, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None)
     stage_table = {}
     for k in sorted(per, key=per.get, reverse=True):
         ent = {"ms": round(per[k], 4), "share": round(per[k] / total_stage_ms, 4)}
@@ -400,6 +519,22 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": B * args.cpu_steps / el, "unit": "vertices/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d full train steps (B=%d) of the same workload, oracle port (numpy sampler + torch-CPU fp32 SAGE-pool + Adam), %.1f s"
                          % (args.cpu_steps, B, el)}
+    aux = None
+    if world == 1 and not args.no_aux:
+        try:
+            sweep = aux_sampler_sweep(g, V)
+        except Exception as e:
+            sweep = {"error": repr(e)[:300]}
+        del plan, g, fs
+        torch.cuda.empty_cache()
+        try:
+            aux = {"elliptic_pbr": aux_elliptic_pbr(faithful=True)}
+            aux["elliptic_pbr"]["mode"] = "faithful (reference choosers: host shuffles, per-batch loss read-back into the Python priority dict)"
+            aux["elliptic_pbr_device"] = aux_elliptic_pbr(faithful=False)
+            aux["elliptic_pbr_device"]["mode"] = "device (counter-RNG draws, stratified proportional sampling and priority updates on the GPU sum tree)"
+            aux["sampler_sweep"] = sweep
+        except Exception as e:                       # the aux leg must never take the headline line with it
+            aux = {"elliptic_pbr": {"error": repr(e)[:300]}}
     line = {"metric": "graphsage_train_vertices_per_s", "value": value, "unit": "vertices/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(w, args.workload, world),
@@ -409,7 +544,7 @@ def run_ours(args, rank, world, local_rank):
                                                       "captures_in_timed_region": gs1["captures"] - gs0["captures"],
                                                       "ms_per_step_direct_launch_profiled": ms_prof / K},
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "mean_level_counts": {"B": lv[0], "N1": lv[1], "N0": lv[2]}, "stages": stage_table,
+            "mean_level_counts": {"B": lv[0], "N1": lv[1], "N0": lv[2]}, "stages": stage_table, "aux": aux,
             "edge_insert": {"stream_edges_per_s": E / (insert_ms / 1e3), "ms": insert_ms, "batch_stream_edges": chunk, "launches": insert_launches,
                             "algorithmic_gbs": 2 * E * (16 + 8 + 8) / (insert_ms / 1e3) / 1e9}}
     print(json.dumps(line), flush=True)
@@ -420,12 +555,13 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
