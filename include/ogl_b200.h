@@ -197,6 +197,10 @@ int ogl_sumtree_values(ogl_sumtree* t, const double** value_dev, int64_t* capaci
 /* C[M,N] (fp32, ldc) = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb), tcgen05 path */
 int ogl_gemm_bf16_nt(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc,
                      int m, int n, int k, void* stream);
+/* same with the fused epilogue options of the plan's GEMMs: bf16 or fp32 output, bias[n], ReLU; cg = 0 auto, 1 one CTA
+ * per 128-row tile, 2 CTA pairs (tcgen05 cta_group::2) */
+int ogl_gemm_bf16_nt_ex(const void* a_dev, int lda, const void* b_dev, int ldb, void* c_dev, int ldc, int m, int n, int k,
+                        int out_bf16, const float* bias_dev, int relu, int cg, void* stream);
 /* C[N,K] (fp32, ldc) = A[M,N]^T (bf16, lda) * B[M,K] (bf16, ldb): the weight-gradient shape (contraction over
  * rows), tcgen05 path with MN-major operands; workspace holds the split partials (may be NULL: no split) */
 int ogl_gemm_bf16_tn(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc,

@@ -90,6 +90,7 @@ SIGNATURES = {
     "ogl_sumtree_sample_stratified": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "ogl_sumtree_values": (_i, [_vp, _pp, C.POINTER(_i64)]),
     "ogl_gemm_bf16_nt": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "ogl_gemm_bf16_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ogl_gemm_bf16_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
 }
 

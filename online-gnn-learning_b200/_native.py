@@ -380,3 +380,14 @@ def gemm_bf16_tn(a, b, n=None, k=None, workspace_elems=1 << 24):
     check(lib.ogl_gemm_bf16_tn(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), k, a.shape[0], n, k,
                                _ptr(ws), int(workspace_elems), _stream()))
     return c
+
+
+def gemm_bf16_nt_ex(a, b, k=None, out_bf16=True, bias=None, relu=False, cg=0):
+    """C[M,N] = act(A[M,:k] @ B[N,:k]^T + bias) with the plan's fused epilogue (bf16 out -> TMA-store path)."""
+    a, b = a.contiguous(), b.contiguous()
+    k = a.shape[1] if k is None else int(k)
+    ldc = (b.shape[0] + 7) // 8 * 8
+    c = torch.empty(a.shape[0], ldc, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+    check(lib.ogl_gemm_bf16_nt_ex(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), ldc, a.shape[0], b.shape[0], k, int(out_bf16),
+                                  _ptr(bias), int(relu), int(cg), _stream()))
+    return c[:, :b.shape[0]]

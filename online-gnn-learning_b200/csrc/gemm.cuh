@@ -15,6 +15,8 @@ struct GemmNT {
   int k[2] = {0, 0};
   int n_seg = 1;
   const int32_t* a_rows_dev[2] = {nullptr, nullptr};  // rows of segment s valid for m < *a_rows_dev[s] (nullptr: all)
+  int a_rows_max[2] = {0, 0};      // rows that exist in segment s's buffer (0: m_max); reads beyond are zero-filled (TMA)
+  int force_cg = 0;                // tcgen05 path: 0 = auto, 1 = single CTA, 2 = CTA pairs (cta_group::2)
   const float* bias = nullptr;     // [n] fp32 (nullable)
   const float* bias2 = nullptr;    // second bias added too (fc_self.bias + fc_neigh.bias)
   int relu = 0;

@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "sage_kernels.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace ogl {
 
@@ -32,7 +33,12 @@ constexpr int RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);   // 192 KB
 constexpr int STORE_BOX_BYTES = 32 * 128;                              // one TMA-store box: 32 rows x 128 B
 constexpr int STORE_BYTES = 4 /*warps*/ * 2 /*buffers*/ * STORE_BOX_BYTES;   // 32 KB epilogue staging
 constexpr int BIAS_BYTES = 2 * BN_MAX * 4;                              // per-accumulator bias slice
-constexpr int SMEM_BYTES = RING_BYTES + STORE_BYTES + BIAS_BYTES + 128 /*barriers + tmem slot*/;
+constexpr int SMEM_BYTES = RING_BYTES + STORE_BYTES + BIAS_BYTES + 256 /*barriers + tmem slot*/;
+// cta_group::2 variant of the NT kernel: a CTA pair shares one B tile (each CTA stages half of it), so a stage is
+// 16 KB of A + 16 KB of B per CTA and the same 192 KB ring holds 6 stages
+constexpr int STAGES2 = 6;
+constexpr int B2_STAGE_BYTES = (BN_MAX / 2) * BK * 2;    // 16 KB
+static_assert(STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) == RING_BYTES, "ring size mismatch");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
@@ -95,6 +101,55 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs of the pair load into their own shared memory; the transaction bytes complete on the LEADER's barrier
+// (shared::cluster address of the same offset in CTA rank 0: peer bit 24 cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint64_t* bar, uint32_t cta) {   // arrive on the same-offset barrier of CTA `cta`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free_pair(uint32_t base) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -136,8 +191,9 @@ __device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int
 struct SmemLayout {
   uint8_t* a0;           // stage i of A at a0 + i * A_STAGE_BYTES
   uint8_t* b0;
+  int b_stage_bytes;
   __device__ __forceinline__ uint8_t* a(int i) const { return a0 + i * A_STAGE_BYTES; }
-  __device__ __forceinline__ uint8_t* b(int i) const { return b0 + i * B_STAGE_BYTES; }
+  __device__ __forceinline__ uint8_t* b(int i) const { return b0 + i * b_stage_bytes; }
   uint8_t* store;        // [4 warps][2][STORE_BOX_BYTES] epilogue staging for TMA stores
   float* bias;           // [2][BN_MAX]
   uint64_t* full;        // [STAGES]
@@ -146,21 +202,22 @@ struct SmemLayout {
   uint64_t* acc_empty;   // [2]
   uint32_t* tmem_slot;
 };
-__device__ __forceinline__ SmemLayout carve(uint8_t* base) {
+__device__ __forceinline__ SmemLayout carve(uint8_t* base, int n_stages = STAGES, int b_stage_bytes = B_STAGE_BYTES) {
   // the dynamic shared window of a kernel without static __shared__ starts 1024-byte aligned (SWIZZLE_128B atoms
   // need it); checked at run time instead of paying 1 KB of slack
   if ((smem_u32(base) & 1023u) != 0) __trap();
   SmemLayout s;
   s.a0 = base;
-  s.b0 = base + STAGES * A_STAGE_BYTES;
+  s.b0 = base + n_stages * A_STAGE_BYTES;
+  s.b_stage_bytes = b_stage_bytes;
   s.store = base + RING_BYTES;
   s.bias = (float*)(base + RING_BYTES + STORE_BYTES);
   uint64_t* bars = (uint64_t*)(base + RING_BYTES + STORE_BYTES + BIAS_BYTES);
   s.full = bars;
-  s.empty = bars + STAGES;
-  s.acc_full = bars + 2 * STAGES;
-  s.acc_empty = bars + 2 * STAGES + 2;
-  s.tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  s.empty = bars + n_stages;
+  s.acc_full = bars + 2 * n_stages;
+  s.acc_empty = bars + 2 * n_stages + 2;
+  s.tmem_slot = (uint32_t*)(bars + 2 * n_stages + 4);
   return s;
 }
 
@@ -188,90 +245,135 @@ struct NtParams {
   int ldc;
   int out_bf16;
   int zero_tail;
+  int debug;                    // perf experiments (OGL_GEMM_DBG): 1 = epilogue drains the accumulator without storing
 };
 
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256-row super
+// tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues UMMA M = 256 that reads
+// both halves, each CTA keeps the accumulator of its own rows in its own TMEM and runs its own epilogue.  Per CTA a
+// k-block then moves 32 KB instead of 48 KB through L2 -> SM, the limiter of the single-CTA kernel.
+template <int CG>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
+  constexpr int NST = CG == 2 ? STAGES2 : STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemLayout s = carve(smem_raw);
+  const SmemLayout s = carve(smem_raw, NST, CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;          // CTA rank inside the pair
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
   const int m_pad = p.zero_tail ? min((m_dyn + 127) / 128 * 128, p.m_max) : m_dyn;
-  const int m_tiles = (m_pad + BM - 1) / BM;
+  const int m_tiles = ((m_pad + BM - 1) / BM + CG - 1) / CG;      // row blocks of CG * 128 rows
   const int total_tiles = m_tiles * p.n_tiles;
   int rows_valid[2];
   rows_valid[0] = p.a_rows_dev[0] ? min(*p.a_rows_dev[0], m_dyn) : m_dyn;
   rows_valid[1] = p.n_seg > 1 ? (p.a_rows_dev[1] ? min(*p.a_rows_dev[1], m_dyn) : m_dyn) : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 4); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<512>(s.tmem_slot);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair<512>(s.tmem_slot);
+    else tmem_alloc<512>(s.tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before any remote arrive / TMA completes on them
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (in pair mode: in both CTAs, each for its own shared memory) =====
+    if (lane == 0 && !(p.debug & 2)) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(A_STAGE_BYTES + p.bn * BK * 2);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mb = t / p.n_tiles, nb = t % p.n_tiles;
+      // bytes landing per stage on the barrier the MMA issuer waits on (pair mode: both CTAs' boxes, on the leader's)
+      const uint32_t tx = CG == 2 ? (uint32_t)(2 * (A_STAGE_BYTES + (p.bn / 2) * BK * 2)) : (uint32_t)(A_STAGE_BYTES + p.bn * BK * 2);
+      for (int t = unit; t < total_tiles; t += n_units) {
+        const int mt = t / p.n_tiles, nb = t % p.n_tiles;
+        const int mb = mt * CG + rank;
+        const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
         for (int seg = 0; seg < p.n_seg; ++seg) {
-          if (mb * BM >= rows_valid[seg]) continue;
+          if (mt * CG * BM >= rows_valid[seg]) continue;          // (pair-uniform: decided on the pair's first row)
           const int nkb = (p.k[seg] + BK - 1) / BK;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&s.empty[stage], phase ^ 1);
-            mbar_expect_tx(&s.full[stage], tx);
-            tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BK, mb * BM);
-            tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BK, nb * BN_MAX);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (CG == 2) {
+              if (rank == 0) mbar_expect_tx(&s.full[stage], tx);
+              tma_load_2d_pair(s.a(stage), &p.ta[seg], &s.full[stage], kb * BK, mb * BM);
+              tma_load_2d_pair(s.b(stage), &p.tb[seg], &s.full[stage], kb * BK, nb * BN_MAX + rank * (bn_tile / 2));
+            } else {
+              mbar_expect_tx(&s.full[stage], tx);
+              tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BK, mb * BM);
+              tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BK, nb * BN_MAX);
+            }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (pair mode: the leader CTA only) =====
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mb = t / p.n_tiles, nb = t % p.n_tiles;
+      const int b_stage_bytes = CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES;
+      const uint64_t a_desc0 = smem_desc(smem_u32(s.a(0)), 16, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), 16, 1024);
+      for (int t = unit; t < total_tiles; t += n_units) {
+        const int mt = t / p.n_tiles, nb = t % p.n_tiles;
         const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
-        const uint32_t idesc = instr_desc(BM, bn_tile, 0, 0);
+        const uint32_t idesc = instr_desc(BM * CG, bn_tile, 0, 0);
         mbar_wait(&s.acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN_MAX);
         uint32_t accumulate = 0;
         for (int seg = 0; seg < p.n_seg; ++seg) {
-          if (mb * BM >= rows_valid[seg]) continue;
+          if (mt * CG * BM >= rows_valid[seg]) continue;
           const int K = p.k[seg];
           const int nkb = (K + BK - 1) / BK;
           for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&s.full[stage], phase);
+            if (!(p.debug & 2)) mbar_wait(&s.full[stage], phase);      // (debug 2: MMA issue rate alone, operands = stale smem)
             tc_fence_after();
+            // descriptors of this stage: the 14-bit address field advances by 2 (= 32 bytes) per 16-element k step; the
+            // issue loop is kept branch-free for full k-blocks so that the tensor pipe never waits on this thread
+            const uint64_t ad = a_desc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+            const uint64_t bd = b_desc0 + (uint64_t)(stage * (b_stage_bytes >> 4));
             const int k_left = K - kb * BK;
-            const int n_k16 = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
-            const uint32_t a_addr = smem_u32(s.a(stage)), b_addr = smem_u32(s.b(stage));
-            for (int k16 = 0; k16 < n_k16; ++k16) {
-              const uint64_t ad = smem_desc(a_addr + k16 * 32, 16, 1024);
-              const uint64_t bd = smem_desc(b_addr + k16 * 32, 16, 1024);
-              tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
+            if (k_left >= BK) {
+              if (CG == 2) {
+                tc_mma_bf16_pair(d_tmem, ad, bd, idesc, accumulate);
+                tc_mma_bf16_pair(d_tmem, ad + 2, bd + 2, idesc, 1);
+                tc_mma_bf16_pair(d_tmem, ad + 4, bd + 4, idesc, 1);
+                tc_mma_bf16_pair(d_tmem, ad + 6, bd + 6, idesc, 1);
+              } else {
+                tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+                tc_mma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
+                tc_mma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
+                tc_mma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
+              }
+            } else {
+              const int n_k16 = (k_left + 15) / 16;
+              for (int k16 = 0; k16 < n_k16; ++k16) {
+                if (CG == 2) tc_mma_bf16_pair(d_tmem, ad + 2 * k16, bd + 2 * k16, idesc, k16 ? 1u : accumulate);
+                else tc_mma_bf16(d_tmem, ad + 2 * k16, bd + 2 * k16, idesc, k16 ? 1u : accumulate);
+              }
             }
-            tc_commit(&s.empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            accumulate = 1;
+            if (!(p.debug & 2)) {
+              if (CG == 2) tc_commit_pair(&s.empty[stage]);
+              else tc_commit(&s.empty[stage]);
+            }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
-        tc_commit(&s.acc_full[acc]);
+        if (CG == 2) tc_commit_pair(&s.acc_full[acc]);
+        else tc_commit(&s.acc_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -284,12 +386,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t boxes_issued = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mb = t / p.n_tiles, nb = t % p.n_tiles;
+    for (int t = unit; t < total_tiles; t += n_units) {
+      const int mb = (t / p.n_tiles) * CG + rank, nb = t % p.n_tiles;
       const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
       const int gm = mb * BM + quarter * 32 + lane;
       const bool row_store = gm < m_pad;
       const bool row_live = gm < m_dyn;
+      const bool tile_live = mb * BM + BM <= m_dyn;
+      const float relu_lo = p.relu ? 0.f : -INFINITY;
       // bias slice of this tile -> shared (broadcast reads below); double-buffered with the accumulator
       float* bias_s = s.bias + acc * BN_MAX;
       for (int j = epi_tid; j < bn_tile; j += 128) {
@@ -304,7 +408,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
       epi_barrier();
       mbar_wait(&s.acc_full[acc], acc_phase);
       tc_fence_after();
-      if (p.out_bf16) {
+      if (p.debug & 1) {
+        // nothing: measures the load + MMA pipeline alone
+      } else if (p.out_bf16) {
         for (int c0 = 0; c0 < bn_tile; c0 += 64) {
           uint8_t* buf = stage_buf + (boxes_issued & 1) * STORE_BOX_BYTES;
           if (boxes_issued >= 2) {                 // the store issued two boxes ago has finished reading this buffer
@@ -334,14 +440,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
             tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + cc), r);
             const int gn0 = nb * BN_MAX + cc;
             float v[32];
+            if (tile_live && gn0 + 32 <= p.n) {
+              // interior chunk (every row live, every column < n): branch-free, bias through 16-byte shared loads
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = 0.f;
-              if (row_live && gn0 + j < p.n) {
-                x = __uint_as_float(r[j]) + bias_s[cc + j];
-                if (p.relu) x = fmaxf(x, 0.f);
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + q * 4);
+                v[q * 4 + 0] = fmaxf(__uint_as_float(r[q * 4 + 0]) + b4.x, relu_lo);
+                v[q * 4 + 1] = fmaxf(__uint_as_float(r[q * 4 + 1]) + b4.y, relu_lo);
+                v[q * 4 + 2] = fmaxf(__uint_as_float(r[q * 4 + 2]) + b4.z, relu_lo);
+                v[q * 4 + 3] = fmaxf(__uint_as_float(r[q * 4 + 3]) + b4.w, relu_lo);
               }
-              v[j] = x;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = 0.f;
+                if (row_live && gn0 + j < p.n) x = fmaxf(__uint_as_float(r[j]) + bias_s[cc + j], relu_lo);
+                v[j] = x;
+              }
             }
             if (p.mask) {                          // mask box staged in `buf` (coalesced loads, see above)
 #pragma unroll
@@ -402,7 +517,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
+      if (lane == 0) {                             // the accumulator is drained: tell the (leader's) MMA issuer
+        if (CG == 2) mbar_arrive_on_cta(&s.acc_empty[acc], 0);
+        else mbar_arrive(&s.acc_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();          // shared memory must stay valid until the last store has read it
@@ -410,9 +528,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                // neither CTA leaves (or frees TMEM) while its peer may still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_free<512>(tmem_base);
+    if (CG == 2) tmem_free_pair<512>(tmem_base);
+    else tmem_free<512>(tmem_base);
   }
 }
 
@@ -480,17 +600,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       // products with stale shared memory and are never stored (rows >= n)
       const uint32_t idesc = instr_desc(BM, bn_tile, 1, 1);
       uint32_t accumulate = 0;
+      // MN-major descriptors: 16 contraction rows = 2048 bytes = 128 in the 14-bit address field; kept branch-free
+      const uint64_t a_desc0 = smem_desc(smem_u32(s.a(0)), 8192, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), 8192, 1024);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.full[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(s.a(stage)), b_addr = smem_u32(s.b(stage));
-#pragma unroll
-        for (int k16 = 0; k16 < BK / 16; ++k16) {
-          const uint64_t ad = smem_desc(a_addr + k16 * 2048, 8192, 1024);
-          const uint64_t bd = smem_desc(b_addr + k16 * 2048, 8192, 1024);
-          tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
-          accumulate = 1;
-        }
+        const uint64_t ad = a_desc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+        const uint64_t bd = b_desc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
+        tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
+        tc_mma_bf16(tmem_base, ad + 128, bd + 128, idesc, 1);
+        tc_mma_bf16(tmem_base, ad + 256, bd + 256, idesc, 1);
+        tc_mma_bf16(tmem_base, ad + 384, bd + 384, idesc, 1);
+        accumulate = 1;
         tc_commit(&s.empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -580,7 +701,8 @@ int tc_init() {
     return -1;
   }
   g_encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(k_gemm_nt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+  if (cudaFuncSetAttribute(k_gemm_nt_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_nt_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
     cudaGetLastError();
     g_tc_state = -1;
@@ -639,11 +761,15 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.n_tiles = (g.n + BN_MAX - 1) / BN_MAX;
   p.bn = p.n_tiles > 1 ? BN_MAX : (g.n + 15) / 16 * 16;
   p.n_seg = g.n_seg;
+  // CTA pairs (cta_group::2) when there are enough 256-row super tiles to occupy every pair of SMs
+  const int64_t super_tiles = ceil_div(ceil_div(g.m_max, BM), 2) * p.n_tiles;
+  const int cg = (g.force_cg == 1 || g.force_cg == 2) ? g.force_cg : ((super_tiles >= sm_count() / 2 && p.bn % 32 == 0) ? 2 : 1);
   for (int i = 0; i < g.n_seg; ++i) {
     p.k[i] = g.k[i];
     p.a_rows_dev[i] = g.a_rows_dev[i];
-    OGL_TRY(make_map(&p.ta[i], g.a[i], g.m_max, g.k[i], g.lda[i], BK, BM));
-    OGL_TRY(make_map(&p.tb[i], g.b[i], g.n, g.k[i], g.ldb[i], BK, p.bn));
+    const int64_t a_rows = g.a_rows_max[i] > 0 ? g.a_rows_max[i] : g.m_max;      // rows that exist in segment i's A buffer
+    OGL_TRY(make_map(&p.ta[i], g.a[i], a_rows, g.k[i], g.lda[i], BK, BM));
+    OGL_TRY(make_map(&p.tb[i], g.b[i], g.n, g.k[i], g.ldb[i], BK, cg == 2 ? p.bn / 2 : p.bn));
   }
   p.m_dev = g.m_dev;
   p.m_max = g.m_max;
@@ -656,13 +782,35 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.ldc = g.ldc;
   p.out_bf16 = g.out_bf16;
   p.zero_tail = g.zero_tail;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("OGL_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   OGL_ARG(!(g.mask && !g.out_bf16), "gemm_nt_tc: the mask epilogue is implemented for bf16 output only");
   if (g.out_bf16) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 64, 32));
   OGL_ARG(g.ldc % 8 == 0 && ((uintptr_t)g.c & 15) == 0, "gemm_nt_tc: output pitch must be a multiple of 8 elements");
   OGL_ARG(!g.mask || (g.ldmask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0), "gemm_nt_tc: mask pitch must be a multiple of 8 elements");
+  if (cg == 2) {
+    const int pairs = (int)(super_tiles < sm_count() / 2 ? super_tiles : sm_count() / 2);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    OGL_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_nt_tc<2>, p));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return OGL_OK;
+  }
   const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  OGL_LAUNCH(k_gemm_nt_tc, grid, THREADS, SMEM_BYTES, s, p);
+  OGL_LAUNCH(k_gemm_nt_tc<1>, grid, THREADS, SMEM_BYTES, s, p);
   return OGL_OK;
 }
 
@@ -719,6 +867,18 @@ extern "C" int ogl_gemm_bf16_nt(const void* a_dev, int lda, const void* b_dev, i
   GemmNT g;
   g.a[0] = a_dev; g.lda[0] = lda; g.b[0] = b_dev; g.ldb[0] = ldb; g.k[0] = k; g.n_seg = 1;
   g.c = c_dev; g.ldc = ldc; g.m_max = m; g.n = n; g.in_bf16 = 1; g.out_bf16 = 0; g.zero_tail = 0;
+  if (const char* e = getenv("OGL_GEMM_CG")) g.force_cg = atoi(e);          // tests: force the 1-CTA / CTA-pair kernel
+  return gemm_nt_tc(g, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_gemm_bf16_nt_ex(const void* a_dev, int lda, const void* b_dev, int ldb, void* c_dev, int ldc, int m, int n, int k,
+                                   int out_bf16, const float* bias_dev, int relu, int cg, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_bf16_nt_ex: bad arguments");
+  GemmNT g;
+  g.a[0] = a_dev; g.lda[0] = lda; g.b[0] = b_dev; g.ldb[0] = ldb; g.k[0] = k; g.n_seg = 1;
+  g.c = c_dev; g.ldc = ldc; g.m_max = m; g.n = n; g.in_bf16 = 1; g.out_bf16 = out_bf16; g.zero_tail = 0;
+  g.bias = bias_dev; g.relu = relu; g.force_cg = cg;
   return gemm_nt_tc(g, (cudaStream_t)stream);
 }
 

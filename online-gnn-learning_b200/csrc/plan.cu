@@ -474,6 +474,7 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       GemmNT d;
       d.a[0] = p->dhp; d.lda[0] = lb.pin; d.b[0] = lb.wpT; d.ldb[0] = lb.pin; d.k[0] = lb.in;
       d.a[1] = lb.dpre; d.lda[1] = lb.pout; d.b[1] = lb.wsT; d.ldb[1] = lb.pout; d.k[1] = lb.out; d.a_rows_dev[1] = p->counts + dl;
+      d.a_rows_max[1] = round_up(p->nmax[dl], 128);
       d.n_seg = 2;
       d.mask = p->act[sl]; d.ldmask = lb.pin;
       d.c = prev.dpre; d.ldc = prev.pout; d.m_max = p->nmax[sl]; d.m_dev = p->counts + sl; d.n = lb.in;
