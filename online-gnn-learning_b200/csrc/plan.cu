@@ -131,6 +131,15 @@ struct ogl_plan {
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
   ShadowSeg* shadow_segs = nullptr;      // device table for the fused Adam + shadow refresh
   int n_shadow_segs = 0;
+  // independent work of a step runs on a side stream (forked / joined with events, also inside graph capture):
+  // the weight / bias gradients of fc_self and fc_neigh overlap the dneigh -> pool_bwd -> dW_pool -> dx chain
+  int use_side = 1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int in_train_step = 0;                 // set by the fused train step: sampling may defer the reverse edge lists to the side stream
+  int side_pending = 0;                  // side-stream work not yet joined into the main stream
+  float* tn_partial2 = nullptr;          // split workspace of the side-stream TN GEMMs
+  float* colsum_partial2 = nullptr;
   // CUDA-graph replay of the train step (fixed launch sequence, all sizes read from device memory)
   int use_graph = 1;
   struct StepKey {
@@ -187,6 +196,13 @@ static void prof_end(ogl_plan* p, cudaStream_t s) {
     prof_begin(p, name, s);          \
     int _sr = (call);                \
     prof_end(p, s);                  \
+    if (_sr != OGL_OK) return _sr;   \
+  } while (0)
+#define STAGE_ON(st, name, call)     \
+  do {                               \
+    prof_begin(p, name, st);         \
+    int _sr = (call);                \
+    prof_end(p, st);                 \
     if (_sr != OGL_OK) return _sr;   \
   } while (0)
 static std::string nm(const char* fmt, int i) {
@@ -301,6 +317,11 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   p->tn_partial_elems = max_nk * 32;
   DM0(p->tn_partial, sizeof(float) * p->tn_partial_elems);
   DM0(p->colsum_partial, sizeof(float) * max_colsum);
+  DM0(p->tn_partial2, sizeof(float) * p->tn_partial_elems);
+  DM0(p->colsum_partial2, sizeof(float) * max_colsum);
+  OGL_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+  OGL_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  OGL_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   DM0(p->per_loss, sizeof(float) * cfg->max_seeds);
   DM0(p->loss_sum, sizeof(float) * 4);
   DM0(p->adam_m, sizeof(float) * p->n_params);
@@ -327,6 +348,11 @@ extern "C" int ogl_plan_destroy(ogl_plan* p) {
                   p->loss_sum, p->adam_m, p->adam_v, p->shadow_segs};
   for (void* q : ptrs) cudaFree(q);
   for (auto& r : p->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  cudaDeviceSynchronize();
+  if (p->side) cudaStreamDestroy(p->side);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  cudaFree(p->tn_partial2); cudaFree(p->colsum_partial2);
   for (auto& sg : p->step_graphs) cudaGraphExecDestroy(sg.exec);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->prof_counts_host) cudaFreeHost(p->prof_counts_host);
@@ -375,8 +401,18 @@ extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_d
                                                   (uint32_t)h, p->edge_gsrc[h], p->edge_eid[h], s));
     STAGE(nm("to_block.h%d", h).c_str(), to_block(&p->tb, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->edge_gsrc[h],
                                                   p->nodes[h + 1], p->counts + h + 1, p->nmax[h + 1], p->edge_lid[h], s));
-    STAGE(nm("rev_edges.h%d", h).c_str(), reverse_edges(&p->tb, p->edge_lid[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->nmax[h + 1],
-                                                        p->rev_ptr[h], p->rev_edge[h], s));
+    // reverse edge lists (only the backward pass reads them): inside the fused train step they are built on the side
+    // stream, overlapping the next hop's sampling and the forward pass; joined at the start of the backward pass
+    if (p->in_train_step && p->use_side && !p->prof_on) {
+      OGL_CUDA(cudaEventRecord(p->ev_fork, s));
+      OGL_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+      OGL_TRY(reverse_edges(&p->tb, p->edge_lid[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->nmax[h + 1], p->rev_ptr[h],
+                            p->rev_edge[h], p->side));
+      p->side_pending = 1;
+    } else {
+      STAGE(nm("rev_edges.h%d", h).c_str(), reverse_edges(&p->tb, p->edge_lid[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h],
+                                                          p->nmax[h + 1], p->rev_ptr[h], p->rev_edge[h], s));
+    }
   }
   return OGL_OK;
 }
@@ -435,20 +471,31 @@ extern "C" int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_s
 
 static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
   const int L = p->L;
+  if (p->side_pending) {                         // reverse edge lists built on the side stream during sampling
+    OGL_CUDA(cudaEventRecord(p->ev_join, p->side));
+    OGL_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+    p->side_pending = 0;
+  }
   for (int l = L - 1; l >= 0; --l) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, sl = h + 1, dl = h;
     float* G = p->grads;
-    // dWs = dpre^T act[src][:n_d] ; dWn = dpre^T neigh
+    // dWs = dpre^T act[src][:n_d] ; dWn = dpre^T neigh ; db = colsum(dpre): independent of the chain below -> side stream
+    const bool ov = p->use_side && !p->prof_on;
+    cudaStream_t ss = ov ? p->side : s;
+    if (ov) {
+      OGL_CUDA(cudaEventRecord(p->ev_fork, s));                 // dpre of this layer is complete on s
+      OGL_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    }
     GemmTN t;
     t.a = lb.dpre; t.lda = lb.pout; t.n = lb.out; t.b = p->act[sl]; t.ldb = lb.pin; t.k = lb.in;
     t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16;
-    t.partial = p->tn_partial; t.partial_elems = p->tn_partial_elems;
-    STAGE(nm("l%d.dW_self", l).c_str(), gemm_tn(p, t, s));
+    t.partial = ov ? p->tn_partial2 : p->tn_partial; t.partial_elems = p->tn_partial_elems;
+    STAGE_ON(ss, nm("l%d.dW_self", l).c_str(), gemm_tn(p, t, ss));
     t.b = lb.neigh; t.c = G + lb.o_wn;
-    STAGE(nm("l%d.dW_neigh", l).c_str(), gemm_tn(p, t, s));
-    STAGE(nm("l%d.db_out", l).c_str(),
-          colsum(p->bf16, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl], p->colsum_partial, G + lb.o_bs, G + lb.o_bn, s));
+    STAGE_ON(ss, nm("l%d.dW_neigh", l).c_str(), gemm_tn(p, t, ss));
+    STAGE_ON(ss, nm("l%d.db_out", l).c_str(), colsum(p->bf16, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl],
+                                                     ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bs, G + lb.o_bn, ss));
     // dneigh = dpre Wn
     GemmNT n1;
     n1.a[0] = lb.dpre; n1.lda[0] = lb.pout; n1.b[0] = lb.wnT; n1.ldb[0] = lb.pout; n1.k[0] = lb.out; n1.n_seg = 1;
@@ -481,6 +528,10 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       d.in_bf16 = p->bf16; d.out_bf16 = p->bf16;
       STAGE(nm("l%d.dx_gemm", l).c_str(), gemm_nt(p, d, s));
     }
+  }
+  if (p->use_side && !p->prof_on) {                                   // join: the side-stream gradients precede Adam / the caller
+    OGL_CUDA(cudaEventRecord(p->ev_join, p->side));
+    OGL_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
   }
   return OGL_OK;
 }
@@ -529,7 +580,10 @@ static int stage_seeds(ogl_plan* p, const int64_t* seeds, int n_seeds, int on_ho
 // the fixed launch sequence of one train step over the seeds already staged in p->seeds_stage
 static int train_step_body(ogl_plan* p, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step, float* per_vertex_loss_dev,
                            float* loss_sum_dev, cudaStream_t s) {
-  OGL_TRY(ogl_plan_sample(p, g, p->seeds_stage, n_seeds, s));
+  p->in_train_step = 1;
+  const int rs = ogl_plan_sample(p, g, p->seeds_stage, n_seeds, s);
+  p->in_train_step = 0;
+  OGL_TRY(rs);
   OGL_TRY(ogl_plan_forward(p, f, nullptr, s));
   OGL_TRY(ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s));
   if (do_step) OGL_TRY(ogl_plan_adam_step(p, s));
@@ -590,6 +644,7 @@ extern "C" int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, c
 extern "C" int ogl_plan_set_option(ogl_plan* p, const char* name, int value) {
   OGL_ARG(p && name, "ogl_plan_set_option: null");
   if (strcmp(name, "cuda_graph") == 0) { p->use_graph = value ? 1 : 0; return OGL_OK; }
+  if (strcmp(name, "side_stream") == 0) { p->use_side = value ? 1 : 0; return OGL_OK; }
   set_error("ogl_plan_set_option: unknown option '%s'", name);
   return OGL_ERR_ARG;
 }

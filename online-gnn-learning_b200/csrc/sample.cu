@@ -142,7 +142,7 @@ int reverse_edges(ToBlockWs* ws, const int32_t* edge_lid, const int32_t* n_dst_d
   OGL_ARG(n_src_max + 1 <= ws->rev_cap, "reverse_edges: workspace too small");
   OGL_CUDA(cudaMemsetAsync(ws->rev_cnt, 0, sizeof(int32_t) * 2 * (size_t)ws->rev_cap, s));     // counters + cursors
   OGL_LAUNCH(k_rev_count, grid_for(ne_max, kBlock), kBlock, 0, s, edge_lid, n_dst_dev, n_dst_max, fanout, ws->rev_cnt);
-  OGL_TRY(exclusive_scan_i32(ws->rev_cnt, rev_ptr, (int64_t)n_src_max + 1, ws->scan_scratch, nullptr, s));
+  OGL_TRY(exclusive_scan_i32(ws->rev_cnt, rev_ptr, (int64_t)n_src_max + 1, ws->rev_scan_scratch, nullptr, s));   // own scratch: may run beside to_block
   OGL_LAUNCH(k_rev_fill, grid_for(ne_max, kBlock), kBlock, 0, s, edge_lid, n_dst_dev, n_dst_max, fanout, rev_ptr, ws->rev_cnt + ws->rev_cap,
              rev_edge);
   return OGL_OK;
@@ -167,6 +167,7 @@ int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max) {
   OGL_CUDA(cudaMalloc(&ws->scan_scratch, sizeof(int32_t) * scan_scratch_elems(scan_n)));
   ws->rev_cap = v_cap + 1;
   OGL_CUDA(cudaMalloc(&ws->rev_cnt, sizeof(int32_t) * 2 * (size_t)ws->rev_cap));
+  OGL_CUDA(cudaMalloc(&ws->rev_scan_scratch, sizeof(int32_t) * scan_scratch_elems(v_cap + 2)));
   OGL_CUDA(cudaMalloc(&ws->n_new, sizeof(int32_t)));
   OGL_LAUNCH(k_fill_i32, grid_for(v_cap, kBlock), kBlock, 0, 0, ws->first, 0x7fffffff, v_cap);
   OGL_CUDA(cudaDeviceSynchronize());
@@ -174,7 +175,7 @@ int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max) {
 }
 
 void to_block_free(ToBlockWs* ws) {
-  cudaFree(ws->first); cudaFree(ws->flags); cudaFree(ws->pos); cudaFree(ws->scan_scratch); cudaFree(ws->n_new); cudaFree(ws->rev_cnt);
+  cudaFree(ws->first); cudaFree(ws->flags); cudaFree(ws->pos); cudaFree(ws->scan_scratch); cudaFree(ws->n_new); cudaFree(ws->rev_cnt); cudaFree(ws->rev_scan_scratch);
   *ws = ToBlockWs();
 }
 

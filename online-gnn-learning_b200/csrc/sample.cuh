@@ -11,6 +11,7 @@ struct ToBlockWs {
   int32_t* scan_scratch = nullptr;
   int32_t* n_new = nullptr;
   int32_t* rev_cnt = nullptr;       // [2 * rev_cap]: per-source counters, then fill cursors
+  int32_t* rev_scan_scratch = nullptr;
   int64_t rev_cap = 0;
   int64_t v_cap = 0, ne_max = 0;
 };
