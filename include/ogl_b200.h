@@ -139,7 +139,14 @@ int ogl_plan_adam_step(ogl_plan* p, void* stream);
 int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds,
                         int seeds_on_host, float loss_scale, int do_step, float* per_vertex_loss_dev,
                         float* loss_sum_dev, void* stream);
-/* options: "cuda_graph" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence
+/* the same step in two calls, for data-parallel pipelining: step_begin = sample + gather (independent of the weights: it
+ * can run while the previous step's gradient all-reduce + Adam are still in flight on another stream); step_finish =
+ * forward + loss + backward (+ Adam if do_step) over the minibatch begun last */
+int ogl_plan_step_begin(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
+                        void* stream);
+int ogl_plan_step_finish(ogl_plan* p, ogl_features* f, float loss_scale, int do_step, float* per_vertex_loss_dev,
+                         float* loss_sum_dev, void* stream);
+/* options: "cuda_graph" (default 1), "side_stream" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence
  * (re-captured when the graph pool, the handles, n_seeds or the output pointers change) */
 int ogl_plan_set_option(ogl_plan* p, const char* name, int value);
 /* out = {graphs captured, graph replays} */

@@ -243,6 +243,19 @@ class Plan:
         self.n_seeds = n
         self._stamp += 1
 
+    def step_begin(self, graph, features, seeds):
+        """sample + gather of the next minibatch (no weights involved)"""
+        n = seeds.numel()
+        assert seeds.dtype == torch.int64 and seeds.is_contiguous()
+        check(lib.ogl_plan_step_begin(self._h, graph._h, features._h, C.c_void_p(seeds.data_ptr()), n, int(not seeds.is_cuda), _stream()))
+        self.n_seeds = n
+        self._stamp += 1
+
+    def step_finish(self, features, loss_scale, do_step=True, per_vertex_out=None, loss_sum_out=None):
+        """forward + loss + backward (+ Adam) over the minibatch begun with step_begin"""
+        check(lib.ogl_plan_step_finish(self._h, features._h, float(loss_scale), int(do_step), _ptr(per_vertex_out), _ptr(loss_sum_out),
+                                       _stream()))
+
     def eval_step(self, graph, features, seeds, logits_out=None, per_vertex_out=None):
         n = seeds.numel()
         on_host = not seeds.is_cuda

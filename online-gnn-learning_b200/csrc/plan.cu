@@ -136,6 +136,7 @@ struct ogl_plan {
   int use_side = 1;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int skip_gather = 0;                   // step_finish: the input rows were already gathered by step_begin
   int in_train_step = 0;                 // set by the fused train step: sampling may defer the reverse edge lists to the side stream
   int side_pending = 0;                  // side-stream work not yet joined into the main stream
   float* tn_partial2 = nullptr;          // split workspace of the side-stream TN GEMMs
@@ -147,9 +148,10 @@ struct ogl_plan {
     uint64_t g_gen;
     int n_seeds, do_step;
     float loss_scale;
+    int kind;            // 0 = whole step, 1 = step_begin (sample + gather), 2 = step_finish (forward .. Adam)
     bool operator==(const StepKey& o) const {
       return g == o.g && f == o.f && per == o.per && loss == o.loss && g_gen == o.g_gen && n_seeds == o.n_seeds && do_step == o.do_step &&
-             loss_scale == o.loss_scale;
+             loss_scale == o.loss_scale && kind == o.kind;
     }
   };
   struct StepGraph { StepKey key; cudaGraphExec_t exec; uint64_t last_use; };
@@ -424,7 +426,8 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
   cudaStream_t s = (cudaStream_t)stream;
   const int L = p->L;
   // f == NULL: the input rows were supplied by ogl_plan_set_input
-  if (f) STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
+  if (f && !p->skip_gather)
+    STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
   for (int l = 0; l < L; ++l) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, sl = h + 1, dl = h;
@@ -460,6 +463,7 @@ static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, f
 }
 
 static int plan_backward_layers(ogl_plan* p, cudaStream_t s);
+static int join_side(ogl_plan* p, cudaStream_t s);
 
 extern "C" int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
                                       void* stream) {
@@ -471,11 +475,7 @@ extern "C" int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_s
 
 static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
   const int L = p->L;
-  if (p->side_pending) {                         // reverse edge lists built on the side stream during sampling
-    OGL_CUDA(cudaEventRecord(p->ev_join, p->side));
-    OGL_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
-    p->side_pending = 0;
-  }
+  OGL_TRY(join_side(p, s));                      // reverse edge lists built on the side stream during sampling
   for (int l = L - 1; l >= 0; --l) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, sl = h + 1, dl = h;
@@ -577,63 +577,113 @@ static int stage_seeds(ogl_plan* p, const int64_t* seeds, int n_seeds, int on_ho
   return OGL_OK;
 }
 
-// the fixed launch sequence of one train step over the seeds already staged in p->seeds_stage
-static int train_step_body(ogl_plan* p, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step, float* per_vertex_loss_dev,
-                           float* loss_sum_dev, cudaStream_t s) {
-  p->in_train_step = 1;
-  const int rs = ogl_plan_sample(p, g, p->seeds_stage, n_seeds, s);
-  p->in_train_step = 0;
-  OGL_TRY(rs);
-  OGL_TRY(ogl_plan_forward(p, f, nullptr, s));
+// ---- the fixed launch sequences of a train step over the seeds already staged in p->seeds_stage ----------------
+// kind 0: everything; kind 1: sample + gather (needs no weights: in data-parallel runs it overlaps the gradient
+// all-reduce + Adam of the previous step); kind 2: forward .. backward (.. Adam)
+static int join_side(ogl_plan* p, cudaStream_t s) {
+  if (p->side_pending) {
+    OGL_CUDA(cudaEventRecord(p->ev_join, p->side));
+    OGL_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+    p->side_pending = 0;
+  }
+  return OGL_OK;
+}
+
+static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step,
+                     float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
+  if (kind == 0 || kind == 1) {
+    p->in_train_step = 1;
+    const int rs = ogl_plan_sample(p, g, p->seeds_stage, n_seeds, s);
+    p->in_train_step = 0;
+    OGL_TRY(rs);
+  }
+  if (kind == 1) {
+    OGL_ARG(f->mode == p->cfg.mode && f->F == p->cfg.dims[0], "ogl_plan_step_begin: feature store does not match the plan (mode/F)");
+    STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[p->L], p->counts + p->L, p->nmax[p->L], p->act[p->L], s));
+    return join_side(p, s);                       // a captured graph must rejoin its forked stream
+  }
+  p->skip_gather = (kind == 2);
+  const int rf = ogl_plan_forward(p, f, nullptr, s);
+  p->skip_gather = 0;
+  OGL_TRY(rf);
   OGL_TRY(ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s));
   if (do_step) OGL_TRY(ogl_plan_adam_step(p, s));
   OGL_TRY(bump(p->ctl, nullptr, s));
   return OGL_OK;
 }
 
+// run step_body directly, or capture it once per key and replay the graph
+static int run_step(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step,
+                    float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
+  if (!p->use_graph || p->prof_on) return step_body(p, kind, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s);
+  const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, g ? graph_generation(g) : 0, n_seeds, do_step, loss_scale, kind};
+  ogl_plan::StepGraph* hit = nullptr;
+  for (auto& sg : p->step_graphs)
+    if (sg.key == key) { hit = &sg; break; }
+  if (!hit) {
+    if (!p->cap_stream) OGL_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+    OGL_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int r = step_body(p, kind, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, p->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
+    if (r != OGL_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    OGL_CUDA(e);
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    OGL_CUDA(ei);
+    if (p->step_graphs.size() >= 8) {          // evict the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < p->step_graphs.size(); ++i)
+        if (p->step_graphs[i].last_use < p->step_graphs[lru].last_use) lru = i;
+      cudaGraphExecDestroy(p->step_graphs[lru].exec);
+      p->step_graphs.erase(p->step_graphs.begin() + lru);
+    }
+    p->step_graphs.push_back({key, exec, 0});
+    hit = &p->step_graphs.back();
+    p->graph_captures++;
+  }
+  hit->last_use = ++p->graph_clock;
+  OGL_CUDA(cudaGraphLaunch(hit->exec, s));
+  p->graph_replays++;
+  if (kind != 2) p->n_seeds = n_seeds;
+  return OGL_OK;
+}
+
+static int stage_step_seeds(ogl_plan* p, const int64_t* seeds, int n_seeds, int seeds_on_host, cudaStream_t s) {
+  OGL_ARG(n_seeds > 0 && n_seeds <= p->cfg.max_seeds, "n_seeds %d not in [1, %d]", n_seeds, p->cfg.max_seeds);
+  // seeds always go through the plan's staging buffer so that a captured graph is independent of the caller's pointer
+  OGL_CUDA(cudaMemcpyAsync(p->seeds_stage, seeds, sizeof(int64_t) * n_seeds, seeds_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  return OGL_OK;
+}
+
 extern "C" int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
                                    float loss_scale, int do_step, float* per_vertex_loss_dev, float* loss_sum_dev, void* stream) {
   OGL_ARG(p && g && f && seeds, "ogl_plan_train_step: null");
-  OGL_ARG(n_seeds > 0 && n_seeds <= p->cfg.max_seeds, "n_seeds %d not in [1, %d]", n_seeds, p->cfg.max_seeds);
   OGL_ARG(p->params, "ogl_plan_train_step: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  // seeds always go through the plan's staging buffer so that the captured graph is independent of the caller's pointer
-  OGL_CUDA(cudaMemcpyAsync(p->seeds_stage, seeds, sizeof(int64_t) * n_seeds, seeds_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-  if (!p->use_graph || p->prof_on) {
-    OGL_TRY(train_step_body(p, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s));
-  } else {
-    const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, graph_generation(g), n_seeds, do_step, loss_scale};
-    ogl_plan::StepGraph* hit = nullptr;
-    for (auto& sg : p->step_graphs)
-      if (sg.key == key) { hit = &sg; break; }
-    if (!hit) {
-      if (!p->cap_stream) OGL_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
-      OGL_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
-      const int r = train_step_body(p, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, p->cap_stream);
-      cudaGraph_t graph = nullptr;
-      const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
-      if (r != OGL_OK) { if (graph) cudaGraphDestroy(graph); return r; }
-      OGL_CUDA(e);
-      cudaGraphExec_t exec = nullptr;
-      const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      OGL_CUDA(ei);
-      if (p->step_graphs.size() >= 8) {          // evict the least recently used
-        size_t lru = 0;
-        for (size_t i = 1; i < p->step_graphs.size(); ++i)
-          if (p->step_graphs[i].last_use < p->step_graphs[lru].last_use) lru = i;
-        cudaGraphExecDestroy(p->step_graphs[lru].exec);
-        p->step_graphs.erase(p->step_graphs.begin() + lru);
-      }
-      p->step_graphs.push_back({key, exec, 0});
-      hit = &p->step_graphs.back();
-      p->graph_captures++;
-    }
-    hit->last_use = ++p->graph_clock;
-    OGL_CUDA(cudaGraphLaunch(hit->exec, s));
-    p->graph_replays++;
-    p->n_seeds = n_seeds;
+  OGL_TRY(stage_step_seeds(p, seeds, n_seeds, seeds_on_host, s));
+  OGL_TRY(run_step(p, 0, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s));
+  if (p->prof_on && p->prof_steps < kProfSteps) {
+    OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
+    p->prof_steps++;
   }
+  return OGL_OK;
+}
+
+extern "C" int ogl_plan_step_begin(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
+                                   void* stream) {
+  OGL_ARG(p && g && f && seeds, "ogl_plan_step_begin: null");
+  cudaStream_t s = (cudaStream_t)stream;
+  OGL_TRY(stage_step_seeds(p, seeds, n_seeds, seeds_on_host, s));
+  return run_step(p, 1, g, f, n_seeds, 0.f, 0, nullptr, nullptr, s);
+}
+
+extern "C" int ogl_plan_step_finish(ogl_plan* p, ogl_features* f, float loss_scale, int do_step, float* per_vertex_loss_dev,
+                                    float* loss_sum_dev, void* stream) {
+  OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish: no step begun / parameters not bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  OGL_TRY(run_step(p, 2, nullptr, f, p->n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s));
   if (p->prof_on && p->prof_steps < kProfSteps) {
     OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
     p->prof_steps++;

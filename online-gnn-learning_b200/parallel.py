@@ -62,3 +62,51 @@ def train_step(plan, graph, features, local_seeds, global_batch, flat_grad, per_
     if w > 1:
         allreduce_grads(flat_grad)
         plan.adam_step()
+
+
+class Pipeline:
+    """Data-parallel train loop with the gradient exchange off the critical path.
+
+    A step is split at the only point where it needs fresh weights: `begin` = sample + gather (reads the graph and the
+    feature store only), `finish` = forward .. backward.  The all-reduce of step t and its Adam update run on a
+    communication stream while the main stream already samples and gathers step t+1; forward(t+1) then waits for
+    Adam(t).  Same arithmetic as the unpipelined loop (no stale gradients)."""
+
+    def __init__(self, plan, graph, features, flat_grad, global_batch):
+        self.plan, self.graph, self.features, self.flat_grad = plan, graph, features, flat_grad
+        self.scale = 1.0 / float(global_batch)
+        self.w = world()
+        self.comm = torch.cuda.Stream() if self.w > 1 else None
+        self.ev_bwd = torch.cuda.Event()
+        self.ev_adam = torch.cuda.Event()
+        self._begun = False
+        self._adam_pending = False
+
+    def begin(self, seeds):
+        self.plan.step_begin(self.graph, self.features, seeds)
+        self._begun = True
+
+    def finish(self, next_seeds=None, per_vertex_out=None, loss_sum_out=None):
+        assert self._begun, "Pipeline.finish() without begin()"
+        self._begun = False
+        main = torch.cuda.current_stream()
+        if self.w == 1:
+            self.plan.step_finish(self.features, self.scale, do_step=True, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
+        else:
+            if self._adam_pending:
+                main.wait_event(self.ev_adam)            # weights (and the gradient buffer) of the previous step are settled
+            self.plan.step_finish(self.features, self.scale, do_step=False, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
+            self.ev_bwd.record(main)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ev_bwd)
+                allreduce_grads(self.flat_grad)
+                self.plan.adam_step()
+                self.ev_adam.record(self.comm)
+            self._adam_pending = True
+        if next_seeds is not None:
+            self.begin(next_seeds)                       # overlaps the all-reduce + Adam in flight
+
+    def flush(self):
+        if self._adam_pending:
+            torch.cuda.current_stream().wait_event(self.ev_adam)
+            self._adam_pending = False

@@ -308,3 +308,28 @@ def test_cuda_graph_replay_equals_direct_launches():
     for (p0, t0), (p1, t1) in zip(runs[0][1], runs[1][1]):
         close(p0, p1, 1e-4, "per-vertex loss graph vs direct")
         close(t0, t1, 1e-4, "loss sum graph vs direct")
+
+
+def test_step_begin_finish_equals_fused_step():
+    """the two-call form used by the data-parallel pipeline (sample + gather | forward .. Adam) is the same step"""
+    runs = []
+    for split in (False, True):
+        c = Case(dims=(64, 32, 5), fanouts=(6, 4), n_seeds=64, mode="bf16", gemm_impl=0)
+        seeds_dev = torch.as_tensor(c.seeds).cuda()
+        pinned = torch.as_tensor(c.seeds).pin_memory()
+        per = torch.empty(len(c.seeds), device="cuda")
+        tot = torch.empty(1, device="cuda")
+        outs = []
+        for step in range(4):
+            sd = pinned if step % 2 else seeds_dev          # host and device seed paths
+            if split:
+                c.plan.step_begin(c.g, c.f, sd)
+                c.plan.step_finish(c.f, 1.0 / len(c.seeds), do_step=True, per_vertex_out=per, loss_sum_out=tot)
+            else:
+                c.plan.train_step(c.g, c.f, sd, loss_scale=1.0 / len(c.seeds), do_step=True, per_vertex_out=per, loss_sum_out=tot)
+            outs.append(per.clone())
+        torch.cuda.synchronize()
+        runs.append((c.flat.clone(), outs))
+    close(runs[0][0], runs[1][0], 1e-4, "params fused vs begin/finish")
+    for a, b in zip(runs[0][1], runs[1][1]):
+        close(a, b, 1e-4, "per-vertex loss fused vs begin/finish")
