@@ -253,7 +253,7 @@ def first_appearance_relabel(src, dst):
     return out[0::2].copy(), out[1::2].copy(), uniq[np.argsort(first, kind="stable")]
 
 
-def aux_elliptic_pbr(n_snapshots=12, faithful=True):
+def aux_elliptic_pbr(n_snapshots=30, faithful=True):
     """configs[1]: Elliptic-shaped edge stream through the drop-in Python API (DynamicGraphEdge + TrainTestGraph + the
     PBR trainer with priority_forward = 2, settings/elliptic.json hyper-parameters): snapshot evolve, priority
     recomputation, 60 minibatches of 32 per timestep.  Reports trained target vertices / s over whole timesteps
@@ -287,18 +287,18 @@ def aux_elliptic_pbr(n_snapshots=12, faithful=True):
             tr.train_timestep(gu)
             gu.evolve()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        trained = 0
+        times = []
         for _ in range(n_snapshots):
+            t0 = time.perf_counter()
             tr.train_timestep(gu)
-            trained += min(60 * 32, 60 * len(gu.get_train_set()))
             gu.evolve()
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        med = float(np.median(times))          # (shared host: single timesteps are occasionally several times slower)
         return {"workload": "elliptic-shaped edge stream (V=%d, %d stream edges, F=%d, hidden %d, samples 45, batch 32 x 60 per timestep), "
                             "PBR, priority_forward=2, through the Python drop-in API" % (V, w["E"], w["F"], w["H"]),
-                "timesteps": n_snapshots, "vertices_per_s": trained / el, "ms_per_timestep": 1e3 * el / n_snapshots,
-                "train_set": len(gu.get_train_set())}
+                "timesteps": n_snapshots, "vertices_per_s": 60 * 32 / med, "ms_per_timestep_median": 1e3 * med,
+                "ms_per_timestep_mean": 1e3 * float(np.mean(times)), "train_set": len(gu.get_train_set())}
     finally:
         ttg.SIZE_BUFFER = old
         config.set_faithful(True)
@@ -326,6 +326,62 @@ def aux_sampler_sweep(g, V, n_rows=1 << 20, fanout=25, iters=5):
             "sector_gbs": (n_rows * 64 + picks * 64 + picks * 12) / (ms * 1e-3) / 1e9,
             "note": "includes the int64->int32 cast of the row list and a stream-ordered scratch allocation per call; sector_gbs counts "
                     "every random 4-byte read as the 32-byte DRAM sector it costs"}
+
+
+def aux_arxiv_vertex_stream(n_snapshots=20):
+    """configs[2]: ogbn-arxiv-shaped VERTEX stream through the drop-in Python API (DynamicGraphVertex: the active set is a
+    prefix of the arrival order, every evolve() re-derives the induced CSR on the GPU) with the RBR trainer and
+    settings/arxiv.json hyper-parameters (hidden 32, samples 40, batch 32 x 1 per timestep, 3500 snapshots)."""
+    import random
+    import ogl_b200
+    from ogl_b200 import config
+    from ogl_b200.graph import train_test_graph as ttg
+    w = WORKLOADS["arxiv"]
+    rng = np.random.default_rng(2)
+    V = w["V"]
+    u, v = rng.integers(0, V, w["E"]), rng.integers(0, V, w["E"])
+    feats = rng.standard_normal((V, w["F"])).astype(np.float32)
+    targets = rng.integers(0, w["C"], (V, 1)).astype(np.int64)
+    config.set_faithful(True)
+    config.set_precision("bf16")
+    random.seed(1)
+    np.random.seed(1)
+    old = ttg.SIZE_BUFFER
+    ttg.SIZE_BUFFER = 1 << 18
+    try:
+        GraphSAGE, RandomT, _, _, _, act = ogl_b200.init(ogl_b200.Lib_supported.PYTORCH, True, -1)
+        pg = ogl_b200.ParentGraph.from_undirected(u, v, V)
+        pg.ndata["feat"], pg.ndata["target"] = feats, targets
+        order = rng.permutation(V)
+        ts = (np.arange(V), np.empty(V))
+        ts[1][order] = np.arange(V, dtype=np.float64)
+        t_build = time.perf_counter()
+        dyn = ogl_b200.DynamicGraphVertex(pg, 3500, np.ones(V, dtype=bool))
+        dyn.build(vertex_timestamps=(ts[0].tolist(), ts[1].tolist()))
+        for _ in range(200):                          # start from a graph with ~10 k active vertices
+            dyn.evolve()
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t_build
+        gu = ttg.TrainTestGraph(dyn, split=0.15, start_prior_alpha=4, end_prior_alpha=50, scale=1, max_priority=10)
+        model = GraphSAGE(w["F"], w["H"], w["C"], 1, act, 0, "pool").cuda()
+        tr = RandomT(model, 1, 32, targets, 40, cuda=True, batch_full=1024, n_workers=0)
+        tr.build_optimizer()
+        for _ in range(3):
+            tr.train_timestep(gu)
+            gu.evolve()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_snapshots):
+            tr.train_timestep(gu)
+            gu.evolve()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        return {"workload": "arxiv-shaped vertex stream (V=%d, %d directed edges, F=%d, hidden %d, samples 40, batch 32 x 1 per timestep, "
+                            "3500 snapshots), RBR, through the Python drop-in API" % (V, 2 * w["E"], w["F"], w["H"]),
+                "timesteps": n_snapshots, "vertices_per_s": 32 * n_snapshots / el, "ms_per_timestep_incl_evolve": 1e3 * el / n_snapshots,
+                "active_vertices": len(dyn.get_graph()), "build_plus_200_evolves_s": build_s}
+    finally:
+        ttg.SIZE_BUFFER = old
 
 
 def workload_config(w, name, world):
@@ -546,6 +602,7 @@ def run_ours(args, rank, world, local_rank):
             aux["elliptic_pbr_device"] = aux_elliptic_pbr(faithful=False)
             aux["elliptic_pbr_device"]["mode"] = "device (counter-RNG draws, stratified proportional sampling and priority updates on the GPU sum tree)"
             aux["sampler_sweep"] = sweep
+            aux["arxiv_rbr"] = aux_arxiv_vertex_stream()
         except Exception as e:                       # the aux leg must never take the headline line with it
             aux = {"elliptic_pbr": {"error": repr(e)[:300]}}
     line = {"metric": "graphsage_train_vertices_per_s", "value": value, "unit": "vertices/s", "n_gpus": world, "steps": K, "warmup": W,

@@ -139,6 +139,11 @@ int ogl_plan_adam_step(ogl_plan* p, void* stream);
 int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds,
                         int seeds_on_host, float loss_scale, int do_step, float* per_vertex_loss_dev,
                         float* loss_sum_dev, void* stream);
+/* n_batches consecutive train steps of `batch` seeds each (seeds = [n_batches * batch]) without returning to the host in
+ * between -- the batch_timestep minibatches of one snapshot (pytorch/model.py:129-134).  per_vertex_loss_dev
+ * [n_batches * batch] and loss_sums_dev [n_batches] may be NULL */
+int ogl_plan_train_steps(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_batches, int batch, int seeds_on_host,
+                         float loss_scale, int do_step, float* per_vertex_loss_dev, float* loss_sums_dev, void* stream);
 /* the same step in two calls, for data-parallel pipelining: step_begin = sample + gather (independent of the weights: it
  * can run while the previous step's gradient all-reduce + Adam are still in flight on another stream); step_finish =
  * forward + loss + backward (+ Adam if do_step) over the minibatch begun last */

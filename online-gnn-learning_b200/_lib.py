@@ -71,6 +71,7 @@ SIGNATURES = {
     "ogl_plan_backward": (_i, [_vp, _vp, _vp]),
     "ogl_plan_adam_step": (_i, [_vp, _vp]),
     "ogl_plan_train_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "ogl_plan_train_steps": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "ogl_plan_step_begin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ogl_plan_step_finish": (_i, [_vp, _vp, _f, _i, _vp, _vp, _vp]),
     "ogl_plan_set_option": (_i, [_vp, C.c_char_p, _i]),

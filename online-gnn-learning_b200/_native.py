@@ -243,6 +243,18 @@ class Plan:
         self.n_seeds = n
         self._stamp += 1
 
+    def train_steps(self, graph, features, seeds, batch, loss_scale=None, do_step=True, per_vertex_out=None, loss_sums_out=None):
+        """seeds: flat int64 tensor of n_batches * batch ids (CUDA or pinned/pageable CPU); all steps in one C call"""
+        n = seeds.numel()
+        assert seeds.dtype == torch.int64 and seeds.is_contiguous() and n % batch == 0
+        if loss_scale is None:
+            loss_scale = 1.0 / batch
+        check(lib.ogl_plan_train_steps(self._h, graph._h, features._h, C.c_void_p(seeds.data_ptr()), n // batch, int(batch),
+                                       int(not seeds.is_cuda), float(loss_scale), int(do_step), _ptr(per_vertex_out), _ptr(loss_sums_out),
+                                       _stream()))
+        self.n_seeds = batch
+        self._stamp += 1
+
     def step_begin(self, graph, features, seeds):
         """sample + gather of the next minibatch (no weights involved)"""
         n = seeds.numel()

@@ -671,6 +671,27 @@ extern "C" int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, c
   return OGL_OK;
 }
 
+// `n_batches` consecutive train steps of `batch` seeds each in ONE call (the reference runs batch_timestep minibatches per
+// snapshot, pytorch/model.py:129-134): no per-step host round trip; per-vertex losses / loss sums of step i land at
+// per_vertex_loss_dev[i * batch ...] / loss_sums_dev[i]
+extern "C" int ogl_plan_train_steps(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_batches, int batch,
+                                    int seeds_on_host, float loss_scale, int do_step, float* per_vertex_loss_dev, float* loss_sums_dev,
+                                    void* stream) {
+  OGL_ARG(p && g && f && seeds && n_batches >= 0, "ogl_plan_train_steps: bad arguments");
+  OGL_ARG(p->params, "ogl_plan_train_steps: parameters not bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < n_batches; ++i) {
+    OGL_TRY(stage_step_seeds(p, seeds + (int64_t)i * batch, batch, seeds_on_host, s));
+    // fixed internal outputs keep one captured graph valid for every step; results are copied out per step
+    OGL_TRY(run_step(p, 0, g, f, batch, loss_scale, do_step, per_vertex_loss_dev ? p->per_loss : nullptr,
+                     loss_sums_dev ? p->loss_sum : nullptr, s));
+    if (per_vertex_loss_dev)
+      OGL_CUDA(cudaMemcpyAsync(per_vertex_loss_dev + (int64_t)i * batch, p->per_loss, sizeof(float) * batch, cudaMemcpyDeviceToDevice, s));
+    if (loss_sums_dev) OGL_CUDA(cudaMemcpyAsync(loss_sums_dev + i, p->loss_sum, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return OGL_OK;
+}
+
 extern "C" int ogl_plan_step_begin(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
                                    void* stream) {
   OGL_ARG(p && g && f && seeds, "ogl_plan_step_begin: null");

@@ -6,6 +6,8 @@ them over PCIe and runs DGL/cuBLAS kernels (:77-107), every minibatch here is ON
 feature gather, the GraphSAGE-pool forward/backward, CE loss, Adam -- stays on the GPU with no host
 synchronisation.  Per-vertex losses for PBR come back only in faithful mode.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -101,6 +103,26 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
             self._pin_busy = torch.cuda.Event()
             self._pin_busy.record()
 
+    def _fused_steps(self, graph, seeds, batch, per_vertex_out=None):
+        """all full minibatches of `batch` seeds in ONE C call (no host round trip between steps), then the ragged tail"""
+        batch = max(int(batch), 1)
+        n = seeds.numel()
+        n_full = n // batch
+        plan = self._train_plan(graph)
+        if os.environ.get("OGL_NO_MULTISTEP"):                     # A/B switch: one C call per minibatch
+            for i in range(0, n, batch):
+                self._fused_step(graph, seeds[i:i + batch], per_vertex_out=None if per_vertex_out is None else per_vertex_out[i:i + batch])
+            return
+        if n_full:
+            plan.train_steps(graph.native, graph.features, seeds[:n_full * batch], batch, loss_scale=1.0 / batch, do_step=True,
+                             per_vertex_out=None if per_vertex_out is None else per_vertex_out[:n_full * batch])
+            self.graphsage_model.mark_updated(plan)
+            self._last_plan = plan
+            self._mark_pin_busy(seeds)
+        if n > n_full * batch:
+            tail = seeds[n_full * batch:]
+            self._fused_step(graph, tail, per_vertex_out=None if per_vertex_out is None else per_vertex_out[n_full * batch:])
+
     def train_step(self, graph, blocks, input_nodes, seeds, subgraph_to_id):
         """DGL-style signature of the reference (:77-107).  The blocks only identify the minibatch: the fused
         kernels re-derive it from the same Philox counters, so this is one fused step on `seeds`."""
@@ -130,8 +152,7 @@ class RandomPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
         n = len(train_vertices)
         if n == 0:
             return
-        for seeds in self._batches(train_vertices, n // self.batch_per_timestep):
-            self._fused_step(graph, seeds)
+        self._fused_steps(graph, self._host_seeds(train_vertices), n // self.batch_per_timestep)
 
     def get_model(self):
         return "random"
@@ -170,13 +191,27 @@ class PrioritizedPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
         self.graphsage_model.train()
         n = len(train_vertices)
         if n:
-            for seeds in self._batches(train_vertices, n // self.batch_per_timestep):
-                if self._per_buf is None or self._per_buf.numel() < seeds.numel():
-                    self._per_buf = torch.empty(max(seeds.numel(), self.batch_size), dtype=torch.float32, device="cuda")
-                per = self._per_buf[:seeds.numel()]       # persistent: keeps the captured CUDA graph of the step valid
-                self._fused_step(graph, seeds, per_vertex_out=per)
-                nodes = subgraph_to_id[seeds.cpu().numpy()]
-                self._push_priorities(graph_util, np.asarray(nodes).tolist(), per)
+            # every minibatch of the timestep runs back to back on the GPU; the per-vertex losses are pushed into the
+            # priority structure afterwards, in batch order (a vertex trained twice keeps the loss of its last batch,
+            # exactly what the reference's per-batch dict updates leave behind, pytorch/model.py:203-206)
+            seeds = self._host_seeds(train_vertices)
+            if self._per_buf is None or self._per_buf.numel() < n:
+                self._per_buf = torch.empty(max(n, self.batch_size), dtype=torch.float32, device="cuda")
+            per = self._per_buf[:n]
+            batch = max(n // self.batch_per_timestep, 1)
+            self._fused_steps(graph, seeds, batch, per_vertex_out=per)
+            nodes = np.asarray(subgraph_to_id[np.asarray(train_vertices, dtype=np.int64)]).tolist()
+            if config.faithful():
+                # one read-back, then the reference's sequence of per-batch dict updates (the running min / max of the
+                # priority transform advances batch by batch, replay_buffer.py:110-130)
+                host = per.cpu().numpy()
+                for i in range(0, n, batch):
+                    pri = self.priority_strategy.get_priorities(nodes[i:i + batch], host[i:i + batch])
+                    graph_util.update_priorities(dict(zip(nodes[i:i + batch], pri)))
+            else:
+                last = {v: i for i, v in enumerate(nodes)}               # a vertex trained twice keeps its last loss
+                idx = torch.as_tensor(list(last.values()), dtype=torch.int64, device="cuda")
+                graph_util.update_priorities_device(list(last.keys()), per[idx])
         self.time_step += 1
 
     def recompute_priorities(self, graph_util, train_set):
@@ -216,8 +251,7 @@ class FullPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
         train_set = torch.as_tensor(np.asarray(batch_nodes, dtype=np.int64))
         for _ in range(self.batch_per_timestep):
             train_set = train_set[torch.randperm(train_set.numel())]
-            for seeds in self._batches(train_set, self.batch_size):
-                self._fused_step(graph, seeds)
+            self._fused_steps(graph, self._host_seeds(train_set), self.batch_size)
 
     def get_model(self):
         return "offline"

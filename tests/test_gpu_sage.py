@@ -333,3 +333,26 @@ def test_step_begin_finish_equals_fused_step():
     close(runs[0][0], runs[1][0], 1e-4, "params fused vs begin/finish")
     for a, b in zip(runs[0][1], runs[1][1]):
         close(a, b, 1e-4, "per-vertex loss fused vs begin/finish")
+
+
+def test_multi_step_call_equals_single_steps():
+    """ogl_plan_train_steps (all minibatches of a timestep in one C call) == the same steps one call at a time"""
+    runs = []
+    for multi in (False, True):
+        c = Case(dims=(64, 32, 5), fanouts=(6, 4), n_seeds=32, mode="bf16", gemm_impl=0)
+        rng = np.random.default_rng(0)
+        seeds = torch.as_tensor(rng.permutation(c.V - 40)[:5 * 32].astype(np.int64)).pin_memory()
+        per = torch.empty(5 * 32, device="cuda")
+        sums = torch.empty(5, device="cuda")
+        if multi:
+            c.plan.train_steps(c.g, c.f, seeds, 32, per_vertex_out=per, loss_sums_out=sums)
+        else:
+            for i in range(5):
+                c.plan.train_step(c.g, c.f, seeds[i * 32:(i + 1) * 32], loss_scale=1.0 / 32, do_step=True,
+                                  per_vertex_out=per[i * 32:(i + 1) * 32], loss_sum_out=sums[i:i + 1])
+        torch.cuda.synchronize()
+        runs.append((c.flat.clone(), per.clone(), sums.clone()))
+    close(runs[0][0], runs[1][0], 1e-4, "params")
+    close(runs[0][1], runs[1][1], 1e-4, "per-vertex losses")
+    close(runs[0][2], runs[1][2], 1e-4, "loss sums")
+    close(runs[0][1].view(5, 32).sum(1), runs[0][2], 1e-5, "loss sum == sum of per-vertex losses")
