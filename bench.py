@@ -321,11 +321,12 @@ def aux_sampler_sweep(g, V, n_rows=1 << 20, fanout=25, iters=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     picks = n_rows * fanout
-    alg = n_rows * (8 + 4 + 8) + picks * (4 + 4) + picks * (4 + 8)      # row meta + (src, eid) reads + (src, eid) writes
+    alg = n_rows * (8 + 4 + 8) + picks * 8 + picks * (4 + 8)            # row meta + (eid, src) entry reads + (src, eid) writes
     return {"rows": n_rows, "fanout": fanout, "ms": ms, "picks_per_s": picks / (ms * 1e-3), "algorithmic_gbs": alg / (ms * 1e-3) / 1e9,
-            "sector_gbs": (n_rows * 64 + picks * 64 + picks * 12) / (ms * 1e-3) / 1e9,
+            "sector_gbs": (n_rows * 64 + picks * 32 + picks * 12) / (ms * 1e-3) / 1e9,
             "note": "includes the int64->int32 cast of the row list and a stream-ordered scratch allocation per call; sector_gbs counts "
-                    "every random 4-byte read as the 32-byte DRAM sector it costs"}
+                    "every random read as the 32-byte DRAM sector it costs (row start + degree: 2 sectors per row; one 8-byte "
+                    "(edge id, source) entry: 1 sector per pick)"}
 
 
 def aux_arxiv_vertex_stream(n_snapshots=20):

@@ -2,7 +2,10 @@
 //
 // Layout in HBM (all arrays device-resident):
 //   row_start[v] int64, deg[v] int32, cap[v] int32      -- one slack row per vertex
-//   adj_src[pool] int32, adj_eid[pool] uint32            -- adjacency pool, rows = [row_start, row_start+cap)
+//   adj[pool] uint64 = (edge id << 32) | source          -- adjacency pool, rows = [row_start, row_start+cap); one 8-byte
+//                                                           entry per edge: a sampled pick costs ONE 32-byte sector, an
+//                                                           insert ONE scattered store, and ordering a tail by edge id is
+//                                                           ordering the entries as integers
 // A snapshot's edges are appended into each touched row's tail (the per-snapshot delta
 // region [deg_old, deg_new)); rows that run out of slack are relocated to the pool top with
 // doubled capacity (bump allocation), so an insert costs O(batch) amortised instead of the
@@ -71,7 +74,7 @@ struct MoveJob { long long from, to; int len; int pad; };
 __global__ void __launch_bounds__(kBlock) k_reserve(const int32_t* __restrict__ touched, const int32_t* __restrict__ add,
                                                     int64_t* __restrict__ row_start, const int32_t* __restrict__ deg,
                                                     int32_t* __restrict__ cap, int32_t* __restrict__ tail_len,
-                                                    int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid, MoveJob* __restrict__ jobs,
+                                                    unsigned long long* __restrict__ adj, MoveJob* __restrict__ jobs,
                                                     int* __restrict__ n_jobs, GraphCtl* ctl) {
   const int nt = ctl->n_touched;
   const int lane = threadIdx.x & 31;
@@ -91,10 +94,7 @@ __global__ void __launch_bounds__(kBlock) k_reserve(const int32_t* __restrict__ 
       off = __shfl_sync(0xffffffffu, off, 0);
       const int64_t old = row_start[v];
       if (d <= kWarpCopyMax) {
-        for (int i = lane; i < d; i += 32) {
-          adj_src[off + i] = adj_src[old + i];
-          adj_eid[off + i] = adj_eid[old + i];
-        }
+        for (int i = lane; i < d; i += 32) adj[off + i] = adj[old + i];
       } else if (lane == 0) {
         jobs[atomicAdd(n_jobs, 1)] = MoveJob{(long long)old, (long long)off, d, 0};
       }
@@ -105,21 +105,19 @@ __global__ void __launch_bounds__(kBlock) k_reserve(const int32_t* __restrict__ 
 }
 
 __global__ void __launch_bounds__(kBlock) k_move_big(const MoveJob* __restrict__ jobs, const int* __restrict__ n_jobs,
-                                                     int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid) {
+                                                     unsigned long long* __restrict__ adj) {
   const int nj = *n_jobs;
   for (int q = 0; q < nj; ++q) {
     const MoveJob j = jobs[q];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < j.len; i += (int64_t)gridDim.x * blockDim.x) {
-      adj_src[j.to + i] = adj_src[j.from + i];
-      adj_eid[j.to + i] = adj_eid[j.from + i];
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < j.len; i += (int64_t)gridDim.x * blockDim.x)
+      adj[j.to + i] = adj[j.from + i];
   }
 }
 
 // claim a slot in the row tail (arbitrary order inside the batch; fixed up by k_fix)
 __global__ void __launch_bounds__(kBlock) k_place(BatchEdges b, int32_t* __restrict__ add, const int64_t* __restrict__ row_start,
-                                                  const int32_t* __restrict__ deg, int32_t* __restrict__ adj_src,
-                                                  uint32_t* __restrict__ adj_eid, uint32_t eid_base, int64_t n_vertices) {
+                                                  const int32_t* __restrict__ deg, unsigned long long* __restrict__ adj,
+                                                  uint32_t eid_base, int64_t n_vertices) {
   const int64_t tot = b.total();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t s, d;
@@ -127,8 +125,7 @@ __global__ void __launch_bounds__(kBlock) k_place(BatchEdges b, int32_t* __restr
     if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) continue;
     const int p = atomicSub(&add[d], 1) - 1;      // add[] returns to zero by the end of the kernel
     const int64_t at = row_start[d] + deg[d] + p;
-    adj_src[at] = (int32_t)s;
-    adj_eid[at] = eid_base + (uint32_t)i;
+    adj[at] = ((unsigned long long)(eid_base + (uint32_t)i) << 32) | (uint32_t)s;
   }
 }
 
@@ -153,7 +150,7 @@ __device__ __forceinline__ void bitonic_step(unsigned long long* s, int i, int j
 
 __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
                                                 const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
-                                                int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
+                                                unsigned long long* __restrict__ adj,
                                                 int32_t* __restrict__ med, int32_t* __restrict__ large, GraphCtl* ctl) {
   const int nt = ctl->n_touched;
   const int lane = threadIdx.x & 31;
@@ -170,8 +167,8 @@ __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touc
       continue;
     }
     if (L >= 2) {
-      uint32_t e = lane < L ? adj_eid[base + lane] : 0xffffffffu;
-      int32_t s = lane < L ? adj_src[base + lane] : 0;
+      const unsigned long long ent = lane < L ? adj[base + lane] : ~0ull;
+      const uint32_t e = (uint32_t)(ent >> 32);
       int rank = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -179,7 +176,7 @@ __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touc
         rank += (j < L && ej < e) ? 1 : 0;
       }
       __syncwarp();
-      if (lane < L) { adj_eid[base + rank] = e; adj_src[base + rank] = s; }
+      if (lane < L) adj[base + rank] = ent;
     }
     __syncwarp();
     if (lane == 0) deg[v] += L;
@@ -188,7 +185,7 @@ __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touc
 
 __global__ void __launch_bounds__(kBlock) k_fix_med(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
                                                     const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
-                                                    int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
+                                                    unsigned long long* __restrict__ adj,
                                                     const int32_t* __restrict__ med, GraphCtl* ctl) {
   __shared__ unsigned long long keys[kBlock / 32][kMedTail];
   const int nm = ctl->n_med;
@@ -202,18 +199,14 @@ __global__ void __launch_bounds__(kBlock) k_fix_med(const int32_t* __restrict__ 
     const int64_t base = row_start[v] + deg[v];
     int P = 64;
     while (P < L) P <<= 1;
-    for (int i = lane; i < P; i += 32)
-      s[i] = i < L ? (((unsigned long long)adj_eid[base + i] << 32) | (uint32_t)adj_src[base + i]) : ~0ull;
+    for (int i = lane; i < P; i += 32) s[i] = i < L ? adj[base + i] : ~0ull;
     __syncwarp();
     for (int k = 2; k <= P; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = lane; i < P; i += 32) bitonic_step(s, i, j, k);
         __syncwarp();
       }
-    for (int i = lane; i < L; i += 32) {
-      adj_eid[base + i] = (uint32_t)(s[i] >> 32);
-      adj_src[base + i] = (int32_t)(uint32_t)s[i];
-    }
+    for (int i = lane; i < L; i += 32) adj[base + i] = s[i];
     __syncwarp();
     if (lane == 0) deg[v] += L;
   }
@@ -222,8 +215,7 @@ __global__ void __launch_bounds__(kBlock) k_fix_med(const int32_t* __restrict__ 
 // long tails (hub rows in a big batch): a whole CTA orders the tail
 __global__ void __launch_bounds__(1024) k_fix_big(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
                                                   const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
-                                                  int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid,
-                                                  int32_t* __restrict__ scr_src, uint32_t* __restrict__ scr_eid,
+                                                  unsigned long long* __restrict__ adj, unsigned long long* __restrict__ scr,
                                                   const int32_t* __restrict__ large, GraphCtl* ctl) {
   extern __shared__ unsigned long long bk[];      // kBigTail keys
   __shared__ unsigned long long s_off;
@@ -236,30 +228,25 @@ __global__ void __launch_bounds__(1024) k_fix_big(const int32_t* __restrict__ to
     if (L <= kBigTail) {
       int P = 1024;
       while (P < L) P <<= 1;
-      for (int i = threadIdx.x; i < P; i += blockDim.x)
-        bk[i] = i < L ? (((unsigned long long)adj_eid[base + i] << 32) | (uint32_t)adj_src[base + i]) : ~0ull;
+      for (int i = threadIdx.x; i < P; i += blockDim.x) bk[i] = i < L ? adj[base + i] : ~0ull;
       __syncthreads();
       for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
           for (int i = threadIdx.x; i < P; i += blockDim.x) bitonic_step(bk, i, j, k);
           __syncthreads();
         }
-      for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        adj_eid[base + i] = (uint32_t)(bk[i] >> 32);
-        adj_src[base + i] = (int32_t)(uint32_t)bk[i];
-      }
+      for (int i = threadIdx.x; i < L; i += blockDim.x) adj[base + i] = bk[i];
     } else {
       if (threadIdx.x == 0) s_off = atomicAdd(&ctl->scratch_top, (unsigned long long)L);
       __syncthreads();
       const unsigned long long off = s_off;
-      for (int i = threadIdx.x; i < L; i += blockDim.x) { scr_eid[off + i] = adj_eid[base + i]; scr_src[off + i] = adj_src[base + i]; }
+      for (int i = threadIdx.x; i < L; i += blockDim.x) scr[off + i] = adj[base + i];
       __syncthreads();
       for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        const uint32_t e = scr_eid[off + i];
+        const unsigned long long e = scr[off + i];
         int rank = 0;
-        for (int j = 0; j < L; ++j) rank += scr_eid[off + j] < e ? 1 : 0;
-        adj_eid[base + rank] = e;
-        adj_src[base + rank] = scr_src[off + i];
+        for (int j = 0; j < L; ++j) rank += scr[off + j] < e ? 1 : 0;
+        adj[base + rank] = e;
       }
     }
     __syncthreads();
@@ -276,15 +263,14 @@ __global__ void __launch_bounds__(kBlock) k_newcap(const int32_t* __restrict__ d
 }
 
 __global__ void __launch_bounds__(kBlock) k_move_rows(const int64_t* __restrict__ old_start, const int64_t* __restrict__ new_start,
-                                                      const int32_t* __restrict__ deg, const int32_t* __restrict__ old_src,
-                                                      const uint32_t* __restrict__ old_eid, int32_t* __restrict__ new_src,
-                                                      uint32_t* __restrict__ new_eid, int64_t n) {
+                                                      const int32_t* __restrict__ deg, const unsigned long long* __restrict__ old_adj,
+                                                      unsigned long long* __restrict__ new_adj, int64_t n) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n; v += warps) {
     const int d = deg[v];
     const int64_t a = old_start[v], b = new_start[v];
-    for (int i = lane; i < d; i += 32) { new_src[b + i] = old_src[a + i]; new_eid[b + i] = old_eid[a + i]; }
+    for (int i = lane; i < d; i += 32) new_adj[b + i] = old_adj[a + i];
   }
 }
 
@@ -294,7 +280,7 @@ __global__ void __launch_bounds__(kBlock) k_deg64(const int32_t* __restrict__ de
 }
 
 __global__ void __launch_bounds__(kBlock) k_export_rows(const int64_t* __restrict__ row_start, const int32_t* __restrict__ deg,
-                                                        const int32_t* __restrict__ adj_src, const uint32_t* __restrict__ adj_eid,
+                                                        const unsigned long long* __restrict__ adj,
                                                         const int64_t* __restrict__ indptr, int64_t* __restrict__ indices,
                                                         int64_t* __restrict__ eids, int64_t n) {
   const int lane = threadIdx.x & 31;
@@ -303,8 +289,9 @@ __global__ void __launch_bounds__(kBlock) k_export_rows(const int64_t* __restric
     const int d = deg[v];
     const int64_t a = row_start[v], b = indptr[v];
     for (int i = lane; i < d; i += 32) {
-      indices[b + i] = adj_src[a + i];
-      if (eids) eids[b + i] = adj_eid[a + i];
+      const unsigned long long ent = adj[a + i];
+      indices[b + i] = (int64_t)(uint32_t)ent;
+      if (eids) eids[b + i] = (int64_t)(ent >> 32);
     }
   }
 }
@@ -337,7 +324,7 @@ __global__ void __launch_bounds__(kBlock) k_prefix_count(const int64_t* __restri
 
 __global__ void __launch_bounds__(kBlock) k_prefix_fill(const int64_t* __restrict__ p_indptr, const int32_t* __restrict__ p_indices,
                                                         const uint32_t* __restrict__ p_eids, const int64_t* __restrict__ row_start,
-                                                        int32_t* __restrict__ adj_src, uint32_t* __restrict__ adj_eid, int64_t n_active) {
+                                                        unsigned long long* __restrict__ adj, int64_t n_active) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n_active; v += warps) {
@@ -350,8 +337,7 @@ __global__ void __launch_bounds__(kBlock) k_prefix_fill(const int64_t* __restric
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if (keep) {
         const int64_t at = out + __popc(m & ((1u << lane) - 1));
-        adj_src[at] = u;
-        adj_eid[at] = p_eids[i];
+        adj[at] = ((unsigned long long)p_eids[i] << 32) | (uint32_t)u;
       }
       out += __popc(m);
     }
@@ -369,15 +355,13 @@ struct ogl_graph {
   int64_t batch_cap = 0;   // stream edges per internal chunk
   int64_t* row_start = nullptr;
   int32_t *deg = nullptr, *cap = nullptr, *add = nullptr;
-  int32_t* adj_src = nullptr;
-  uint32_t* adj_eid = nullptr;
+  unsigned long long* adj = nullptr;     // (eid << 32) | src
   GraphCtl* ctl = nullptr;
   GraphCtl* h_ctl = nullptr;     // pinned mirror
   int32_t *touched = nullptr, *tail_len = nullptr, *large = nullptr, *med = nullptr;
   ogl::MoveJob* jobs = nullptr;
   int* n_jobs = nullptr;
-  int32_t* scr_src = nullptr;
-  uint32_t* scr_eid = nullptr;
+  unsigned long long* scr = nullptr;
   int64_t *stage_src = nullptr, *stage_dst = nullptr;   // host-insert staging
   int32_t* newcap = nullptr;
   int64_t* scan_scratch = nullptr;
@@ -394,8 +378,7 @@ struct ogl_graph {
 
 static int graph_alloc_pool(ogl_graph* g, int64_t cap) {
   g->generation++;
-  OGL_CUDA(cudaMalloc(&g->adj_src, sizeof(int32_t) * (size_t)cap));
-  OGL_CUDA(cudaMalloc(&g->adj_eid, sizeof(uint32_t) * (size_t)cap));
+  OGL_CUDA(cudaMalloc(&g->adj, sizeof(unsigned long long) * (size_t)cap));
   g->pool_cap = cap;
   return OGL_OK;
 }
@@ -424,8 +407,7 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
   A(g->med, sizeof(int32_t) * (2 * g->batch_cap / 32 + 64));
   A(g->jobs, sizeof(MoveJob) * ((v_cap < 2 * g->batch_cap ? v_cap : 2 * g->batch_cap) + 64));   // <= one job per touched row
   A(g->n_jobs, sizeof(int));
-  A(g->scr_src, sizeof(int32_t) * 2 * g->batch_cap);
-  A(g->scr_eid, sizeof(uint32_t) * 2 * g->batch_cap);
+  A(g->scr, sizeof(unsigned long long) * 2 * g->batch_cap);
   A(g->stage_src, sizeof(int64_t) * g->batch_cap);
   A(g->stage_dst, sizeof(int64_t) * g->batch_cap);
   A(g->scan_scratch, sizeof(int64_t) * scan_scratch_elems(v_cap + 1));
@@ -444,8 +426,8 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
 
 extern "C" int ogl_graph_destroy(ogl_graph* g) {
   if (!g) return OGL_OK;
-  void* ptrs[] = {g->row_start, g->deg, g->cap, g->add, g->adj_src, g->adj_eid, g->ctl, g->touched, g->tail_len, g->large, g->med, g->jobs, g->n_jobs,
-                  g->scr_src, g->scr_eid, g->stage_src, g->stage_dst, g->newcap, g->scan_scratch, g->total_dev, g->new_start,
+  void* ptrs[] = {g->row_start, g->deg, g->cap, g->add, g->adj, g->ctl, g->touched, g->tail_len, g->large, g->med, g->jobs, g->n_jobs,
+                  g->scr, g->stage_src, g->stage_dst, g->newcap, g->scan_scratch, g->total_dev, g->new_start,
                   g->p_indptr, g->p_indices, g->p_eids};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (g->h_ctl) cudaFreeHost(g->h_ctl);
@@ -473,18 +455,15 @@ static int graph_rebuild_pool(ogl_graph* g, int64_t extra, cudaStream_t s) {
   OGL_CUDA(cudaStreamSynchronize(s));
   int64_t want = total + total / 2 + extra + 1024;
   if (want < g->pool_cap) want = g->pool_cap;
-  int32_t* old_src = g->adj_src;
-  uint32_t* old_eid = g->adj_eid;
+  unsigned long long* old_adj = g->adj;
   OGL_TRY(graph_alloc_pool(g, want));
-  OGL_LAUNCH(k_move_rows, grid_for(V * 32, kBlock), kBlock, 0, s, g->row_start, g->new_start, g->deg, old_src, old_eid,
-             g->adj_src, g->adj_eid, V);
+  OGL_LAUNCH(k_move_rows, grid_for(V * 32, kBlock), kBlock, 0, s, g->row_start, g->new_start, g->deg, old_adj, g->adj, V);
   OGL_CUDA(cudaMemcpyAsync(g->row_start, g->new_start, sizeof(int64_t) * V, cudaMemcpyDeviceToDevice, s));
   OGL_CUDA(cudaMemcpyAsync(g->cap, g->newcap, sizeof(int32_t) * V, cudaMemcpyDeviceToDevice, s));
   unsigned long long top = (unsigned long long)total;
   OGL_CUDA(cudaMemcpyAsync(&g->ctl->pool_top, &top, sizeof(top), cudaMemcpyHostToDevice, s));
   OGL_CUDA(cudaStreamSynchronize(s));
-  cudaFree(old_src);
-  cudaFree(old_eid);
+  cudaFree(old_adj);
   g->pool_used_host = total;
   g->compactions++;
   return OGL_OK;
@@ -515,16 +494,16 @@ static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_
   const int nt = g->h_ctl->n_touched;
   const int wgrid = grid_for((int64_t)nt * 32, kBlock);
   OGL_CUDA(cudaMemsetAsync(g->n_jobs, 0, sizeof(int), s));
-  OGL_LAUNCH(k_reserve, wgrid, kBlock, 0, s, g->touched, g->add, g->row_start, g->deg, g->cap, g->tail_len, g->adj_src, g->adj_eid, g->jobs,
+  OGL_LAUNCH(k_reserve, wgrid, kBlock, 0, s, g->touched, g->add, g->row_start, g->deg, g->cap, g->tail_len, g->adj, g->jobs,
              g->n_jobs, g->ctl);
-  OGL_LAUNCH(k_move_big, sm_count() * 4, kBlock, 0, s, g->jobs, g->n_jobs, g->adj_src, g->adj_eid);
-  OGL_LAUNCH(k_place, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->row_start, g->deg, g->adj_src, g->adj_eid,
+  OGL_LAUNCH(k_move_big, sm_count() * 4, kBlock, 0, s, g->jobs, g->n_jobs, g->adj);
+  OGL_LAUNCH(k_place, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->row_start, g->deg, g->adj,
              (uint32_t)g->n_edges, g->n_vertices);
-  OGL_LAUNCH(k_fix, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid, g->med, g->large, g->ctl);
-  OGL_LAUNCH(k_fix_med, grid_for((int64_t)nt * 4, kBlock, 4), kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj_src, g->adj_eid,
+  OGL_LAUNCH(k_fix, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj, g->med, g->large, g->ctl);
+  OGL_LAUNCH(k_fix_med, grid_for((int64_t)nt * 4, kBlock, 4), kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj,
              g->med, g->ctl);
   OGL_LAUNCH(k_fix_big, sm_count() * 2, 1024, kBigTail * sizeof(unsigned long long), s, g->touched, g->tail_len, g->row_start, g->deg,
-             g->adj_src, g->adj_eid, g->scr_src, g->scr_eid, g->large, g->ctl);
+             g->adj, g->scr, g->large, g->ctl);
   g->n_edges += tot;
   return OGL_OK;
 }
@@ -583,7 +562,7 @@ extern "C" int ogl_graph_export_csr(ogl_graph* g, int64_t* indptr_dev, int64_t* 
   OGL_TRY(exclusive_scan_i32_to_i64(g->deg, indptr_dev, V, g->scan_scratch, g->total_dev, s));
   OGL_LAUNCH(k_set_last, 1, 1, 0, s, indptr_dev, g->total_dev, V);
   if (V > 0 && g->n_edges > 0)
-    OGL_LAUNCH(k_export_rows, grid_for(V * 32, kBlock), kBlock, 0, s, g->row_start, g->deg, g->adj_src, g->adj_eid, indptr_dev,
+    OGL_LAUNCH(k_export_rows, grid_for(V * 32, kBlock), kBlock, 0, s, g->row_start, g->deg, g->adj, indptr_dev,
                indices_dev, eids_dev, V);
   return OGL_OK;
 }
@@ -606,7 +585,7 @@ extern "C" int ogl_graph_load_parent(ogl_graph* g, const int64_t* indptr_dev, co
   OGL_CUDA(cudaStreamSynchronize(s));
   OGL_ARG(e >= 0 && e <= 0xffffffffLL, "ogl_graph_load_parent: bad edge count");
   if (e > g->pool_cap) {
-    cudaFree(g->adj_src); cudaFree(g->adj_eid);
+    cudaFree(g->adj);
     OGL_TRY(graph_alloc_pool(g, e + 1024));
   }
   OGL_CUDA(cudaMalloc(&g->p_indptr, sizeof(int64_t) * (n_vertices + 1)));
@@ -629,7 +608,7 @@ extern "C" int ogl_graph_set_active_prefix(ogl_graph* g, int64_t n_active, void*
   OGL_TRY(exclusive_scan_i32_to_i64(g->deg, g->row_start, V, g->scan_scratch, g->total_dev, s));
   if (n_active > 0)
     OGL_LAUNCH(k_prefix_fill, grid_for(n_active * 32, kBlock), kBlock, 0, s, g->p_indptr, g->p_indices, g->p_eids, g->row_start,
-               g->adj_src, g->adj_eid, n_active);
+               g->adj, n_active);
   int64_t total = 0;
   OGL_CUDA(cudaMemcpyAsync(&total, g->total_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   OGL_CUDA(cudaStreamSynchronize(s));
@@ -642,7 +621,7 @@ namespace ogl {
 uint64_t graph_generation(const ogl_graph* g) { return g->generation; }
 GraphView graph_view(const ogl_graph* g) {
   GraphView v;
-  v.row_start = g->row_start; v.deg = g->deg; v.adj_src = g->adj_src; v.adj_eid = g->adj_eid; v.n_vertices = g->n_vertices;
+  v.row_start = g->row_start; v.deg = g->deg; v.adj = g->adj; v.n_vertices = g->n_vertices;
   return v;
 }
 }  // namespace ogl

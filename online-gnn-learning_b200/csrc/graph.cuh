@@ -19,8 +19,7 @@ struct GraphCtl {
 struct GraphView {
   const int64_t* row_start;
   const int32_t* deg;
-  const int32_t* adj_src;
-  const uint32_t* adj_eid;
+  const unsigned long long* adj;   // (edge id << 32) | source vertex
   int64_t n_vertices;
 };
 

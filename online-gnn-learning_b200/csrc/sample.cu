@@ -31,8 +31,9 @@ __global__ void __launch_bounds__(kBlock) k_sample(GraphView g, const int32_t* _
         const int64_t o = (int64_t)row * fanout + j;
         if (deg > 0) {
           const uint32_t r = __umulhi(pick4(w, i), (uint32_t)deg);
-          out_src[o] = g.adj_src[start + r];
-          if (out_eid) out_eid[o] = (int64_t)g.adj_eid[start + r];
+          const unsigned long long ent = __ldg(g.adj + start + r);      // one 8-byte entry: source + edge id in one sector
+          out_src[o] = (int32_t)(uint32_t)ent;
+          if (out_eid) out_eid[o] = (int64_t)(ent >> 32);
         } else {
           out_src[o] = -1;
           if (out_eid) out_eid[o] = -1;
