@@ -400,7 +400,9 @@ extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_d
   OGL_LAUNCH(k_set_i32, 1, 1, 0, s, p->counts, n_seeds);
   for (int h = 0; h < p->L; ++h) {
     STAGE(nm("sample.h%d", h).c_str(), sample_hop(gv, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->cfg.seed, p->ctl, 0,
-                                                  (uint32_t)h, p->edge_gsrc[h], p->edge_eid[h], s));
+                                                  (uint32_t)h, p->edge_gsrc[h],
+                                                  p->in_train_step ? nullptr : p->edge_eid[h],   // edge ids: only the DGL-style block API reads them
+                                                  s));
     STAGE(nm("to_block.h%d", h).c_str(), to_block(&p->tb, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->edge_gsrc[h],
                                                   p->nodes[h + 1], p->counts + h + 1, p->nmax[h + 1], p->edge_lid[h], s));
     // reverse edge lists (only the backward pass reads them): inside the fused train step they are built on the side

@@ -120,18 +120,38 @@ __global__ void __launch_bounds__(kBlock) k_pool_bwd(const T* __restrict__ dng, 
     for (int i = 0; i < NV; ++i) sum[i] = 0.f;
     if (r < n) {
       const int e0 = __ldg(rev_ptr + r), e1 = __ldg(rev_ptr + r + 1);
-      for (int k = e0; k < e1; ++k) {
-        const int e = __ldg(rev_edge + k);
-        const int d = e / fanout, j = e - d * fanout;
+      // the list walk is a chain of dependent loads (offset -> edge -> rows): two edges are kept in flight at a time
+      auto fetch = [&](int e, uint4& graw, uint8_t (&sl)[NV], int& j) {
+        const int d = e / fanout;
+        j = e - d * fanout;
         const int64_t at = (int64_t)d * pitch + strip * NV;
-        const uint4 graw = __ldg(reinterpret_cast<const uint4*>(dng + at));
-        const T* gv = reinterpret_cast<const T*>(&graw);
-        uint8_t sl[NV];
+        graw = __ldg(reinterpret_cast<const uint4*>(dng + at));
         if (NV == 8) *reinterpret_cast<uint2*>(sl) = __ldg(reinterpret_cast<const uint2*>(arg + at));
         else *reinterpret_cast<uint32_t*>(sl) = __ldg(reinterpret_cast<const uint32_t*>(arg + at));
+      };
+      auto add = [&](const uint4& graw, const uint8_t (&sl)[NV], int j) {
+        const T* gv = reinterpret_cast<const T*>(&graw);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
           if (sl[i] == j) sum[i] += to_f32<T>(gv[i]);
+      };
+      int k = e0;
+      for (; k + 1 < e1; k += 2) {
+        const int ea = __ldg(rev_edge + k), eb = __ldg(rev_edge + k + 1);
+        uint4 ga, gb;
+        uint8_t sa[NV], sb[NV];
+        int ja, jb;
+        fetch(ea, ga, sa, ja);
+        fetch(eb, gb, sb, jb);
+        add(ga, sa, ja);
+        add(gb, sb, jb);
+      }
+      if (k < e1) {
+        uint4 ga;
+        uint8_t sa[NV];
+        int ja;
+        fetch(__ldg(rev_edge + k), ga, sa, ja);
+        add(ga, sa, ja);
       }
     }
     T o[NV];
