@@ -215,6 +215,8 @@ def stage_bytes(stage, w, lv, es=2):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 per rank; the other ranks have exited, so rank 0 takes every host core
+    torch.set_num_threads(os.cpu_count() or 1)
     w = WORKLOADS[args.workload]
     torch.manual_seed(0)
     t_setup = time.time()
@@ -583,6 +585,7 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if host_csr is not None:
+        torch.set_num_threads(os.cpu_count() or 1)
         path = CpuPath(w, host_csr[0], host_csr[1], feats_host, labels_host, params)
         cb = seed_batches(w, args.cpu_steps + 1, 0, 1, seed=5)
         el = time_cpu(path, cb, 1)

@@ -251,6 +251,12 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     if (n > cfg->v_cap) n = cfg->v_cap;
     p->nmax[h + 1] = (int)n;
   }
+  for (int h = 0; h < L; ++h)
+    if (p->nmax[h] >= (1 << 23)) {
+      set_error("ogl_plan_create: level %d may hold %d destination rows; the packed reverse edge entries allow < 2^23", h, p->nmax[h]);
+      delete p;
+      return OGL_ERR_ARG;
+    }
   p->nodes.resize(L + 1); p->act.resize(L + 1);
   p->edge_lid.resize(L); p->edge_gsrc.resize(L); p->edge_eid.resize(L); p->layer.resize(L);
   p->rev_ptr.resize(L); p->rev_edge.resize(L);

@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(kBlock) k_pool_bwd(const T* __restrict__ dng, 
       const int e0 = __ldg(rev_ptr + r), e1 = __ldg(rev_ptr + r + 1);
       // the list walk is a chain of dependent loads (offset -> edge -> rows): two edges are kept in flight at a time
       auto fetch = [&](int e, uint4& graw, uint8_t (&sl)[NV], int& j) {
-        const int d = e / fanout;
-        j = e - d * fanout;
+        const int d = e >> 8;                      // entry = (destination row << 8) | slot
+        j = e & 255;
         const int64_t at = (int64_t)d * pitch + strip * NV;
         graw = __ldg(reinterpret_cast<const uint4*>(dng + at));
         if (NV == 8) *reinterpret_cast<uint2*>(sl) = __ldg(reinterpret_cast<const uint2*>(arg + at));

@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(kBlock) k_rev_fill(const int32_t* __restrict__
   const int64_t ne = (int64_t)min(*n_dst_dev, n_dst_max) * fanout;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ne; p += (int64_t)gridDim.x * blockDim.x) {
     const int lid = edge_lid[p];
-    if (lid >= 0) rev_edge[rev_ptr[lid] + atomicAdd(&cursor[lid], 1)] = (int32_t)p;
+    // entry = (destination row << 8) | slot: the consumer (k_pool_bwd) then needs no division per column strip
+    if (lid >= 0) rev_edge[rev_ptr[lid] + atomicAdd(&cursor[lid], 1)] = (int32_t)(((p / fanout) << 8) | (p % fanout));
   }
 }
 

@@ -27,7 +27,7 @@ int sample_hop(const GraphView& g, const int32_t* dst_nodes, const int32_t* n_ds
 int to_block(ToBlockWs* ws, const int32_t* dst_nodes, const int32_t* n_dst_dev, int n_dst_max, int fanout, const int32_t* picked,
              int32_t* src_nodes, int32_t* n_src_dev, int n_src_max, int32_t* edge_lid, cudaStream_t s);
 
-// reverse edge lists of a sampled block: rev_ptr[n_src_max + 1] (exclusive offsets), rev_edge[p] = slot index d * fanout + j
+// reverse edge lists of a sampled block: rev_ptr[n_src_max + 1] (exclusive offsets), rev_edge[k] = (destination row d << 8) | slot j   (fan-outs < 255, d < 2^23)
 int reverse_edges(ToBlockWs* ws, const int32_t* edge_lid, const int32_t* n_dst_dev, int n_dst_max, int fanout, int n_src_max,
                   int32_t* rev_ptr, int32_t* rev_edge, cudaStream_t s);
 
