@@ -13,9 +13,9 @@ from .graph.device_graph import DeviceGraph           # noqa: F401
 from .graph.train_test_graph import TrainTestGraph    # noqa: F401
 from .prioritized_replay.replay_buffer import PrioritizedReplayBuffer      # noqa: F401
 from .prioritized_replay.segment_tree import SumSegmentTree                # noqa: F401
-from .prioritized_replay.generate_priority import LossPriority             # noqa: F401
+from .prioritized_replay.generate_priority import LossPriority, TrendPriority, HybridPriority   # noqa: F401
 from .graphsage.pytorch.graphsage_dgl import GraphSAGE                      # noqa: F401
 
 __all__ = ["config", "native", "utils", "sampling", "parallel", "init", "Lib_supported", "DynamicGraph", "DynamicGraphEdge",
            "DynamicGraphVertex", "ParentGraph", "DeviceGraph", "TrainTestGraph", "PrioritizedReplayBuffer",
-           "SumSegmentTree", "LossPriority", "GraphSAGE", "kernel_launches"]
+           "SumSegmentTree", "LossPriority", "TrendPriority", "HybridPriority", "GraphSAGE", "kernel_launches"]

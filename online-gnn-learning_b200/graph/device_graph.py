@@ -49,6 +49,28 @@ class DeviceGraph:
     def to(self, device):
         return self
 
+    def predecessors(self, v):
+        """source vertices of the in-edges of `v`, in edge-id order (DGL `g.predecessors`; used by the reference's disabled
+        change-propagation code, train_test_graph.py:151-157)"""
+        indptr, indices, _ = self._csr_cache()
+        return indices[int(indptr[v]):int(indptr[v + 1])]
+
+    def in_degree(self, v):
+        indptr, _, _ = self._csr_cache()
+        return int(indptr[v + 1] - indptr[v])
+
+    def out_degree(self, v):
+        """out-degree == in-degree here: every stream of the reference is symmetrised (both directions are inserted,
+        dynamic_graph_edge.py:214-215 / dgl.from_networkx of an undirected graph)"""
+        return self.in_degree(v)
+
+    def _csr_cache(self):
+        key = (self.native.num_vertices, self.native.num_edges)
+        if getattr(self, "_csr_key", None) != key:
+            self._csr = tuple(t.cpu() for t in self.native.export_csr(with_eids=False)[:2]) + (None,)
+            self._csr_key = key
+        return self._csr
+
     def add_nodes(self, n, data=None):
         row0 = self.number_of_nodes()
         self.native.insert_vertices(n)

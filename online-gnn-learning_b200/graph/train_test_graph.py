@@ -67,6 +67,25 @@ class TrainTestGraph:
     def __len__(self):
         return len(self.temporal_graph)
 
+    def _get_affected_nodes(self, source_node, depth=2):
+        """{vertex: priority bump} of the vertices within `depth` in-hops of a changed vertex, each hop scaled by
+        1 / out_degree and `scale`, capped at 1 (mirror of train_test_graph.py:139-166; the reference's only caller is
+        commented out, so this is offered for completeness -- SURVEY 8(f)-4)."""
+        g = self.temporal_graph.get_graph()
+        nbrs = {source_node: 1 * self.scale}
+        for _ in range(depth):
+            tmp = {}
+            for k, v in nbrs.items():
+                for nbr in g.predecessors(k).tolist():
+                    w = (1 / g.out_degree(nbr)) * v * self.scale
+                    if nbr in tmp:
+                        tmp[nbr] = min(tmp[nbr] + w, 1)
+                    else:
+                        tmp[nbr] = w
+            for k, v in tmp.items():
+                nbrs[k] = max(nbrs[k], v) if k in nbrs else v
+        return nbrs
+
     def evolve(self):
         g = self.temporal_graph
         span = self.end_prior_alpha - self.start_prior_alpha

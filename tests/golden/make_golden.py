@@ -12,6 +12,7 @@ Outputs (all small .npz, committed):
   vertex_stream.npz   DynamicGraphVertex.build/evolve: active lists + both id maps
   train_test.npz      TrainTestGraph over the edge stream under random.seed(1) /
                       np.random.seed(1): train/test sets and RBR/PBR/new-node draws
+  priority_strategies.npz  TrendPriority / HybridPriority outputs over 12 batches
 """
 import os
 import io
@@ -206,8 +207,34 @@ def gen_train_test():
              final_train=final_train, final_test=final_test, final_priorities=pri)
 
 
+def gen_priority_strategies():
+    """TrendPriority / HybridPriority of the reference (generate_priority.py:11-58).  They use the removed `np.float` alias,
+    so it is restored for the duration of the call (numpy 2 in this container); nothing else is touched."""
+    import numpy
+    had = hasattr(numpy, "float")
+    if not had:
+        numpy.float = float
+    try:
+        from prioritized_replay import generate_priority as gp
+        rng = np.random.default_rng(11)
+        V = 60
+        trend, hybrid = gp.TrendPriority(V, alpha=0.85), gp.HybridPriority(V, alpha=0.7, loss_contrib=0.4)
+        nodes, losses, out_t, out_h = [], [], [], []
+        for step in range(12):
+            b = rng.permutation(V)[:16]
+            l = (rng.random(16) * 3).astype(np.float64)
+            nodes.append(b); losses.append(l)
+            out_t.append(np.array(trend.get_priorities(b.tolist(), l.copy()), dtype=np.float64))
+            out_h.append(np.array(hybrid.get_priorities(b.tolist(), l.copy()), dtype=np.float64))
+        np.savez(os.path.join(OUT, "priority_strategies.npz"), V=V, nodes=np.array(nodes), losses=np.array(losses),
+                 trend=np.array(out_t), hybrid=np.array(out_h), trend_avg=trend.avg, trend_values=trend.values)
+    finally:
+        if not had:
+            del numpy.float
+
+
 if __name__ == "__main__":
-    gen_tree(); gen_buffer(); gen_edge_stream(); gen_vertex_stream(); gen_train_test()
+    gen_tree(); gen_buffer(); gen_edge_stream(); gen_vertex_stream(); gen_train_test(); gen_priority_strategies()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

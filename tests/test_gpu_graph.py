@@ -183,3 +183,46 @@ def test_dynamic_graph_edge_mirror_matches_reference_fixture(golden):
     assert np.array_equal(got, g["feat"][:, 0])
     added, lab = dyn.get_added_vertices(3)
     assert np.array_equal(np.asarray(sorted(added)), g["added3_vertices"])
+
+
+def test_predecessors_and_change_propagation():
+    """DGL-style predecessors / out_degree on the device graph and the reference's (disabled) 2-hop priority bump"""
+    import ogl_b200
+    from ogl_b200.graph import train_test_graph as ttg
+    rng = np.random.default_rng(4)
+    V, E = 300, 900
+    src, dst = rng.integers(0, V, E), rng.integers(0, V, E)
+    m = np.full(V, -1)
+    order = {}
+    for a, b in zip(src.tolist(), dst.tolist()):
+        for w in (a, b):
+            order.setdefault(w, len(order))
+    perm = np.array(sorted(order, key=order.get))
+    m[perm] = np.arange(len(perm))
+    src, dst = m[src], m[dst]
+    Vn = len(perm)
+    dyn = ogl_b200.DynamicGraphEdge(1, set(range(Vn)))
+    dyn.build(np.zeros((Vn, 4), np.float32), np.zeros((Vn, 1), np.int64), edge_timestamps={"src": src, "dst": dst})
+    g = dyn.get_graph()
+    ip, ix, _ = in_csr(np.concatenate([src, dst]), np.concatenate([dst, src]), Vn)
+    for v in (0, 1, 17, Vn - 1):
+        assert g.predecessors(v).tolist() == ix[ip[v]:ip[v + 1]].tolist()
+        assert g.out_degree(v) == g.in_degree(v) == ip[v + 1] - ip[v]
+    old = ttg.SIZE_BUFFER
+    ttg.SIZE_BUFFER = 1 << 10
+    try:
+        tt = ttg.TrainTestGraph(dyn, split=0.15, start_prior_alpha=4, end_prior_alpha=50, scale=1, max_priority=10)
+        got = tt._get_affected_nodes(5, depth=2)
+    finally:
+        ttg.SIZE_BUFFER = old
+    # restatement of the reference loop over the oracle CSR
+    nbrs = {5: 1}
+    for _ in range(2):
+        tmp = {}
+        for k, val in nbrs.items():
+            for nb in ix[ip[k]:ip[k + 1]].tolist():
+                w = (1 / (ip[nb + 1] - ip[nb])) * val
+                tmp[nb] = min(tmp[nb] + w, 1) if nb in tmp else w
+        for k, val in tmp.items():
+            nbrs[k] = max(nbrs[k], val) if k in nbrs else val
+    assert got == nbrs

@@ -146,3 +146,17 @@ def test_utils_init_contract():
     m = ogl_b200.utils.sparse1d(5)
     m[np.array([1, 3])] = np.array([7, 9])
     assert m[3] == 9 and m[np.array([1, 0])].tolist() == [7, 0]
+
+
+def test_priority_strategies_match_reference(golden):
+    """TrendPriority / HybridPriority vs the reference's own classes (fixture recorded with np.float restored)"""
+    from ogl_b200.prioritized_replay.generate_priority import TrendPriority, HybridPriority, LossPriority
+    g = golden("priority_strategies")
+    V = int(g["V"])
+    trend, hybrid = TrendPriority(V, alpha=0.85), HybridPriority(V, alpha=0.7, loss_contrib=0.4)
+    for b, l, rt, rh in zip(g["nodes"], g["losses"], g["trend"], g["hybrid"]):
+        assert np.array_equal(trend.get_priorities(b.tolist(), l.copy()), rt)
+        assert np.array_equal(hybrid.get_priorities(b.tolist(), l.copy()), rh)
+    assert trend.avg == float(g["trend_avg"]) and np.array_equal(trend.values, g["trend_values"])
+    x = np.arange(3.0)
+    assert LossPriority().get_priorities([0, 1, 2], x) is x

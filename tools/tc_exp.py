@@ -4,9 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ogl_b200 import native
 
-m, n, k = 89000, 602, 602
-a = torch.randn(m, 608, device="cuda").bfloat16()
-b = (torch.randn(n, 608, device="cuda") * 0.05).bfloat16()
+m, n, k = 89000, int(os.environ.get("EXP_N", "602")), int(os.environ.get("EXP_K", "602"))
+ldk = (k + 7) // 8 * 8
+a = torch.randn(m, ldk, device="cuda").bfloat16()
+b = (torch.randn(n, ldk, device="cuda") * 0.05).bfloat16()
 bias = torch.randn(n, device="cuda")
 ref = torch.relu(a[:, :k].float() @ b[:, :k].float().t() + bias)
 
