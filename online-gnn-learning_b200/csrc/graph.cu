@@ -66,8 +66,11 @@ __global__ void __launch_bounds__(kBlock) k_need(const int32_t* __restrict__ tou
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(&ctl->need, local);
 }
 
-// relocate rows without enough slack: one warp per touched row claims the new space and copies short rows; long rows
-// are queued and copied by all CTAs of k_move_big together (a hub row of 10^5 entries must not hang on one warp)
+// relocate rows without enough slack.  One THREAD per touched row claims the new space; rows of <= kThreadCopyMax
+// entries (the overwhelming majority in a sparse batch) are copied by that thread, longer rows are queued: one warp
+// per job up to kWarpCopyMax entries, all CTAs together beyond (a hub row of 10^5 entries must not hang on one warp).
+// The global relocation counter and the job queue are updated once per warp / per job, not once per row.
+constexpr int kThreadCopyMax = 16;
 constexpr int kWarpCopyMax = 2048;
 struct MoveJob { long long from, to; int len; int pad; };
 
@@ -75,40 +78,49 @@ __global__ void __launch_bounds__(kBlock) k_reserve(const int32_t* __restrict__ 
                                                     int64_t* __restrict__ row_start, const int32_t* __restrict__ deg,
                                                     int32_t* __restrict__ cap, int32_t* __restrict__ tail_len,
                                                     unsigned long long* __restrict__ adj, MoveJob* __restrict__ jobs,
-                                                    int* __restrict__ n_jobs, GraphCtl* ctl) {
+                                                    int* __restrict__ n_jobs, int jobs_cap, GraphCtl* ctl) {
   const int nt = ctl->n_touched;
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nt; t += warps) {
-    const int v = touched[t];
-    const int a = add[v], d = deg[v];
-    if (lane == 0) tail_len[t] = a;
-    const int need = d + a;
-    if (need > cap[v]) {
-      const int nc = grow_cap(need);
-      unsigned long long off = 0;
-      if (lane == 0) {
-        off = atomicAdd(&ctl->pool_top, (unsigned long long)nc);
-        atomicAdd(&ctl->relocations, 1ULL);
+  for (int t0 = blockIdx.x * blockDim.x; t0 < nt; t0 += gridDim.x * blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    bool moved = false;
+    if (t < nt) {
+      const int v = touched[t];
+      const int a = add[v], d = deg[v];
+      tail_len[t] = a;
+      const int need = d + a;
+      if (need > cap[v]) {
+        moved = true;
+        const int nc = grow_cap(need);
+        const unsigned long long off = atomicAdd(&ctl->pool_top, (unsigned long long)nc);
+        const int64_t old = row_start[v];
+        if (d <= kThreadCopyMax) {
+          for (int i = 0; i < d; ++i) adj[off + i] = adj[old + i];
+        } else if (d <= kWarpCopyMax) {
+          jobs[atomicAdd(n_jobs, 1)] = MoveJob{(long long)old, (long long)off, d, 0};                 // warp jobs: from the front
+        } else {
+          jobs[jobs_cap - 1 - atomicAdd(n_jobs + 1, 1)] = MoveJob{(long long)old, (long long)off, d, 0};   // big jobs: from the back
+        }
+        row_start[v] = (int64_t)off;
+        cap[v] = nc;
       }
-      off = __shfl_sync(0xffffffffu, off, 0);
-      const int64_t old = row_start[v];
-      if (d <= kWarpCopyMax) {
-        for (int i = lane; i < d; i += 32) adj[off + i] = adj[old + i];
-      } else if (lane == 0) {
-        jobs[atomicAdd(n_jobs, 1)] = MoveJob{(long long)old, (long long)off, d, 0};
-      }
-      __syncwarp();
-      if (lane == 0) { row_start[v] = (int64_t)off; cap[v] = nc; }
     }
+    const unsigned m = __ballot_sync(0xffffffffu, moved);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ctl->relocations, (unsigned long long)__popc(m));
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_move_big(const MoveJob* __restrict__ jobs, const int* __restrict__ n_jobs,
-                                                     unsigned long long* __restrict__ adj) {
-  const int nj = *n_jobs;
-  for (int q = 0; q < nj; ++q) {
+// queued row copies: warp jobs (front of the queue) go one per warp, big jobs (back of the queue) are swept by every CTA
+__global__ void __launch_bounds__(kBlock) k_move_jobs(const MoveJob* __restrict__ jobs, const int* __restrict__ n_jobs, int jobs_cap,
+                                                      unsigned long long* __restrict__ adj) {
+  const int nw = n_jobs[0], nb = n_jobs[1];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nw; q += warps) {
     const MoveJob j = jobs[q];
+    for (int i = lane; i < j.len; i += 32) adj[j.to + i] = adj[j.from + i];
+  }
+  for (int q = 0; q < nb; ++q) {
+    const MoveJob j = jobs[jobs_cap - 1 - q];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < j.len; i += (int64_t)gridDim.x * blockDim.x)
       adj[j.to + i] = adj[j.from + i];
   }
@@ -148,36 +160,49 @@ __device__ __forceinline__ void bitonic_step(unsigned long long* s, int i, int j
   }
 }
 
+// classification, one THREAD per touched row: tails of 0 / 1 edges need no ordering (the common case in a sparse
+// batch) and are finalised here; longer tails are queued by size class
 __global__ void __launch_bounds__(kBlock) k_fix(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
-                                                const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
-                                                unsigned long long* __restrict__ adj,
-                                                int32_t* __restrict__ med, int32_t* __restrict__ large, GraphCtl* ctl) {
+                                                int32_t* __restrict__ deg, int32_t* __restrict__ small, int32_t* __restrict__ med,
+                                                int32_t* __restrict__ large, GraphCtl* ctl) {
   const int nt = ctl->n_touched;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int L = tail_len[t];
+    if (L <= 1) {
+      if (L == 1) deg[touched[t]] += 1;
+    } else if (L <= 32) {
+      small[atomicAdd(&ctl->n_small, 1)] = t;
+    } else if (L <= kMedTail) {
+      med[atomicAdd(&ctl->n_med, 1)] = t;
+    } else {
+      large[atomicAdd(&ctl->n_large, 1)] = t;
+    }
+  }
+}
+
+// tails of 2..32 edges: one warp, rank by shuffles, in registers
+__global__ void __launch_bounds__(kBlock) k_fix_small(const int32_t* __restrict__ touched, const int32_t* __restrict__ tail_len,
+                                                      const int64_t* __restrict__ row_start, int32_t* __restrict__ deg,
+                                                      unsigned long long* __restrict__ adj, const int32_t* __restrict__ small,
+                                                      GraphCtl* ctl) {
+  const int ns = ctl->n_small;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nt; t += warps) {
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < ns; q += warps) {
+    const int t = small[q];
     const int v = touched[t];
     const int L = tail_len[t];
     const int64_t base = row_start[v] + deg[v];
-    if (L > 32) {
-      if (lane == 0) {
-        if (L <= kMedTail) med[atomicAdd(&ctl->n_med, 1)] = t;
-        else large[atomicAdd(&ctl->n_large, 1)] = t;
-      }
-      continue;
-    }
-    if (L >= 2) {
-      const unsigned long long ent = lane < L ? adj[base + lane] : ~0ull;
-      const uint32_t e = (uint32_t)(ent >> 32);
-      int rank = 0;
+    const unsigned long long ent = lane < L ? adj[base + lane] : ~0ull;
+    const uint32_t e = (uint32_t)(ent >> 32);
+    int rank = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        uint32_t ej = __shfl_sync(0xffffffffu, e, j);
-        rank += (j < L && ej < e) ? 1 : 0;
-      }
-      __syncwarp();
-      if (lane < L) adj[base + rank] = ent;
+    for (int j = 0; j < 32; ++j) {
+      uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+      rank += (j < L && ej < e) ? 1 : 0;
     }
+    __syncwarp();
+    if (lane < L) adj[base + rank] = ent;
     __syncwarp();
     if (lane == 0) deg[v] += L;
   }
@@ -358,9 +383,10 @@ struct ogl_graph {
   unsigned long long* adj = nullptr;     // (eid << 32) | src
   GraphCtl* ctl = nullptr;
   GraphCtl* h_ctl = nullptr;     // pinned mirror
-  int32_t *touched = nullptr, *tail_len = nullptr, *large = nullptr, *med = nullptr;
+  int32_t *touched = nullptr, *tail_len = nullptr, *large = nullptr, *med = nullptr, *small = nullptr;
   ogl::MoveJob* jobs = nullptr;
-  int* n_jobs = nullptr;
+  int* n_jobs = nullptr;               // [0] warp jobs (queue front), [1] big jobs (queue back)
+  int jobs_cap = 0;
   unsigned long long* scr = nullptr;
   int64_t *stage_src = nullptr, *stage_dst = nullptr;   // host-insert staging
   int32_t* newcap = nullptr;
@@ -405,8 +431,10 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
   A(g->tail_len, sizeof(int32_t) * 2 * g->batch_cap);
   A(g->large, sizeof(int32_t) * (2 * g->batch_cap / kMedTail + 64));
   A(g->med, sizeof(int32_t) * (2 * g->batch_cap / 32 + 64));
-  A(g->jobs, sizeof(MoveJob) * ((v_cap < 2 * g->batch_cap ? v_cap : 2 * g->batch_cap) + 64));   // <= one job per touched row
-  A(g->n_jobs, sizeof(int));
+  A(g->small, sizeof(int32_t) * (g->batch_cap + 64));              // tails of >= 2 edges: at most tot / 2 rows
+  g->jobs_cap = (int)((v_cap < 2 * g->batch_cap ? v_cap : 2 * g->batch_cap) + 64);   // <= one job per touched row
+  A(g->jobs, sizeof(MoveJob) * g->jobs_cap);
+  A(g->n_jobs, 2 * sizeof(int));
   A(g->scr, sizeof(unsigned long long) * 2 * g->batch_cap);
   A(g->stage_src, sizeof(int64_t) * g->batch_cap);
   A(g->stage_dst, sizeof(int64_t) * g->batch_cap);
@@ -426,7 +454,7 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
 
 extern "C" int ogl_graph_destroy(ogl_graph* g) {
   if (!g) return OGL_OK;
-  void* ptrs[] = {g->row_start, g->deg, g->cap, g->add, g->adj, g->ctl, g->touched, g->tail_len, g->large, g->med, g->jobs, g->n_jobs,
+  void* ptrs[] = {g->row_start, g->deg, g->cap, g->add, g->adj, g->ctl, g->touched, g->tail_len, g->large, g->med, g->small, g->jobs, g->n_jobs,
                   g->scr, g->stage_src, g->stage_dst, g->newcap, g->scan_scratch, g->total_dev, g->new_start,
                   g->p_indptr, g->p_indices, g->p_eids};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -493,13 +521,15 @@ static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_
   }
   const int nt = g->h_ctl->n_touched;
   const int wgrid = grid_for((int64_t)nt * 32, kBlock);
-  OGL_CUDA(cudaMemsetAsync(g->n_jobs, 0, sizeof(int), s));
-  OGL_LAUNCH(k_reserve, wgrid, kBlock, 0, s, g->touched, g->add, g->row_start, g->deg, g->cap, g->tail_len, g->adj, g->jobs,
-             g->n_jobs, g->ctl);
-  OGL_LAUNCH(k_move_big, sm_count() * 4, kBlock, 0, s, g->jobs, g->n_jobs, g->adj);
+  const int tgrid = grid_for(nt, kBlock);
+  OGL_CUDA(cudaMemsetAsync(g->n_jobs, 0, 2 * sizeof(int), s));
+  OGL_LAUNCH(k_reserve, tgrid, kBlock, 0, s, g->touched, g->add, g->row_start, g->deg, g->cap, g->tail_len, g->adj, g->jobs,
+             g->n_jobs, g->jobs_cap, g->ctl);
+  OGL_LAUNCH(k_move_jobs, sm_count() * 8, kBlock, 0, s, g->jobs, g->n_jobs, g->jobs_cap, g->adj);
   OGL_LAUNCH(k_place, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->row_start, g->deg, g->adj,
              (uint32_t)g->n_edges, g->n_vertices);
-  OGL_LAUNCH(k_fix, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj, g->med, g->large, g->ctl);
+  OGL_LAUNCH(k_fix, tgrid, kBlock, 0, s, g->touched, g->tail_len, g->deg, g->small, g->med, g->large, g->ctl);
+  OGL_LAUNCH(k_fix_small, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj, g->small, g->ctl);
   OGL_LAUNCH(k_fix_med, grid_for((int64_t)nt * 4, kBlock, 4), kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj,
              g->med, g->ctl);
   OGL_LAUNCH(k_fix_big, sm_count() * 2, 1024, kBigTail * sizeof(unsigned long long), s, g->touched, g->tail_len, g->row_start, g->deg,

@@ -12,6 +12,8 @@ struct GraphCtl {
   int bad_id;
   int n_large;                      // rows whose tail is ordered by a whole CTA
   int n_med;                        // rows whose tail is ordered by one warp in shared memory
+  int n_small;                      // rows whose tail (2..32 edges) is ordered by one warp in registers
+  int pad_;
   unsigned long long need;          // slots this batch takes from the pool top
   unsigned long long scratch_top;   // bump pointer into the tail-ordering scratch
 };
