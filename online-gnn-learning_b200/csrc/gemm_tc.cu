@@ -40,7 +40,9 @@ constexpr int STAGES2 = 6;
 constexpr int B2_STAGE_BYTES = (BN_MAX / 2) * BK * 2;    // 16 KB
 static_assert(STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) == RING_BYTES, "ring size mismatch");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
-constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int THREADS = 192;     // TN kernel: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
+constexpr int THREADS_NT = 320;  // NT kernel: the same roles with EIGHT epilogue warps (two per TMEM lane quarter, each taking
+                                 // every other 64-column box) so that draining a tile stays well below the tile's MMA time
 
 // ------------------------------------------------------------------ PTX wrappers ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,7 +89,7 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps (NT kernel)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -253,7 +255,7 @@ struct NtParams {
 // both halves, each CTA keeps the accumulator of its own rows in its own TMEM and runs its own epilogue.  Per CTA a
 // k-block then moves 32 KB instead of 48 KB through L2 -> SM, the limiter of the single-CTA kernel.
 template <int CG>
-__global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
+__global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
   constexpr int NST = CG == 2 ? STAGES2 : STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemLayout s = carve(smem_raw, NST, CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES);
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 4 * CG); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -381,8 +383,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
   } else {
     // ===== epilogue: TMEM -> registers -> bias / ReLU / mask -> swizzled smem box -> TMA store =====
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
+    const int parity = (warp - 2) >> 2;           // which of the two warps of that quarter: takes boxes box_idx % 2 == parity
     const int epi_tid = (warp - 2) * 32 + lane;
-    uint8_t* const stage_buf = s.store + (warp - 2) * 2 * STORE_BOX_BYTES;
+    uint8_t* const buf = s.store + (warp - 2) * STORE_BOX_BYTES;      // one staging box per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t boxes_issued = 0;
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
       const float relu_lo = p.relu ? 0.f : -INFINITY;
       // bias slice of this tile -> shared (broadcast reads below); double-buffered with the accumulator
       float* bias_s = s.bias + acc * BN_MAX;
-      for (int j = epi_tid; j < bn_tile; j += 128) {
+      for (int j = epi_tid; j < bn_tile; j += 256) {
         const int gn = nb * BN_MAX + j;
         float bv = 0.f;
         if (gn < p.n) {
@@ -411,10 +414,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
       if (p.debug & 1) {
         // nothing: measures the load + MMA pipeline alone
       } else if (p.out_bf16) {
-        for (int c0 = 0; c0 < bn_tile; c0 += 64) {
-          uint8_t* buf = stage_buf + (boxes_issued & 1) * STORE_BOX_BYTES;
-          if (boxes_issued >= 2) {                 // the store issued two boxes ago has finished reading this buffer
-            if (lane == 0) tma_store_wait_read<1>();
+        for (int c0 = parity * 64; c0 < bn_tile; c0 += 128) {
+          if (boxes_issued >= 1) {                 // this warp's previous store has finished reading the staging box
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
           }
           if (p.mask) {
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_nt_tc(const __grid_constant
           ++boxes_issued;
         }
       } else {
-        for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+        for (int c0 = parity * 32; c0 < bn_tile; c0 += 64) {
           uint32_t r[32];
           tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + c0), r);
           const int gn0 = nb * BN_MAX + c0;
@@ -796,7 +798,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(THREADS_NT);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr;
@@ -810,7 +812,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   }
   const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  OGL_LAUNCH(k_gemm_nt_tc<1>, grid, THREADS, SMEM_BYTES, s, p);
+  OGL_LAUNCH(k_gemm_nt_tc<1>, grid, THREADS_NT, SMEM_BYTES, s, p);
   return OGL_OK;
 }
 
