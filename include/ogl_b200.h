@@ -151,6 +151,11 @@ int ogl_plan_step_begin(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_
                         void* stream);
 int ogl_plan_step_finish(ogl_plan* p, ogl_features* f, float loss_scale, int do_step, float* per_vertex_loss_dev,
                          float* loss_sum_dev, void* stream);
+/* step_finish (without Adam) in two pieces for a bucketed gradient exchange: after _head every gradient except layer 0's
+ * fc_pool.weight (the first in*in floats of the flat buffer) is final; _tail computes that last one */
+int ogl_plan_step_finish_head(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
+                              void* stream);
+int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream);
 /* options: "cuda_graph" (default 1), "side_stream" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence
  * (re-captured when the graph pool, the handles, n_seeds or the output pointers change) */
 int ogl_plan_set_option(ogl_plan* p, const char* name, int value);

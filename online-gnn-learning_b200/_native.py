@@ -268,6 +268,18 @@ class Plan:
         check(lib.ogl_plan_step_finish(self._h, features._h, float(loss_scale), int(do_step), _ptr(per_vertex_out), _ptr(loss_sum_out),
                                        _stream()))
 
+    def step_finish_head(self, features, loss_scale, per_vertex_out=None, loss_sum_out=None):
+        """forward + loss + backward except the last weight-gradient GEMM (layer 0 fc_pool.weight)"""
+        check(lib.ogl_plan_step_finish_head(self._h, features._h, float(loss_scale), _ptr(per_vertex_out), _ptr(loss_sum_out), _stream()))
+
+    def step_finish_tail(self, features):
+        check(lib.ogl_plan_step_finish_tail(self._h, features._h, _stream()))
+
+    @property
+    def tail_params(self):
+        """number of leading floats of the flat gradient buffer that step_finish_tail produces (layer 0 fc_pool.weight)"""
+        return self.dims[0] * self.dims[0]
+
     def eval_step(self, graph, features, seeds, logits_out=None, per_vertex_out=None):
         n = seeds.numel()
         on_host = not seeds.is_cuda

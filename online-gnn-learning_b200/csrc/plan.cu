@@ -137,6 +137,8 @@ struct ogl_plan {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int skip_gather = 0;                   // step_finish: the input rows were already gathered by step_begin
+  int tail_mode = 0;                     // backward: 0 = all, 1 = everything but the last weight-gradient GEMM (layer 0 fc_pool),
+                                         // 2 = only that GEMM (data-parallel: its predecessors' gradients are already on the wire)
   int in_train_step = 0;                 // set by the fused train step: sampling may defer the reverse edge lists to the side stream
   int side_pending = 0;                  // side-stream work not yet joined into the main stream
   float* tn_partial2 = nullptr;          // split workspace of the side-stream TN GEMMs
@@ -148,7 +150,8 @@ struct ogl_plan {
     uint64_t g_gen;
     int n_seeds, do_step;
     float loss_scale;
-    int kind;            // 0 = whole step, 1 = step_begin (sample + gather), 2 = step_finish (forward .. Adam)
+    int kind;            // 0 = whole step, 1 = step_begin (sample + gather), 2 = step_finish (forward .. Adam),
+                         // 3 = step_finish minus the last weight-gradient GEMM, 4 = that GEMM
     bool operator==(const StepKey& o) const {
       return g == o.g && f == o.f && per == o.per && loss == o.loss && g_gen == o.g_gen && n_seeds == o.n_seeds && do_step == o.do_step &&
              loss_scale == o.loss_scale && kind == o.kind;
@@ -483,6 +486,16 @@ extern "C" int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_s
 
 static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
   const int L = p->L;
+  if (p->tail_mode == 2) {                        // only dWp of layer 0 = dhp^T x (dhp was left in place by the tail_mode 1 pass)
+    LayerBuf& lb = p->layer[0];
+    const int sl = L;
+    GemmTN tp;
+    tp.a = p->dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
+    tp.c = p->grads + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16;
+    tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
+    STAGE("l0.dW_pool", gemm_tn(p, tp, s));
+    return OGL_OK;
+  }
   OGL_TRY(join_side(p, s));                      // reverse edge lists built on the side stream during sampling
   for (int l = L - 1; l >= 0; --l) {
     LayerBuf& lb = p->layer[l];
@@ -522,7 +535,7 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     tp.a = p->dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
     tp.c = G + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16;
     tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
-    STAGE(nm("l%d.dW_pool", l).c_str(), gemm_tn(p, tp, s));
+    if (!(l == 0 && p->tail_mode == 1)) STAGE(nm("l%d.dW_pool", l).c_str(), gemm_tn(p, tp, s));
     if (l > 0) {
       // dpre[l-1] = relu'(act[src]) * ( dhp Wp + [dpre Ws on the first n_d rows] )
       LayerBuf& prev = p->layer[l - 1];
@@ -610,11 +623,20 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
     STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[p->L], p->counts + p->L, p->nmax[p->L], p->act[p->L], s));
     return join_side(p, s);                       // a captured graph must rejoin its forked stream
   }
-  p->skip_gather = (kind == 2);
+  if (kind == 4) {
+    p->tail_mode = 2;
+    const int rb = plan_backward_layers(p, s);
+    p->tail_mode = 0;
+    return rb;
+  }
+  p->skip_gather = (kind == 2 || kind == 3);
   const int rf = ogl_plan_forward(p, f, nullptr, s);
   p->skip_gather = 0;
   OGL_TRY(rf);
-  OGL_TRY(ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s));
+  p->tail_mode = (kind == 3) ? 1 : 0;
+  const int rl = ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s);
+  p->tail_mode = 0;
+  OGL_TRY(rl);
   if (do_step) OGL_TRY(ogl_plan_adam_step(p, s));
   OGL_TRY(bump(p->ctl, nullptr, s));
   return OGL_OK;
@@ -654,7 +676,7 @@ static int run_step(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_
   hit->last_use = ++p->graph_clock;
   OGL_CUDA(cudaGraphLaunch(hit->exec, s));
   p->graph_replays++;
-  if (kind != 2) p->n_seeds = n_seeds;
+  if (kind < 2) p->n_seeds = n_seeds;
   return OGL_OK;
 }
 
@@ -706,6 +728,26 @@ extern "C" int ogl_plan_step_begin(ogl_plan* p, ogl_graph* g, ogl_features* f, c
   cudaStream_t s = (cudaStream_t)stream;
   OGL_TRY(stage_step_seeds(p, seeds, n_seeds, seeds_on_host, s));
   return run_step(p, 1, g, f, n_seeds, 0.f, 0, nullptr, nullptr, s);
+}
+
+// step_finish in two pieces for bucketed gradient exchange: `head` leaves only the last weight-gradient GEMM (layer 0's
+// fc_pool.weight, the first parameter of the flat buffer) undone, `tail` runs it.  Every other gradient is final after
+// `head`, so its all-reduce can overlap `tail`.
+extern "C" int ogl_plan_step_finish_head(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
+                                         void* stream) {
+  OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish_head: no step begun / parameters not bound");
+  return run_step(p, 3, nullptr, f, p->n_seeds, loss_scale, 0, per_vertex_loss_dev, loss_sum_dev, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream) {
+  OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish_tail: no step begun / parameters not bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  OGL_TRY(run_step(p, 4, nullptr, f, p->n_seeds, 0.f, 0, nullptr, nullptr, s));
+  if (p->prof_on && p->prof_steps < kProfSteps) {
+    OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
+    p->prof_steps++;
+  }
+  return OGL_OK;
 }
 
 extern "C" int ogl_plan_step_finish(ogl_plan* p, ogl_features* f, float loss_scale, int do_step, float* per_vertex_loss_dev,

@@ -78,6 +78,7 @@ class Pipeline:
         self.w = world()
         self.comm = torch.cuda.Stream() if self.w > 1 else None
         self.ev_bwd = torch.cuda.Event()
+        self.ev_head = torch.cuda.Event()
         self.ev_adam = torch.cuda.Event()
         self._begun = False
         self._adam_pending = False
@@ -95,11 +96,19 @@ class Pipeline:
         else:
             if self._adam_pending:
                 main.wait_event(self.ev_adam)            # weights (and the gradient buffer) of the previous step are settled
-            self.plan.step_finish(self.features, self.scale, do_step=False, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
+            # two gradient buckets: everything except layer 0's fc_pool.weight is final before the last weight-gradient GEMM
+            # runs, so its all-reduce overlaps that GEMM; the small second bucket + Adam overlap the next sample + gather
+            n0 = self.plan.tail_params
+            self.plan.step_finish_head(self.features, self.scale, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
+            self.ev_head.record(main)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ev_head)
+                allreduce_grads(self.flat_grad[n0:])
+            self.plan.step_finish_tail(self.features)
             self.ev_bwd.record(main)
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(self.ev_bwd)
-                allreduce_grads(self.flat_grad)
+                allreduce_grads(self.flat_grad[:n0])
                 self.plan.adam_step()
                 self.ev_adam.record(self.comm)
             self._adam_pending = True

@@ -313,7 +313,7 @@ def test_cuda_graph_replay_equals_direct_launches():
 def test_step_begin_finish_equals_fused_step():
     """the two-call form used by the data-parallel pipeline (sample + gather | forward .. Adam) is the same step"""
     runs = []
-    for split in (False, True):
+    for split in (0, 1, 2):
         c = Case(dims=(64, 32, 5), fanouts=(6, 4), n_seeds=64, mode="bf16", gemm_impl=0)
         seeds_dev = torch.as_tensor(c.seeds).cuda()
         pinned = torch.as_tensor(c.seeds).pin_memory()
@@ -322,17 +322,24 @@ def test_step_begin_finish_equals_fused_step():
         outs = []
         for step in range(4):
             sd = pinned if step % 2 else seeds_dev          # host and device seed paths
-            if split:
+            if split == 1:
                 c.plan.step_begin(c.g, c.f, sd)
                 c.plan.step_finish(c.f, 1.0 / len(c.seeds), do_step=True, per_vertex_out=per, loss_sum_out=tot)
+            elif split == 2:                                 # bucketed form: head | tail (last weight-gradient GEMM) | Adam
+                c.plan.step_begin(c.g, c.f, sd)
+                c.plan.step_finish_head(c.f, 1.0 / len(c.seeds), per_vertex_out=per, loss_sum_out=tot)
+                assert c.plan.tail_params == 64 * 64
+                c.plan.step_finish_tail(c.f)
+                c.plan.adam_step()
             else:
                 c.plan.train_step(c.g, c.f, sd, loss_scale=1.0 / len(c.seeds), do_step=True, per_vertex_out=per, loss_sum_out=tot)
             outs.append(per.clone())
         torch.cuda.synchronize()
         runs.append((c.flat.clone(), outs))
-    close(runs[0][0], runs[1][0], 1e-4, "params fused vs begin/finish")
-    for a, b in zip(runs[0][1], runs[1][1]):
-        close(a, b, 1e-4, "per-vertex loss fused vs begin/finish")
+    for other in (1, 2):
+        close(runs[0][0], runs[other][0], 1e-4, "params fused vs split form %d" % other)
+        for a, b in zip(runs[0][1], runs[other][1]):
+            close(a, b, 1e-4, "per-vertex loss fused vs split form %d" % other)
 
 
 def test_multi_step_call_equals_single_steps():
