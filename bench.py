@@ -390,7 +390,8 @@ def aux_arxiv_vertex_stream(n_snapshots=20):
 def workload_config(w, name, world):
     return {"workload": "%s-shaped synthetic graph: V=%d, %d stream edges (%d directed), F=%d, C=%d, hidden %d, B=%d per GPU, fan-outs %s, "
                         "2-layer GraphSAGE-pool, Adam" % (name, w["V"], w["E"], 2 * w["E"], w["F"], w["C"], w["H"], w["B"], w["fanouts"]),
-            "global_batch": w["B"] * world, "parallelism": "dp%d (replicated graph+features, NCCL grad all-reduce + Adam on a comm stream overlapping the next step's sample+gather)" % world if world > 1 else "single GPU",
+            "global_batch": w["B"] * world, "parallelism": ("dp%d (replicated graph+features, bucketed NCCL grad all-reduce + Adam on a comm stream)" % world if world > 1 else "single GPU") +
+                           "; sample+gather of step t+1 prefetched (second buffer set, own stream) under forward/backward of step t",
             "l2": "inputs larger than L2: feature table %.0f MB + CSR %.0f MB resident, random row gathers; no explicit flush"
                   % (w["V"] * ((w["F"] + 7) // 8 * 8) * 2 / 1e6, 2 * w["E"] * 8 * 1.5 / 1e6)}
 
@@ -460,11 +461,12 @@ def run_ours(args, rank, world, local_rank):
         # local sample / forward / backward -> (N > 1: one NCCL all-reduce of the flat gradient) -> fused Adam
         ogl_b200.parallel.train_step(plan, g, fs, seeds, B * world, grad, loss_sum_out=loss_dev)
 
-    pipe = ogl_b200.parallel.Pipeline(plan, g, fs, grad, B * world) if world > 1 else None
+    pipe = ogl_b200.parallel.Pipeline(plan, g, fs, grad, B * world) if not args.no_pipeline else None
 
     def run_steps(inputs, read_back, losses):
-        """N = 1: one fused (graph-replayed) call per step.  N > 1: pipelined loop -- sample + gather of step t+1 overlap the
-        all-reduce + Adam of step t (ogl_b200.parallel.Pipeline)"""
+        """pipelined loop (ogl_b200.parallel.Pipeline): sample + gather of step t+1 (ogl_plan_prefetch, the plan's second buffer
+        set) overlap forward / backward of step t; N > 1 adds the bucketed gradient all-reduce + Adam on a comm stream.
+        --no-pipeline: one fused (graph-replayed) ogl_plan_train_step per step."""
         if pipe is None:
             for s in inputs:
                 step(s)
@@ -613,7 +615,7 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(w, args.workload, world),
             "e2e": {"value": e2e, "unit": "vertices/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
-                    "api": "ogl_plan_train_step(host seeds) + loss read-back", "last_loss": losses[-1] / (B * world) if losses else None},
+                    "api": "ogl_plan_prefetch(pinned host seeds of step t+1) + ogl_plan_step_finish(step t) + loss read-back every step", "last_loss": losses[-1] / (B * world) if losses else None},
             "gpu_launches": launches, "cuda_graph": {"replays_in_timed_region": gs1["replays"] - gs0["replays"],
                                                       "captures_in_timed_region": gs1["captures"] - gs0["captures"],
                                                       "ms_per_step_direct_launch_profiled": ms_prof / K},
@@ -636,6 +638,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="one fused ogl_plan_train_step per step instead of the prefetch pipeline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

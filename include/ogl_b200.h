@@ -156,6 +156,14 @@ int ogl_plan_step_finish(ogl_plan* p, ogl_features* f, float loss_scale, int do_
 int ogl_plan_step_finish_head(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
                               void* stream);
 int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream);
+/* software pipeline (the job of NodeDataLoader's worker processes, pytorch/model.py:128-131): sample + gather of a FUTURE minibatch,
+ * enqueued on the plan's own stream into the plan's second buffer set, ordered after everything enqueued on `stream` so far.  Up to
+ * two minibatches may be pending.  The next ogl_plan_train_step / ogl_plan_step_finish[_head] on the plan consumes the oldest pending
+ * minibatch (forward .. Adam only; its `seeds` argument is then ignored, n_seeds must match).  Call order for full overlap:
+ *   prefetch(0); for i: { prefetch(i+1); train_step(i); }
+ * ogl_plan_train_steps pipelines its minibatches this way internally (option "pipeline", default 1). */
+int ogl_plan_prefetch(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host, void* stream);
+int ogl_plan_prefetch_pending(const ogl_plan* p);   /* number of prefetched minibatches not yet consumed (0..2) */
 /* options: "cuda_graph" (default 1), "side_stream" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence
  * (re-captured when the graph pool, the handles, n_seeds or the output pointers change) */
 int ogl_plan_set_option(ogl_plan* p, const char* name, int value);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "ogl_plan_step_finish": (_i, [_vp, _vp, _f, _i, _vp, _vp, _vp]),
     "ogl_plan_step_finish_head": (_i, [_vp, _vp, _f, _vp, _vp, _vp]),
     "ogl_plan_step_finish_tail": (_i, [_vp, _vp, _vp]),
+    "ogl_plan_prefetch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "ogl_plan_prefetch_pending": (_i, [_vp]),
     "ogl_plan_set_option": (_i, [_vp, C.c_char_p, _i]),
     "ogl_plan_graph_stats": (_i, [_vp, C.POINTER(_i64 * 2)]),
     "ogl_plan_eval_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -263,6 +263,20 @@ class Plan:
         self.n_seeds = n
         self._stamp += 1
 
+    def prefetch(self, graph, features, seeds):
+        """sample + gather of a FUTURE minibatch on the plan's own stream / second buffer set (the role of NodeDataLoader's
+        workers): it overlaps whatever train step is running.  The next train_step / step_finish consumes the oldest pending
+        minibatch.  Order for full overlap: prefetch(0); for i: prefetch(i+1); train_step(i)"""
+        n = seeds.numel()
+        assert seeds.dtype == torch.int64 and seeds.is_contiguous()
+        check(lib.ogl_plan_prefetch(self._h, graph._h, features._h, C.c_void_p(seeds.data_ptr()), n, int(not seeds.is_cuda), _stream()))
+        self._prefetch_refs = (getattr(self, "_prefetch_refs", ()) + (seeds,))[-3:]      # seeds stay alive until consumed
+        self._stamp += 1
+
+    @property
+    def prefetch_pending(self):
+        return int(lib.ogl_plan_prefetch_pending(self._h))
+
     def step_finish(self, features, loss_scale, do_step=True, per_vertex_out=None, loss_sum_out=None):
         """forward + loss + backward (+ Adam) over the minibatch begun with step_begin"""
         check(lib.ogl_plan_step_finish(self._h, features._h, float(loss_scale), int(do_step), _ptr(per_vertex_out), _ptr(loss_sum_out),

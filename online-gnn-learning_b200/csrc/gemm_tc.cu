@@ -33,13 +33,19 @@ constexpr int RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);   // 192 KB
 constexpr int STORE_BOX_BYTES = 32 * 128;                              // one TMA-store box: 32 rows x 128 B
 constexpr int STORE_BYTES = 4 /*warps*/ * 2 /*buffers*/ * STORE_BOX_BYTES;   // 32 KB epilogue staging
 constexpr int BIAS_BYTES = 2 * BN_MAX * 4;                              // per-accumulator bias slice
-constexpr int SMEM_BYTES = RING_BYTES + STORE_BYTES + BIAS_BYTES + 256 /*barriers + tmem slot*/;
+constexpr int TAIL_BYTES = 256;                                         // barriers + tmem slot
+constexpr int SMEM_NT1 = RING_BYTES + STORE_BYTES + BIAS_BYTES + TAIL_BYTES;
 // cta_group::2 variant of the NT kernel: a CTA pair shares one B tile (each CTA stages half of it), so a stage is
-// 16 KB of A + 16 KB of B per CTA and the same 192 KB ring holds 6 stages
-constexpr int STAGES2 = 6;
+// 16 KB of A + 16 KB of B per CTA.  FIVE stages (160 KB): together with the staging boxes the CTA then leaves ~33 KB of
+// the SM's shared memory free, so the small kernels of the side / prefetch streams (sampling, to_block, scans, column sums;
+// all <= 9 KB) can be resident next to it instead of waiting for the GEMM to leave the SM
+constexpr int STAGES2 = 5;
 constexpr int B2_STAGE_BYTES = (BN_MAX / 2) * BK * 2;    // 16 KB
-static_assert(STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) == RING_BYTES, "ring size mismatch");
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
+constexpr int RING2_BYTES = STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES);
+constexpr int SMEM_NT2 = RING2_BYTES + STORE_BYTES + BIAS_BYTES + TAIL_BYTES;
+// TN kernel: its epilogue starts after the last MMA has retired, so its staging boxes alias the (then idle) operand ring
+constexpr int SMEM_TN = RING_BYTES + TAIL_BYTES;
+static_assert(SMEM_NT1 <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 constexpr int THREADS = 192;     // TN kernel: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
 constexpr int THREADS_NT = 320;  // NT kernel: the same roles with EIGHT epilogue warps (two per TMEM lane quarter, each taking
                                  // every other 64-column box) so that draining a tile stays well below the tile's MMA time
@@ -204,7 +210,8 @@ struct SmemLayout {
   uint64_t* acc_empty;   // [2]
   uint32_t* tmem_slot;
 };
-__device__ __forceinline__ SmemLayout carve(uint8_t* base, int n_stages = STAGES, int b_stage_bytes = B_STAGE_BYTES) {
+__device__ __forceinline__ SmemLayout carve(uint8_t* base, int n_stages = STAGES, int b_stage_bytes = B_STAGE_BYTES,
+                                            int ring_bytes = RING_BYTES, bool store_in_ring = false) {
   // the dynamic shared window of a kernel without static __shared__ starts 1024-byte aligned (SWIZZLE_128B atoms
   // need it); checked at run time instead of paying 1 KB of slack
   if ((smem_u32(base) & 1023u) != 0) __trap();
@@ -212,9 +219,10 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* base, int n_stages = STAGES
   s.a0 = base;
   s.b0 = base + n_stages * A_STAGE_BYTES;
   s.b_stage_bytes = b_stage_bytes;
-  s.store = base + RING_BYTES;
-  s.bias = (float*)(base + RING_BYTES + STORE_BYTES);
-  uint64_t* bars = (uint64_t*)(base + RING_BYTES + STORE_BYTES + BIAS_BYTES);
+  s.store = store_in_ring ? base : base + ring_bytes;
+  uint8_t* tail = base + ring_bytes + (store_in_ring ? 0 : STORE_BYTES);
+  s.bias = (float*)tail;                                   // (unused when store_in_ring: the TN kernel has no bias)
+  uint64_t* bars = (uint64_t*)(tail + (store_in_ring ? 0 : BIAS_BYTES));
   s.full = bars;
   s.empty = bars + n_stages;
   s.acc_full = bars + 2 * n_stages;
@@ -258,7 +266,7 @@ template <int CG>
 __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
   constexpr int NST = CG == 2 ? STAGES2 : STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemLayout s = carve(smem_raw, NST, CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES);
+  const SmemLayout s = carve(smem_raw, NST, CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES, CG == 2 ? RING2_BYTES : RING_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;          // CTA rank inside the pair
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -554,7 +562,7 @@ struct TnParams {
 
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant__ TnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemLayout s = carve(smem_raw);
+  const SmemLayout s = carve(smem_raw, STAGES, B_STAGE_BYTES, RING_BYTES, true);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int tile = blockIdx.x % (p.n_tiles * p.k_tiles);
@@ -703,9 +711,9 @@ int tc_init() {
     return -1;
   }
   g_encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(k_gemm_nt_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_gemm_nt_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_gemm_nt_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT1) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_nt_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT2) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess) {
     cudaGetLastError();
     g_tc_state = -1;
     return -1;
@@ -799,7 +807,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(THREADS_NT);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.dynamicSmemBytes = SMEM_NT2;
     cfg.stream = s;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
@@ -812,7 +820,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   }
   const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  OGL_LAUNCH(k_gemm_nt_tc<1>, grid, THREADS_NT, SMEM_BYTES, s, p);
+  OGL_LAUNCH(k_gemm_nt_tc<1>, grid, THREADS_NT, SMEM_NT1, s, p);
   return OGL_OK;
 }
 
@@ -853,7 +861,7 @@ int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
     p.use_tma_store = 1;
     OGL_TRY(make_map_f32_3d(&p.tout, g.partial, g.k, g.n, splits, ldo));
   }
-  OGL_LAUNCH(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_BYTES, s, p);
+  OGL_LAUNCH(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_TN, s, p);
   if (staged) return reduce_splits_ld(g.partial, splits, g.n, g.k, ldo, g.c, g.ldc, s);
   return OGL_OK;
 }

@@ -116,6 +116,26 @@ struct ogl_plan {
   std::vector<LayerBuf> layer;
   ToBlockWs tb;
   int64_t* seeds_stage = nullptr;
+  // software pipeline: everything one sampled minibatch owns (node lists, counts, ELL / reverse edge lists, the gathered input rows,
+  // the staged seeds) exists twice, so that sample + gather of minibatch i+1 runs on the `pre` stream while forward / backward /
+  // Adam of minibatch i runs on the caller's stream.  The members above / below are the CURRENT set; `alt` is the other one.
+  struct SampleBufs {
+    std::vector<int32_t*> nodes, edge_lid, edge_gsrc, rev_ptr, rev_edge;
+    int32_t* counts = nullptr;
+    void* x = nullptr;
+    int64_t* seeds_stage = nullptr;
+  } alt;
+  int have_alt = 0, parity = 0;
+  int use_pipeline = 1;
+  cudaStream_t pre = nullptr;
+  cudaEvent_t ev_tail = nullptr, ev_ready[2] = {nullptr, nullptr};
+  int pend[2] = {0, 0};                  // [0]: the current set holds a prefetched minibatch; [1]: `alt` holds the one after it
+  int pend_n[2] = {0, 0};
+  static constexpr int kSeedRing = 4;
+  int64_t* seed_ring = nullptr;          // pinned [kSeedRing][max_seeds]: private copies of host seeds handed to ogl_plan_prefetch
+  cudaEvent_t ev_ring[kSeedRing] = {nullptr, nullptr, nullptr, nullptr};
+  int ring_next = 0;
+  int cur_open = 0;                      // ogl_plan_step_begin filled the current set and its finish has not been enqueued yet
   uint32_t* ctl = nullptr;               // [0]=philox step, [1]=adam t
   int n_seeds = 0;
   // backward scratch
@@ -152,9 +172,10 @@ struct ogl_plan {
     float loss_scale;
     int kind;            // 0 = whole step, 1 = step_begin (sample + gather), 2 = step_finish (forward .. Adam),
                          // 3 = step_finish minus the last weight-gradient GEMM, 4 = that GEMM
+    int parity;          // which of the two minibatch buffer sets the captured pointers belong to
     bool operator==(const StepKey& o) const {
       return g == o.g && f == o.f && per == o.per && loss == o.loss && g_gen == o.g_gen && n_seeds == o.n_seeds && do_step == o.do_step &&
-             loss_scale == o.loss_scale && kind == o.kind;
+             loss_scale == o.loss_scale && kind == o.kind && parity == o.parity;
     }
   };
   struct StepGraph { StepKey key; cudaGraphExec_t exec; uint64_t last_use; };
@@ -355,12 +376,19 @@ extern "C" int ogl_plan_destroy(ogl_plan* p) {
     for (void* q : ptrs) cudaFree(q);
   }
   to_block_free(&p->tb);
+  for (auto* v : {&p->alt.nodes, &p->alt.edge_lid, &p->alt.edge_gsrc, &p->alt.rev_ptr, &p->alt.rev_edge})
+    for (auto x : *v) cudaFree(x);
+  cudaFree(p->alt.counts); cudaFree(p->alt.x); cudaFree(p->alt.seeds_stage);
   void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dhp, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
                   p->loss_sum, p->adam_m, p->adam_v, p->shadow_segs};
   for (void* q : ptrs) cudaFree(q);
   for (auto& r : p->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   cudaDeviceSynchronize();
   if (p->side) cudaStreamDestroy(p->side);
+  if (p->pre) cudaStreamDestroy(p->pre);
+  for (cudaEvent_t e : {p->ev_tail, p->ev_ready[0], p->ev_ready[1], p->ev_ring[0], p->ev_ring[1], p->ev_ring[2], p->ev_ring[3]})
+    if (e) cudaEventDestroy(e);
+  if (p->seed_ring) cudaFreeHost(p->seed_ring);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
   cudaFree(p->tn_partial2); cudaFree(p->colsum_partial2);
@@ -401,6 +429,7 @@ __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_dev, int n_seeds, void* stream) {
   OGL_ARG(p && g && seeds_dev, "ogl_plan_sample: null");
   OGL_ARG(n_seeds > 0 && n_seeds <= p->cfg.max_seeds, "ogl_plan_sample: n_seeds %d not in [1, %d]", n_seeds, p->cfg.max_seeds);
+  OGL_ARG(p->in_train_step || !p->pend[0], "ogl_plan_sample: a prefetched minibatch is pending (run its train step first)");
   cudaStream_t s = (cudaStream_t)stream;
   const GraphView gv = graph_view(g);
   OGL_ARG(gv.n_vertices <= p->cfg.v_cap, "ogl_plan_sample: graph has more vertices than the plan's v_cap");
@@ -621,6 +650,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
   if (kind == 1) {
     OGL_ARG(f->mode == p->cfg.mode && f->F == p->cfg.dims[0], "ogl_plan_step_begin: feature store does not match the plan (mode/F)");
     STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[p->L], p->counts + p->L, p->nmax[p->L], p->act[p->L], s));
+    OGL_TRY(bump(p->ctl, nullptr, s));            // the Philox step advances with the sampling, not with the (possibly later) finish
     return join_side(p, s);                       // a captured graph must rejoin its forked stream
   }
   if (kind == 4) {
@@ -638,7 +668,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
   p->tail_mode = 0;
   OGL_TRY(rl);
   if (do_step) OGL_TRY(ogl_plan_adam_step(p, s));
-  OGL_TRY(bump(p->ctl, nullptr, s));
+  if (kind == 0) OGL_TRY(bump(p->ctl, nullptr, s));
   return OGL_OK;
 }
 
@@ -646,7 +676,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
 static int run_step(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step,
                     float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
   if (!p->use_graph || p->prof_on) return step_body(p, kind, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s);
-  const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, g ? graph_generation(g) : 0, n_seeds, do_step, loss_scale, kind};
+  const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, g ? graph_generation(g) : 0, n_seeds, do_step, loss_scale, kind, p->parity};
   ogl_plan::StepGraph* hit = nullptr;
   for (auto& sg : p->step_graphs)
     if (sg.key == key) { hit = &sg; break; }
@@ -662,7 +692,7 @@ static int run_step(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_
     const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     OGL_CUDA(ei);
-    if (p->step_graphs.size() >= 8) {          // evict the least recently used
+    if (p->step_graphs.size() >= 16) {          // evict the least recently used
       size_t lru = 0;
       for (size_t i = 1; i < p->step_graphs.size(); ++i)
         if (p->step_graphs[i].last_use < p->step_graphs[lru].last_use) lru = i;
@@ -687,13 +717,137 @@ static int stage_step_seeds(ogl_plan* p, const int64_t* seeds, int n_seeds, int 
   return OGL_OK;
 }
 
+
+// ------------------------------------------------------------------ software pipeline ---------------
+// sample + gather of a minibatch need the graph, the feature table and the seeds, but no weights: they run ahead, on the plan's
+// `pre` stream and into the other buffer set, while the previous minibatch's forward / backward / Adam occupies the caller's stream
+// (the reference gets the same effect from NodeDataLoader worker processes, pytorch/model.py:128-131).
+static int ensure_pipeline(ogl_plan* p) {
+  if (p->have_alt) return OGL_OK;
+  const int L = p->L;
+  ogl_plan::SampleBufs& a = p->alt;
+  a.nodes.assign(L + 1, nullptr); a.edge_lid.assign(L, nullptr); a.edge_gsrc.assign(L, nullptr);
+  a.rev_ptr.assign(L, nullptr); a.rev_edge.assign(L, nullptr);
+  DM0(a.counts, sizeof(int32_t) * (L + 1));
+  DM0(a.seeds_stage, sizeof(int64_t) * p->cfg.max_seeds);
+  for (int lv = 0; lv <= L; ++lv) DM0(a.nodes[lv], sizeof(int32_t) * p->nmax[lv]);
+  for (int h = 0; h < L; ++h) {
+    const int64_t ne = (int64_t)p->nmax[h] * p->cfg.fanouts[h];
+    DM0(a.edge_lid[h], sizeof(int32_t) * ne);
+    DM0(a.edge_gsrc[h], sizeof(int32_t) * ne);
+    DM0(a.rev_ptr[h], sizeof(int32_t) * ((size_t)p->nmax[h + 1] + 2));
+    DM0(a.rev_edge[h], sizeof(int32_t) * ne);
+  }
+  DM0(a.x, p->es * (size_t)round_up(p->nmax[L], 128) * pitch_of(p->cfg.dims[0]));
+  {
+    // OGL_PRE_PRIO (experiments): 1 = highest stream priority for the prefetch stream, -1 = lowest, 0 / unset = default
+    int least = 0, greatest = 0, prio = 0;
+    OGL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    if (const char* e = getenv("OGL_PRE_PRIO")) prio = atoi(e) > 0 ? greatest : (atoi(e) < 0 ? least : 0);
+    OGL_CUDA(cudaStreamCreateWithPriority(&p->pre, cudaStreamNonBlocking, prio));
+  }
+  OGL_CUDA(cudaEventCreateWithFlags(&p->ev_tail, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) OGL_CUDA(cudaEventCreateWithFlags(&p->ev_ready[i], cudaEventDisableTiming));
+  OGL_CUDA(cudaMallocHost(&p->seed_ring, sizeof(int64_t) * ogl_plan::kSeedRing * p->cfg.max_seeds));
+  for (int i = 0; i < ogl_plan::kSeedRing; ++i) OGL_CUDA(cudaEventCreateWithFlags(&p->ev_ring[i], cudaEventDisableTiming));
+  p->have_alt = 1;
+  return OGL_OK;
+}
+
+static void swap_bufs(ogl_plan* p) {
+  ogl_plan::SampleBufs& a = p->alt;
+  std::swap(p->nodes, a.nodes); std::swap(p->edge_lid, a.edge_lid); std::swap(p->edge_gsrc, a.edge_gsrc);
+  std::swap(p->rev_ptr, a.rev_ptr); std::swap(p->rev_edge, a.rev_edge);
+  std::swap(p->counts, a.counts); std::swap(p->act[p->L], a.x); std::swap(p->seeds_stage, a.seeds_stage);
+  p->parity ^= 1;
+}
+
+// enqueue sample + gather of one minibatch on the `pre` stream, ordered after everything enqueued on `s` so far (graph inserts,
+// feature writes, the producer of device-resident seeds, and the step that last read the target buffer set)
+static int prefetch_impl(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host, cudaStream_t s) {
+  OGL_ARG(n_seeds > 0 && n_seeds <= p->cfg.max_seeds, "ogl_plan_prefetch: n_seeds %d not in [1, %d]", n_seeds, p->cfg.max_seeds);
+  OGL_TRY(ensure_pipeline(p));
+  OGL_ARG(!(p->pend[0] && p->pend[1]), "ogl_plan_prefetch: two minibatches are already pending");
+  const int slot = (p->pend[0] || p->cur_open) ? 1 : 0;
+  OGL_ARG(!(slot && p->pend[1]), "ogl_plan_prefetch: the other buffer set already holds a prefetched minibatch");
+  // host seeds are copied into a pinned ring slot at once (the caller's buffer is free when this returns; pageable memory costs no
+  // stream synchronisation); device seeds may still be in production on the caller's stream and must stay valid until consumed
+  const int64_t* src = seeds;
+  if (seeds_on_host) {
+    const int k = p->ring_next;
+    p->ring_next = (k + 1) % ogl_plan::kSeedRing;
+    OGL_CUDA(cudaEventSynchronize(p->ev_ring[k]));           // the H2D copy that last used this slot has run (normally long ago)
+    memcpy(p->seed_ring + (size_t)k * p->cfg.max_seeds, seeds, sizeof(int64_t) * n_seeds);
+    src = p->seed_ring + (size_t)k * p->cfg.max_seeds;
+  }
+  OGL_CUDA(cudaEventRecord(p->ev_tail, s));
+  OGL_CUDA(cudaStreamWaitEvent(p->pre, p->ev_tail, 0));
+  if (slot) swap_bufs(p);
+  int r = OGL_OK;
+  if (cudaMemcpyAsync(p->seeds_stage, src, sizeof(int64_t) * n_seeds, seeds_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                      p->pre) != cudaSuccess) {
+    set_error("ogl_plan_prefetch: seed copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    r = OGL_ERR_CUDA;
+  }
+  if (seeds_on_host && r == OGL_OK && cudaEventRecord(p->ev_ring[(p->ring_next + ogl_plan::kSeedRing - 1) % ogl_plan::kSeedRing], p->pre) != cudaSuccess)
+    r = OGL_ERR_CUDA;
+  const int n_keep = p->n_seeds;
+  if (r == OGL_OK) r = run_step(p, 1, g, f, n_seeds, 0.f, 0, nullptr, nullptr, p->pre);
+  p->n_seeds = n_keep;                                       // n_seeds describes the minibatch the caller's stream works on
+  if (r == OGL_OK && cudaEventRecord(p->ev_ready[p->parity], p->pre) != cudaSuccess) r = OGL_ERR_CUDA;
+  // stage profiling wants every stage alone on the device: the caller's stream waits for the prefetch at once (no overlap)
+  if (r == OGL_OK && p->prof_on && cudaStreamWaitEvent(s, p->ev_ready[p->parity], 0) != cudaSuccess) r = OGL_ERR_CUDA;
+  if (slot) swap_bufs(p);
+  OGL_TRY(r);
+  p->pend[slot] = 1;
+  p->pend_n[slot] = n_seeds;
+  return OGL_OK;
+}
+
+// the caller's stream takes over the prefetched minibatch held by the current buffer set
+static int consume_prefetched(ogl_plan* p, int n_seeds, cudaStream_t s) {
+  OGL_ARG(p->pend[0], "internal: no prefetched minibatch");
+  OGL_ARG(n_seeds == p->pend_n[0], "train step of %d seeds, but the prefetched minibatch has %d", n_seeds, p->pend_n[0]);
+  OGL_CUDA(cudaStreamWaitEvent(s, p->ev_ready[p->parity], 0));
+  p->n_seeds = n_seeds;
+  return OGL_OK;
+}
+static void advance_prefetched(ogl_plan* p) {                // after the finish of the current minibatch has been enqueued
+  p->pend[0] = 0;
+  p->cur_open = 0;
+  if (p->pend[1]) {
+    swap_bufs(p);
+    p->pend[0] = 1; p->pend_n[0] = p->pend_n[1];
+    p->pend[1] = 0;
+  }
+}
+
+extern "C" int ogl_plan_prefetch(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
+                                 void* stream) {
+  OGL_ARG(p && g && f && seeds, "ogl_plan_prefetch: null");
+  OGL_ARG(f->mode == p->cfg.mode && f->F == p->cfg.dims[0], "ogl_plan_prefetch: feature store does not match the plan (mode/F)");
+  return prefetch_impl(p, g, f, seeds, n_seeds, seeds_on_host, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_plan_prefetch_pending(const ogl_plan* p) { return p ? p->pend[0] + p->pend[1] : 0; }
+
 extern "C" int ogl_plan_train_step(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host,
                                    float loss_scale, int do_step, float* per_vertex_loss_dev, float* loss_sum_dev, void* stream) {
   OGL_ARG(p && g && f && seeds, "ogl_plan_train_step: null");
   OGL_ARG(p->params, "ogl_plan_train_step: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  OGL_TRY(stage_step_seeds(p, seeds, n_seeds, seeds_on_host, s));
-  OGL_TRY(run_step(p, 0, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s));
+  if (p->pend[0]) {
+    // the minibatch was sampled + gathered ahead by ogl_plan_prefetch (same seeds, by contract): only forward .. Adam remain
+    OGL_TRY(consume_prefetched(p, n_seeds, s));
+    const int r = run_step(p, 2, nullptr, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s);
+    advance_prefetched(p);
+    OGL_TRY(r);
+  } else {
+    OGL_ARG(!p->pend[1], "ogl_plan_train_step: a prefetched minibatch is pending behind an unfinished ogl_plan_step_begin");
+    OGL_TRY(stage_step_seeds(p, seeds, n_seeds, seeds_on_host, s));
+    OGL_TRY(run_step(p, 0, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s));
+    p->cur_open = 0;
+  }
   if (p->prof_on && p->prof_steps < kProfSteps) {
     OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
     p->prof_steps++;
@@ -710,6 +864,24 @@ extern "C" int ogl_plan_train_steps(ogl_plan* p, ogl_graph* g, ogl_features* f, 
   OGL_ARG(p && g && f && seeds && n_batches >= 0, "ogl_plan_train_steps: bad arguments");
   OGL_ARG(p->params, "ogl_plan_train_steps: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
+  OGL_ARG(!p->pend[0], "ogl_plan_train_steps: a prefetched minibatch is pending");
+  if (n_batches >= 2 && p->use_pipeline && p->use_graph && !p->prof_on) {
+    // software-pipelined: sample + gather of minibatch i+1 (pre stream, other buffer set) overlap forward .. Adam of minibatch i
+    OGL_ARG(f->mode == p->cfg.mode && f->F == p->cfg.dims[0], "ogl_plan_train_steps: feature store does not match the plan (mode/F)");
+    OGL_TRY(prefetch_impl(p, g, f, seeds, batch, seeds_on_host, s));
+    for (int i = 0; i < n_batches; ++i) {
+      if (i + 1 < n_batches) OGL_TRY(prefetch_impl(p, g, f, seeds + (int64_t)(i + 1) * batch, batch, seeds_on_host, s));
+      OGL_TRY(consume_prefetched(p, batch, s));
+      const int r = run_step(p, 2, nullptr, f, batch, loss_scale, do_step, per_vertex_loss_dev ? p->per_loss : nullptr,
+                             loss_sums_dev ? p->loss_sum : nullptr, s);
+      advance_prefetched(p);
+      OGL_TRY(r);
+      if (per_vertex_loss_dev)
+        OGL_CUDA(cudaMemcpyAsync(per_vertex_loss_dev + (int64_t)i * batch, p->per_loss, sizeof(float) * batch, cudaMemcpyDeviceToDevice, s));
+      if (loss_sums_dev) OGL_CUDA(cudaMemcpyAsync(loss_sums_dev + i, p->loss_sum, sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return OGL_OK;
+  }
   for (int i = 0; i < n_batches; ++i) {
     OGL_TRY(stage_step_seeds(p, seeds + (int64_t)i * batch, batch, seeds_on_host, s));
     // fixed internal outputs keep one captured graph valid for every step; results are copied out per step
@@ -726,8 +898,11 @@ extern "C" int ogl_plan_step_begin(ogl_plan* p, ogl_graph* g, ogl_features* f, c
                                    void* stream) {
   OGL_ARG(p && g && f && seeds, "ogl_plan_step_begin: null");
   cudaStream_t s = (cudaStream_t)stream;
+  OGL_ARG(!p->pend[0] && !p->pend[1], "ogl_plan_step_begin: a prefetched minibatch is pending");
   OGL_TRY(stage_step_seeds(p, seeds, n_seeds, seeds_on_host, s));
-  return run_step(p, 1, g, f, n_seeds, 0.f, 0, nullptr, nullptr, s);
+  OGL_TRY(run_step(p, 1, g, f, n_seeds, 0.f, 0, nullptr, nullptr, s));
+  p->cur_open = 1;
+  return OGL_OK;
 }
 
 // step_finish in two pieces for bucketed gradient exchange: `head` leaves only the last weight-gradient GEMM (layer 0's
@@ -735,14 +910,17 @@ extern "C" int ogl_plan_step_begin(ogl_plan* p, ogl_graph* g, ogl_features* f, c
 // `head`, so its all-reduce can overlap `tail`.
 extern "C" int ogl_plan_step_finish_head(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
                                          void* stream) {
-  OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish_head: no step begun / parameters not bound");
+  OGL_ARG(p && f && p->params && (p->n_seeds > 0 || p->pend[0]), "ogl_plan_step_finish_head: no step begun / parameters not bound");
+  if (p->pend[0]) OGL_TRY(consume_prefetched(p, p->pend_n[0], (cudaStream_t)stream));   // (released by _tail)
   return run_step(p, 3, nullptr, f, p->n_seeds, loss_scale, 0, per_vertex_loss_dev, loss_sum_dev, (cudaStream_t)stream);
 }
 
 extern "C" int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream) {
   OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish_tail: no step begun / parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  OGL_TRY(run_step(p, 4, nullptr, f, p->n_seeds, 0.f, 0, nullptr, nullptr, s));
+  const int r4 = run_step(p, 4, nullptr, f, p->n_seeds, 0.f, 0, nullptr, nullptr, s);
+  advance_prefetched(p);
+  OGL_TRY(r4);
   if (p->prof_on && p->prof_steps < kProfSteps) {
     OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
     p->prof_steps++;
@@ -752,9 +930,13 @@ extern "C" int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* str
 
 extern "C" int ogl_plan_step_finish(ogl_plan* p, ogl_features* f, float loss_scale, int do_step, float* per_vertex_loss_dev,
                                     float* loss_sum_dev, void* stream) {
-  OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish: no step begun / parameters not bound");
+  OGL_ARG(p && f && p->params && (p->n_seeds > 0 || p->pend[0]), "ogl_plan_step_finish: no step begun / parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  OGL_TRY(run_step(p, 2, nullptr, f, p->n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s));
+  const int was_pending = p->pend[0];
+  if (was_pending) OGL_TRY(consume_prefetched(p, p->pend_n[0], s));
+  const int r2 = run_step(p, 2, nullptr, f, p->n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s);
+  advance_prefetched(p);
+  OGL_TRY(r2);
   if (p->prof_on && p->prof_steps < kProfSteps) {
     OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
     p->prof_steps++;
@@ -766,6 +948,7 @@ extern "C" int ogl_plan_set_option(ogl_plan* p, const char* name, int value) {
   OGL_ARG(p && name, "ogl_plan_set_option: null");
   if (strcmp(name, "cuda_graph") == 0) { p->use_graph = value ? 1 : 0; return OGL_OK; }
   if (strcmp(name, "side_stream") == 0) { p->use_side = value ? 1 : 0; return OGL_OK; }
+  if (strcmp(name, "pipeline") == 0) { p->use_pipeline = value ? 1 : 0; return OGL_OK; }
   set_error("ogl_plan_set_option: unknown option '%s'", name);
   return OGL_ERR_ARG;
 }

@@ -65,12 +65,15 @@ def train_step(plan, graph, features, local_seeds, global_batch, flat_grad, per_
 
 
 class Pipeline:
-    """Data-parallel train loop with the gradient exchange off the critical path.
+    """Train loop with everything that does not need fresh weights off the critical path (any number of GPUs).
 
     A step is split at the only point where it needs fresh weights: `begin` = sample + gather (reads the graph and the
-    feature store only), `finish` = forward .. backward.  The all-reduce of step t and its Adam update run on a
-    communication stream while the main stream already samples and gathers step t+1; forward(t+1) then waits for
-    Adam(t).  Same arithmetic as the unpipelined loop (no stale gradients)."""
+    feature store only), `finish` = forward .. backward (.. Adam).  `begin` of step t+1 is a prefetch (Plan.prefetch: the
+    plan's own stream and second buffer set), so it overlaps forward / backward of step t -- the job NodeDataLoader's worker
+    processes do in the reference (pytorch/model.py:128-131).  With more than one rank the gradient exchange is bucketed:
+    the all-reduce of everything but layer 0's fc_pool.weight overlaps the last weight-gradient GEMM, the small second
+    bucket + Adam run on a communication stream; forward(t+1) waits for Adam(t).  Same arithmetic as the unpipelined loop
+    (no stale gradients, same Philox step per minibatch)."""
 
     def __init__(self, plan, graph, features, flat_grad, global_batch):
         self.plan, self.graph, self.features, self.flat_grad = plan, graph, features, flat_grad
@@ -80,40 +83,40 @@ class Pipeline:
         self.ev_bwd = torch.cuda.Event()
         self.ev_head = torch.cuda.Event()
         self.ev_adam = torch.cuda.Event()
-        self._begun = False
+        self._begun = 0
         self._adam_pending = False
 
     def begin(self, seeds):
-        self.plan.step_begin(self.graph, self.features, seeds)
-        self._begun = True
+        self.plan.prefetch(self.graph, self.features, seeds)
+        self._begun += 1
 
     def finish(self, next_seeds=None, per_vertex_out=None, loss_sum_out=None):
-        assert self._begun, "Pipeline.finish() without begin()"
-        self._begun = False
+        assert self._begun > 0, "Pipeline.finish() without begin()"
+        if next_seeds is not None and self._begun < 2:
+            self.begin(next_seeds)                       # enqueued first: overlaps this step's forward / backward
+        self._begun -= 1
         main = torch.cuda.current_stream()
         if self.w == 1:
             self.plan.step_finish(self.features, self.scale, do_step=True, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
-        else:
-            if self._adam_pending:
-                main.wait_event(self.ev_adam)            # weights (and the gradient buffer) of the previous step are settled
-            # two gradient buckets: everything except layer 0's fc_pool.weight is final before the last weight-gradient GEMM
-            # runs, so its all-reduce overlaps that GEMM; the small second bucket + Adam overlap the next sample + gather
-            n0 = self.plan.tail_params
-            self.plan.step_finish_head(self.features, self.scale, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
-            self.ev_head.record(main)
-            with torch.cuda.stream(self.comm):
-                self.comm.wait_event(self.ev_head)
-                allreduce_grads(self.flat_grad[n0:])
-            self.plan.step_finish_tail(self.features)
-            self.ev_bwd.record(main)
-            with torch.cuda.stream(self.comm):
-                self.comm.wait_event(self.ev_bwd)
-                allreduce_grads(self.flat_grad[:n0])
-                self.plan.adam_step()
-                self.ev_adam.record(self.comm)
-            self._adam_pending = True
-        if next_seeds is not None:
-            self.begin(next_seeds)                       # overlaps the all-reduce + Adam in flight
+            return
+        if self._adam_pending:
+            main.wait_event(self.ev_adam)                # weights (and the gradient buffer) of the previous step are settled
+        # two gradient buckets: everything except layer 0's fc_pool.weight is final before the last weight-gradient GEMM
+        # runs, so its all-reduce overlaps that GEMM; the small second bucket + Adam overlap the next step's start
+        n0 = self.plan.tail_params
+        self.plan.step_finish_head(self.features, self.scale, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
+        self.ev_head.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ev_head)
+            allreduce_grads(self.flat_grad[n0:])
+        self.plan.step_finish_tail(self.features)
+        self.ev_bwd.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ev_bwd)
+            allreduce_grads(self.flat_grad[:n0])
+            self.plan.adam_step()
+            self.ev_adam.record(self.comm)
+        self._adam_pending = True
 
     def flush(self):
         if self._adam_pending:

@@ -342,6 +342,77 @@ def test_step_begin_finish_equals_fused_step():
             close(a, b, 1e-4, "per-vertex loss fused vs split form %d" % other)
 
 
+def test_prefetch_pipeline_equals_fused_steps():
+    """software pipeline (ogl_plan_prefetch: sample + gather of minibatch i+1 on the plan's own stream / second buffer set while
+    minibatch i trains) == the same minibatches through the fused step: same sampled frontiers (bit-exact), same losses / weights"""
+    runs = []
+    n_steps, B = 7, 48
+    for mode in ("fused", "prefetch", "pipeline-class"):
+        c = Case(dims=(64, 32, 5), fanouts=(6, 4), n_seeds=B, mode="bf16", gemm_impl=0)
+        rng = np.random.default_rng(3)
+        allseeds = rng.permutation(c.V - 40)[:n_steps * B].astype(np.int64)
+        batches = [torch.as_tensor(allseeds[i * B:(i + 1) * B]) for i in range(n_steps)]
+        batches = [b.cuda() if i % 3 == 0 else (b.pin_memory() if i % 3 == 1 else b.clone()) for i, b in enumerate(batches)]
+        per = torch.empty(B, device="cuda")
+        tot = torch.empty(1, device="cuda")
+        outs, fronts = [], []
+        if mode == "fused":
+            for sd in batches:
+                c.plan.train_step(c.g, c.f, sd, loss_scale=1.0 / B, do_step=True, per_vertex_out=per, loss_sum_out=tot)
+                outs.append((per.clone(), tot.clone()))
+                fronts.append(c.plan.level_nodes(2).clone())
+        elif mode == "prefetch":
+            c.plan.prefetch(c.g, c.f, batches[0])
+            for i, sd in enumerate(batches):
+                if i + 1 < n_steps:
+                    c.plan.prefetch(c.g, c.f, batches[i + 1])
+                    assert c.plan.prefetch_pending == 2
+                c.plan.train_step(c.g, c.f, sd, loss_scale=1.0 / B, do_step=True, per_vertex_out=per, loss_sum_out=tot)
+                outs.append((per.clone(), tot.clone()))
+            assert c.plan.prefetch_pending == 0
+        else:
+            import ogl_b200
+            pipe = ogl_b200.parallel.Pipeline(c.plan, c.g, c.f, c.grad, B)
+            pipe.begin(batches[0])
+            for i in range(n_steps):
+                pipe.finish(batches[i + 1] if i + 1 < n_steps else None, per_vertex_out=per, loss_sum_out=tot)
+                outs.append((per.clone(), tot.clone()))
+            pipe.flush()
+        torch.cuda.synchronize()
+        runs.append((c.flat.clone(), outs, fronts))
+    for other in (1, 2):
+        close(runs[0][0], runs[other][0], 1e-4, "params fused vs pipelined (%d)" % other)
+        for (p0, t0), (p1, t1) in zip(runs[0][1], runs[other][1]):
+            close(p0, p1, 1e-4, "per-vertex loss fused vs pipelined (%d)" % other)
+            close(t0, t1, 1e-4, "loss sum fused vs pipelined (%d)" % other)
+
+
+def test_prefetched_frontier_is_bit_exact_and_guarded():
+    """a prefetched minibatch has the frontier the fused step samples at the same Philox step; sampling while one is pending is refused"""
+    B = 40
+    c0 = Case(dims=(64, 32, 5), fanouts=(6, 4), n_seeds=B, mode="bf16", gemm_impl=0)
+    c1 = Case(dims=(64, 32, 5), fanouts=(6, 4), n_seeds=B, mode="bf16", gemm_impl=0)
+    rng = np.random.default_rng(5)
+    seeds = [torch.as_tensor(rng.permutation(c0.V - 40)[:B].astype(np.int64)).cuda() for _ in range(3)]
+    want = []
+    for sd in seeds:
+        c0.plan.train_step(c0.g, c0.f, sd, loss_scale=1.0 / B, do_step=True)
+        want.append([c0.plan.level_nodes(lv).clone() for lv in range(3)])
+    c1.plan.prefetch(c1.g, c1.f, seeds[0])
+    with pytest.raises(Exception):
+        c1.plan.eval_step(c1.g, c1.f, seeds[0])
+    for i, sd in enumerate(seeds):
+        if i + 1 < len(seeds):
+            c1.plan.prefetch(c1.g, c1.f, seeds[i + 1])
+        c1.plan.step_finish(c1.f, 1.0 / B, do_step=True)
+        torch.cuda.synchronize()
+        # after the finish the current buffer set is the NEXT minibatch's (if one is pending): check it against the fused run
+        if i + 1 < len(seeds):
+            for lv in range(3):
+                assert torch.equal(c1.plan.level_nodes(lv), want[i + 1][lv]), "prefetched frontier level %d of step %d" % (lv, i + 1)
+    close(c0.flat, c1.flat, 1e-4, "params fused vs prefetched")
+
+
 def test_multi_step_call_equals_single_steps():
     """ogl_plan_train_steps (all minibatches of a timestep in one C call) == the same steps one call at a time"""
     runs = []

@@ -1,18 +1,14 @@
-"""Perf experiments on the NT tcgen05 kernel (bf16 output + bias + ReLU = the fc_pool GEMM of the Reddit-shaped step)."""
+"""Perf experiments on the tcgen05 kernels at the shapes of the Reddit-shaped step, next to cuBLAS (torch.matmul) on the same
+operands.  OGL_GEMM_DBG: 1 = no epilogue stores, 2 = no loads (MMA issue rate alone), 3 = both.  EXP_SKIP_REF=1 skips the checks."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ogl_b200 import native
 
-m, n, k = 89000, int(os.environ.get("EXP_N", "602")), int(os.environ.get("EXP_K", "602"))
-ldk = (k + 7) // 8 * 8
-a = torch.randn(m, ldk, device="cuda").bfloat16()
-b = (torch.randn(n, ldk, device="cuda") * 0.05).bfloat16()
-bias = torch.randn(n, device="cuda")
-ref = torch.relu(a[:, :k].float() @ b[:, :k].float().t() + bias)
+dbg = os.environ.get("OGL_GEMM_DBG", "0")
 
 
-def bench(fn, iters=30):
+def bench(fn, iters=20):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -25,8 +21,35 @@ def bench(fn, iters=30):
     return e0.elapsed_time(e1) / iters
 
 
-for cg in (1, 2):
-    out = native.gemm_bf16_nt_ex(a, b, k=k, out_bf16=True, bias=bias, relu=True, cg=cg)
-    err = (out.float() - ref).abs().max().item()
-    ms = bench(lambda: native.gemm_bf16_nt_ex(a, b, k=k, out_bf16=True, bias=bias, relu=True, cg=cg))
-    print("cg=%d dbg=%s  %.4f ms  %.0f TFLOP/s  max_err %.3g" % (cg, os.environ.get("OGL_GEMM_DBG", "0"), ms, 2.0 * m * n * k / ms / 1e9, err), flush=True)
+for (m, n, k) in ((89000, 602, 602), (18432, 600, 600), (18432, 602, 600)):
+    ldk = (k + 7) // 8 * 8
+    a = torch.randn(m, ldk, device="cuda").bfloat16()
+    b = (torch.randn(n, ldk, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(n, device="cuda")
+    fl = 2.0 * m * n * k
+    if dbg == "0":
+        ref = torch.relu(a[:, :k].float() @ b[:, :k].float().t() + bias)
+        ac, bc = a[:, :k].contiguous(), b[:, :k].contiguous()
+        ms = bench(lambda: torch.matmul(ac, bc.t()))
+        print("NT m=%d n=%d k=%d cuBLAS (no epilogue)      %.4f ms  %.0f TFLOP/s" % (m, n, k, ms, fl / ms / 1e9), flush=True)
+    for cg in (1, 2):
+        out = native.gemm_bf16_nt_ex(a, b, k=k, out_bf16=True, bias=bias, relu=True, cg=cg)
+        err = (out.float() - ref).abs().max().item() if dbg == "0" else float("nan")
+        ms = bench(lambda: native.gemm_bf16_nt_ex(a, b, k=k, out_bf16=True, bias=bias, relu=True, cg=cg))
+        print("NT m=%d n=%d k=%d cg=%d dbg=%s  %.4f ms  %.0f TFLOP/s  max_err %.3g" % (m, n, k, cg, dbg, ms, fl / ms / 1e9, err), flush=True)
+
+if dbg == "0":
+    for (m, n, k) in ((89000, 602, 602), (18432, 600, 602), (18432, 600, 600), (18432, 41, 600)):
+        ldn, ldk = (n + 7) // 8 * 8, (k + 7) // 8 * 8
+        a = torch.randn(m, ldn, device="cuda").bfloat16()
+        b = torch.randn(m, ldk, device="cuda").bfloat16()
+        fl = 2.0 * m * n * k
+        ref = a[:, :n].float().t() @ b[:, :k].float()
+        ac, bc = a[:, :n].contiguous(), b[:, :k].contiguous()
+        ms = bench(lambda: torch.matmul(ac.t(), bc))
+        print("TN m=%d n=%d k=%d cuBLAS                    %.4f ms  %.0f TFLOP/s" % (m, n, k, ms, fl / ms / 1e9), flush=True)
+        ws = torch.empty(1 << 24, device="cuda")
+        got = native.gemm_bf16_tn(a, b, n=n, k=k, workspace_elems=1 << 24)
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        ms = bench(lambda: native.gemm_bf16_tn(a, b, n=n, k=k, workspace_elems=1 << 24))
+        print("TN m=%d n=%d k=%d ours                      %.4f ms  %.0f TFLOP/s  rel_err %.3g" % (m, n, k, ms, fl / ms / 1e9, err), flush=True)
