@@ -38,6 +38,9 @@ WORKLOADS = {
     "arxiv": dict(V=169343, E=1166243, F=128, C=40, H=32, B=32, fanouts=[40, 40]),
     "pubmed": dict(V=19717, E=44338, F=500, C=3, H=32, B=32, fanouts=[10, 10]),
 }
+EXCHANGE = ["peer"]
+EXCHANGE_NAME = {"peer": "gradient sum over NVLink peer memory (P2P loads) fused with Adam in one kernel per bucket, no NCCL on the data path",
+                 "nccl": "NCCL all-reduce + Adam"}
 NAMES = ("fc_pool.weight", "fc_pool.bias", "fc_self.weight", "fc_self.bias", "fc_neigh.weight", "fc_neigh.bias")
 
 
@@ -184,6 +187,8 @@ def stage_flops(stage, w, lv):
     fin, fout = dims[l], dims[l + 1]
     n_src, n_dst = (N0, N1) if l == 0 else (N1, B)
     kind = stage.split(".", 1)[1]
+    if kind == "dW_group":     # one launch: fc_self + fc_neigh weight gradients of layer l (+ the fc_pool weight gradient of layer l+1)
+        return 4.0 * n_dst * fin * fout + (2.0 * n_dst * fout * fout if l + 1 < 2 else 0.0)
     return {"pool_gemm": 2.0 * n_src * fin * fin, "out_gemm": 4.0 * n_dst * fin * fout, "dW_self": 2.0 * n_dst * fin * fout,
             "dW_neigh": 2.0 * n_dst * fin * fout, "dneigh_gemm": 2.0 * n_dst * fin * fout, "dW_pool": 2.0 * n_src * fin * fin,
             "dx_gemm": 2.0 * n_src * fin * fin + 2.0 * n_dst * fin * fout}.get(kind)
@@ -390,7 +395,7 @@ def aux_arxiv_vertex_stream(n_snapshots=20):
 def workload_config(w, name, world):
     return {"workload": "%s-shaped synthetic graph: V=%d, %d stream edges (%d directed), F=%d, C=%d, hidden %d, B=%d per GPU, fan-outs %s, "
                         "2-layer GraphSAGE-pool, Adam" % (name, w["V"], w["E"], 2 * w["E"], w["F"], w["C"], w["H"], w["B"], w["fanouts"]),
-            "global_batch": w["B"] * world, "parallelism": ("dp%d (replicated graph+features, bucketed NCCL grad all-reduce + Adam on a comm stream)" % world if world > 1 else "single GPU") +
+            "global_batch": w["B"] * world, "parallelism": ("dp%d (replicated graph+features, two gradient buckets, %s, on a comm stream)" % (world, EXCHANGE_NAME.get(EXCHANGE[0], "?")) if world > 1 else "single GPU") +
                            "; sample+gather of step t+1 prefetched (second buffer set, own stream) under forward/backward of step t",
             "l2": "inputs larger than L2: feature table %.0f MB + CSR %.0f MB resident, random row gathers; no explicit flush"
                   % (w["V"] * ((w["F"] + 7) // 8 * 8) * 2 / 1e6, 2 * w["E"] * 8 * 1.5 / 1e6)}
@@ -450,6 +455,12 @@ def run_ours(args, rank, world, local_rank):
     grad = torch.zeros_like(flat)
     plan = native.Plan([w["F"], w["H"], w["C"]], w["fanouts"], w["B"], V, mode=mode, seed=11)
     plan.bind_params(flat, grad)
+    peer = None
+    if world > 1 and args.exchange == "peer":
+        # gradient exchange + Adam as ONE kernel per bucket over NVLink peer memory (csrc/peer.cu); the gradient buffer moves into
+        # the peer-visible allocation
+        peer = ogl_b200.parallel.make_peer_exchange(plan, flat)
+        grad = peer.grads
     B = w["B"]
     K, W = args.steps, args.warmup
     batches = seed_batches(w, K + W, rank, world)
@@ -461,7 +472,7 @@ def run_ours(args, rank, world, local_rank):
         # local sample / forward / backward -> (N > 1: one NCCL all-reduce of the flat gradient) -> fused Adam
         ogl_b200.parallel.train_step(plan, g, fs, seeds, B * world, grad, loss_sum_out=loss_dev)
 
-    pipe = ogl_b200.parallel.Pipeline(plan, g, fs, grad, B * world) if not args.no_pipeline else None
+    pipe = ogl_b200.parallel.Pipeline(plan, g, fs, grad, B * world, peer=peer) if not args.no_pipeline else None
 
     def run_steps(inputs, read_back, losses):
         """pipelined loop (ogl_b200.parallel.Pipeline): sample + gather of step t+1 (ogl_plan_prefetch, the plan's second buffer
@@ -541,7 +552,7 @@ def run_ours(args, rank, world, local_rank):
         kind = k.split(".", 1)[1] if is_layer(k) else k.split(".")[0]
         if kind in ("pool_gemm", "out_gemm", "dneigh_gemm", "dx_gemm"):
             return "k_gemm_nt_tc"
-        if kind in ("dW_self", "dW_neigh", "dW_pool"):
+        if kind in ("dW_self", "dW_neigh", "dW_pool", "dW_group"):
             return "k_gemm_tn_tc"
         return {"pool_bwd": "k_pool_bwd", "segmax": "k_segmax_fwd", "gather": "k_gather_rows", "sample": "k_sample",
                 "to_block": "k_tb_*", "rev_edges": "k_rev_*", "db_out": "k_colsum_*", "db_pool": "k_colsum_*"}.get(kind, kind)
@@ -638,8 +649,11 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient exchange + Adam fused in one kernel over NVLink peer memory, or NCCL all-reduce + Adam")
     ap.add_argument("--no-pipeline", action="store_true", help="one fused ogl_plan_train_step per step instead of the prefetch pipeline")
     args = ap.parse_args()
+    EXCHANGE[0] = args.exchange
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

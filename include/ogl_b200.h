@@ -32,6 +32,7 @@ typedef struct ogl_graph ogl_graph;       /* streaming in-edge CSR (slack rows +
 typedef struct ogl_features ogl_features; /* device feature / label store (padded rows) */
 typedef struct ogl_plan ogl_plan;         /* sampler + GraphSAGE-pool model + optimiser workspace */
 typedef struct ogl_sumtree ogl_sumtree;   /* fp64 sum-tree for PBR */
+typedef struct ogl_peer ogl_peer;         /* one rank's end of the NVLink peer-memory gradient exchange */
 
 enum { OGL_F32 = 0, OGL_BF16 = 1 };      /* arithmetic mode of the dense path */
 enum { OGL_OK = 0, OGL_ERR_CUDA = -1, OGL_ERR_ARG = -2, OGL_ERR_CAPACITY = -3, OGL_ERR_NODEVICE = -4 };
@@ -164,6 +165,23 @@ int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream);
  * ogl_plan_train_steps pipelines its minibatches this way internally (option "pipeline", default 1). */
 int ogl_plan_prefetch(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64_t* seeds, int n_seeds, int seeds_on_host, void* stream);
 int ogl_plan_prefetch_pending(const ogl_plan* p);   /* number of prefetched minibatches not yet consumed (0..2) */
+/* ---- data-parallel gradient exchange over NVLink peer memory, fused with Adam (the reference is single-process) ----
+ * Every rank owns a gradient buffer inside an allocation its peers map through CUDA IPC.  ogl_plan_peer_adam launches ONE kernel:
+ * barrier over peer-memory flags -> gradients [lo, hi) summed over the ranks in rank order with P2P loads (bit-identical replicas) ->
+ * Adam on the local fp32 parameters + bf16 weight shadows -> "done reading" flags to the peers.  Replaces
+ * all_reduce(flat_grad) + ogl_plan_adam_step.  Protocol per step, identical on every rank:
+ *     ogl_peer_wait_readers   (before the backward pass overwrites the gradient buffer)
+ *     ... backward ...        (the plan's gradient buffer must be ogl_peer_buffer)
+ *     ogl_plan_peer_adam(lo, hi, last) for each bucket, the same buckets in the same order on every rank
+ * Setup: create -> exchange the 64-byte ogl_peer_handle of every rank (any transport) -> ogl_peer_connect(all handles, rank order). */
+int ogl_peer_create(ogl_peer** out, int rank, int world, int64_t n_floats);
+int ogl_peer_destroy(ogl_peer* p);
+int ogl_peer_handle(ogl_peer* p, void* handle64);
+int ogl_peer_connect(ogl_peer* p, const void* handles /* world x 64 bytes */);
+int ogl_peer_connect_local(ogl_peer* p, ogl_peer* const* all /* the world peers of ONE process, rank order */);
+int ogl_peer_buffer(ogl_peer* p, float** grads_dev);
+int ogl_peer_wait_readers(ogl_peer* p, void* stream);
+int ogl_plan_peer_adam(ogl_plan* p, ogl_peer* peer, int64_t lo, int64_t hi, int last, float* reduced_out_dev /* may be NULL */, void* stream);
 /* options: "cuda_graph" (default 1), "side_stream" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence
  * (re-captured when the graph pool, the handles, n_seeds or the output pointers change) */
 int ogl_plan_set_option(ogl_plan* p, const char* name, int value);

@@ -78,6 +78,14 @@ SIGNATURES = {
     "ogl_plan_step_finish_tail": (_i, [_vp, _vp, _vp]),
     "ogl_plan_prefetch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ogl_plan_prefetch_pending": (_i, [_vp]),
+    "ogl_peer_create": (_i, [C.POINTER(_vp), _i, _i, _i64]),
+    "ogl_peer_destroy": (_i, [_vp]),
+    "ogl_peer_handle": (_i, [_vp, _vp]),
+    "ogl_peer_connect": (_i, [_vp, _vp]),
+    "ogl_peer_connect_local": (_i, [_vp, C.POINTER(_vp)]),
+    "ogl_peer_buffer": (_i, [_vp, C.POINTER(_vp)]),
+    "ogl_peer_wait_readers": (_i, [_vp, _vp]),
+    "ogl_plan_peer_adam": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp]),
     "ogl_plan_set_option": (_i, [_vp, C.c_char_p, _i]),
     "ogl_plan_graph_stats": (_i, [_vp, C.POINTER(_i64 * 2)]),
     "ogl_plan_eval_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -231,6 +231,10 @@ class Plan:
     def adam_step(self):
         check(lib.ogl_plan_adam_step(self._h, _stream()))
 
+    def peer_adam(self, peer, lo, hi, last, reduced_out=None):
+        """data-parallel Adam: gradients [lo, hi) summed over the ranks through peer memory inside the Adam kernel"""
+        check(lib.ogl_plan_peer_adam(self._h, peer._h, int(lo), int(hi), int(last), _ptr(reduced_out), _stream()))
+
     def train_step(self, graph, features, seeds, loss_scale=None, do_step=True, per_vertex_out=None, loss_sum_out=None):
         """seeds: CUDA int64 tensor (device path) or pinned/pageable CPU int64 tensor (host path)."""
         n = seeds.numel()
@@ -347,6 +351,45 @@ class Plan:
         check(lib.ogl_plan_tensor(self._h, name.encode(), C.byref(p), C.byref(r), C.byref(pt), C.byref(eb)))
         dt = {1: torch.uint8, 2: torch.bfloat16, 4: torch.float32}[eb.value]
         return wrap_device(p.value, (rows if rows is not None else r.value, pt.value), dt)
+
+
+class Peer:
+    """ogl_peer handle: one rank's end of the NVLink peer-memory gradient exchange (csrc/peer.cu).  `grads` is the rank's gradient
+    buffer (library-owned, mapped by the peers): bind it as the plan's gradient buffer."""
+
+    def __init__(self, rank, world, n_floats):
+        self._h = C.c_void_p()
+        check(lib.ogl_peer_create(C.byref(self._h), int(rank), int(world), int(n_floats)))
+        self.rank, self.world, self.n_floats = int(rank), int(world), int(n_floats)
+        p = C.c_void_p()
+        check(lib.ogl_peer_buffer(self._h, C.byref(p)))
+        self.grads = wrap_device(p.value, (self.n_floats,), torch.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and lib is not None:
+            lib.ogl_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def handle(self):
+        buf = C.create_string_buffer(64)
+        check(lib.ogl_peer_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: the 64-byte handles of all ranks, rank order (bytes of length 64 * world)"""
+        assert len(handles) == 64 * self.world
+        check(lib.ogl_peer_connect(self._h, C.c_char_p(handles)))
+
+    @staticmethod
+    def connect_local(peers):
+        """wire up peers that live in one process (tests: several ranks on one GPU)"""
+        arr = (C.c_void_p * len(peers))(*[p._h.value for p in peers])
+        for p in peers:
+            check(lib.ogl_peer_connect_local(p._h, arr))
+
+    def wait_readers(self):
+        """enqueue: wait until every peer has finished reading this rank's gradients of the previous exchange"""
+        check(lib.ogl_peer_wait_readers(self._h, _stream()))
 
 
 class SumTree:

@@ -53,6 +53,15 @@ int gemm_tn_simt(const GemmTN& g, cudaStream_t s);
 // tcgen05 / TMA / TMEM versions (bf16 in, fp32 accumulate); same contracts
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s);
 int gemm_tn_tc(const GemmTN& g, cudaStream_t s);
+// up to 4 weight-gradient GEMMs contracting over the same rows (same m_dev / m_max) in one launch; g[0].partial is the workspace
+int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s);
+
+// deterministic reduction of the split partials of up to 4 problems in one launch: c = sum over z (ascending) of partial[z]
+struct ReduceGroup {
+  struct Problem { const float* partial; float* c; int n, k, ldp, ldc; } pr[4];
+  int count, splits;
+};
+int reduce_splits_group(const ReduceGroup& g, cudaStream_t s);
 bool gemm_tc_available();
 
 }  // namespace ogl

@@ -153,6 +153,41 @@ __global__ void __launch_bounds__(256) k_reduce_splits_ld(const float* __restric
   }
 }
 
+// grouped form: blockIdx.y = problem; 16-byte loads of the partial rows (pitch % 4 == 0), fixed summation order
+__global__ void __launch_bounds__(256) k_reduce_splits_group(const ReduceGroup g) {
+  const ReduceGroup::Problem& q = g.pr[blockIdx.y];
+  const int quads = q.ldp / 4;
+  const int64_t total = (int64_t)q.n * quads;
+  const int64_t stride = (int64_t)q.n * q.ldp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / quads;
+    const int col = (int)(i % quads) * 4;
+    if (col >= q.k) continue;
+    const float* src = q.partial + r * q.ldp + col;
+    float4 acc = __ldcs(reinterpret_cast<const float4*>(src));
+    for (int z = 1; z < g.splits; ++z) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)z * stride));
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    float* dst = q.c + r * q.ldc + col;
+    dst[0] = acc.x;
+    if (col + 1 < q.k) dst[1] = acc.y;
+    if (col + 2 < q.k) dst[2] = acc.z;
+    if (col + 3 < q.k) dst[3] = acc.w;
+  }
+}
+
+int reduce_splits_group(const ReduceGroup& g, cudaStream_t s) {
+  int64_t most = 1;
+  for (int i = 0; i < g.count; ++i) {
+    const int64_t t = (int64_t)g.pr[i].n * (g.pr[i].ldp / 4);
+    if (t > most) most = t;
+  }
+  dim3 grid((unsigned)grid_for(most, 256), (unsigned)g.count);
+  OGL_LAUNCH(k_reduce_splits_group, grid, 256, 0, s, g);
+  return OGL_OK;
+}
+
 int reduce_splits_ld(const float* partial, int splits, int n, int k, int ldp, float* c, int ldc, cudaStream_t s) {
   OGL_LAUNCH(k_reduce_splits_ld, grid_for((int64_t)n * k, 256), 256, 0, s, partial, splits, n, k, ldp, c, ldc);
   return OGL_OK;

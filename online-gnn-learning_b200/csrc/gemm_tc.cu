@@ -547,17 +547,26 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
 }
 
 // ------------------------------------------------------------------ TN kernel --------------------
-struct TnParams {
+// up to kTnGroup weight-gradient GEMMs that contract over the same rows share ONE launch (e.g. dW_self and dW_neigh of a layer, both
+// dpre^T x [h_self | neigh]): every GEMM launch pays ~10 us of prologue / pipeline fill / drain, and one grid over all tiles keeps
+// the splits long (tiles * splits <= #SMs)
+constexpr int kTnGroup = 4;
+struct TnProblem {
   CUtensorMap ta, tb;            // boxes of 64 (inner, n / k index) x 64 (rows m)
   CUtensorMap tout;              // fp32 partials [splits][n][k] (pitch ldo), box 32 x 32 x 1 (TMA store)
-  int use_tma_store;
-  const int32_t* m_dev;
-  int m_max;
   int n, k;                      // output [n, k]
-  int n_tiles, k_tiles, splits;
+  int k_tiles, tile0;            // tiles of this problem are [tile0, tile0 + n_tiles * k_tiles)
   float* out;                    // partial [splits][n][ldo] (or C itself when splits == 1)
   int ldo;
   int64_t split_stride;
+};
+struct TnParams {
+  TnProblem pr[kTnGroup];
+  int n_prob;
+  int total_tiles, splits;
+  int use_tma_store;
+  const int32_t* m_dev;
+  int m_max;
 };
 
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant__ TnParams p) {
@@ -565,16 +574,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   const SmemLayout s = carve(smem_raw, STAGES, B_STAGE_BYTES, RING_BYTES, true);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int tile = blockIdx.x % (p.n_tiles * p.k_tiles);
-  const int z = blockIdx.x / (p.n_tiles * p.k_tiles);
-  const int nb = tile / p.k_tiles, kt = tile % p.k_tiles;
+  const int gtile = blockIdx.x % p.total_tiles;
+  const int z = blockIdx.x / p.total_tiles;
+  int which = 0;
+  while (which + 1 < p.n_prob && gtile >= p.pr[which + 1].tile0) ++which;
+  const TnProblem& q = p.pr[which];
+  const int tile = gtile - q.tile0;
+  const int nb = tile / q.k_tiles, kt = tile % q.k_tiles;
   const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
   // contraction range of this split, in 64-row blocks (rows in [m_dyn, round_up(m_dyn, 64)) are zero: zero-tail rule)
   const int blocks_total = (m_dyn + BK - 1) / BK;
   const int per = (blocks_total + p.splits - 1) / p.splits;
   const int kb0 = min(z * per, blocks_total), kb1 = min(kb0 + per, blocks_total);
-  const int n_chunks_a = min(2, (p.n - nb * BM + 63) / 64);                 // 64-wide TMA boxes actually needed
-  const int bn_tile = min(BN_MAX, (p.k - kt * BN_MAX + 63) / 64 * 64);
+  const int n_chunks_a = min(2, (q.n - nb * BM + 63) / 64);                 // 64-wide TMA boxes actually needed
+  const int bn_tile = min(BN_MAX, (q.k - kt * BN_MAX + 63) / 64 * 64);
   const int n_chunks_b = bn_tile / 64;
 
   if (threadIdx.x == 0) {
@@ -596,8 +609,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.empty[stage], phase ^ 1);
         mbar_expect_tx(&s.full[stage], tx);
-        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(s.a(stage) + c * 8192, &p.ta, &s.full[stage], nb * BM + c * 64, kb * BK);
-        for (int c = 0; c < n_chunks_b; ++c) tma_load_2d(s.b(stage) + c * 8192, &p.tb, &s.full[stage], kt * BN_MAX + c * 64, kb * BK);
+        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(s.a(stage) + c * 8192, &q.ta, &s.full[stage], nb * BM + c * 64, kb * BK);
+        for (int c = 0; c < n_chunks_b; ++c) tma_load_2d(s.b(stage) + c * 8192, &q.tb, &s.full[stage], kt * BN_MAX + c * 64, kb * BK);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -640,7 +653,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       uint8_t* const stage_buf = s.store + (warp - 2) * 2 * STORE_BOX_BYTES;
       uint32_t boxes_issued = 0;
       for (int c0 = 0; c0 < bn_tile; c0 += 32) {
-        if (kt * BN_MAX + c0 >= p.k) break;                  // whole box clipped
+        if (kt * BN_MAX + c0 >= q.k) break;                  // whole box clipped
         uint8_t* buf = stage_buf + (boxes_issued & 1) * STORE_BOX_BYTES;
         if (boxes_issued >= 2) {
           if (lane == 0) tma_store_wait_read<1>();
@@ -659,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&p.tout, buf, kt * BN_MAX + c0, nb * BM + quarter * 32, z);   // rows >= n / cols >= k clipped
+          tma_store_3d(&q.tout, buf, kt * BN_MAX + c0, nb * BM + quarter * 32, z);   // rows >= n / cols >= k clipped
           tma_store_commit();
         }
         ++boxes_issued;
@@ -667,7 +680,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       if (lane == 0) tma_store_wait_all();
       __syncwarp();
     } else {
-      float* orow = p.out + (int64_t)z * p.split_stride + (int64_t)gn * p.ldo;
+      float* orow = q.out + (int64_t)z * q.split_stride + (int64_t)gn * q.ldo;
       for (int c0 = 0; c0 < bn_tile; c0 += 32) {
         uint32_t r[32];
         if (have) {
@@ -676,11 +689,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        if (gn < p.n) {
+        if (gn < q.n) {
           const int gk0 = kt * BN_MAX + c0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (gk0 + j < p.k) orow[gk0 + j] = __uint_as_float(r[j]);
+            if (gk0 + j < q.k) orow[gk0 + j] = __uint_as_float(r[j]);
         }
       }
     }
@@ -824,47 +837,70 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   return OGL_OK;
 }
 
-int gemm_tn_tc(const GemmTN& g, cudaStream_t s) {
+int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
   OGL_ARG(tc_init() == 1, "gemm_tn_tc: tcgen05 path unavailable");
-  OGL_ARG(g.in_bf16 && g.n > 0 && g.k > 0 && g.m_max > 0, "gemm_tn_tc: bad arguments");
+  OGL_ARG(g && count >= 1 && count <= kTnGroup, "gemm_tn_tc: 1..%d problems per launch", kTnGroup);
   TnParams p;
   memset(&p, 0, sizeof(p));
-  OGL_TRY(make_map(&p.ta, g.a, g.m_max, g.n, g.lda, 64, BK));
-  OGL_TRY(make_map(&p.tb, g.b, g.m_max, g.k, g.ldb, 64, BK));
-  p.m_dev = g.m_dev;
-  p.m_max = g.m_max;
-  p.n = g.n;
-  p.k = g.k;
-  p.n_tiles = (g.n + BM - 1) / BM;
-  p.k_tiles = (g.k + BN_MAX - 1) / BN_MAX;
-  const int tiles = p.n_tiles * p.k_tiles;
+  p.n_prob = count;
+  p.m_dev = g[0].m_dev;
+  p.m_max = g[0].m_max;
+  int tiles = 0;
+  int64_t per_total = 0;
+  for (int i = 0; i < count; ++i) {
+    OGL_ARG(g[i].in_bf16 && g[i].n > 0 && g[i].k > 0 && g[i].m_max > 0, "gemm_tn_tc: bad arguments");
+    OGL_ARG(g[i].m_dev == g[0].m_dev && g[i].m_max == g[0].m_max, "gemm_tn_tc: grouped problems must contract over the same rows");
+    TnProblem& q = p.pr[i];
+    OGL_TRY(make_map(&q.ta, g[i].a, g[i].m_max, g[i].n, g[i].lda, 64, BK));
+    OGL_TRY(make_map(&q.tb, g[i].b, g[i].m_max, g[i].k, g[i].ldb, 64, BK));
+    q.n = g[i].n;
+    q.k = g[i].k;
+    q.k_tiles = (g[i].k + BN_MAX - 1) / BN_MAX;
+    q.tile0 = tiles;
+    tiles += ((g[i].n + BM - 1) / BM) * q.k_tiles;
+    q.ldo = (g[i].k + 3) / 4 * 4;
+    per_total += (int64_t)g[i].n * q.ldo;
+  }
+  p.total_tiles = tiles;
   // one CTA per SM and exactly one wave: tiles * splits <= #SMs (150 CTAs on 148 SMs would run as two waves)
   int splits = sm_count() / tiles;
-  const int by_rows = (int)ceil_div(g.m_max, 4 * BK);          // at least 4 contraction blocks per split
+  const int by_rows = (int)ceil_div(g[0].m_max, 4 * BK);          // at least 4 contraction blocks per split
   if (splits > by_rows) splits = by_rows;
-  const int ldo = (g.k + 3) / 4 * 4;
-  const int64_t per = (int64_t)g.n * ldo;
-  if ((int64_t)splits * per > g.partial_elems) splits = (int)(g.partial_elems / per);
+  float* ws = g[0].partial;
+  const int64_t ws_elems = ws ? g[0].partial_elems : 0;
+  if ((int64_t)splits * per_total > ws_elems) splits = (int)(ws_elems / per_total);
   if (splits < 1) splits = 1;
   p.splits = splits;
-  const bool staged = g.partial != nullptr && per <= g.partial_elems;   // partials (pitch % 4 == 0) take TMA stores
-  if (!staged) {
-    OGL_ARG(splits == 1, "gemm_tn_tc: internal: split without workspace");
-    p.out = g.c;
-    p.ldo = g.ldc;
-    p.split_stride = 0;
-    p.use_tma_store = 0;
-  } else {
-    p.out = g.partial;
-    p.ldo = ldo;
-    p.split_stride = per;
-    p.use_tma_store = 1;
-    OGL_TRY(make_map_f32_3d(&p.tout, g.partial, g.k, g.n, splits, ldo));
+  const bool staged = ws != nullptr && per_total <= ws_elems;       // partials (pitch % 4 == 0) take TMA stores
+  OGL_ARG(staged || count == 1, "gemm_tn_tc: a grouped launch needs the split workspace");
+  ReduceGroup rg;
+  memset(&rg, 0, sizeof(rg));
+  rg.count = count;
+  rg.splits = splits;
+  int64_t off = 0;
+  for (int i = 0; i < count; ++i) {
+    TnProblem& q = p.pr[i];
+    if (!staged) {
+      OGL_ARG(splits == 1, "gemm_tn_tc: internal: split without workspace");
+      q.out = g[i].c;
+      q.ldo = g[i].ldc;
+      q.split_stride = 0;
+    } else {
+      const int64_t per = (int64_t)g[i].n * q.ldo;
+      q.out = ws + off;
+      q.split_stride = per;
+      OGL_TRY(make_map_f32_3d(&q.tout, q.out, g[i].k, g[i].n, splits, q.ldo));
+      rg.pr[i] = {q.out, g[i].c, g[i].n, g[i].k, q.ldo, g[i].ldc};
+      off += (int64_t)splits * per;
+    }
   }
+  p.use_tma_store = staged ? 1 : 0;
   OGL_LAUNCH(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_TN, s, p);
-  if (staged) return reduce_splits_ld(g.partial, splits, g.n, g.k, ldo, g.c, g.ldc, s);
+  if (staged) return reduce_splits_group(rg, s);
   return OGL_OK;
 }
+
+int gemm_tn_tc(const GemmTN& g, cudaStream_t s) { return gemm_tn_tc_group(&g, 1, s); }
 
 }  // namespace ogl
 

@@ -8,6 +8,7 @@
 #include "sample.cuh"
 #include "gemm.cuh"
 #include "sage_kernels.cuh"
+#include "peer.cuh"
 #include <vector>
 #include <string>
 
@@ -99,6 +100,8 @@ struct LayerBuf {
   void* neigh = nullptr;    // [nmax[dst], pin]
   uint8_t* arg = nullptr;   // [nmax[dst], pin]
   void* dpre = nullptr;     // [nmax[dst], pout]   gradient wrt this layer's pre-activation output
+  void* dhp = nullptr;      // [nmax[src], pin]    gradient wrt hp (per layer: the fc_pool weight gradient of layer l is computed
+                            //                     later, grouped with layer l-1's fc_self / fc_neigh weight gradients)
 };
 
 struct ogl_plan {
@@ -139,7 +142,6 @@ struct ogl_plan {
   uint32_t* ctl = nullptr;               // [0]=philox step, [1]=adam t
   int n_seeds = 0;
   // backward scratch
-  void* dhp = nullptr;
   void* dng = nullptr;
   float* tn_partial = nullptr;
   int64_t tn_partial_elems = 0;
@@ -245,6 +247,12 @@ static int gemm_tn(const ogl_plan* p, const GemmTN& g, cudaStream_t s) {
   if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_tn_tc(g, s);
   return gemm_tn_simt(g, s);
 }
+// weight-gradient GEMMs that contract over the same rows: one launch on the tcgen05 path
+static int gemm_tn_group(const ogl_plan* p, const GemmTN* g, int count, cudaStream_t s) {
+  if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_tn_tc_group(g, count, s);
+  for (int i = 0; i < count; ++i) OGL_TRY(gemm_tn_simt(g[i], s));
+  return OGL_OK;
+}
 
 static int dmalloc0(void** ptr, size_t bytes) {
   OGL_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
@@ -323,6 +331,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     DM0(lb.neigh, p->es * rows(p->nmax[d]) * lb.pin);
     DM0(lb.arg, rows(p->nmax[d]) * lb.pin);
     DM0(lb.dpre, p->es * rows(p->nmax[d]) * lb.pout);
+    DM0(lb.dhp, p->es * rows(p->nmax[s]) * lb.pin);
     // layer output: logits are always fp32
     const size_t oes = (l == L - 1) ? 4 : p->es;
     DM0(p->act[d], oes * rows(p->nmax[d]) * lb.pout);
@@ -344,7 +353,6 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     DM0(p->shadow_segs, sizeof(ShadowSeg) * segs.size());
     OGL_CUDA(cudaMemcpy(p->shadow_segs, segs.data(), sizeof(ShadowSeg) * segs.size(), cudaMemcpyHostToDevice));
   }
-  DM0(p->dhp, p->es * max_src_elems);
   DM0(p->dng, p->es * max_dst_in_elems);
   p->tn_partial_elems = max_nk * 32;
   DM0(p->tn_partial, sizeof(float) * p->tn_partial_elems);
@@ -372,14 +380,14 @@ extern "C" int ogl_plan_destroy(ogl_plan* p) {
   for (auto x : p->rev_edge) cudaFree(x);
   for (auto x : p->act) cudaFree(x);
   for (auto& lb : p->layer) {
-    void* ptrs[] = {lb.wp, lb.wpT, lb.ws, lb.wsT, lb.wn, lb.wnT, lb.hp, lb.neigh, lb.arg, lb.dpre};
+    void* ptrs[] = {lb.wp, lb.wpT, lb.ws, lb.wsT, lb.wn, lb.wnT, lb.hp, lb.neigh, lb.arg, lb.dpre, lb.dhp};
     for (void* q : ptrs) cudaFree(q);
   }
   to_block_free(&p->tb);
   for (auto* v : {&p->alt.nodes, &p->alt.edge_lid, &p->alt.edge_gsrc, &p->alt.rev_ptr, &p->alt.rev_edge})
     for (auto x : *v) cudaFree(x);
   cudaFree(p->alt.counts); cudaFree(p->alt.x); cudaFree(p->alt.seeds_stage);
-  void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dhp, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
+  void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
                   p->loss_sum, p->adam_m, p->adam_v, p->shadow_segs};
   for (void* q : ptrs) cudaFree(q);
   for (auto& r : p->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -515,14 +523,17 @@ extern "C" int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_s
 
 static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
   const int L = p->L;
-  if (p->tail_mode == 2) {                        // only dWp of layer 0 = dhp^T x (dhp was left in place by the tail_mode 1 pass)
-    LayerBuf& lb = p->layer[0];
-    const int sl = L;
+  auto dw_pool = [&](int l) {                     // dWp = dhp^T act[src] of layer l
+    LayerBuf& lb = p->layer[l];
+    const int sl = L - l;
     GemmTN tp;
-    tp.a = p->dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
+    tp.a = lb.dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
     tp.c = p->grads + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16;
     tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
-    STAGE("l0.dW_pool", gemm_tn(p, tp, s));
+    return tp;
+  };
+  if (p->tail_mode == 2) {                        // only dWp of layer 0 (its dhp was left in place by the tail_mode 1 pass)
+    STAGE("l0.dW_pool", gemm_tn(p, dw_pool(0), s));
     return OGL_OK;
   }
   OGL_TRY(join_side(p, s));                      // reverse edge lists built on the side stream during sampling
@@ -530,20 +541,26 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, sl = h + 1, dl = h;
     float* G = p->grads;
-    // dWs = dpre^T act[src][:n_d] ; dWn = dpre^T neigh ; db = colsum(dpre): independent of the chain below -> side stream
+    // dWs = dpre^T act[src][:n_d] ; dWn = dpre^T neigh ; db = colsum(dpre): independent of the chain below -> side stream.
+    // They contract over the rows of level dl -- and so does the fc_pool weight gradient of the layer ABOVE (dhp[l+1]^T act[dl]),
+    // which was held back for this: the three GEMMs go out as ONE grouped launch.
     const bool ov = p->use_side && !p->prof_on;
     cudaStream_t ss = ov ? p->side : s;
     if (ov) {
-      OGL_CUDA(cudaEventRecord(p->ev_fork, s));                 // dpre of this layer is complete on s
+      OGL_CUDA(cudaEventRecord(p->ev_fork, s));                 // dpre of this layer (and dhp of the layer above) are complete on s
       OGL_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     }
+    GemmTN grp[3];
+    int ng = 0;
+    if (l + 1 < L) grp[ng++] = dw_pool(l + 1);
     GemmTN t;
     t.a = lb.dpre; t.lda = lb.pout; t.n = lb.out; t.b = p->act[sl]; t.ldb = lb.pin; t.k = lb.in;
     t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16;
-    t.partial = ov ? p->tn_partial2 : p->tn_partial; t.partial_elems = p->tn_partial_elems;
-    STAGE_ON(ss, nm("l%d.dW_self", l).c_str(), gemm_tn(p, t, ss));
+    grp[ng++] = t;
     t.b = lb.neigh; t.c = G + lb.o_wn;
-    STAGE_ON(ss, nm("l%d.dW_neigh", l).c_str(), gemm_tn(p, t, ss));
+    grp[ng++] = t;
+    for (int i = 0; i < ng; ++i) { grp[i].partial = ov ? p->tn_partial2 : p->tn_partial; grp[i].partial_elems = p->tn_partial_elems; }
+    STAGE_ON(ss, nm("l%d.dW_group", l).c_str(), gemm_tn_group(p, grp, ng, ss));
     STAGE_ON(ss, nm("l%d.db_out", l).c_str(), colsum(p->bf16, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl],
                                                      ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bs, G + lb.o_bn, ss));
     // dneigh = dpre Wn
@@ -558,18 +575,15 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
           colsum(p->bf16, p->dng, lb.pin, lb.in, p->counts + dl, p->nmax[dl], p->colsum_partial, G + lb.o_bp, nullptr, s));
     // max-pool backward as a gather over the reverse edge lists
     STAGE(nm("l%d.pool_bwd", l).c_str(), pool_bwd(p->bf16, p->dng, lb.pin, lb.arg, p->rev_ptr[h], p->rev_edge[h], p->cfg.fanouts[h],
-                                                  p->counts + sl, p->nmax[sl], p->dhp, s));
-    // dWp = dhp^T act[src]
-    GemmTN tp;
-    tp.a = p->dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
-    tp.c = G + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16;
-    tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
-    if (!(l == 0 && p->tail_mode == 1)) STAGE(nm("l%d.dW_pool", l).c_str(), gemm_tn(p, tp, s));
+                                                  p->counts + sl, p->nmax[sl], lb.dhp, s));
+    // dWp = dhp^T act[src]: layer 0 computes it here (the step's last and largest weight gradient; data-parallel runs peel it off
+    // as the second gradient bucket); the layers above hold it back for the next grouped launch
+    if (l == 0 && p->tail_mode != 1) STAGE("l0.dW_pool", gemm_tn(p, dw_pool(0), s));
     if (l > 0) {
       // dpre[l-1] = relu'(act[src]) * ( dhp Wp + [dpre Ws on the first n_d rows] )
       LayerBuf& prev = p->layer[l - 1];
       GemmNT d;
-      d.a[0] = p->dhp; d.lda[0] = lb.pin; d.b[0] = lb.wpT; d.ldb[0] = lb.pin; d.k[0] = lb.in;
+      d.a[0] = lb.dhp; d.lda[0] = lb.pin; d.b[0] = lb.wpT; d.ldb[0] = lb.pin; d.k[0] = lb.in;
       d.a[1] = lb.dpre; d.lda[1] = lb.pout; d.b[1] = lb.wsT; d.ldb[1] = lb.pout; d.k[1] = lb.out; d.a_rows_dev[1] = p->counts + dl;
       d.a_rows_max[1] = round_up(p->nmax[dl], 128);
       d.n_seg = 2;
@@ -613,6 +627,21 @@ extern "C" int ogl_plan_adam_step(ogl_plan* p, void* stream) {
   STAGE("adam", adam_shadow(p->bf16, p->params, p->grads, p->adam_m, p->adam_v, p->n_params, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps,
                             p->ctl + 1, p->shadow_segs, p->n_shadow_segs, s));
   OGL_TRY(bump(nullptr, p->ctl + 1, s));
+  return OGL_OK;
+}
+
+// data-parallel twin of ogl_plan_adam_step: gradients [lo, hi) are summed over the ranks of `peer` through NVLink peer memory inside
+// the Adam kernel (peer.cu).  `last` != 0 on the final bucket of a step: the Adam step counter advances after it.
+extern "C" int ogl_plan_peer_adam(ogl_plan* p, ogl_peer* peer, int64_t lo, int64_t hi, int last, float* reduced_out_dev, void* stream) {
+  OGL_ARG(p && p->params && peer, "ogl_plan_peer_adam: parameters not bound / null peer group");
+  OGL_ARG(lo >= 0 && hi <= p->n_params, "ogl_plan_peer_adam: range outside the %lld parameters", (long long)p->n_params);
+  cudaStream_t s = (cudaStream_t)stream;
+  PeerAdamArgs a;
+  a.bf16 = p->bf16; a.params = p->params; a.grads = p->grads; a.m = p->adam_m; a.v = p->adam_v;
+  a.lr = p->cfg.lr; a.b1 = p->cfg.beta1; a.b2 = p->cfg.beta2; a.eps = p->cfg.eps;
+  a.t_dev = p->ctl + 1; a.segs = p->shadow_segs; a.n_segs = p->n_shadow_segs; a.reduced_out = reduced_out_dev;
+  OGL_TRY(peer_sum_adam(peer, a, lo, hi, s));
+  if (last) OGL_TRY(bump(nullptr, p->ctl + 1, s));
   return OGL_OK;
 }
 

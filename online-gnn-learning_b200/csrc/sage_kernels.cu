@@ -305,11 +305,10 @@ __global__ void __launch_bounds__(kBlock) k_adam_shadow(float* __restrict__ p, c
   const float step = lr / bc1, isq = rsqrtf(bc2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float mi = m[i], vi = v[i];
+    const float pi = adam_math(gi, mi, vi, p[i], b1, b2, eps, step, isq);
     m[i] = mi;
     v[i] = vi;
-    const float pi = p[i] - step * mi / (sqrtf(vi) * isq + eps);
     p[i] = pi;
     int sg = 0;
     while (sg < n_segs && i >= ss[sg].end) ++sg;

@@ -12,6 +12,16 @@ struct ShadowSeg {
   void* wt;               // W^T [in, pitch_out]
 };
 
+#ifdef __CUDACC__
+// one element of Adam (torch.optim.Adam defaults as the reference uses them, pytorch/model.py:22-25); shared by the single-GPU
+// kernel (sage_kernels.cu) and the peer-memory data-parallel kernel (peer.cu) so that both round identically
+__device__ __forceinline__ float adam_math(float gi, float& mi, float& vi, float pi, float b1, float b2, float eps, float step, float isq) {
+  mi = b1 * mi + (1.f - b1) * gi;
+  vi = b2 * vi + (1.f - b2) * gi * gi;
+  return pi - step * mi / (sqrtf(vi) * isq + eps);
+}
+#endif
+
 int feat_write(int bf16, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s);
 int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t* dst, int64_t row0, cudaStream_t s);
 int gather_rows(int bf16, const void* table, int pitch, const int32_t* nodes, const int32_t* n_dev, int n_max, void* out, cudaStream_t s);

@@ -64,6 +64,23 @@ def train_step(plan, graph, features, local_seeds, global_batch, flat_grad, per_
         plan.adam_step()
 
 
+def make_peer_exchange(plan, flat_params, group=None):
+    """NVLink peer-memory gradient exchange for `plan` (csrc/peer.cu): allocates the rank's peer-visible gradient buffer, binds it
+    as the plan's gradient buffer, exchanges the CUDA IPC handles over the process group and maps the peers.  Returns the
+    native.Peer (its `.grads` is the new flat gradient tensor).  One rank: a plain local buffer, no peers."""
+    from . import _native as native
+    w, r = world(), rank()
+    peer = native.Peer(r, w, plan.n_params)
+    if w > 1:
+        mine = torch.frombuffer(bytearray(peer.handle()), dtype=torch.uint8).cuda()
+        every = [torch.empty_like(mine) for _ in range(w)]
+        dist.all_gather(every, mine, group=group)
+        peer.connect(b"".join(bytes(t.cpu().numpy().tobytes()) for t in every))
+        dist.barrier(group=group)
+    plan.bind_params(flat_params, peer.grads)
+    return peer
+
+
 class Pipeline:
     """Train loop with everything that does not need fresh weights off the critical path (any number of GPUs).
 
@@ -75,8 +92,13 @@ class Pipeline:
     bucket + Adam run on a communication stream; forward(t+1) waits for Adam(t).  Same arithmetic as the unpipelined loop
     (no stale gradients, same Philox step per minibatch)."""
 
-    def __init__(self, plan, graph, features, flat_grad, global_batch):
+    def __init__(self, plan, graph, features, flat_grad, global_batch, peer=None):
+        """peer: a native.Peer from make_peer_exchange -> the gradient exchange + Adam is ONE kernel per bucket over NVLink peer
+        memory (no NCCL on the data path); None -> NCCL all-reduce + ogl_plan_adam_step"""
         self.plan, self.graph, self.features, self.flat_grad = plan, graph, features, flat_grad
+        self.peer = peer
+        if peer is not None:
+            assert flat_grad.data_ptr() == peer.grads.data_ptr(), "the plan must be bound to the peer group's gradient buffer"
         self.scale = 1.0 / float(global_batch)
         self.w = world()
         self.comm = torch.cuda.Stream() if self.w > 1 else None
@@ -103,18 +125,26 @@ class Pipeline:
             main.wait_event(self.ev_adam)                # weights (and the gradient buffer) of the previous step are settled
         # two gradient buckets: everything except layer 0's fc_pool.weight is final before the last weight-gradient GEMM
         # runs, so its all-reduce overlaps that GEMM; the small second bucket + Adam overlap the next step's start
-        n0 = self.plan.tail_params
+        n0, n = self.plan.tail_params, self.plan.n_params
+        if self.peer is not None:
+            self.peer.wait_readers()                     # every peer has read this rank's gradients of the previous step
         self.plan.step_finish_head(self.features, self.scale, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
         self.ev_head.record(main)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.ev_head)
-            allreduce_grads(self.flat_grad[n0:])
+            if self.peer is not None:
+                self.plan.peer_adam(self.peer, n0, n, last=False)     # P2P sum + Adam of bucket 1, beside the tail GEMM
+            else:
+                allreduce_grads(self.flat_grad[n0:])
         self.plan.step_finish_tail(self.features)
         self.ev_bwd.record(main)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.ev_bwd)
-            allreduce_grads(self.flat_grad[:n0])
-            self.plan.adam_step()
+            if self.peer is not None:
+                self.plan.peer_adam(self.peer, 0, n0, last=True)
+            else:
+                allreduce_grads(self.flat_grad[:n0])
+                self.plan.adam_step()
             self.ev_adam.record(self.comm)
         self._adam_pending = True
 
