@@ -496,6 +496,8 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(inputs, read_back):
         """K steps bracketed by barrier + synchronize; device time by CUDA events, max over ranks"""
         barrier()
@@ -504,7 +506,9 @@ def run_ours(args, rank, world, local_rank):
         wall0 = time.time()
         t0.record()
         losses = []
+        h0 = time.perf_counter()
         run_steps(inputs, read_back, losses)
+        host_ms[0] = (time.perf_counter() - h0) * 1e3      # host time to ENQUEUE the steps (well below the device time = not host-bound)
         t1.record()
         barrier()
         ms = t0.elapsed_time(t1)
@@ -519,6 +523,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- value: inputs resident in HBM (the step's launch sequence is replayed as one CUDA graph)
     gs0 = plan.graph_stats()
     ms_dev, wall0, wall1, _ = timed(dev_batches[W:], read_back=False)
+    host_enqueue_ms = host_ms[0]
     gs1 = plan.graph_stats()
     # ---- the same K steps once more with the library's per-stage CUDA events on (direct launches, no graph):
     #      stage shares + the roofline of the dominant kernel
@@ -627,7 +632,7 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic", "config": workload_config(w, args.workload, world),
             "e2e": {"value": e2e, "unit": "vertices/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
                     "api": "ogl_plan_prefetch(pinned host seeds of step t+1) + ogl_plan_step_finish(step t) + loss read-back every step", "last_loss": losses[-1] / (B * world) if losses else None},
-            "gpu_launches": launches, "cuda_graph": {"replays_in_timed_region": gs1["replays"] - gs0["replays"],
+            "host_enqueue_ms_per_step": host_enqueue_ms / K, "gpu_launches": launches, "cuda_graph": {"replays_in_timed_region": gs1["replays"] - gs0["replays"],
                                                       "captures_in_timed_region": gs1["captures"] - gs0["captures"],
                                                       "ms_per_step_direct_launch_profiled": ms_prof / K},
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,

@@ -100,6 +100,7 @@ struct LayerBuf {
   void* neigh = nullptr;    // [nmax[dst], pin]
   uint8_t* arg = nullptr;   // [nmax[dst], pin]
   void* dpre = nullptr;     // [nmax[dst], pout]   gradient wrt this layer's pre-activation output
+  void* dng = nullptr;      // [nmax[dst], pin]    gradient wrt neigh (per layer: its column sums run on the side stream)
   void* dhp = nullptr;      // [nmax[src], pin]    gradient wrt hp (per layer: the fc_pool weight gradient of layer l is computed
                             //                     later, grouped with layer l-1's fc_self / fc_neigh weight gradients)
 };
@@ -142,7 +143,6 @@ struct ogl_plan {
   uint32_t* ctl = nullptr;               // [0]=philox step, [1]=adam t
   int n_seeds = 0;
   // backward scratch
-  void* dng = nullptr;
   float* tn_partial = nullptr;
   int64_t tn_partial_elems = 0;
   float* colsum_partial = nullptr;
@@ -159,6 +159,8 @@ struct ogl_plan {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int skip_gather = 0;                   // step_finish: the input rows were already gathered by step_begin
+  int adam_in_backward = 0;              // fused step with do_step: the backward pass runs Adam on all but the last gradient itself
+  int64_t adam_done_from = 0;            // ... and leaves [0, adam_done_from) to ogl_plan_adam_step
   int tail_mode = 0;                     // backward: 0 = all, 1 = everything but the last weight-gradient GEMM (layer 0 fc_pool),
                                          // 2 = only that GEMM (data-parallel: its predecessors' gradients are already on the wire)
   int in_train_step = 0;                 // set by the fused train step: sampling may defer the reverse edge lists to the side stream
@@ -332,6 +334,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     DM0(lb.arg, rows(p->nmax[d]) * lb.pin);
     DM0(lb.dpre, p->es * rows(p->nmax[d]) * lb.pout);
     DM0(lb.dhp, p->es * rows(p->nmax[s]) * lb.pin);
+    DM0(lb.dng, p->es * rows(p->nmax[d]) * lb.pin);
     // layer output: logits are always fp32
     const size_t oes = (l == L - 1) ? 4 : p->es;
     DM0(p->act[d], oes * rows(p->nmax[d]) * lb.pout);
@@ -353,7 +356,6 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     DM0(p->shadow_segs, sizeof(ShadowSeg) * segs.size());
     OGL_CUDA(cudaMemcpy(p->shadow_segs, segs.data(), sizeof(ShadowSeg) * segs.size(), cudaMemcpyHostToDevice));
   }
-  DM0(p->dng, p->es * max_dst_in_elems);
   p->tn_partial_elems = max_nk * 32;
   DM0(p->tn_partial, sizeof(float) * p->tn_partial_elems);
   DM0(p->colsum_partial, sizeof(float) * max_colsum);
@@ -380,14 +382,14 @@ extern "C" int ogl_plan_destroy(ogl_plan* p) {
   for (auto x : p->rev_edge) cudaFree(x);
   for (auto x : p->act) cudaFree(x);
   for (auto& lb : p->layer) {
-    void* ptrs[] = {lb.wp, lb.wpT, lb.ws, lb.wsT, lb.wn, lb.wnT, lb.hp, lb.neigh, lb.arg, lb.dpre, lb.dhp};
+    void* ptrs[] = {lb.wp, lb.wpT, lb.ws, lb.wsT, lb.wn, lb.wnT, lb.hp, lb.neigh, lb.arg, lb.dpre, lb.dhp, lb.dng};
     for (void* q : ptrs) cudaFree(q);
   }
   to_block_free(&p->tb);
   for (auto* v : {&p->alt.nodes, &p->alt.edge_lid, &p->alt.edge_gsrc, &p->alt.rev_ptr, &p->alt.rev_edge})
     for (auto x : *v) cudaFree(x);
   cudaFree(p->alt.counts); cudaFree(p->alt.x); cudaFree(p->alt.seeds_stage);
-  void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->dng, p->tn_partial, p->colsum_partial, p->per_loss,
+  void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->tn_partial, p->colsum_partial, p->per_loss,
                   p->loss_sum, p->adam_m, p->adam_v, p->shadow_segs};
   for (void* q : ptrs) cudaFree(q);
   for (auto& r : p->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -512,6 +514,10 @@ static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, f
 
 static int plan_backward_layers(ogl_plan* p, cudaStream_t s);
 static int join_side(ogl_plan* p, cudaStream_t s);
+static int adam_range(ogl_plan* p, int64_t lo, int64_t hi, cudaStream_t s) {
+  return adam_shadow(p->bf16, p->params, p->grads, p->adam_m, p->adam_v, lo, hi, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps, p->ctl + 1,
+                     p->shadow_segs, p->n_shadow_segs, s);
+}
 
 extern "C" int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
                                       void* stream) {
@@ -566,15 +572,20 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     // dneigh = dpre Wn
     GemmNT n1;
     n1.a[0] = lb.dpre; n1.lda[0] = lb.pout; n1.b[0] = lb.wnT; n1.ldb[0] = lb.pout; n1.k[0] = lb.out; n1.n_seg = 1;
-    n1.c = p->dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
+    n1.c = lb.dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
     n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.zero_tail = 0;
     n1.mask = lb.neigh; n1.ldmask = lb.pin;        // relu'(hp) at the argmax: neigh[d, f] == hp[src(arg), f]
     STAGE(nm("l%d.dneigh_gemm", l).c_str(), gemm_nt(p, n1, s));
-    // fc_pool bias gradient: every dng[d, f] lands in exactly one source row, so colsum(dhp) == colsum(dng)
-    STAGE(nm("l%d.db_pool", l).c_str(),
-          colsum(p->bf16, p->dng, lb.pin, lb.in, p->counts + dl, p->nmax[dl], p->colsum_partial, G + lb.o_bp, nullptr, s));
+    // fc_pool bias gradient: every dng[d, f] lands in exactly one source row, so colsum(dhp) == colsum(dng).  Side stream too (behind the
+    // weight-gradient group): only Adam reads it
+    if (ov) {
+      OGL_CUDA(cudaEventRecord(p->ev_fork, s));
+      OGL_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    }
+    STAGE_ON(ss, nm("l%d.db_pool", l).c_str(), colsum(p->bf16, lb.dng, lb.pin, lb.in, p->counts + dl, p->nmax[dl],
+                                                      ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bp, nullptr, ss));
     // max-pool backward as a gather over the reverse edge lists
-    STAGE(nm("l%d.pool_bwd", l).c_str(), pool_bwd(p->bf16, p->dng, lb.pin, lb.arg, p->rev_ptr[h], p->rev_edge[h], p->cfg.fanouts[h],
+    STAGE(nm("l%d.pool_bwd", l).c_str(), pool_bwd(p->bf16, lb.dng, lb.pin, lb.arg, p->rev_ptr[h], p->rev_edge[h], p->cfg.fanouts[h],
                                                   p->counts + sl, p->nmax[sl], lb.dhp, s));
     // dWp = dhp^T act[src]: layer 0 computes it here (the step's last and largest weight gradient; data-parallel runs peel it off
     // as the second gradient bucket); the layers above hold it back for the next grouped launch
@@ -594,6 +605,12 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     }
   }
   if (p->use_side && !p->prof_on) {                                   // join: the side-stream gradients precede Adam / the caller
+    // fused step with Adam: every gradient except layer 0's fc_pool.weight (the first in*in floats) is final on the side stream
+    // while the main stream still computes that last, largest one: their Adam update runs there, beside it
+    if (p->adam_in_backward && p->n_params > p->layer[0].o_bp) {
+      OGL_TRY(adam_range(p, p->layer[0].o_bp, p->n_params, p->side));
+      p->adam_done_from = p->layer[0].o_bp;
+    }
     OGL_CUDA(cudaEventRecord(p->ev_join, p->side));
     OGL_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
   }
@@ -624,8 +641,10 @@ extern "C" int ogl_plan_backward(ogl_plan* p, const float* dlogits_dev, void* st
 extern "C" int ogl_plan_adam_step(ogl_plan* p, void* stream) {
   OGL_ARG(p && p->params, "ogl_plan_adam_step: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  STAGE("adam", adam_shadow(p->bf16, p->params, p->grads, p->adam_m, p->adam_v, p->n_params, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps,
-                            p->ctl + 1, p->shadow_segs, p->n_shadow_segs, s));
+  // (a fused step has already updated [adam_done_from, n_params) on the side stream, see plan_backward_layers)
+  const int64_t hi = p->adam_done_from > 0 ? p->adam_done_from : p->n_params;
+  p->adam_done_from = 0;
+  STAGE("adam", adam_range(p, 0, hi, s));
   OGL_TRY(bump(nullptr, p->ctl + 1, s));
   return OGL_OK;
 }
@@ -693,8 +712,10 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
   p->skip_gather = 0;
   OGL_TRY(rf);
   p->tail_mode = (kind == 3) ? 1 : 0;
+  p->adam_in_backward = (do_step && kind != 3) ? 1 : 0;
   const int rl = ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s);
   p->tail_mode = 0;
+  p->adam_in_backward = 0;
   OGL_TRY(rl);
   if (do_step) OGL_TRY(ogl_plan_adam_step(p, s));
   if (kind == 0) OGL_TRY(bump(p->ctl, nullptr, s));

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kBlock) k_adam(float* __restrict__ p, const fl
 // the flat parameter buffer: the updated value is written to its shadow slots straight from the register.
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_adam_shadow(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                        float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                        float* __restrict__ v, int64_t lo, int64_t n, float lr, float b1, float b2, float eps,
                                                         const uint32_t* __restrict__ t_dev, const ShadowSeg* __restrict__ segs, int n_segs) {
   __shared__ ShadowSeg ss[48];
   for (int i = threadIdx.x; i < n_segs; i += blockDim.x) ss[i] = segs[i];
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kBlock) k_adam_shadow(float* __restrict__ p, c
   const uint32_t t = *t_dev + 1;
   const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
   const float step = lr / bc1, isq = rsqrtf(bc2);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i];
     float mi = m[i], vi = v[i];
     const float pi = adam_math(gi, mi, vi, p[i], b1, b2, eps, step, isq);
@@ -409,11 +409,13 @@ int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, floa
   OGL_LAUNCH(k_adam, grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev);
   return OGL_OK;
 }
-int adam_shadow(int bf16, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, uint32_t* t_dev,
-                const ShadowSeg* segs_dev, int n_segs, cudaStream_t s) {
+int adam_shadow(int bf16, float* p, const float* g, float* m, float* v, int64_t lo, int64_t hi, float lr, float b1, float b2, float eps,
+                uint32_t* t_dev, const ShadowSeg* segs_dev, int n_segs, cudaStream_t s) {
   OGL_ARG(n_segs <= 48, "adam_shadow: too many weight segments");
-  if (bf16) OGL_LAUNCH((k_adam_shadow<__nv_bfloat16>), grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
-  else OGL_LAUNCH((k_adam_shadow<float>), grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
+  OGL_ARG(lo >= 0 && hi > lo, "adam_shadow: empty range");
+  const int grid = grid_for(hi - lo, kBlock);
+  if (bf16) OGL_LAUNCH((k_adam_shadow<__nv_bfloat16>), grid, kBlock, 0, s, p, g, m, v, lo, hi, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
+  else OGL_LAUNCH((k_adam_shadow<float>), grid, kBlock, 0, s, p, g, m, v, lo, hi, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
   return OGL_OK;
 }
 int bump(uint32_t* a, uint32_t* b, cudaStream_t s) {

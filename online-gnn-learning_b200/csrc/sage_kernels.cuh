@@ -35,7 +35,8 @@ int xent(int bf16, const float* logits, int ldl, int C, const int32_t* labels, c
          int rows_buf, float scale, float* per_loss, void* dlogits, int ldd, int want_grad, cudaStream_t s);
 int sum_f32(const float* x, const int32_t* n_dev, int n_max, float* out, cudaStream_t s);
 int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, uint32_t* t_dev, cudaStream_t s);
-int adam_shadow(int bf16, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, uint32_t* t_dev,
+// Adam over the parameter range [lo, hi) (the step counter *t_dev is read, not advanced)
+int adam_shadow(int bf16, float* p, const float* g, float* m, float* v, int64_t lo, int64_t hi, float lr, float b1, float b2, float eps, uint32_t* t_dev,
                 const ShadowSeg* segs_dev, int n_segs, cudaStream_t s);
 int bump(uint32_t* a, uint32_t* b, cudaStream_t s);
 int weight_shadow(int bf16, const float* w, int out, int in, void* ws, int pitch_in, void* wt, int pitch_out, cudaStream_t s);

@@ -10,9 +10,12 @@ pytestmark = pytest.mark.gpu
 from test_gpu_sage import Case  # noqa: E402
 
 
+@pytest.mark.parametrize("two_shot", [0, 1])
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
-def test_peer_adam_two_ranks_equals_summed_gradient_adam(mode):
+def test_peer_adam_two_ranks_equals_summed_gradient_adam(mode, two_shot, monkeypatch):
+    """two_shot = 0: every rank loads every peer's gradients; 1: reduce-scatter + all-gather inside the kernel (default for >= 4 ranks)"""
     from ogl_b200 import native
+    monkeypatch.setenv("OGL_PEER_TWO_SHOT", str(two_shot))
     W, B = 2, 64
     kw = dict(dims=(64, 32, 5), fanouts=(6, 4), n_seeds=B, mode=mode, gemm_impl=0 if mode == "bf16" else 1)
     ranks = [Case(**kw) for _ in range(W)]
