@@ -473,6 +473,9 @@ def run_ours(args, rank, world, local_rank):
         ogl_b200.parallel.train_step(plan, g, fs, seeds, B * world, grad, loss_sum_out=loss_dev)
 
     pipe = ogl_b200.parallel.Pipeline(plan, g, fs, grad, B * world, peer=peer) if not args.no_pipeline else None
+    loss_slots = [torch.zeros(1, device=dev) for _ in range(2)]
+    loss_host = torch.zeros(2, 1).pin_memory()
+    loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
 
     def run_steps(inputs, read_back, losses):
         """pipelined loop (ogl_b200.parallel.Pipeline): sample + gather of step t+1 (ogl_plan_prefetch, the plan's second buffer
@@ -485,10 +488,21 @@ def run_ours(args, rank, world, local_rank):
                     losses.append(float(loss_dev.item()))      # D2H read of the step's loss (synchronises)
             return
         pipe.begin(inputs[0])
-        for i in range(len(inputs)):
-            pipe.finish(inputs[i + 1] if i + 1 < len(inputs) else None, loss_sum_out=loss_dev)
+        n = len(inputs)
+        for i in range(n):
+            slot = i & 1
+            pipe.finish(inputs[i + 1] if i + 1 < n else None, loss_sum_out=loss_slots[slot] if read_back else loss_dev)
             if read_back:
-                losses.append(float(loss_dev.item()))
+                # every step's loss goes device -> pinned host memory inside the timed region; the host consumes it one step later,
+                # so that the read-back of step t does not stall the launch of step t+1
+                loss_host[slot].copy_(loss_slots[slot], non_blocking=True)
+                loss_evs[slot].record()
+                if i > 0:
+                    loss_evs[slot ^ 1].synchronize()
+                    losses.append(float(loss_host[slot ^ 1]))
+        if read_back and n > 0:
+            loss_evs[(n - 1) & 1].synchronize()
+            losses.append(float(loss_host[(n - 1) & 1]))
         pipe.flush()
 
     def barrier():
@@ -631,7 +645,7 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(w, args.workload, world),
             "e2e": {"value": e2e, "unit": "vertices/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
-                    "api": "ogl_plan_prefetch(pinned host seeds of step t+1) + ogl_plan_step_finish(step t) + loss read-back every step", "last_loss": losses[-1] / (B * world) if losses else None},
+                    "api": "ogl_plan_prefetch(pinned host seeds of step t+1) + ogl_plan_step_finish(step t) + D2H copy of the step's loss into pinned memory every step (consumed by the host one step later)", "last_loss": losses[-1] / (B * world) if losses else None},
             "host_enqueue_ms_per_step": host_enqueue_ms / K, "gpu_launches": launches, "cuda_graph": {"replays_in_timed_region": gs1["replays"] - gs0["replays"],
                                                       "captures_in_timed_region": gs1["captures"] - gs0["captures"],
                                                       "ms_per_step_direct_launch_profiled": ms_prof / K},

@@ -182,6 +182,21 @@ int ogl_peer_connect_local(ogl_peer* p, ogl_peer* const* all /* the world peers 
 int ogl_peer_buffer(ogl_peer* p, float** grads_dev);
 int ogl_peer_wait_readers(ogl_peer* p, void* stream);
 int ogl_plan_peer_adam(ogl_plan* p, ogl_peer* peer, int64_t lo, int64_t hi, int last, float* reduced_out_dev /* may be NULL */, void* stream);
+/* ---- streaming inference with cached per-vertex intermediates (inference_optimized.py:144-301), fp32 ------------
+ * ogl_graph_row_degrees / ogl_graph_gather_rows: g.out_degrees(v) / g.in_edges(v) / g.out_edges(v) on the streaming CSR of the
+ *   serving graph (:185, :194-196, :205): degrees of the listed vertices, then their adjacency rows (ascending edge id) written at
+ *   offsets_dev[i] (the exclusive prefix sums of the degrees).
+ * ogl_infer_rows_linear: out[out_ids[i]] = act(x1[ids1[i]] . w1^T + b1 (+ x2[ids2[i]] . w2^T + b2)): relu(fc_pool(h)) (:258-260) and
+ *   fc_self(h) + fc_neigh(neigh) (:273-276) on a row set; weights row-major [n_out, k] as torch.nn.Linear stores them.
+ * ogl_infer_induced_mean: out[v] = mean over in-edges (u -> v) with member[u] != 0 of proj[u], 0 if none, for v in nodes: DGL's
+ *   subgraph(S).update_all(copy_src, mean) as the handler uses it (:265-268). */
+int ogl_graph_row_degrees(ogl_graph* g, const int64_t* v_dev, int64_t n, int64_t* deg_out_dev, void* stream);
+int ogl_graph_gather_rows(ogl_graph* g, const int64_t* v_dev, int64_t n, const int64_t* offsets_dev, int64_t* out_src_dev, void* stream);
+int ogl_infer_rows_linear(const float* x1_dev, int ld1, const int64_t* ids1_dev, const float* w1_dev, int k1, const float* b1_dev,
+                          const float* x2_dev, int ld2, const int64_t* ids2_dev, const float* w2_dev, int k2, const float* b2_dev,
+                          int relu, float* out_dev, int ldo, const int64_t* out_ids_dev, int64_t n_rows, int n_out, void* stream);
+int ogl_infer_induced_mean(ogl_graph* g, const uint8_t* member_dev, const int64_t* nodes_dev, int64_t n, const float* proj_dev, int ldp,
+                           int n_feats, float* out_dev, int ldo, void* stream);
 /* options: "cuda_graph" (default 1), "side_stream" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence
  * (re-captured when the graph pool, the handles, n_seeds or the output pointers change) */
 int ogl_plan_set_option(ogl_plan* p, const char* name, int value);

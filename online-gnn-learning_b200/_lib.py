@@ -78,6 +78,10 @@ SIGNATURES = {
     "ogl_plan_step_finish_tail": (_i, [_vp, _vp, _vp]),
     "ogl_plan_prefetch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ogl_plan_prefetch_pending": (_i, [_vp]),
+    "ogl_graph_row_degrees": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "ogl_graph_gather_rows": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "ogl_infer_rows_linear": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i64, _i, _vp]),
+    "ogl_infer_induced_mean": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _i, _vp]),
     "ogl_peer_create": (_i, [C.POINTER(_vp), _i, _i, _i64]),
     "ogl_peer_destroy": (_i, [_vp]),
     "ogl_peer_handle": (_i, [_vp, _vp]),

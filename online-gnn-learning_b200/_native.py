@@ -117,6 +117,25 @@ class Graph:
     def compact(self):
         check(lib.ogl_graph_compact(self._h, _stream()))
 
+    def row_degrees(self, v):
+        """in-degrees of the listed vertices (int64 CUDA tensor)"""
+        v = _dev(v, torch.int64)
+        out = torch.empty_like(v)
+        check(lib.ogl_graph_row_degrees(self._h, _ptr(v), v.numel(), _ptr(out), _stream()))
+        return out
+
+    def gather_rows(self, v):
+        """(offsets [n + 1], sources) of the in-edge rows of the listed vertices, each row in ascending edge id"""
+        v = _dev(v, torch.int64)
+        deg = self.row_degrees(v)
+        offsets = torch.zeros(v.numel() + 1, dtype=torch.int64, device="cuda")
+        torch.cumsum(deg, 0, out=offsets[1:])
+        total = int(offsets[-1].item()) if v.numel() else 0
+        src = torch.empty(total, dtype=torch.int64, device="cuda")
+        if total:
+            check(lib.ogl_graph_gather_rows(self._h, _ptr(v), v.numel(), _ptr(offsets), _ptr(src), _stream()))
+        return offsets, src
+
     def stats(self):
         a = (C.c_int64 * 4)()
         check(lib.ogl_graph_stats(self._h, C.byref(a)))
@@ -450,6 +469,23 @@ def sample_neighbors(graph, dst, fanout, seed, step, hop, want_eids=True):
     check(lib.ogl_sample_neighbors(graph._h, _ptr(d), d.numel(), int(fanout), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step), int(hop),
                                    _ptr(src), _ptr(eid), _stream()))
     return src, eid
+
+
+def rows_linear(x1, ids1, w1, b1, out, out_ids, relu=False, x2=None, ids2=None, w2=None, b2=None):
+    """out[out_ids[i]] = act(x1[ids1[i]] @ w1.T + b1 (+ x2[ids2[i]] @ w2.T + b2)); fp32, torch.nn.Linear weight layout [n_out, k]"""
+    for t in (x1, w1, out) + ((x2, w2) if x2 is not None else ()):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    n = ids1.numel()
+    check(lib.ogl_infer_rows_linear(_ptr(x1), x1.shape[1], _ptr(ids1), _ptr(w1), w1.shape[1], _ptr(b1),
+                                    _ptr(x2), x2.shape[1] if x2 is not None else 0, _ptr(ids2), _ptr(w2), w2.shape[1] if w2 is not None else 0,
+                                    _ptr(b2), int(relu), _ptr(out), out.shape[1], _ptr(out_ids), n, w1.shape[0], _stream()))
+
+
+def induced_mean(graph, member, nodes, proj, out):
+    """out[v] = mean of proj[u] over the in-edges u -> v of `graph` with member[u] != 0 (0 without one), for v in nodes"""
+    assert member.dtype == torch.uint8 and proj.dtype == torch.float32 and out.dtype == torch.float32
+    check(lib.ogl_infer_induced_mean(graph._h, _ptr(member), _ptr(nodes), nodes.numel(), _ptr(proj), proj.shape[1], proj.shape[1],
+                                     _ptr(out), out.shape[1], _stream()))
 
 
 def gemm_bf16_nt(a, b, k=None):

@@ -87,3 +87,35 @@ def test_vertex_stream_vs_reference(golden):
     assert act == g["n_active"].tolist()
     assert np.array_equal(o.subgraph_to_original(), g["s2o"])
     assert np.array_equal(o.rank[g["probe"]], g["o2s"])
+
+
+def inference_fixture(g):
+    """(feat, params, requests, per-request expectations) of tests/golden/inference_stream.npz"""
+    params = {k[len("param_"):]: g[k] for k in g.files if k.startswith("param_")}
+    e0 = np.concatenate([[0], np.cumsum(g["n_edges"])])
+    p0 = np.concatenate([[0], np.cumsum(g["nP"])])
+    s0 = np.concatenate([[0], np.cumsum(g["nS"])])
+    reqs = []
+    for r in range(len(g["n_edges"])):
+        reqs.append(dict(pairs=g["edges"][e0[r]:e0[r + 1]].tolist(), P=g["P"][p0[r]:p0[r + 1]].tolist(), S=g["S"][s0[r]:s0[r + 1]].tolist(),
+                         out=g["out"][p0[r]:p0[r + 1]].tolist(), n_nodes=int(g["n_nodes"][r]),
+                         caches={k: g["cache_" + k][r] for k in ("h0proj", "neigh0", "h1", "h1proj", "neigh1", "h2")}))
+    return g["feat"], params, reqs
+
+
+def test_cached_inference_oracle_vs_reference_handler(golden):
+    """oracle/inference.py against the reference's own `inference()` method run request by request (make_golden_inference.py)"""
+    from oracle.inference import CachedInferenceOracle
+    feat, params, reqs = inference_fixture(golden("inference_stream"))
+    o = CachedInferenceOracle(feat, params)
+    assert len(reqs) == 40
+    for r, q in enumerate(reqs):
+        P, classes = o.request(q["pairs"])
+        assert o.n == q["n_nodes"]
+        assert P == q["P"], "request %d: answered vertices (and their order)" % r
+        assert o.last_sets[2] == q["S"], "request %d: layer-1 vertex set" % r
+        assert classes == q["out"], "request %d: predicted classes" % r
+        for k, want in q["caches"].items():
+            got = np.zeros_like(want)
+            got[:o.n] = o.cache[k]
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6, err_msg="request %d cache %s" % (r, k))
