@@ -392,6 +392,49 @@ def aux_arxiv_vertex_stream(n_snapshots=20):
         ttg.SIZE_BUFFER = old
 
 
+def aux_cached_inference(n_requests=400, cpu_requests=60):
+    """the reference's streaming-inference request loop (inference_optimized.py:144-301) on an Elliptic-shaped model
+    (F=166, hidden 256, 2 classes): requests of 1-5 new edges through ogl_b200.inference.CachedInference, and a bounded sample of the
+    same stream through the CPU oracle port (oracle/inference.py), which is pinned to the reference's own method."""
+    from ogl_b200.inference import CachedInference
+    from oracle.inference import CachedInferenceOracle
+    rng = np.random.default_rng(31)
+    V, F, H, C = 20000, 166, 256, 2
+    feat = rng.standard_normal((V, F)).astype(np.float32)
+    params = {}
+    for l, (i, o) in enumerate(((F, H), (H, C))):
+        for name, (oo, ii) in (("fc_pool", (i, i)), ("fc_self", (o, i)), ("fc_neigh", (o, i))):
+            params["layers.%d.%s.weight" % (l, name)] = (rng.standard_normal((oo, ii)) / np.sqrt(ii)).astype(np.float32)
+            params["layers.%d.%s.bias" % (l, name)] = (0.1 * rng.standard_normal(oo)).astype(np.float32)
+    reqs, hi = [], 50
+    for r in range(n_requests + 20):
+        hi = min(V, hi + int(rng.integers(5, 40)))
+        pairs = []
+        for _ in range(int(rng.integers(1, 6))):
+            a, b = int(rng.integers(0, hi)), int(rng.integers(0, hi))
+            pairs += [[a, b]] + ([[b, a]] if rng.random() < 0.5 else [])
+        reqs.append(pairs)
+    d = CachedInference(feat, {k: torch.from_numpy(v) for k, v in params.items()})
+    for q in reqs[:20]:
+        d.request(q)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for q in reqs[20:]:
+        d.request(q)
+    torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    o = CachedInferenceOracle(feat, params)
+    for q in reqs[:20]:
+        o.request(q)
+    t0 = time.perf_counter()
+    for q in reqs[20:20 + cpu_requests]:
+        o.request(q)
+    cpu_s = time.perf_counter() - t0
+    return {"workload": "cached streaming inference, Elliptic-shaped model (F=%d, hidden %d, %d classes), %d requests of 1-5 new edges" % (F, H, C, n_requests),
+            "requests_per_s": n_requests / gpu_s, "ms_per_request": 1e3 * gpu_s / n_requests,
+            "cpu_port_requests_per_s": cpu_requests / cpu_s, "cpu_port_sample": "%d requests of the same stream, oracle/inference.py" % cpu_requests}
+
+
 def workload_config(w, name, world):
     return {"workload": "%s-shaped synthetic graph: V=%d, %d stream edges (%d directed), F=%d, C=%d, hidden %d, B=%d per GPU, fan-outs %s, "
                         "2-layer GraphSAGE-pool, Adam" % (name, w["V"], w["E"], 2 * w["E"], w["F"], w["C"], w["H"], w["B"], w["fanouts"]),
@@ -639,6 +682,7 @@ def run_ours(args, rank, world, local_rank):
             aux["elliptic_pbr_device"]["mode"] = "device (counter-RNG draws, stratified proportional sampling and priority updates on the GPU sum tree)"
             aux["sampler_sweep"] = sweep
             aux["arxiv_rbr"] = aux_arxiv_vertex_stream()
+            aux["cached_inference"] = aux_cached_inference()
         except Exception as e:                       # the aux leg must never take the headline line with it
             aux = {"elliptic_pbr": {"error": repr(e)[:300]}}
     line = {"metric": "graphsage_train_vertices_per_s", "value": value, "unit": "vertices/s", "n_gpus": world, "steps": K, "warmup": W,

@@ -53,3 +53,23 @@ if dbg == "0":
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         ms = bench(lambda: native.gemm_bf16_tn(a, b, n=n, k=k, workspace_elems=1 << 24))
         print("TN m=%d n=%d k=%d ours                      %.4f ms  %.0f TFLOP/s  rel_err %.3g" % (m, n, k, ms, fl / ms / 1e9, err), flush=True)
+
+# ---- launch floor: the same kernels on one or two tiles (prologue + pipeline fill + drain + teardown, no steady state)
+if dbg == "0":
+    for (m, n, k) in ((256, 600, 600), (2048, 600, 600), (1024, 41, 600)):
+        ldk = (k + 7) // 8 * 8
+        a = torch.randn(m, ldk, device="cuda").bfloat16()
+        b = (torch.randn(n, ldk, device="cuda") * 0.05).bfloat16()
+        bias = torch.randn(n, device="cuda")
+        for cg in (1, 2):
+            ms = bench(lambda: native.gemm_bf16_nt_ex(a, b, k=k, out_bf16=True, bias=bias, relu=True, cg=cg), iters=50)
+            print("floor NT m=%d n=%d k=%d cg=%d  %.2f us" % (m, n, k, cg, ms * 1e3), flush=True)
+    for (m, n, k) in ((512, 600, 600), (1024, 41, 600)):
+        ldn, ldk = (n + 7) // 8 * 8, (k + 7) // 8 * 8
+        a = torch.randn(m, ldn, device="cuda").bfloat16()
+        b = torch.randn(m, ldk, device="cuda").bfloat16()
+        ms = bench(lambda: native.gemm_bf16_tn(a, b, n=n, k=k, workspace_elems=1 << 24), iters=50)
+        print("floor TN m=%d n=%d k=%d (+ split reduce)  %.2f us" % (m, n, k, ms * 1e3), flush=True)
+    x = torch.zeros(1 << 20, device="cuda")
+    ms = bench(lambda: x.add_(1.0), iters=200)
+    print("floor torch elementwise 4 MB  %.2f us" % (ms * 1e3), flush=True)
