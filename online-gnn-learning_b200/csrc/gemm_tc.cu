@@ -569,9 +569,18 @@ struct TnParams {
   int m_max;
 };
 
+// CTA tile = 256 output rows x <= 256 output columns: TWO 128-row accumulators (TMEM columns [0, 256) and [256, 512)) share every B
+// stage.  The kernel is bound by what one SM can pull from L2 (~43 B / clock, profiles/r1d_gemm_tn_tc_full.txt: 87 GB/s per SM with
+// 128-row tiles); per 128 x 256 x 64 of MMA work a stage now moves 16 KB of A + 16 KB of B instead of 16 + 32.
+constexpr int TN_ROWS = 2 * BM;                       // output rows per CTA tile
+constexpr int TN_STAGES = 3;
+constexpr int TN_A_STAGE_BYTES = 2 * A_STAGE_BYTES;   // two 128-row sub-tiles, each two 64-row chunks of 8 KB
+static_assert(TN_STAGES * (TN_A_STAGE_BYTES + B_STAGE_BYTES) == RING_BYTES, "TN ring size mismatch");
+
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant__ TnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemLayout s = carve(smem_raw, STAGES, B_STAGE_BYTES, RING_BYTES, true);
+  SmemLayout s = carve(smem_raw, TN_STAGES, B_STAGE_BYTES, RING_BYTES, true);
+  s.b0 = smem_raw + TN_STAGES * TN_A_STAGE_BYTES;     // (carve assumes 16 KB A stages)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int gtile = blockIdx.x % p.total_tiles;
@@ -581,25 +590,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   const TnProblem& q = p.pr[which];
   const int tile = gtile - q.tile0;
   const int nb = tile / q.k_tiles, kt = tile % q.k_tiles;
+  const int row0 = nb * TN_ROWS;
   const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
   // contraction range of this split, in 64-row blocks (rows in [m_dyn, round_up(m_dyn, 64)) are zero: zero-tail rule)
   const int blocks_total = (m_dyn + BK - 1) / BK;
   const int per = (blocks_total + p.splits - 1) / p.splits;
   const int kb0 = min(z * per, blocks_total), kb1 = min(kb0 + per, blocks_total);
-  const int n_chunks_a = min(2, (q.n - nb * BM + 63) / 64);                 // 64-wide TMA boxes actually needed
+  const int n_sub = (q.n - row0 > BM) ? 2 : 1;                                 // 128-row sub-tiles that hold output rows
+  const int n_chunks_a = min(4, (q.n - row0 + 63) / 64);                       // 64-wide TMA boxes actually needed (chunk c -> sub-tile c / 2)
   const int bn_tile = min(BN_MAX, (q.k - kt * BN_MAX + 63) / 64 * 64);
   const int n_chunks_b = bn_tile / 64;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < TN_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.acc_full[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<256>(s.tmem_slot);
+  if (warp == 1) tmem_alloc<512>(s.tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
+  auto a_stage = [&](int i) { return smem_raw + i * TN_A_STAGE_BYTES; };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -609,9 +621,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.empty[stage], phase ^ 1);
         mbar_expect_tx(&s.full[stage], tx);
-        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(s.a(stage) + c * 8192, &q.ta, &s.full[stage], nb * BM + c * 64, kb * BK);
+        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(a_stage(stage) + c * 8192, &q.ta, &s.full[stage], row0 + c * 64, kb * BK);
         for (int c = 0; c < n_chunks_b; ++c) tma_load_2d(s.b(stage) + c * 8192, &q.tb, &s.full[stage], kt * BN_MAX + c * 64, kb * BK);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -619,90 +631,110 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // M is always issued as 128: when only one 64-chunk of A was loaded the upper 64 accumulator rows hold
+      // M is always issued as 128: when only one 64-chunk of a sub-tile was loaded its upper 64 accumulator rows hold
       // products with stale shared memory and are never stored (rows >= n)
       const uint32_t idesc = instr_desc(BM, bn_tile, 1, 1);
       uint32_t accumulate = 0;
       // MN-major descriptors: 16 contraction rows = 2048 bytes = 128 in the 14-bit address field; kept branch-free
-      const uint64_t a_desc0 = smem_desc(smem_u32(s.a(0)), 8192, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), 8192, 1024);
+      const uint64_t a_desc0 = smem_desc(smem_u32(a_stage(0)), 8192, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), 8192, 1024);
+      const uint32_t acc1 = tmem_base + (uint32_t)BN_MAX;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.full[stage], phase);
         tc_fence_after();
-        const uint64_t ad = a_desc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+        const uint64_t ad = a_desc0 + (uint64_t)(stage * (TN_A_STAGE_BYTES >> 4));
+        const uint64_t ad1 = ad + (uint64_t)(A_STAGE_BYTES >> 4);              // second 128-row sub-tile
         const uint64_t bd = b_desc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
-        tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
-        tc_mma_bf16(tmem_base, ad + 128, bd + 128, idesc, 1);
-        tc_mma_bf16(tmem_base, ad + 256, bd + 256, idesc, 1);
-        tc_mma_bf16(tmem_base, ad + 384, bd + 384, idesc, 1);
+        if (n_sub == 2) {
+          tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
+          tc_mma_bf16(acc1, ad1, bd, idesc, accumulate);
+          tc_mma_bf16(tmem_base, ad + 128, bd + 128, idesc, 1);
+          tc_mma_bf16(acc1, ad1 + 128, bd + 128, idesc, 1);
+          tc_mma_bf16(tmem_base, ad + 256, bd + 256, idesc, 1);
+          tc_mma_bf16(acc1, ad1 + 256, bd + 256, idesc, 1);
+          tc_mma_bf16(tmem_base, ad + 384, bd + 384, idesc, 1);
+          tc_mma_bf16(acc1, ad1 + 384, bd + 384, idesc, 1);
+        } else {
+          tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
+          tc_mma_bf16(tmem_base, ad + 128, bd + 128, idesc, 1);
+          tc_mma_bf16(tmem_base, ad + 256, bd + 256, idesc, 1);
+          tc_mma_bf16(tmem_base, ad + 384, bd + 384, idesc, 1);
+        }
         accumulate = 1;
         tc_commit(&s.empty[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
       }
       tc_commit(&s.acc_full[0]);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const int gn = nb * BM + quarter * 32 + lane;            // output row
     const bool have = kb1 > kb0;
     if (have) {
       mbar_wait(&s.acc_full[0], 0);
       tc_fence_after();
     }
-    if (p.use_tma_store) {
-      uint8_t* const stage_buf = s.store + (warp - 2) * 2 * STORE_BOX_BYTES;
-      uint32_t boxes_issued = 0;
-      for (int c0 = 0; c0 < bn_tile; c0 += 32) {
-        if (kt * BN_MAX + c0 >= q.k) break;                  // whole box clipped
-        uint8_t* buf = stage_buf + (boxes_issued & 1) * STORE_BOX_BYTES;
-        if (boxes_issued >= 2) {
-          if (lane == 0) tma_store_wait_read<1>();
+    uint8_t* const stage_buf = s.store + (warp - 2) * 2 * STORE_BOX_BYTES;
+    uint32_t boxes_issued = 0;
+    for (int sub = 0; sub < n_sub; ++sub) {
+      const int grow0 = row0 + sub * BM + quarter * 32;      // first output row of this warp's TMEM lane quarter
+      const uint32_t tcol0 = (uint32_t)(sub * BN_MAX);
+      if (p.use_tma_store) {
+        if (grow0 >= q.n) continue;                          // whole boxes clipped
+        for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+          if (kt * BN_MAX + c0 >= q.k) break;                // whole box clipped
+          uint8_t* buf = stage_buf + (boxes_issued & 1) * STORE_BOX_BYTES;
+          if (boxes_issued >= 2) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          uint32_t r[32];
+          if (have) {
+            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + tcol0 + (uint32_t)c0, r);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq)
+            *reinterpret_cast<uint4*>(buf + lane * 128 + ((qq ^ (lane & 7)) << 4)) = make_uint4(r[qq * 4], r[qq * 4 + 1], r[qq * 4 + 2], r[qq * 4 + 3]);
+          fence_async_smem();
           __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&q.tout, buf, kt * BN_MAX + c0, grow0, z);   // rows >= n / cols >= k clipped
+            tma_store_commit();
+          }
+          ++boxes_issued;
         }
-        uint32_t r[32];
-        if (have) {
-          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-        } else {
+      } else {
+        const int gn = grow0 + lane;                         // output row
+        float* orow = q.out + (int64_t)z * q.split_stride + (int64_t)gn * q.ldo;
+        for (int c0 = 0; c0 < bn_tile; c0 += 32) {
+          uint32_t r[32];
+          if (have) {
+            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + tcol0 + (uint32_t)c0, r);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          if (gn < q.n) {
+            const int gk0 = kt * BN_MAX + c0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&q.tout, buf, kt * BN_MAX + c0, nb * BM + quarter * 32, z);   // rows >= n / cols >= k clipped
-          tma_store_commit();
+            for (int j = 0; j < 32; ++j)
+              if (gk0 + j < q.k) orow[gk0 + j] = __uint_as_float(r[j]);
+          }
         }
-        ++boxes_issued;
       }
+    }
+    if (p.use_tma_store) {
       if (lane == 0) tma_store_wait_all();
       __syncwarp();
-    } else {
-      float* orow = q.out + (int64_t)z * q.split_stride + (int64_t)gn * q.ldo;
-      for (int c0 = 0; c0 < bn_tile; c0 += 32) {
-        uint32_t r[32];
-        if (have) {
-          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        if (gn < q.n) {
-          const int gk0 = kt * BN_MAX + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (gk0 + j < q.k) orow[gk0 + j] = __uint_as_float(r[j]);
-        }
-      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_free<256>(tmem_base);
+    tmem_free<512>(tmem_base);
   }
 }
 
@@ -857,7 +889,7 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
     q.k = g[i].k;
     q.k_tiles = (g[i].k + BN_MAX - 1) / BN_MAX;
     q.tile0 = tiles;
-    tiles += ((g[i].n + BM - 1) / BM) * q.k_tiles;
+    tiles += ((g[i].n + TN_ROWS - 1) / TN_ROWS) * q.k_tiles;
     q.ldo = (g[i].k + 3) / 4 * 4;
     per_total += (int64_t)g[i].n * q.ldo;
   }
