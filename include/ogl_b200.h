@@ -195,6 +195,10 @@ int ogl_graph_gather_rows(ogl_graph* g, const int64_t* v_dev, int64_t n, const i
 int ogl_infer_rows_linear(const float* x1_dev, int ld1, const int64_t* ids1_dev, const float* w1_dev, int k1, const float* b1_dev,
                           const float* x2_dev, int ld2, const int64_t* ids2_dev, const float* w2_dev, int k2, const float* b2_dev,
                           int relu, float* out_dev, int ldo, const int64_t* out_ids_dev, int64_t n_rows, int n_out, void* stream);
+/* the neighbourhood query of one request in one launch: rows [0, v_off) of g hold in-edge sources, rows [v_off, 2 v_off) out-edge targets.
+ * out_dev (int64): [overflow, total_in, total_out, out_deg[n], in_off[n+1], out_off[n+1], in_src[cap_in], out_dst[cap_out], out_deg_of_dst[cap_out]];
+ * in / out rows are listed only for vertices whose out-degree is < th */
+int ogl_infer_query(ogl_graph* g, const int64_t* v_dev, int n, int64_t v_off, int th, int cap_in, int cap_out, int64_t* out_dev, void* stream);
 int ogl_infer_induced_mean(ogl_graph* g, const uint8_t* member_dev, const int64_t* nodes_dev, int64_t n, const float* proj_dev, int ldp,
                            int n_feats, float* out_dev, int ldo, void* stream);
 /* options: "cuda_graph" (default 1), "side_stream" (default 1): ogl_plan_train_step replays a captured CUDA graph of its launch sequence

@@ -81,6 +81,7 @@ SIGNATURES = {
     "ogl_graph_row_degrees": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "ogl_graph_gather_rows": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "ogl_infer_rows_linear": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i64, _i, _vp]),
+    "ogl_infer_query": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp]),
     "ogl_infer_induced_mean": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _i, _vp]),
     "ogl_peer_create": (_i, [C.POINTER(_vp), _i, _i, _i64]),
     "ogl_peer_destroy": (_i, [_vp]),

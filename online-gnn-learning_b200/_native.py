@@ -481,6 +481,11 @@ def rows_linear(x1, ids1, w1, b1, out, out_ids, relu=False, x2=None, ids2=None, 
                                     _ptr(b2), int(relu), _ptr(out), out.shape[1], _ptr(out_ids), n, w1.shape[0], _stream()))
 
 
+def infer_query(graph, v, v_off, th, cap_in, cap_out, out):
+    """one-launch neighbourhood query (csrc/infer.cu: k_infer_query); `out`: int64 CUDA scratch of 5 + 3 n + cap_in + 2 cap_out"""
+    check(lib.ogl_infer_query(graph._h, _ptr(v), v.numel(), int(v_off), int(th), int(cap_in), int(cap_out), _ptr(out), _stream()))
+
+
 def induced_mean(graph, member, nodes, proj, out):
     """out[v] = mean of proj[u] over the in-edges u -> v of `graph` with member[u] != 0 (0 without one), for v in nodes"""
     assert member.dtype == torch.uint8 and proj.dtype == torch.float32 and out.dtype == torch.float32

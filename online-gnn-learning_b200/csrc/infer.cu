@@ -91,11 +91,65 @@ __global__ void __launch_bounds__(256) k_induced_mean(GraphView g, const uint8_t
   }
 }
 
+// The whole neighbourhood query of one request in ONE launch and one D2H copy.  Row x of the view holds the sources of x's in-edges,
+// row x + v_off the targets of x's out-edges (the serving graph stores every edge in both).  For the request's vertices v[0 .. n):
+//   out[0] = 1 if a section overflowed (nothing is copied then), out[1] / out[2] = total in / out entries,
+//   out[3 + i] = out-degree of v[i];  in-rows and out-rows are copied only for vertices with out-degree < th (inference_optimized.py:186-192):
+//   in offsets [n + 1] | out offsets [n + 1] | in sources [cap_in] | out targets [cap_out] | out-degree of every target [cap_out]
+__global__ void __launch_bounds__(256) k_infer_query(GraphView g, const int64_t* __restrict__ v, int n, int64_t v_off, int th, int cap_in,
+                                                     int cap_out, int64_t* __restrict__ out) {
+  int64_t* deg_out = out + 3;
+  int64_t* off_in = out + 3 + n;
+  int64_t* off_out = off_in + n + 1;
+  int64_t* in_src = off_out + n + 1;
+  int64_t* out_dst = in_src + cap_in;
+  int64_t* out_deg_dst = out_dst + cap_out;
+  __shared__ int overflow;
+  if (threadIdx.x == 0) {
+    int64_t ti = 0, to = 0;
+    for (int i = 0; i < n; ++i) {
+      const int64_t x = v[i];
+      const int dgo = g.deg[x + v_off];
+      deg_out[i] = dgo;
+      off_in[i] = ti;
+      off_out[i] = to;
+      if (dgo < th) { ti += g.deg[x]; to += dgo; }
+    }
+    off_in[n] = ti;
+    off_out[n] = to;
+    out[1] = ti;
+    out[2] = to;
+    overflow = (ti > cap_in || to > cap_out) ? 1 : 0;
+    out[0] = overflow;
+  }
+  __syncthreads();
+  if (overflow) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < n; i += 8) {
+    const int64_t x = v[i];
+    const int n_in = (int)(off_in[i + 1] - off_in[i]), n_out = (int)(off_out[i + 1] - off_out[i]);
+    const int64_t bi = g.row_start[x], bo = g.row_start[x + v_off];
+    for (int j = lane; j < n_in; j += 32) in_src[off_in[i] + j] = (int64_t)(g.adj[bi + j] & 0xFFFFFFFFull);
+    for (int j = lane; j < n_out; j += 32) {
+      const int64_t t = (int64_t)(g.adj[bo + j] & 0xFFFFFFFFull);
+      out_dst[off_out[i] + j] = t;
+      out_deg_dst[off_out[i] + j] = g.deg[t + v_off];
+    }
+  }
+}
+
 }  // namespace
 
 }  // namespace ogl
 
 using namespace ogl;
+
+extern "C" int ogl_infer_query(ogl_graph* g, const int64_t* v_dev, int n, int64_t v_off, int th, int cap_in, int cap_out, int64_t* out_dev,
+                               void* stream) {
+  OGL_ARG(g && v_dev && out_dev && n > 0 && v_off >= 0 && cap_in > 0 && cap_out > 0, "ogl_infer_query: bad arguments");
+  OGL_LAUNCH(k_infer_query, 1, 256, 0, stream, graph_view(g), v_dev, n, v_off, th, cap_in, cap_out, out_dev);
+  return OGL_OK;
+}
 
 extern "C" int ogl_graph_row_degrees(ogl_graph* g, const int64_t* v_dev, int64_t n, int64_t* deg_out_dev, void* stream) {
   OGL_ARG(g && (n == 0 || (v_dev && deg_out_dev)), "ogl_graph_row_degrees: null");
