@@ -57,7 +57,8 @@ class Graph:
         self.v_cap = int(v_cap)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
+        # (at interpreter shutdown the module globals may already be gone: nothing left to free then)
+        if getattr(self, "_h", None) and self._h.value and lib is not None and C is not None:
             lib.ogl_graph_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -151,7 +152,8 @@ class Features:
         self.v_cap, self.n_feats, self.mode = int(v_cap), int(n_feats), int(mode)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
+        # (at interpreter shutdown the module globals may already be gone: nothing left to free then)
+        if getattr(self, "_h", None) and self._h.value and lib is not None and C is not None:
             lib.ogl_features_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -204,7 +206,8 @@ class Plan:
         self._version = 0
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
+        # (at interpreter shutdown the module globals may already be gone: nothing left to free then)
+        if getattr(self, "_h", None) and self._h.value and lib is not None and C is not None:
             lib.ogl_plan_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -385,7 +388,8 @@ class Peer:
         self.grads = wrap_device(p.value, (self.n_floats,), torch.float32)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value and lib is not None:
+        # (at interpreter shutdown the module globals may already be gone: nothing left to free then)
+        if getattr(self, "_h", None) and self._h.value and lib is not None and C is not None:
             lib.ogl_peer_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -420,7 +424,8 @@ class SumTree:
         self.capacity = int(capacity)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
+        # (at interpreter shutdown the module globals may already be gone: nothing left to free then)
+        if getattr(self, "_h", None) and self._h.value and lib is not None and C is not None:
             lib.ogl_sumtree_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -90,6 +90,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {     // descriptor fetch off the first load's critical path
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -280,6 +283,10 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   rows_valid[0] = p.a_rows_dev[0] ? min(*p.a_rows_dev[0], m_dyn) : m_dyn;
   rows_valid[1] = p.n_seg > 1 ? (p.a_rows_dev[1] ? min(*p.a_rows_dev[1], m_dyn) : m_dyn) : 0;
 
+  if (threadIdx.x == 32) {                        // (a lane of the MMA warp: off the barrier-initialising thread)
+    for (int i = 0; i < p.n_seg; ++i) { prefetch_tensormap(&p.ta[i]); prefetch_tensormap(&p.tb[i]); }
+    if (p.out_bf16) prefetch_tensormap(&p.tc);
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 8 * CG); }
@@ -601,6 +608,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   const int bn_tile = min(BN_MAX, (q.k - kt * BN_MAX + 63) / 64 * 64);
   const int n_chunks_b = bn_tile / 64;
 
+  if (threadIdx.x == 64) {
+    prefetch_tensormap(&q.ta);
+    prefetch_tensormap(&q.tb);
+    if (p.use_tma_store) prefetch_tensormap(&q.tout);
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < TN_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.acc_full[0], 1);
