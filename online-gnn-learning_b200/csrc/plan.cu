@@ -422,6 +422,12 @@ extern "C" int ogl_plan_refresh_params(ogl_plan* p, void* stream) {
 
 extern "C" int ogl_plan_bind_params(ogl_plan* p, float* params_dev, float* grads_dev, void* stream) {
   OGL_ARG(p && params_dev && grads_dev, "ogl_plan_bind_params: null");
+  OGL_ARG(!p->pend[0] && !p->pend[1], "ogl_plan_bind_params: a prefetched minibatch is pending");
+  if (params_dev != p->params || grads_dev != p->grads) {          // captured step graphs hold the old pointers
+    OGL_CUDA(cudaDeviceSynchronize());
+    for (auto& sg : p->step_graphs) cudaGraphExecDestroy(sg.exec);
+    p->step_graphs.clear();
+  }
   p->params = params_dev;
   p->grads = grads_dev;
   return ogl_plan_refresh_params(p, stream);

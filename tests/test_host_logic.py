@@ -160,3 +160,61 @@ def test_priority_strategies_match_reference(golden):
     assert trend.avg == float(g["trend_avg"]) and np.array_equal(trend.values, g["trend_values"])
     x = np.arange(3.0)
     assert LossPriority().get_priorities([0, 1, 2], x) is x
+
+
+def test_cached_inference_oracle_edge_cases():
+    """requests whose vertices are all above the handler's out-degree threshold (empty V0 / P / S), repeated pairs, self pairs"""
+    from oracle.inference import CachedInferenceOracle, TH
+    rng = np.random.default_rng(0)
+    V, F, H, C = 40, 6, 5, 3
+    feat = rng.standard_normal((V, F)).astype(np.float32)
+    params = {}
+    for l, (i, o) in enumerate(((F, H), (H, C))):
+        for name, (oo, ii) in (("fc_pool", (i, i)), ("fc_self", (o, i)), ("fc_neigh", (o, i))):
+            params["layers.%d.%s.weight" % (l, name)] = rng.standard_normal((oo, ii)).astype(np.float32)
+            params["layers.%d.%s.bias" % (l, name)] = rng.standard_normal(oo).astype(np.float32)
+    o = CachedInferenceOracle(feat, params)
+    # vertex 0 becomes a hub: it is stored as the SOURCE of TH edges (pairs [x, 0] are stored as 0 -> x)
+    P, cls = o.request([[x, 0] for x in range(1, TH + 1)])
+    assert sorted(P) == [0] and len(cls) == 1                      # every a's only in-neighbour is the hub
+    before = {k: v.copy() for k, v in o.cache.items()}
+    P, cls = o.request([[0, 0]])                                   # the hub itself: out-degree TH + 1 -> filtered out, nothing to answer
+    assert P == [] and cls == []
+    for k in before:
+        assert np.array_equal(before[k], o.cache[k][:len(before[k])]), k
+    P, cls = o.request([[3, 4], [3, 4], [4, 3]])                   # parallel edges count twice in the mean
+    assert set(P) == {0, 3, 4} and len(cls) == 3
+    assert o.n == TH + 1
+
+
+def test_pipeline_call_order_single_rank():
+    """parallel.Pipeline on one rank: the next minibatch is prefetched BEFORE the current one is finished (that is what lets the
+    two overlap), at most two are ever pending, and every minibatch is finished exactly once, in order"""
+    import types
+    import ogl_b200
+    calls = []
+
+    class FakePlan:
+        tail_params, n_params = 4, 10
+
+        def prefetch(self, graph, features, seeds):
+            calls.append(("prefetch", seeds))
+
+        def step_finish(self, features, scale, do_step=True, per_vertex_out=None, loss_sum_out=None):
+            calls.append(("finish", scale, do_step))
+
+    real_stream = ogl_b200.parallel.torch.cuda.current_stream
+    real_event = ogl_b200.parallel.torch.cuda.Event
+    ogl_b200.parallel.torch.cuda.current_stream = lambda: types.SimpleNamespace(wait_event=lambda e: None)
+    ogl_b200.parallel.torch.cuda.Event = lambda *a, **k: types.SimpleNamespace(record=lambda s=None: None)
+    try:
+        pipe = ogl_b200.parallel.Pipeline(FakePlan(), "g", "f", None, 8)
+        pipe.begin("s0")
+        for t in range(3):
+            pipe.finish("s%d" % (t + 1) if t < 2 else None)
+        pipe.flush()
+    finally:
+        ogl_b200.parallel.torch.cuda.current_stream = real_stream
+        ogl_b200.parallel.torch.cuda.Event = real_event
+    assert calls == [("prefetch", "s0"), ("prefetch", "s1"), ("finish", 1.0 / 8, True), ("prefetch", "s2"), ("finish", 1.0 / 8, True),
+                     ("finish", 1.0 / 8, True)]
