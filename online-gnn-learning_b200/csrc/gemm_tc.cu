@@ -90,6 +90,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                "r"(c1), "r"(c2)
                : "memory");
 }
+// programmatic dependent launch: a GEMM launched with the attribute may start (barrier init, TMEM allocation, descriptor prefetch) while
+// the kernel before it in the stream is still draining; everything that touches that kernel's results comes after this wait
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {     // descriptor fetch off the first load's critical path
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   if (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before any remote arrive / TMA completes on them
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
+  pdl_wait();                            // operands (and the output buffer's previous readers) belong to the preceding kernel
 
   if (warp == 0) {
     // ===== TMA producer (in pair mode: in both CTAs, each for its own shared memory) =====
@@ -624,6 +628,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
   auto a_stage = [&](int i) { return smem_raw + i * TN_A_STAGE_BYTES; };
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -818,6 +823,40 @@ int make_map_f32_3d(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1, i
 
 bool gemm_tc_available() { return tc_init() == 1; }
 
+// programmatic dependent launch on every tcgen05 GEMM (OGL_PDL=0 turns it off): the row counts the kernels read before their
+// griddepcontrol.wait are written by the sampling kernels of an earlier launch sequence, never by the immediate predecessor
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("OGL_PDL"); v = e ? (atoi(e) != 0) : 1; }
+  return v == 1;
+}
+template <typename Kernel, typename Params>
+static int launch_gemm(Kernel kernel, int grid, int block, int smem, int cluster, const Params& p, cudaStream_t s) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  int n = 0;
+  if (cluster > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = (unsigned)cluster; attrs[n].val.clusterDim.y = 1; attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (use_pdl()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = (unsigned)n;
+  OGL_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OGL_OK;
+}
+
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   OGL_ARG(tc_init() == 1, "gemm_nt_tc: tcgen05 path unavailable (driver lacks cuTensorMapEncodeTiled?)");
   OGL_ARG(g.in_bf16, "gemm_nt_tc: bf16 operands only");
@@ -860,25 +899,12 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   OGL_ARG(!g.mask || (g.ldmask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0), "gemm_nt_tc: mask pitch must be a multiple of 8 elements");
   if (cg == 2) {
     const int pairs = (int)(super_tiles < sm_count() / 2 ? super_tiles : sm_count() / 2);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(THREADS_NT);
-    cfg.dynamicSmemBytes = SMEM_NT2;
-    cfg.stream = s;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    OGL_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_nt_tc<2>, p));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    OGL_TRY(launch_gemm(k_gemm_nt_tc<2>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
     return OGL_OK;
   }
   const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  OGL_LAUNCH(k_gemm_nt_tc<1>, grid, THREADS_NT, SMEM_NT1, s, p);
-  return OGL_OK;
+  return launch_gemm(k_gemm_nt_tc<1>, grid, THREADS_NT, SMEM_NT1, 1, p, s);
 }
 
 int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
@@ -939,7 +965,7 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
     }
   }
   p.use_tma_store = staged ? 1 : 0;
-  OGL_LAUNCH(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_TN, s, p);
+  OGL_TRY(launch_gemm(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_TN, 1, p, s));
   if (staged) return reduce_splits_group(rg, s);
   return OGL_OK;
 }
