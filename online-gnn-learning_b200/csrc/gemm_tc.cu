@@ -93,6 +93,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 // programmatic dependent launch: a GEMM launched with the attribute may start (barrier init, TMEM allocation, descriptor prefetch) while
 // the kernel before it in the stream is still draining; everything that touches that kernel's results comes after this wait
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {     // descriptor fetch off the first load's critical path
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -305,6 +306,8 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
   pdl_wait();                            // operands (and the output buffer's previous readers) belong to the preceding kernel
+  pdl_trigger();                         // a GEMM behind this one cannot share an SM with it (shared memory): it takes each SM as this
+                                         // kernel's CTA leaves it, instead of waiting for the whole grid
 
   if (warp == 0) {
     // ===== TMA producer (in pair mode: in both CTAs, each for its own shared memory) =====
