@@ -312,7 +312,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   // activations (row counts padded to 128 for the zero-tail rule)
   auto rows = [](int n) { return (size_t)round_up(n, 128); };
   DM0(p->act[L], p->es * rows(p->nmax[L]) * pitch_of(cfg->dims[0]));
-  int64_t off = 0, max_src_elems = 0, max_dst_in_elems = 0, max_nk = 0, max_colsum = 0;
+  int64_t off = 0, max_nk = 0, max_colsum = 0;
   for (int l = 0; l < L; ++l) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, s = h + 1, d = h;
@@ -338,8 +338,6 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     // layer output: logits are always fp32
     const size_t oes = (l == L - 1) ? 4 : p->es;
     DM0(p->act[d], oes * rows(p->nmax[d]) * lb.pout);
-    max_src_elems = std::max<int64_t>(max_src_elems, (int64_t)rows(p->nmax[s]) * lb.pin);
-    max_dst_in_elems = std::max<int64_t>(max_dst_in_elems, (int64_t)rows(p->nmax[d]) * lb.pin);
     max_nk = std::max<int64_t>(max_nk, (int64_t)std::max(lb.in, lb.out) * lb.in);
     max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[d], lb.pin));
     max_colsum = std::max<int64_t>(max_colsum, colsum_partial_elems(p->nmax[d], lb.pout));
