@@ -835,8 +835,7 @@ static bool use_pdl() {
 }
 template <typename Kernel, typename Params>
 static int launch_gemm(Kernel kernel, int grid, int block, int smem, int cluster, const Params& p, cudaStream_t s) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = (size_t)smem;
