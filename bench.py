@@ -642,13 +642,14 @@ def run_ours(args, rank, world, local_rank):
     if fl:
         ach = fl / (per[top] * 1e-3) / 1e12
         roof = dict(common, bound="tensor", achieved=ach, peak=tc_peak, unit="TFLOP/s", frac=ach / tc_peak,
-                    peak_source=peak_src + ", sustained bf16", flops_per_launch=fl)
+                    peak_source=peak_src + ", sustained bf16", flops_per_launch=fl,
+                    peak_nominal=2250.0, frac_nominal=ach / 2250.0)          # B200 dense bf16 data-sheet figure beside the measured one
         fam_fl = sum(stage_flops(k, w, lv) or 0.0 for k in fam[top_family])
         roof["kernel_avg_tflops"] = fam_fl / (fam_ms[top_family] * 1e-3) / 1e12
     elif by:
         ach = by / (per[top] * 1e-3) / 1e9
         roof = dict(common, bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src,
-                    bytes_per_launch=by)
+                    bytes_per_launch=by, peak_nominal=8000.0, frac_nominal=ach / 8000.0)
     else:
         roof = dict(common, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None)
     stage_table = {}
