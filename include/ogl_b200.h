@@ -34,7 +34,11 @@ typedef struct ogl_plan ogl_plan;         /* sampler + GraphSAGE-pool model + op
 typedef struct ogl_sumtree ogl_sumtree;   /* fp64 sum-tree for PBR */
 typedef struct ogl_peer ogl_peer;         /* one rank's end of the NVLink peer-memory gradient exchange */
 
-enum { OGL_F32 = 0, OGL_BF16 = 1 };      /* arithmetic mode of the dense path */
+/* arithmetic mode of the dense path.  OGL_F32: fp32 storage, SIMT FFMA GEMMs (exact; rtol 1e-5 against the fp32 reference path).
+ * OGL_BF16: bf16 storage, tcgen05 kind::f16 GEMMs with fp32 accumulation (fastest; ~2^-9 per stored value).
+ * OGL_TF32: fp32 storage with every GEMM operand rounded to TF32 where it is produced, tcgen05 kind::tf32 GEMMs with fp32
+ *           accumulation -- the tensor-core mode that meets rtol 1e-3 against the reference's fp32 path (utils.py:63-64). */
+enum { OGL_F32 = 0, OGL_BF16 = 1, OGL_TF32 = 2 };
 enum { OGL_OK = 0, OGL_ERR_CUDA = -1, OGL_ERR_ARG = -2, OGL_ERR_CAPACITY = -3, OGL_ERR_NODEVICE = -4 };
 
 const char* ogl_last_error(void);
@@ -103,8 +107,8 @@ typedef struct {
   int fanouts[8];        /* fanouts[0] at the seeds hop, [1] next hop out, ... */
   int max_seeds;
   int64_t v_cap;
-  int mode;              /* OGL_F32 | OGL_BF16 */
-  int gemm_impl;         /* 0 = default for mode (tcgen05 for bf16), 1 = force SIMT (tests) */
+  int mode;              /* OGL_F32 | OGL_BF16 | OGL_TF32 */
+  int gemm_impl;         /* 0 = default for mode (tcgen05 for bf16 / tf32, SIMT for f32), 1 = force SIMT (tests) */
   uint64_t seed;         /* Philox key */
   float lr, beta1, beta2, eps;
 } ogl_plan_config;
@@ -119,6 +123,10 @@ int ogl_plan_bind_params(ogl_plan* p, float* params_dev, float* grads_dev, void*
 /* call after params were changed outside the library (load_state_dict) */
 int ogl_plan_refresh_params(ogl_plan* p, void* stream);
 int ogl_plan_set_step(ogl_plan* p, uint32_t step, void* stream);
+/* sticky device-side error flags since the last call (synchronises; clears them).  bit 0: a seed id outside [0, n_vertices) was
+ * passed to a sampling / train / eval call -- it was replaced by vertex 0 so that no row metadata is read out of bounds (DGL's
+ * NodeDataLoader raises on such ids, pytorch/model.py:128-131) */
+int ogl_plan_error_flags(ogl_plan* p, uint32_t* out);
 
 /* sample the L-hop minibatch for `seeds` (device int64, n_seeds <= max_seeds) */
 int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_dev, int n_seeds, void* stream);
@@ -266,6 +274,13 @@ int ogl_gemm_bf16_nt_ex(const void* a_dev, int lda, const void* b_dev, int ldb, 
 /* C[N,K] (fp32, ldc) = A[M,N]^T (bf16, lda) * B[M,K] (bf16, ldb): the weight-gradient shape (contraction over
  * rows), tcgen05 path with MN-major operands; workspace holds the split partials (may be NULL: no split) */
 int ogl_gemm_bf16_tn(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc,
+                     int m, int n, int k, float* workspace_dev, int64_t workspace_elems, void* stream);
+/* the tcgen05 kind::tf32 flavour of the two calls above (mode OGL_TF32: fp32 operands holding TF32-rounded values, fp32
+ * accumulation; the arithmetic that replaces the reference's fp32 cuBLAS GEMMs, train/utils.py:63-64).  tma_out != 0: the
+ * activation epilogue (TF32-rounded fp32 output through TMA stores, optional mask: out = mask > 0 ? out : 0) */
+int ogl_gemm_tf32_nt_ex(const float* a_dev, int lda, const float* b_dev, int ldb, float* c_dev, int ldc, int m, int n, int k,
+                        int tma_out, const float* bias_dev, int relu, const float* mask_dev, int ldmask, int cg, void* stream);
+int ogl_gemm_tf32_tn(const float* a_dev, int lda, const float* b_dev, int ldb, float* c_dev, int ldc,
                      int m, int n, int k, float* workspace_dev, int64_t workspace_elems, void* stream);
 
 #pragma GCC visibility pop

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libogl_b200.so")
 
-OGL_F32, OGL_BF16 = 0, 1
+OGL_F32, OGL_BF16, OGL_TF32 = 0, 1, 2
 
 
 class OglError(RuntimeError):
@@ -64,6 +64,7 @@ SIGNATURES = {
     "ogl_plan_bind_params": (_i, [_vp, _vp, _vp, _vp]),
     "ogl_plan_refresh_params": (_i, [_vp, _vp]),
     "ogl_plan_set_step": (_i, [_vp, _u32, _vp]),
+    "ogl_plan_error_flags": (_i, [_vp, C.POINTER(_u32)]),
     "ogl_plan_sample": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ogl_plan_forward": (_i, [_vp, _vp, _vp, _vp]),
     "ogl_plan_loss_backward": (_i, [_vp, _vp, _f, _vp, _vp, _vp]),
@@ -112,6 +113,8 @@ SIGNATURES = {
     "ogl_gemm_bf16_nt": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "ogl_gemm_bf16_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ogl_gemm_bf16_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "ogl_gemm_tf32_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "ogl_gemm_tf32_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

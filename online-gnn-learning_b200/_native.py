@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import lib, check, PlanConfig, OGL_F32, OGL_BF16, kernel_launches  # noqa: F401
+from ._lib import lib, check, PlanConfig, OGL_F32, OGL_BF16, OGL_TF32, kernel_launches  # noqa: F401
 
 
 def _stream():
@@ -329,6 +329,12 @@ class Plan:
         self.n_seeds = n
         self._stamp += 1
 
+    def error_flags(self):
+        """sticky device error bits since the last call (bit 0: out-of-range seed id); synchronises"""
+        v = C.c_uint32()
+        check(lib.ogl_plan_error_flags(self._h, C.byref(v)))
+        return int(v.value)
+
     def set_option(self, name, value):
         check(lib.ogl_plan_set_option(self._h, name.encode(), int(value)))
 
@@ -531,3 +537,36 @@ def gemm_bf16_nt_ex(a, b, k=None, out_bf16=True, bias=None, relu=False, cg=0):
     check(lib.ogl_gemm_bf16_nt_ex(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), ldc, a.shape[0], b.shape[0], k, int(out_bf16),
                                   _ptr(bias), int(relu), int(cg), _stream()))
     return c[:, :b.shape[0]]
+
+
+def round_tf32(x):
+    """fp32 tensor rounded to TF32 (10 explicit mantissa bits, round to nearest, ties away from zero = cvt.rna.tf32.f32)"""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def gemm_tf32_nt_ex(a, b, k=None, tma_out=True, bias=None, relu=False, mask=None, cg=0):
+    """C[M,N] fp32 = act(A[M,:k] @ B[N,:k]^T + bias) on the tcgen05 kind::tf32 path; tma_out: TF32-rounded activation epilogue"""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_cuda and b.is_cuda
+    a, b = a.contiguous(), b.contiguous()
+    k = a.shape[1] if k is None else int(k)
+    ldc = (b.shape[0] + 7) // 8 * 8
+    c = torch.empty(a.shape[0], ldc, dtype=torch.float32, device="cuda")
+    if mask is not None:
+        mask = mask.contiguous()
+    check(lib.ogl_gemm_tf32_nt_ex(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), ldc, a.shape[0], b.shape[0], k, int(tma_out),
+                                  _ptr(bias), int(relu), _ptr(mask), mask.shape[1] if mask is not None else 0, int(cg), _stream()))
+    return c[:, :b.shape[0]]
+
+
+def gemm_tf32_tn(a, b, n=None, k=None, workspace_elems=1 << 24):
+    """C[N,K] fp32 = A[M,:n]^T @ B[M,:k] on the tcgen05 kind::tf32 path (MN-major operands)"""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_cuda and b.is_cuda and a.shape[0] == b.shape[0]
+    a, b = a.contiguous(), b.contiguous()
+    n = a.shape[1] if n is None else int(n)
+    k = b.shape[1] if k is None else int(k)
+    c = torch.empty(n, k, dtype=torch.float32, device="cuda")
+    ws = torch.empty(workspace_elems, dtype=torch.float32, device="cuda") if workspace_elems else None
+    check(lib.ogl_gemm_tf32_tn(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), k, a.shape[0], n, k,
+                               _ptr(ws), int(workspace_elems), _stream()))
+    return c

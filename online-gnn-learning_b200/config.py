@@ -1,13 +1,14 @@
 """Process-wide settings of the B200 backend."""
-from ._lib import OGL_F32, OGL_BF16
+from ._lib import OGL_F32, OGL_BF16, OGL_TF32
 
 _STATE = {"precision": "bf16", "seed": 1, "faithful": True}
 
 
 def set_precision(name):
-    """'bf16' (tcgen05 tensor-core path, rtol 1e-3 vs the bf16-operand oracle) or
+    """'bf16' (tcgen05 kind::f16 tensor-core path, bf16 storage: fastest; a few 1e-3 of the tensor scale away from the reference's fp32
+    path), 'tf32' (tcgen05 kind::tf32 on fp32 storage: the tensor-core mode that meets rtol 1e-3 against the fp32 path) or
     'fp32' (SIMT FFMA path, rtol 1e-5 vs the fp32 oracle)."""
-    assert name in ("bf16", "fp32")
+    assert name in ("bf16", "tf32", "fp32")
     _STATE["precision"] = name
 
 
@@ -16,7 +17,7 @@ def precision():
 
 
 def mode():
-    return OGL_BF16 if _STATE["precision"] == "bf16" else OGL_F32
+    return {"bf16": OGL_BF16, "tf32": OGL_TF32}.get(_STATE["precision"], OGL_F32)
 
 
 def set_seed(seed):

@@ -1,6 +1,8 @@
 // Error plumbing, device checks and the deterministic 3-phase exclusive scan.
 #include "common.cuh"
 #include <stdarg.h>
+#include <mutex>
+#include <vector>
 
 namespace ogl {
 
@@ -12,6 +14,34 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_err, sizeof(t_err), fmt, ap);
   va_end(ap);
+}
+
+namespace {
+struct Reader { const void *a, *b; cudaEvent_t ev; const void* owner; };
+std::mutex g_readers_mu;
+std::vector<Reader> g_readers;
+}  // namespace
+void readers_add(const void* res_a, const void* res_b, cudaEvent_t ev, const void* owner) {
+  std::lock_guard<std::mutex> lk(g_readers_mu);
+  for (auto& r : g_readers)
+    if (r.ev == ev) { r.a = res_a; r.b = res_b; r.owner = owner; return; }
+  g_readers.push_back({res_a, res_b, ev, owner});
+}
+void readers_remove(cudaEvent_t ev) {
+  std::lock_guard<std::mutex> lk(g_readers_mu);
+  for (size_t i = 0; i < g_readers.size(); ++i)
+    if (g_readers[i].ev == ev) { g_readers.erase(g_readers.begin() + i); return; }
+}
+void readers_remove_owner(const void* owner) {
+  std::lock_guard<std::mutex> lk(g_readers_mu);
+  for (size_t i = g_readers.size(); i-- > 0;)
+    if (g_readers[i].owner == owner) g_readers.erase(g_readers.begin() + i);
+}
+int readers_wait(const void* res, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_readers_mu);
+  for (auto& r : g_readers)
+    if (r.a == res || r.b == res) OGL_CUDA(cudaStreamWaitEvent(s, r.ev, 0));
+  return OGL_OK;
 }
 
 static int g_sm_count = 0;

@@ -46,6 +46,16 @@ extern std::atomic<long long> g_launches;
   } while (0)
 
 int require_device();   // OGL_OK iff an sm_100 device is current
+
+// ---- readers of a graph / feature store that run on a stream of their own --------------------------------------------------
+// A prefetched minibatch (plan.cu: ogl_plan_prefetch) samples the CSR and gathers feature rows on the plan's private stream,
+// possibly long after the call returned.  It registers its completion event against the handles it reads; every entry point
+// that MUTATES such a handle (edge / vertex insert, prefix activation, compaction, feature writes) first makes its own stream
+// wait for the registered events, so a snapshot's evolve() can never run under a pending prefetch's feet.
+void readers_add(const void* res_a, const void* res_b, cudaEvent_t ev, const void* owner);
+void readers_remove(cudaEvent_t ev);
+void readers_remove_owner(const void* owner);
+int readers_wait(const void* res, cudaStream_t s);
 int sm_count();
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -91,5 +101,17 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// mode OGL_TF32: fp32 storage whose VALUE is rounded to TF32 (10 explicit mantissa bits, round to nearest) wherever a GEMM
+// operand is produced, so that tcgen05.mma.kind::tf32 -- which drops the low 13 mantissa bits of what it reads -- sees it exactly
+// (truncating unrounded fp32 inside the tensor core would bias every product towards zero by ~2^-11)
+struct tf32_t { float v; };
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+template <> __device__ __forceinline__ float to_f32<tf32_t>(tf32_t v) { return v.v; }
+template <> __device__ __forceinline__ tf32_t from_f32<tf32_t>(float v) { return tf32_t{round_tf32(v)}; }
 
 }  // namespace ogl

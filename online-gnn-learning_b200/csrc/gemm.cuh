@@ -1,4 +1,4 @@
-// Dense GEMM entry points of the GraphSAGE-pool path (SIMT fp32-accumulate + tcgen05 bf16).
+// Dense GEMM entry points of the GraphSAGE-pool path (SIMT fp32-accumulate + tcgen05 bf16 / tf32).
 #pragma once
 #include "common.cuh"
 
@@ -28,6 +28,8 @@ struct GemmNT {
   const int32_t* m_dev = nullptr;  // dynamic row count on device (nullptr: m_max)
   int n = 0;
   int in_bf16 = 0, out_bf16 = 0;
+  int tf32 = 0;                    // mode OGL_TF32: operands are fp32 holding TF32-rounded values (tcgen05 kind::tf32 / exact on the SIMT path)
+  int out_tf32 = 0;                // ... and the fp32 output is rounded to TF32 too (it is a later GEMM's operand)
   int zero_tail = 1;               // write zeros to rows [m, round_up(m, 128)) (contraction padding for later TN GEMMs)
 };
 
@@ -43,6 +45,7 @@ struct GemmTN {
   int m_max = 0;
   const int32_t* m_dev = nullptr;
   int in_bf16 = 0;
+  int tf32 = 0;              // operands are fp32 holding TF32-rounded values
   float* partial = nullptr;  // split workspace [splits, n, k]
   int64_t partial_elems = 0;
 };
@@ -50,7 +53,7 @@ struct GemmTN {
 int gemm_nt_simt(const GemmNT& g, cudaStream_t s);
 int gemm_tn_simt(const GemmTN& g, cudaStream_t s);
 
-// tcgen05 / TMA / TMEM versions (bf16 in, fp32 accumulate); same contracts
+// tcgen05 / TMA / TMEM versions (bf16 or tf32 operands, fp32 accumulate); same contracts
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s);
 int gemm_tn_tc(const GemmTN& g, cudaStream_t s);
 // up to 4 weight-gradient GEMMs contracting over the same rows (same m_dev / m_max) in one launch; g[0].partial is the workspace

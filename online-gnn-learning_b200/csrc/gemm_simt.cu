@@ -202,6 +202,7 @@ int gemm_nt_simt(const GemmNT& g, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(g.n, BN), (unsigned)ceil_div(g.m_max, BM));
   if (g.in_bf16 && g.out_bf16) OGL_LAUNCH((k_gemm_nt<__nv_bfloat16, __nv_bfloat16>), grid, 256, 0, s, g);
   else if (g.in_bf16) OGL_LAUNCH((k_gemm_nt<__nv_bfloat16, float>), grid, 256, 0, s, g);
+  else if (!g.out_bf16 && g.out_tf32) OGL_LAUNCH((k_gemm_nt<float, tf32_t>), grid, 256, 0, s, g);
   else if (!g.out_bf16) OGL_LAUNCH((k_gemm_nt<float, float>), grid, 256, 0, s, g);
   else { set_error("gemm_nt_simt: f32 in / bf16 out unsupported"); return OGL_ERR_ARG; }
   return OGL_OK;

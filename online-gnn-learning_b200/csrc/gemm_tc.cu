@@ -1,4 +1,6 @@
-// tcgen05 / TMA / TMEM GEMMs of the GraphSAGE-pool path (bf16 operands, fp32 accumulation in tensor memory).
+// tcgen05 / TMA / TMEM GEMMs of the GraphSAGE-pool path (bf16 or tf32 operands, fp32 accumulation in tensor memory).
+// Template parameter TF = 1 selects tcgen05.mma.kind::tf32 on fp32 operands (mode OGL_TF32): a 128-byte swizzle row then holds 32
+// contraction elements instead of 64 and one MMA contracts 8 instead of 16, so stages, descriptors and barriers are byte-identical.
 //
 // Two warp-specialised kernels, both with 128 x <=256 output tiles, 64-deep contraction stages moved by TMA
 // (SWIZZLE_128B) into a 4-stage shared-memory ring, one elected thread issuing tcgen05.mma (UMMA 128 x N x 16,
@@ -116,6 +118,14 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // ---- cta_group::2 (CTA pair) variants ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -146,6 +156,25 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_des
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one MMA of the kernel's flavour: CG = CTAs per tile (cta_group), TF = tf32 operands
+template <int CG, int TF>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 2) {
+    if constexpr (TF) tc_mma_tf32_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else tc_mma_bf16_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+  } else {
+    if constexpr (TF) tc_mma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else tc_mma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  }
 }
 __device__ __forceinline__ void mbar_arrive_on_cta(uint64_t* bar, uint32_t cta) {   // arrive on the same-offset barrier of CTA `cta`
   asm volatile(
@@ -196,10 +225,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor for kind::f16: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), majors at
-// bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28
-__device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// instruction descriptor for kind::f16 / kind::tf32: D = f32 (bits 4-5 = 1), A / B format at bits 7-9 / 10-12 (1 = bf16,
+// 2 = tf32), majors at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major, int tf32 = 0) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
@@ -256,11 +286,13 @@ struct NtParams {
   const float* bias;
   const float* bias2;
   int relu;
-  const __nv_bfloat16* mask;
+  const void* mask;             // operand-typed (bf16 | fp32) [m, ldmask]
   int ldmask;
   void* c;
   int ldc;
-  int out_bf16;
+  int out_bf16;                 // bf16 output through TMA stores
+  int out_f32_tma;              // TF kernels: fp32 output through TMA stores (activations), rounded to TF32 if round_out
+  int round_out;
   int zero_tail;
   int debug;                    // perf experiments (OGL_GEMM_DBG): 1 = epilogue drains the accumulator without storing
 };
@@ -269,9 +301,11 @@ struct NtParams {
 // tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues UMMA M = 256 that reads
 // both halves, each CTA keeps the accumulator of its own rows in its own TMEM and runs its own epilogue.  Per CTA a
 // k-block then moves 32 KB instead of 48 KB through L2 -> SM, the limiter of the single-CTA kernel.
-template <int CG>
+template <int CG, int TF>
 __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
   constexpr int NST = CG == 2 ? STAGES2 : STAGES;
+  constexpr int BKE = TF ? 32 : 64;               // contraction elements per stage = one 128-byte swizzle row
+  constexpr int KI = TF ? 8 : 16;                 // contraction elements per tcgen05.mma
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemLayout s = carve(smem_raw, NST, CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES, CG == 2 ? RING2_BYTES : RING_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,7 +323,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
 
   if (threadIdx.x == 32) {                        // (a lane of the MMA warp: off the barrier-initialising thread)
     for (int i = 0; i < p.n_seg; ++i) { prefetch_tensormap(&p.ta[i]); prefetch_tensormap(&p.tb[i]); }
-    if (p.out_bf16) prefetch_tensormap(&p.tc);
+    if (p.out_bf16 || p.out_f32_tma) prefetch_tensormap(&p.tc);
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -315,24 +349,24 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       // bytes landing per stage on the barrier the MMA issuer waits on (pair mode: both CTAs' boxes, on the leader's)
-      const uint32_t tx = CG == 2 ? (uint32_t)(2 * (A_STAGE_BYTES + (p.bn / 2) * BK * 2)) : (uint32_t)(A_STAGE_BYTES + p.bn * BK * 2);
+      const uint32_t tx = CG == 2 ? (uint32_t)(2 * (A_STAGE_BYTES + (p.bn / 2) * 128)) : (uint32_t)(A_STAGE_BYTES + p.bn * 128);
       for (int t = unit; t < total_tiles; t += n_units) {
         const int mt = t / p.n_tiles, nb = t % p.n_tiles;
         const int mb = mt * CG + rank;
         const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
         for (int seg = 0; seg < p.n_seg; ++seg) {
           if (mt * CG * BM >= rows_valid[seg]) continue;          // (pair-uniform: decided on the pair's first row)
-          const int nkb = (p.k[seg] + BK - 1) / BK;
+          const int nkb = (p.k[seg] + BKE - 1) / BKE;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&s.empty[stage], phase ^ 1);
             if (CG == 2) {
               if (rank == 0) mbar_expect_tx(&s.full[stage], tx);
-              tma_load_2d_pair(s.a(stage), &p.ta[seg], &s.full[stage], kb * BK, mb * BM);
-              tma_load_2d_pair(s.b(stage), &p.tb[seg], &s.full[stage], kb * BK, nb * BN_MAX + rank * (bn_tile / 2));
+              tma_load_2d_pair(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
+              tma_load_2d_pair(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX + rank * (bn_tile / 2));
             } else {
               mbar_expect_tx(&s.full[stage], tx);
-              tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BK, mb * BM);
-              tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BK, nb * BN_MAX);
+              tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
+              tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX);
             }
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
@@ -352,7 +386,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       for (int t = unit; t < total_tiles; t += n_units) {
         const int mt = t / p.n_tiles, nb = t % p.n_tiles;
         const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
-        const uint32_t idesc = instr_desc(BM * CG, bn_tile, 0, 0);
+        const uint32_t idesc = instr_desc(BM * CG, bn_tile, 0, 0, TF);
         mbar_wait(&s.acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN_MAX);
@@ -360,33 +394,23 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
         for (int seg = 0; seg < p.n_seg; ++seg) {
           if (mt * CG * BM >= rows_valid[seg]) continue;
           const int K = p.k[seg];
-          const int nkb = (K + BK - 1) / BK;
+          const int nkb = (K + BKE - 1) / BKE;
           for (int kb = 0; kb < nkb; ++kb) {
             if (!(p.debug & 2)) mbar_wait(&s.full[stage], phase);      // (debug 2: MMA issue rate alone, operands = stale smem)
             tc_fence_after();
-            // descriptors of this stage: the 14-bit address field advances by 2 (= 32 bytes) per 16-element k step; the
-            // issue loop is kept branch-free for full k-blocks so that the tensor pipe never waits on this thread
+            // descriptors of this stage: the 14-bit address field advances by 2 (= 32 bytes) per k step of one MMA (16 bf16 /
+            // 8 tf32 elements); the issue loop is kept branch-free for full k-blocks so that the tensor pipe never waits on this thread
             const uint64_t ad = a_desc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
             const uint64_t bd = b_desc0 + (uint64_t)(stage * (b_stage_bytes >> 4));
-            const int k_left = K - kb * BK;
-            if (k_left >= BK) {
-              if (CG == 2) {
-                tc_mma_bf16_pair(d_tmem, ad, bd, idesc, accumulate);
-                tc_mma_bf16_pair(d_tmem, ad + 2, bd + 2, idesc, 1);
-                tc_mma_bf16_pair(d_tmem, ad + 4, bd + 4, idesc, 1);
-                tc_mma_bf16_pair(d_tmem, ad + 6, bd + 6, idesc, 1);
-              } else {
-                tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                tc_mma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
-                tc_mma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
-                tc_mma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
-              }
+            const int k_left = K - kb * BKE;
+            if (k_left >= BKE) {
+              tc_mma<CG, TF>(d_tmem, ad, bd, idesc, accumulate);
+              tc_mma<CG, TF>(d_tmem, ad + 2, bd + 2, idesc, 1);
+              tc_mma<CG, TF>(d_tmem, ad + 4, bd + 4, idesc, 1);
+              tc_mma<CG, TF>(d_tmem, ad + 6, bd + 6, idesc, 1);
             } else {
-              const int n_k16 = (k_left + 15) / 16;
-              for (int k16 = 0; k16 < n_k16; ++k16) {
-                if (CG == 2) tc_mma_bf16_pair(d_tmem, ad + 2 * k16, bd + 2 * k16, idesc, k16 ? 1u : accumulate);
-                else tc_mma_bf16(d_tmem, ad + 2 * k16, bd + 2 * k16, idesc, k16 ? 1u : accumulate);
-              }
+              const int n_ki = (k_left + KI - 1) / KI;
+              for (int ki = 0; ki < n_ki; ++ki) tc_mma<CG, TF>(d_tmem, ad + 2 * ki, bd + 2 * ki, idesc, ki ? 1u : accumulate);
             }
             accumulate = 1;
             if (!(p.debug & 2)) {
@@ -435,7 +459,72 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       tc_fence_after();
       if (p.debug & 1) {
         // nothing: measures the load + MMA pipeline alone
-      } else if (p.out_bf16) {
+      } else if (TF && p.out_f32_tma) {
+        // fp32 activations of the tf32 mode: one 32 x 32 fp32 box (32 rows of 128 bytes) per step, TF32-rounded, TMA store
+        for (int c0 = parity * 32; c0 < bn_tile; c0 += 64) {
+          if (boxes_issued >= 1) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          if (p.mask) {                            // 32 x 32 fp32 mask box staged with coalesced 512-byte warp loads (see the bf16 path)
+            const int rbase = mb * BM + quarter * 32, cbase = nb * BN_MAX + c0 + (lane & 7) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3);
+              uint4 mraw = make_uint4(0u, 0u, 0u, 0u);
+              if (rbase + r < m_dyn && cbase < p.ldmask)
+                mraw = __ldg(reinterpret_cast<const uint4*>((const float*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
+              *reinterpret_cast<uint4*>(buf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = mraw;
+            }
+            __syncwarp();
+          }
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + c0), r);
+          const int gn0 = nb * BN_MAX + c0;
+          float v[32];
+          if (tile_live && gn0 + 32 <= p.n) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + q * 4);
+              v[q * 4 + 0] = fmaxf(__uint_as_float(r[q * 4 + 0]) + b4.x, relu_lo);
+              v[q * 4 + 1] = fmaxf(__uint_as_float(r[q * 4 + 1]) + b4.y, relu_lo);
+              v[q * 4 + 2] = fmaxf(__uint_as_float(r[q * 4 + 2]) + b4.z, relu_lo);
+              v[q * 4 + 3] = fmaxf(__uint_as_float(r[q * 4 + 3]) + b4.w, relu_lo);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = 0.f;
+              if (row_live && gn0 + j < p.n) x = fmaxf(__uint_as_float(r[j]) + bias_s[c0 + j], relu_lo);
+              v[j] = x;
+            }
+          }
+          if (p.mask) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 mv = *reinterpret_cast<const float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4));
+              if (!(mv.x > 0.f)) v[q * 4 + 0] = 0.f;
+              if (!(mv.y > 0.f)) v[q * 4 + 1] = 0.f;
+              if (!(mv.z > 0.f)) v[q * 4 + 2] = 0.f;
+              if (!(mv.w > 0.f)) v[q * 4 + 3] = 0.f;
+            }
+          }
+          if (p.round_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tc, buf, nb * BN_MAX + c0, mb * BM + quarter * 32);
+            tma_store_commit();
+          }
+          ++boxes_issued;
+        }
+      } else if (!TF && p.out_bf16) {
         for (int c0 = parity * 64; c0 < bn_tile; c0 += 128) {
           if (boxes_issued >= 1) {                 // this warp's previous store has finished reading the staging box
             if (lane == 0) tma_store_wait_read<0>();
@@ -451,7 +540,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
               const int r = i * 4 + (lane >> 3);
               uint4 mraw = make_uint4(0u, 0u, 0u, 0u);
               if (rbase + r < m_dyn && cbase < p.ldmask)
-                mraw = __ldg(reinterpret_cast<const uint4*>(p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
+                mraw = __ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
               *reinterpret_cast<uint4*>(buf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = mraw;
             }
             __syncwarp();
@@ -591,7 +680,15 @@ constexpr int TN_STAGES = 3;
 constexpr int TN_A_STAGE_BYTES = 2 * A_STAGE_BYTES;   // two 128-row sub-tiles, each two 64-row chunks of 8 KB
 static_assert(TN_STAGES * (TN_A_STAGE_BYTES + B_STAGE_BYTES) == RING_BYTES, "TN ring size mismatch");
 
+template <int TF>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant__ TnParams p) {
+  // a TMA box = CW output-index elements (128 bytes) x BKR contraction rows; bf16: 64 x 64 (8 KB), tf32: 32 x 32 (4 KB).  Stages
+  // hold the same bytes either way: 256 output rows of A + up to 256 of B over BKR contraction rows = 32 KB + 32 KB
+  constexpr int CW = TF ? 32 : 64;
+  constexpr int BKR = TF ? 32 : 64;
+  constexpr int CHUNK_BYTES = BKR * 128;
+  constexpr int NCH_A = TN_ROWS / CW;
+  constexpr int KSTEP = (TF ? 8 : 16) * 128 / 16;           // descriptor address units (16 B) per MMA: its contraction rows x 128 B
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout s = carve(smem_raw, TN_STAGES, B_STAGE_BYTES, RING_BYTES, true);
   s.b0 = smem_raw + TN_STAGES * TN_A_STAGE_BYTES;     // (carve assumes 16 KB A stages)
@@ -607,13 +704,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   const int row0 = nb * TN_ROWS;
   const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
   // contraction range of this split, in 64-row blocks (rows in [m_dyn, round_up(m_dyn, 64)) are zero: zero-tail rule)
-  const int blocks_total = (m_dyn + BK - 1) / BK;
+  const int blocks_total = (m_dyn + BKR - 1) / BKR;
   const int per = (blocks_total + p.splits - 1) / p.splits;
   const int kb0 = min(z * per, blocks_total), kb1 = min(kb0 + per, blocks_total);
   const int n_sub = (q.n - row0 > BM) ? 2 : 1;                                 // 128-row sub-tiles that hold output rows
-  const int n_chunks_a = min(4, (q.n - row0 + 63) / 64);                       // 64-wide TMA boxes actually needed (chunk c -> sub-tile c / 2)
-  const int bn_tile = min(BN_MAX, (q.k - kt * BN_MAX + 63) / 64 * 64);
-  const int n_chunks_b = bn_tile / 64;
+  const int n_chunks_a = min(NCH_A, (q.n - row0 + CW - 1) / CW);               // TMA boxes actually needed (sub-tile s = chunks [s, s+1) * NCH_A / 2)
+  const int bn_tile = min(BN_MAX, (q.k - kt * BN_MAX + CW - 1) / CW * CW);
+  const int n_chunks_b = bn_tile / CW;
 
   if (threadIdx.x == 64) {
     prefetch_tensormap(&q.ta);
@@ -637,12 +734,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)((n_chunks_a + n_chunks_b) * 64 * BK * 2);
+      const uint32_t tx = (uint32_t)((n_chunks_a + n_chunks_b) * CHUNK_BYTES);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.empty[stage], phase ^ 1);
         mbar_expect_tx(&s.full[stage], tx);
-        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(a_stage(stage) + c * 8192, &q.ta, &s.full[stage], row0 + c * 64, kb * BK);
-        for (int c = 0; c < n_chunks_b; ++c) tma_load_2d(s.b(stage) + c * 8192, &q.tb, &s.full[stage], kt * BN_MAX + c * 64, kb * BK);
+        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(a_stage(stage) + c * CHUNK_BYTES, &q.ta, &s.full[stage], row0 + c * CW, kb * BKR);
+        for (int c = 0; c < n_chunks_b; ++c) tma_load_2d(s.b(stage) + c * CHUNK_BYTES, &q.tb, &s.full[stage], kt * BN_MAX + c * CW, kb * BKR);
         if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -651,12 +748,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // M is always issued as 128: when only one 64-chunk of a sub-tile was loaded its upper 64 accumulator rows hold
+      // M is always issued as 128: when only part of a sub-tile's chunks was loaded its upper accumulator rows hold
       // products with stale shared memory and are never stored (rows >= n)
-      const uint32_t idesc = instr_desc(BM, bn_tile, 1, 1);
+      const uint32_t idesc = instr_desc(BM, bn_tile, 1, 1, TF);
       uint32_t accumulate = 0;
-      // MN-major descriptors: 16 contraction rows = 2048 bytes = 128 in the 14-bit address field; kept branch-free
-      const uint64_t a_desc0 = smem_desc(smem_u32(a_stage(0)), 8192, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), 8192, 1024);
+      // MN-major descriptors (LBO = distance between 128-byte-wide chunks of the M / N index, SBO = 8 contraction rows): one MMA
+      // covers 16 (bf16) / 8 (tf32) contraction rows = 2048 / 1024 bytes = KSTEP in the 14-bit address field; kept branch-free
+      const uint64_t a_desc0 = smem_desc(smem_u32(a_stage(0)), CHUNK_BYTES, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), CHUNK_BYTES, 1024);
       const uint32_t acc1 = tmem_base + (uint32_t)BN_MAX;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.full[stage], phase);
@@ -665,19 +763,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
         const uint64_t ad1 = ad + (uint64_t)(A_STAGE_BYTES >> 4);              // second 128-row sub-tile
         const uint64_t bd = b_desc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
         if (n_sub == 2) {
-          tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
-          tc_mma_bf16(acc1, ad1, bd, idesc, accumulate);
-          tc_mma_bf16(tmem_base, ad + 128, bd + 128, idesc, 1);
-          tc_mma_bf16(acc1, ad1 + 128, bd + 128, idesc, 1);
-          tc_mma_bf16(tmem_base, ad + 256, bd + 256, idesc, 1);
-          tc_mma_bf16(acc1, ad1 + 256, bd + 256, idesc, 1);
-          tc_mma_bf16(tmem_base, ad + 384, bd + 384, idesc, 1);
-          tc_mma_bf16(acc1, ad1 + 384, bd + 384, idesc, 1);
+          tc_mma<1, TF>(tmem_base, ad, bd, idesc, accumulate);
+          tc_mma<1, TF>(acc1, ad1, bd, idesc, accumulate);
+          tc_mma<1, TF>(tmem_base, ad + KSTEP, bd + KSTEP, idesc, 1);
+          tc_mma<1, TF>(acc1, ad1 + KSTEP, bd + KSTEP, idesc, 1);
+          tc_mma<1, TF>(tmem_base, ad + 2 * KSTEP, bd + 2 * KSTEP, idesc, 1);
+          tc_mma<1, TF>(acc1, ad1 + 2 * KSTEP, bd + 2 * KSTEP, idesc, 1);
+          tc_mma<1, TF>(tmem_base, ad + 3 * KSTEP, bd + 3 * KSTEP, idesc, 1);
+          tc_mma<1, TF>(acc1, ad1 + 3 * KSTEP, bd + 3 * KSTEP, idesc, 1);
         } else {
-          tc_mma_bf16(tmem_base, ad, bd, idesc, accumulate);
-          tc_mma_bf16(tmem_base, ad + 128, bd + 128, idesc, 1);
-          tc_mma_bf16(tmem_base, ad + 256, bd + 256, idesc, 1);
-          tc_mma_bf16(tmem_base, ad + 384, bd + 384, idesc, 1);
+          tc_mma<1, TF>(tmem_base, ad, bd, idesc, accumulate);
+          tc_mma<1, TF>(tmem_base, ad + KSTEP, bd + KSTEP, idesc, 1);
+          tc_mma<1, TF>(tmem_base, ad + 2 * KSTEP, bd + 2 * KSTEP, idesc, 1);
+          tc_mma<1, TF>(tmem_base, ad + 3 * KSTEP, bd + 3 * KSTEP, idesc, 1);
         }
         accumulate = 1;
         tc_commit(&s.empty[stage]);
@@ -776,9 +874,12 @@ int tc_init() {
     return -1;
   }
   g_encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(k_gemm_nt_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT1) != cudaSuccess ||
-      cudaFuncSetAttribute(k_gemm_nt_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT2) != cudaSuccess ||
-      cudaFuncSetAttribute(k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_gemm_nt_tc<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT1) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_nt_tc<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT2) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_nt_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT1) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_nt_tc<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT2) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_tn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_tn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess) {
     cudaGetLastError();
     g_tc_state = -1;
     return -1;
@@ -787,14 +888,15 @@ int tc_init() {
   return 1;
 }
 
-// 2-D bf16 tensor [rows, cols] with row pitch ld (elements), box = box_cols x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
-  OGL_ARG(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "gemm_tc: operand not 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
+// 2-D bf16 (es = 2) or fp32 (es = 4) tensor [rows, cols] with row pitch ld (elements), box = box_cols x box_rows (box_cols * es
+// = 128 bytes), 128-byte swizzle
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int es = 2) {
+  OGL_ARG(((uintptr_t)ptr & 15) == 0 && (ld * es) % 16 == 0, "gemm_tc: operand not 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)es};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -861,8 +963,12 @@ static int launch_gemm(Kernel kernel, int grid, int block, int smem, int cluster
 
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   OGL_ARG(tc_init() == 1, "gemm_nt_tc: tcgen05 path unavailable (driver lacks cuTensorMapEncodeTiled?)");
-  OGL_ARG(g.in_bf16, "gemm_nt_tc: bf16 operands only");
+  OGL_ARG((g.in_bf16 != 0) != (g.tf32 != 0), "gemm_nt_tc: bf16 or tf32 operands only");
+  OGL_ARG(!(g.tf32 && g.out_bf16), "gemm_nt_tc: tf32 operands give fp32 output");
   OGL_ARG(g.n > 0 && g.m_max > 0 && g.n_seg >= 1 && g.n_seg <= 2, "gemm_nt_tc: bad shape");
+  const int tf = g.tf32 ? 1 : 0;
+  const int es = tf ? 4 : 2;                 // operand element bytes
+  const int bke = 128 / es;                  // contraction elements per 128-byte swizzle row
   NtParams p;
   memset(&p, 0, sizeof(p));
   p.n = g.n;
@@ -876,37 +982,44 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     p.k[i] = g.k[i];
     p.a_rows_dev[i] = g.a_rows_dev[i];
     const int64_t a_rows = g.a_rows_max[i] > 0 ? g.a_rows_max[i] : g.m_max;      // rows that exist in segment i's A buffer
-    OGL_TRY(make_map(&p.ta[i], g.a[i], a_rows, g.k[i], g.lda[i], BK, BM));
-    OGL_TRY(make_map(&p.tb[i], g.b[i], g.n, g.k[i], g.ldb[i], BK, cg == 2 ? p.bn / 2 : p.bn));
+    OGL_TRY(make_map(&p.ta[i], g.a[i], a_rows, g.k[i], g.lda[i], bke, BM, es));
+    OGL_TRY(make_map(&p.tb[i], g.b[i], g.n, g.k[i], g.ldb[i], bke, cg == 2 ? p.bn / 2 : p.bn, es));
   }
   p.m_dev = g.m_dev;
   p.m_max = g.m_max;
   p.bias = g.bias;
   p.bias2 = g.bias2;
   p.relu = g.relu;
-  p.mask = (const __nv_bfloat16*)g.mask;
+  p.mask = g.mask;
   p.ldmask = g.ldmask;
   p.c = g.c;
   p.ldc = g.ldc;
   p.out_bf16 = g.out_bf16;
+  // tf32 mode: activations leave through 32 x 32 fp32 TMA-store boxes (the logits GEMM -- no rounding, not a later operand -- keeps
+  // the direct fp32 stores, its 41 columns are no 16-byte multiple of anything)
+  p.out_f32_tma = (tf && (g.out_tf32 || g.mask)) ? 1 : 0;
+  p.round_out = g.out_tf32;
   p.zero_tail = g.zero_tail;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("OGL_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
-  OGL_ARG(!(g.mask && !g.out_bf16), "gemm_nt_tc: the mask epilogue is implemented for bf16 output only");
+  OGL_ARG(!(g.mask && !(g.out_bf16 || p.out_f32_tma)), "gemm_nt_tc: the mask epilogue is implemented for the TMA-store outputs only");
   if (g.out_bf16) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 64, 32));
+  if (p.out_f32_tma) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 32, 32, 4));
   OGL_ARG(g.ldc % 8 == 0 && ((uintptr_t)g.c & 15) == 0, "gemm_nt_tc: output pitch must be a multiple of 8 elements");
   OGL_ARG(!g.mask || (g.ldmask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0), "gemm_nt_tc: mask pitch must be a multiple of 8 elements");
   if (cg == 2) {
     const int pairs = (int)(super_tiles < sm_count() / 2 ? super_tiles : sm_count() / 2);
-    OGL_TRY(launch_gemm(k_gemm_nt_tc<2>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
+    if (tf) OGL_TRY(launch_gemm(k_gemm_nt_tc<2, 1>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
+    else OGL_TRY(launch_gemm(k_gemm_nt_tc<2, 0>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
     return OGL_OK;
   }
   const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  return launch_gemm(k_gemm_nt_tc<1>, grid, THREADS_NT, SMEM_NT1, 1, p, s);
+  if (tf) return launch_gemm(k_gemm_nt_tc<1, 1>, grid, THREADS_NT, SMEM_NT1, 1, p, s);
+  return launch_gemm(k_gemm_nt_tc<1, 0>, grid, THREADS_NT, SMEM_NT1, 1, p, s);
 }
 
 int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
@@ -917,14 +1030,18 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
   p.n_prob = count;
   p.m_dev = g[0].m_dev;
   p.m_max = g[0].m_max;
+  const int tf = g[0].tf32 ? 1 : 0;
+  const int es = tf ? 4 : 2;
+  const int cw = 128 / es;                   // TMA box: cw output-index elements (128 bytes) x cw contraction rows
   int tiles = 0;
   int64_t per_total = 0;
   for (int i = 0; i < count; ++i) {
-    OGL_ARG(g[i].in_bf16 && g[i].n > 0 && g[i].k > 0 && g[i].m_max > 0, "gemm_tn_tc: bad arguments");
-    OGL_ARG(g[i].m_dev == g[0].m_dev && g[i].m_max == g[0].m_max, "gemm_tn_tc: grouped problems must contract over the same rows");
+    OGL_ARG((g[i].in_bf16 || g[i].tf32) && g[i].n > 0 && g[i].k > 0 && g[i].m_max > 0, "gemm_tn_tc: bad arguments");
+    OGL_ARG(g[i].m_dev == g[0].m_dev && g[i].m_max == g[0].m_max && g[i].tf32 == g[0].tf32,
+            "gemm_tn_tc: grouped problems must contract over the same rows in the same arithmetic");
     TnProblem& q = p.pr[i];
-    OGL_TRY(make_map(&q.ta, g[i].a, g[i].m_max, g[i].n, g[i].lda, 64, BK));
-    OGL_TRY(make_map(&q.tb, g[i].b, g[i].m_max, g[i].k, g[i].ldb, 64, BK));
+    OGL_TRY(make_map(&q.ta, g[i].a, g[i].m_max, g[i].n, g[i].lda, cw, cw, es));
+    OGL_TRY(make_map(&q.tb, g[i].b, g[i].m_max, g[i].k, g[i].ldb, cw, cw, es));
     q.n = g[i].n;
     q.k = g[i].k;
     q.k_tiles = (g[i].k + BN_MAX - 1) / BN_MAX;
@@ -936,7 +1053,7 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
   p.total_tiles = tiles;
   // one CTA per SM and exactly one wave: tiles * splits <= #SMs (150 CTAs on 148 SMs would run as two waves)
   int splits = sm_count() / tiles;
-  const int by_rows = (int)ceil_div(g[0].m_max, 4 * BK);          // at least 4 contraction blocks per split
+  const int by_rows = (int)ceil_div(g[0].m_max, 4 * cw);          // at least 4 contraction blocks per split
   if (splits > by_rows) splits = by_rows;
   float* ws = g[0].partial;
   const int64_t ws_elems = ws ? g[0].partial_elems : 0;
@@ -967,7 +1084,8 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
     }
   }
   p.use_tma_store = staged ? 1 : 0;
-  OGL_TRY(launch_gemm(k_gemm_tn_tc, tiles * splits, THREADS, SMEM_TN, 1, p, s));
+  if (tf) OGL_TRY(launch_gemm(k_gemm_tn_tc<1>, tiles * splits, THREADS, SMEM_TN, 1, p, s));
+  else OGL_TRY(launch_gemm(k_gemm_tn_tc<0>, tiles * splits, THREADS, SMEM_TN, 1, p, s));
   if (staged) return reduce_splits_group(rg, s);
   return OGL_OK;
 }
@@ -1006,6 +1124,28 @@ extern "C" int ogl_gemm_bf16_tn(const void* a_dev, int lda, const void* b_dev, i
   OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_bf16_tn: bad arguments");
   GemmTN g;
   g.a = a_dev; g.lda = lda; g.b = b_dev; g.ldb = ldb; g.c = c_dev; g.ldc = ldc; g.n = n; g.k = k; g.m_max = m; g.in_bf16 = 1;
+  g.partial = workspace_dev; g.partial_elems = workspace_dev ? workspace_elems : 0;
+  return gemm_tn_tc(g, (cudaStream_t)stream);
+}
+
+// tf32 flavour of the two entry points above (fp32 operands that hold TF32-rounded values; tests / bench)
+extern "C" int ogl_gemm_tf32_nt_ex(const float* a_dev, int lda, const float* b_dev, int ldb, float* c_dev, int ldc, int m, int n, int k,
+                                   int tma_out, const float* bias_dev, int relu, const float* mask_dev, int ldmask, int cg, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_tf32_nt_ex: bad arguments");
+  GemmNT g;
+  g.a[0] = a_dev; g.lda[0] = lda; g.b[0] = b_dev; g.ldb[0] = ldb; g.k[0] = k; g.n_seg = 1;
+  g.c = c_dev; g.ldc = ldc; g.m_max = m; g.n = n; g.tf32 = 1; g.out_tf32 = tma_out; g.zero_tail = 0;
+  g.bias = bias_dev; g.relu = relu; g.force_cg = cg; g.mask = mask_dev; g.ldmask = ldmask;
+  return gemm_nt_tc(g, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_gemm_tf32_tn(const float* a_dev, int lda, const float* b_dev, int ldb, float* c_dev, int ldc, int m, int n, int k,
+                                float* workspace_dev, int64_t workspace_elems, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_tf32_tn: bad arguments");
+  GemmTN g;
+  g.a = a_dev; g.lda = lda; g.b = b_dev; g.ldb = ldb; g.c = c_dev; g.ldc = ldc; g.n = n; g.k = k; g.m_max = m; g.tf32 = 1;
   g.partial = workspace_dev; g.partial_elems = workspace_dev ? workspace_elems : 0;
   return gemm_tn_tc(g, (cudaStream_t)stream);
 }

@@ -545,6 +545,7 @@ static int graph_insert(ogl_graph* g, const int64_t* src, const int64_t* dst, in
   // edge ids inside one call are forward-then-reverse over the WHOLE call (dynamic_graph_edge.py:214-215), so a
   // symmetric call that does not fit one chunk is issued as forward chunks followed by reverse chunks.
   if (n == 0) return OGL_OK;
+  OGL_TRY(readers_wait(g, s));                 // a prefetched minibatch may still be sampling this CSR on its plan's stream
   if (!symmetric || n <= g->batch_cap) {
     for (int64_t o = 0; o < n; o += g->batch_cap) {
       const int64_t m = (n - o < g->batch_cap) ? n - o : g->batch_cap;
@@ -572,6 +573,7 @@ extern "C" int ogl_graph_insert_edges_host(ogl_graph* g, const int64_t* src_host
 extern "C" int ogl_graph_compact(ogl_graph* g, void* stream) {
   OGL_ARG(g, "ogl_graph_compact: null graph");
   if (g->p_indptr) return OGL_OK;
+  OGL_TRY(readers_wait(g, (cudaStream_t)stream));
   return graph_rebuild_pool(g, 0, (cudaStream_t)stream);
 }
 
@@ -634,6 +636,7 @@ extern "C" int ogl_graph_set_active_prefix(ogl_graph* g, int64_t n_active, void*
   OGL_ARG(n_active >= 0 && n_active <= g->p_v, "ogl_graph_set_active_prefix: n_active out of range");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t V = g->p_v;
+  OGL_TRY(readers_wait(g, s));
   OGL_LAUNCH(k_prefix_count, grid_for(V * 32, kBlock), kBlock, 0, s, g->p_indptr, g->p_indices, g->deg, g->cap, n_active, V);
   OGL_TRY(exclusive_scan_i32_to_i64(g->deg, g->row_start, V, g->scan_scratch, g->total_dev, s));
   if (n_active > 0)

@@ -330,9 +330,12 @@ int peer_sum_adam(ogl_peer* p, const PeerAdamArgs& a, int64_t lo, int64_t hi, cu
 #define OGL_PEER_LAUNCH(T, TWO)                                                                                                          \
   OGL_LAUNCH((k_peer_sum_adam<T, TWO>), grid, 256, 0, s, p->view, p->epoch, lo, hi, a.params, a.m, a.v, a.lr, a.b1, a.b2, a.eps, a.t_dev, \
              a.segs, a.n_segs, a.reduced_out)
-  if (a.bf16) {
+  if (a.mode == OGL_BF16) {
     if (two) OGL_PEER_LAUNCH(__nv_bfloat16, true);
     else OGL_PEER_LAUNCH(__nv_bfloat16, false);
+  } else if (a.mode == OGL_TF32) {
+    if (two) OGL_PEER_LAUNCH(tf32_t, true);
+    else OGL_PEER_LAUNCH(tf32_t, false);
   } else {
     if (two) OGL_PEER_LAUNCH(float, true);
     else OGL_PEER_LAUNCH(float, false);

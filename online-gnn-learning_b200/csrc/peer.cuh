@@ -7,7 +7,7 @@ struct ogl_peer;
 namespace ogl {
 
 struct PeerAdamArgs {
-  int bf16 = 0;
+  int mode = 0;                      // OGL_F32 | OGL_BF16 | OGL_TF32: element type of the weight shadows
   float* params = nullptr;
   const float* grads = nullptr;      // the plan's gradient buffer: must be the peer group's local buffer
   float *m = nullptr, *v = nullptr;

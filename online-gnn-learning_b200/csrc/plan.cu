@@ -29,7 +29,7 @@ struct ogl_features {
 
 extern "C" int ogl_features_create(ogl_features** out, int64_t v_cap, int n_feats, int mode) {
   OGL_TRY(require_device());
-  OGL_ARG(out && v_cap > 0 && n_feats > 0 && (mode == OGL_F32 || mode == OGL_BF16), "ogl_features_create: bad arguments");
+  OGL_ARG(out && v_cap > 0 && n_feats > 0 && (mode == OGL_F32 || mode == OGL_BF16 || mode == OGL_TF32), "ogl_features_create: bad arguments");
   ogl_features* f = new ogl_features();
   f->v_cap = v_cap; f->F = n_feats; f->pitch = pitch_of(n_feats); f->mode = mode;
   const size_t es = mode == OGL_BF16 ? 2 : 4;
@@ -53,6 +53,7 @@ extern "C" int ogl_features_write(ogl_features* f, int64_t row0, int64_t n, cons
   OGL_ARG(f && row0 >= 0 && n >= 0 && row0 + n <= f->v_cap, "ogl_features_write: rows [%lld, %lld) out of range", (long long)row0, (long long)(row0 + n));
   if (n == 0) return OGL_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  OGL_TRY(readers_wait(f, s));                 // a prefetched minibatch may still be gathering rows on its plan's stream
   if (src_is_host) {
     // chunked H2D through a device staging buffer (fp32 rows are converted/padded on the GPU)
     const int64_t chunk = 1 << 16;
@@ -65,7 +66,7 @@ extern "C" int ogl_features_write(ogl_features* f, int64_t row0, int64_t n, cons
       const int64_t m = n - o < chunk ? n - o : chunk;
       if (feats) {
         OGL_CUDA(cudaMemcpyAsync(f->stage_f, feats + o * f->F, sizeof(float) * m * f->F, cudaMemcpyHostToDevice, s));
-        OGL_TRY(feat_write(f->mode == OGL_BF16, f->stage_f, nullptr, m, f->F, f->table, f->pitch, row0 + o, s));
+        OGL_TRY(feat_write(f->mode, f->stage_f, nullptr, m, f->F, f->table, f->pitch, row0 + o, s));
       }
       if (labels) {
         OGL_CUDA(cudaMemcpyAsync(f->stage_l, labels + o, sizeof(int64_t) * m, cudaMemcpyHostToDevice, s));
@@ -74,7 +75,7 @@ extern "C" int ogl_features_write(ogl_features* f, int64_t row0, int64_t n, cons
     }
     return OGL_OK;
   }
-  if (feats) OGL_TRY(feat_write(f->mode == OGL_BF16, feats, nullptr, n, f->F, f->table, f->pitch, row0, s));
+  if (feats) OGL_TRY(feat_write(f->mode, feats, nullptr, n, f->F, f->table, f->pitch, row0, s));
   if (labels) OGL_TRY(label_write(labels, nullptr, n, f->labels, row0, s));
   return OGL_OK;
 }
@@ -83,7 +84,8 @@ extern "C" int ogl_features_write_permuted(ogl_features* f, int64_t n, const flo
                                            const int64_t* src_rows_dev, void* stream) {
   OGL_ARG(f && n >= 0 && n <= f->v_cap && src_rows_dev, "ogl_features_write_permuted: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  if (feats_dev) OGL_TRY(feat_write(f->mode == OGL_BF16, feats_dev, src_rows_dev, n, f->F, f->table, f->pitch, 0, s));
+  OGL_TRY(readers_wait(f, s));
+  if (feats_dev) OGL_TRY(feat_write(f->mode, feats_dev, src_rows_dev, n, f->F, f->table, f->pitch, 0, s));
   if (labels_dev) OGL_TRY(label_write(labels_dev, src_rows_dev, n, f->labels, 0, s));
   return OGL_OK;
 }
@@ -108,7 +110,7 @@ struct LayerBuf {
 struct ogl_plan {
   ogl_plan_config cfg;
   int L = 0;
-  int bf16 = 0;
+  int bf16 = 0, tf32 = 0, mode = 0;      // mode = cfg.mode (OGL_F32 | OGL_BF16 | OGL_TF32); bf16 / tf32 = mode == ...
   size_t es = 4;
   std::vector<int> nmax;                 // [L+1]
   std::vector<int32_t*> nodes;           // [L+1]
@@ -242,16 +244,16 @@ static std::string nm(const char* fmt, int i) {
 }
 
 static int gemm_nt(const ogl_plan* p, const GemmNT& g, cudaStream_t s) {
-  if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_nt_tc(g, s);
+  if ((p->bf16 || p->tf32) && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_nt_tc(g, s);
   return gemm_nt_simt(g, s);
 }
 static int gemm_tn(const ogl_plan* p, const GemmTN& g, cudaStream_t s) {
-  if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_tn_tc(g, s);
+  if ((p->bf16 || p->tf32) && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_tn_tc(g, s);
   return gemm_tn_simt(g, s);
 }
 // weight-gradient GEMMs that contract over the same rows: one launch on the tcgen05 path
 static int gemm_tn_group(const ogl_plan* p, const GemmTN* g, int count, cudaStream_t s) {
-  if (p->bf16 && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_tn_tc_group(g, count, s);
+  if ((p->bf16 || p->tf32) && p->cfg.gemm_impl == 0 && gemm_tc_available()) return gemm_tn_tc_group(g, count, s);
   for (int i = 0; i < count; ++i) OGL_TRY(gemm_tn_simt(g[i], s));
   return OGL_OK;
 }
@@ -270,19 +272,22 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   OGL_ARG(out && cfg, "ogl_plan_create: null");
   OGL_ARG(cfg->n_layers >= 1 && cfg->n_layers <= 7, "ogl_plan_create: n_layers must be in [1,7]");
   OGL_ARG(cfg->max_seeds > 0 && cfg->v_cap > 0, "ogl_plan_create: max_seeds / v_cap must be positive");
-  OGL_ARG(cfg->mode == OGL_F32 || cfg->mode == OGL_BF16, "ogl_plan_create: bad mode");
+  OGL_ARG(cfg->mode == OGL_F32 || cfg->mode == OGL_BF16 || cfg->mode == OGL_TF32, "ogl_plan_create: bad mode");
   for (int i = 0; i <= cfg->n_layers; ++i) OGL_ARG(cfg->dims[i] > 0, "ogl_plan_create: dims[%d] must be positive", i);
   for (int i = 0; i < cfg->n_layers; ++i) OGL_ARG(cfg->fanouts[i] > 0 && cfg->fanouts[i] < 255, "ogl_plan_create: fanouts[%d] must be in [1,254]", i);
   ogl_plan* p = new ogl_plan();
   p->cfg = *cfg;
   const int L = p->L = cfg->n_layers;
+  p->mode = cfg->mode;
   p->bf16 = cfg->mode == OGL_BF16;
+  p->tf32 = cfg->mode == OGL_TF32;
   p->es = p->bf16 ? 2 : 4;
   p->nmax.resize(L + 1);
   p->nmax[0] = cfg->max_seeds;
   for (int h = 0; h < L; ++h) {
+    // a frontier = the destination rows themselves (seed lists may hold duplicates, DGL allows them) + the distinct new sources
     int64_t n = (int64_t)p->nmax[h] * (1 + cfg->fanouts[h]);
-    if (n > cfg->v_cap) n = cfg->v_cap;
+    if (n > cfg->v_cap + p->nmax[h]) n = cfg->v_cap + p->nmax[h];
     p->nmax[h + 1] = (int)n;
   }
   for (int h = 0; h < L; ++h)
@@ -308,7 +313,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
     DM0(p->rev_ptr[h], sizeof(int32_t) * ((size_t)p->nmax[h + 1] + 2));
     DM0(p->rev_edge[h], sizeof(int32_t) * ne);
   }
-  OGL_TRY(to_block_init(&p->tb, cfg->v_cap, ne_max));
+  OGL_TRY(to_block_init(&p->tb, cfg->v_cap, ne_max, p->nmax[L]));
   // activations (row counts padded to 128 for the zero-tail rule)
   auto rows = [](int n) { return (size_t)round_up(n, 128); };
   DM0(p->act[L], p->es * rows(p->nmax[L]) * pitch_of(cfg->dims[0]));
@@ -372,6 +377,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
 
 extern "C" int ogl_plan_destroy(ogl_plan* p) {
   if (!p) return OGL_OK;
+  readers_remove_owner(p);
   for (auto x : p->nodes) cudaFree(x);
   for (auto x : p->edge_lid) cudaFree(x);
   for (auto x : p->edge_gsrc) cudaFree(x);
@@ -411,9 +417,9 @@ extern "C" int ogl_plan_refresh_params(ogl_plan* p, void* stream) {
   OGL_ARG(p && p->params, "ogl_plan_refresh_params: parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
   for (auto& lb : p->layer) {
-    OGL_TRY(weight_shadow(p->bf16, p->params + lb.o_wp, lb.in, lb.in, lb.wp, lb.pin, lb.wpT, lb.pin, s));
-    OGL_TRY(weight_shadow(p->bf16, p->params + lb.o_ws, lb.out, lb.in, lb.ws, lb.pin, lb.wsT, lb.pout, s));
-    OGL_TRY(weight_shadow(p->bf16, p->params + lb.o_wn, lb.out, lb.in, lb.wn, lb.pin, lb.wnT, lb.pout, s));
+    OGL_TRY(weight_shadow(p->mode, p->params + lb.o_wp, lb.in, lb.in, lb.wp, lb.pin, lb.wpT, lb.pin, s));
+    OGL_TRY(weight_shadow(p->mode, p->params + lb.o_ws, lb.out, lb.in, lb.ws, lb.pin, lb.wsT, lb.pout, s));
+    OGL_TRY(weight_shadow(p->mode, p->params + lb.o_wn, lb.out, lb.in, lb.wn, lb.pin, lb.wnT, lb.pout, s));
   }
   return OGL_OK;
 }
@@ -448,7 +454,7 @@ extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_d
   const GraphView gv = graph_view(g);
   OGL_ARG(gv.n_vertices <= p->cfg.v_cap, "ogl_plan_sample: graph has more vertices than the plan's v_cap");
   p->n_seeds = n_seeds;
-  OGL_TRY(cast_nodes(seeds_dev, p->nodes[0], n_seeds, s));
+  OGL_TRY(cast_nodes(seeds_dev, p->nodes[0], n_seeds, gv.n_vertices, p->ctl + 2, s));
   OGL_LAUNCH(k_set_i32, 1, 1, 0, s, p->counts, n_seeds);
   for (int h = 0; h < p->L; ++h) {
     STAGE(nm("sample.h%d", h).c_str(), sample_hop(gv, p->nodes[h], p->counts + h, p->nmax[h], p->cfg.fanouts[h], p->cfg.seed, p->ctl, 0,
@@ -481,7 +487,7 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
   const int L = p->L;
   // f == NULL: the input rows were supplied by ogl_plan_set_input
   if (f && !p->skip_gather)
-    STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
+    STAGE("gather", gather_rows(p->mode, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
   for (int l = 0; l < L; ++l) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, sl = h + 1, dl = h;
@@ -489,16 +495,16 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
     g1.a[0] = p->act[sl]; g1.lda[0] = lb.pin; g1.b[0] = lb.wp; g1.ldb[0] = lb.pin; g1.k[0] = lb.in; g1.n_seg = 1;
     g1.bias = p->params + lb.o_bp; g1.relu = 1;
     g1.c = lb.hp; g1.ldc = lb.pin; g1.m_max = p->nmax[sl]; g1.m_dev = p->counts + sl; g1.n = lb.in;
-    g1.in_bf16 = p->bf16; g1.out_bf16 = p->bf16;
+    g1.in_bf16 = p->bf16; g1.out_bf16 = p->bf16; g1.tf32 = p->tf32; g1.out_tf32 = p->tf32;
     STAGE(nm("l%d.pool_gemm", l).c_str(), gemm_nt(p, g1, s));
     STAGE(nm("l%d.segmax", l).c_str(),
-          segmax_fwd(p->bf16, lb.hp, lb.pin, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], lb.neigh, lb.arg, s));
+          segmax_fwd(p->mode, lb.hp, lb.pin, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], lb.neigh, lb.arg, s));
     GemmNT g2;
     g2.a[0] = p->act[sl]; g2.lda[0] = lb.pin; g2.b[0] = lb.ws; g2.ldb[0] = lb.pin; g2.k[0] = lb.in;
     g2.a[1] = lb.neigh; g2.lda[1] = lb.pin; g2.b[1] = lb.wn; g2.ldb[1] = lb.pin; g2.k[1] = lb.in; g2.n_seg = 2;
     g2.bias = p->params + lb.o_bs; g2.bias2 = p->params + lb.o_bn; g2.relu = (l < L - 1);
     g2.c = p->act[dl]; g2.ldc = lb.pout; g2.m_max = p->nmax[dl]; g2.m_dev = p->counts + dl; g2.n = lb.out;
-    g2.in_bf16 = p->bf16; g2.out_bf16 = (l < L - 1) ? p->bf16 : 0;
+    g2.in_bf16 = p->bf16; g2.out_bf16 = (l < L - 1) ? p->bf16 : 0; g2.tf32 = p->tf32; g2.out_tf32 = (l < L - 1) ? p->tf32 : 0;
     STAGE(nm("l%d.out_gemm", l).c_str(), gemm_nt(p, g2, s));
   }
   if (logits_dev)
@@ -510,7 +516,7 @@ static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, f
   const int L = p->L;
   LayerBuf& last = p->layer[L - 1];
   float* per = per_vertex_loss_dev ? per_vertex_loss_dev : p->per_loss;
-  STAGE("xent", xent(p->bf16, (const float*)p->act[0], last.pout, p->cfg.dims[L], f->labels, p->nodes[0], p->counts, p->nmax[0],
+  STAGE("xent", xent(p->mode, (const float*)p->act[0], last.pout, p->cfg.dims[L], f->labels, p->nodes[0], p->counts, p->nmax[0],
                      round_up(p->nmax[0], 128), scale, per, last.dpre, last.pout, want_grad, s));
   if (loss_sum_dev) STAGE("loss_sum", sum_f32(per, p->counts, p->nmax[0], loss_sum_dev, s));
   return OGL_OK;
@@ -519,7 +525,7 @@ static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, f
 static int plan_backward_layers(ogl_plan* p, cudaStream_t s);
 static int join_side(ogl_plan* p, cudaStream_t s);
 static int adam_range(ogl_plan* p, int64_t lo, int64_t hi, cudaStream_t s) {
-  return adam_shadow(p->bf16, p->params, p->grads, p->adam_m, p->adam_v, lo, hi, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps, p->ctl + 1,
+  return adam_shadow(p->mode, p->params, p->grads, p->adam_m, p->adam_v, lo, hi, p->cfg.lr, p->cfg.beta1, p->cfg.beta2, p->cfg.eps, p->ctl + 1,
                      p->shadow_segs, p->n_shadow_segs, s);
 }
 
@@ -538,7 +544,7 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     const int sl = L - l;
     GemmTN tp;
     tp.a = lb.dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
-    tp.c = p->grads + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16;
+    tp.c = p->grads + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16; tp.tf32 = p->tf32;
     tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
     return tp;
   };
@@ -565,19 +571,19 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     if (l + 1 < L) grp[ng++] = dw_pool(l + 1);
     GemmTN t;
     t.a = lb.dpre; t.lda = lb.pout; t.n = lb.out; t.b = p->act[sl]; t.ldb = lb.pin; t.k = lb.in;
-    t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16;
+    t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16; t.tf32 = p->tf32;
     grp[ng++] = t;
     t.b = lb.neigh; t.c = G + lb.o_wn;
     grp[ng++] = t;
     for (int i = 0; i < ng; ++i) { grp[i].partial = ov ? p->tn_partial2 : p->tn_partial; grp[i].partial_elems = p->tn_partial_elems; }
     STAGE_ON(ss, nm("l%d.dW_group", l).c_str(), gemm_tn_group(p, grp, ng, ss));
-    STAGE_ON(ss, nm("l%d.db_out", l).c_str(), colsum(p->bf16, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl],
+    STAGE_ON(ss, nm("l%d.db_out", l).c_str(), colsum(p->mode, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl],
                                                      ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bs, G + lb.o_bn, ss));
     // dneigh = dpre Wn
     GemmNT n1;
     n1.a[0] = lb.dpre; n1.lda[0] = lb.pout; n1.b[0] = lb.wnT; n1.ldb[0] = lb.pout; n1.k[0] = lb.out; n1.n_seg = 1;
     n1.c = lb.dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
-    n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.zero_tail = 0;
+    n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.tf32 = p->tf32; n1.out_tf32 = p->tf32; n1.zero_tail = 0;
     n1.mask = lb.neigh; n1.ldmask = lb.pin;        // relu'(hp) at the argmax: neigh[d, f] == hp[src(arg), f]
     STAGE(nm("l%d.dneigh_gemm", l).c_str(), gemm_nt(p, n1, s));
     // fc_pool bias gradient: every dng[d, f] lands in exactly one source row, so colsum(dhp) == colsum(dng).  Side stream too (behind the
@@ -586,10 +592,10 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       OGL_CUDA(cudaEventRecord(p->ev_fork, s));
       OGL_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     }
-    STAGE_ON(ss, nm("l%d.db_pool", l).c_str(), colsum(p->bf16, lb.dng, lb.pin, lb.in, p->counts + dl, p->nmax[dl],
+    STAGE_ON(ss, nm("l%d.db_pool", l).c_str(), colsum(p->mode, lb.dng, lb.pin, lb.in, p->counts + dl, p->nmax[dl],
                                                       ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bp, nullptr, ss));
     // max-pool backward as a gather over the reverse edge lists
-    STAGE(nm("l%d.pool_bwd", l).c_str(), pool_bwd(p->bf16, lb.dng, lb.pin, lb.arg, p->rev_ptr[h], p->rev_edge[h], p->cfg.fanouts[h],
+    STAGE(nm("l%d.pool_bwd", l).c_str(), pool_bwd(p->mode, lb.dng, lb.pin, lb.arg, p->rev_ptr[h], p->rev_edge[h], p->cfg.fanouts[h],
                                                   p->counts + sl, p->nmax[sl], lb.dhp, s));
     // dWp = dhp^T act[src]: layer 0 computes it here (the step's last and largest weight gradient; data-parallel runs peel it off
     // as the second gradient bucket); the layers above hold it back for the next grouped launch
@@ -604,7 +610,7 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       d.n_seg = 2;
       d.mask = p->act[sl]; d.ldmask = lb.pin;
       d.c = prev.dpre; d.ldc = prev.pout; d.m_max = p->nmax[sl]; d.m_dev = p->counts + sl; d.n = lb.in;
-      d.in_bf16 = p->bf16; d.out_bf16 = p->bf16;
+      d.in_bf16 = p->bf16; d.out_bf16 = p->bf16; d.tf32 = p->tf32; d.out_tf32 = p->tf32;
       STAGE(nm("l%d.dx_gemm", l).c_str(), gemm_nt(p, d, s));
     }
   }
@@ -625,7 +631,7 @@ extern "C" int ogl_plan_set_input(ogl_plan* p, const float* x_dev, int n_rows, v
   OGL_ARG(p && x_dev && n_rows > 0 && n_rows <= p->nmax[p->L], "ogl_plan_set_input: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int L = p->L, F = p->cfg.dims[0], pt = pitch_of(F);
-  OGL_TRY(feat_write(p->bf16, x_dev, nullptr, n_rows, F, p->act[L], pt, 0, s));
+  OGL_TRY(feat_write(p->mode, x_dev, nullptr, n_rows, F, p->act[L], pt, 0, s));
   const int np = std::min(round_up(n_rows, 128), round_up(p->nmax[L], 128));
   if (np > n_rows) OGL_CUDA(cudaMemsetAsync((char*)p->act[L] + p->es * (size_t)n_rows * pt, 0, p->es * (size_t)(np - n_rows) * pt, s));
   return OGL_OK;
@@ -636,7 +642,7 @@ extern "C" int ogl_plan_backward(ogl_plan* p, const float* dlogits_dev, void* st
   cudaStream_t s = (cudaStream_t)stream;
   LayerBuf& last = p->layer[p->L - 1];
   const int n = p->n_seeds;
-  OGL_TRY(feat_write(p->bf16, dlogits_dev, nullptr, n, last.out, last.dpre, last.pout, 0, s));
+  OGL_TRY(feat_write(p->mode, dlogits_dev, nullptr, n, last.out, last.dpre, last.pout, 0, s));
   const int np = round_up(n, 128);
   if (np > n) OGL_CUDA(cudaMemsetAsync((char*)last.dpre + p->es * (size_t)n * last.pout, 0, p->es * (size_t)(np - n) * last.pout, s));
   return plan_backward_layers(p, s);
@@ -660,7 +666,7 @@ extern "C" int ogl_plan_peer_adam(ogl_plan* p, ogl_peer* peer, int64_t lo, int64
   OGL_ARG(lo >= 0 && hi <= p->n_params, "ogl_plan_peer_adam: range outside the %lld parameters", (long long)p->n_params);
   cudaStream_t s = (cudaStream_t)stream;
   PeerAdamArgs a;
-  a.bf16 = p->bf16; a.params = p->params; a.grads = p->grads; a.m = p->adam_m; a.v = p->adam_v;
+  a.mode = p->mode; a.params = p->params; a.grads = p->grads; a.m = p->adam_m; a.v = p->adam_v;
   a.lr = p->cfg.lr; a.b1 = p->cfg.beta1; a.b2 = p->cfg.beta2; a.eps = p->cfg.eps;
   a.t_dev = p->ctl + 1; a.segs = p->shadow_segs; a.n_segs = p->n_shadow_segs; a.reduced_out = reduced_out_dev;
   OGL_TRY(peer_sum_adam(peer, a, lo, hi, s));
@@ -701,7 +707,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
   }
   if (kind == 1) {
     OGL_ARG(f->mode == p->cfg.mode && f->F == p->cfg.dims[0], "ogl_plan_step_begin: feature store does not match the plan (mode/F)");
-    STAGE("gather", gather_rows(p->bf16, f->table, f->pitch, p->nodes[p->L], p->counts + p->L, p->nmax[p->L], p->act[p->L], s));
+    STAGE("gather", gather_rows(p->mode, f->table, f->pitch, p->nodes[p->L], p->counts + p->L, p->nmax[p->L], p->act[p->L], s));
     OGL_TRY(bump(p->ctl, nullptr, s));            // the Philox step advances with the sampling, not with the (possibly later) finish
     return join_side(p, s);                       // a captured graph must rejoin its forked stream
   }
@@ -849,6 +855,8 @@ static int prefetch_impl(ogl_plan* p, ogl_graph* g, ogl_features* f, const int64
   if (r == OGL_OK) r = run_step(p, 1, g, f, n_seeds, 0.f, 0, nullptr, nullptr, p->pre);
   p->n_seeds = n_keep;                                       // n_seeds describes the minibatch the caller's stream works on
   if (r == OGL_OK && cudaEventRecord(p->ev_ready[p->parity], p->pre) != cudaSuccess) r = OGL_ERR_CUDA;
+  // writers of the graph / feature store order themselves after this prefetch from now on (common.cu: readers_wait)
+  if (r == OGL_OK) readers_add(g, f, p->ev_ready[p->parity], p);
   // stage profiling wants every stage alone on the device: the caller's stream waits for the prefetch at once (no overlap)
   if (r == OGL_OK && p->prof_on && cudaStreamWaitEvent(s, p->ev_ready[p->parity], 0) != cudaSuccess) r = OGL_ERR_CUDA;
   if (slot) swap_bufs(p);
@@ -1005,6 +1013,16 @@ extern "C" int ogl_plan_set_option(ogl_plan* p, const char* name, int value) {
   if (strcmp(name, "pipeline") == 0) { p->use_pipeline = value ? 1 : 0; return OGL_OK; }
   set_error("ogl_plan_set_option: unknown option '%s'", name);
   return OGL_ERR_ARG;
+}
+
+// bit 0: a seed id outside [0, n_vertices) was handed to a sampling call since the last read (it was replaced by vertex 0);
+// synchronises the device, clears the flags
+extern "C" int ogl_plan_error_flags(ogl_plan* p, uint32_t* out) {
+  OGL_ARG(p && out, "ogl_plan_error_flags: null");
+  OGL_CUDA(cudaDeviceSynchronize());
+  OGL_CUDA(cudaMemcpy(out, p->ctl + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  OGL_CUDA(cudaMemset(p->ctl + 2, 0, sizeof(uint32_t)));
+  return OGL_OK;
 }
 
 extern "C" int ogl_plan_graph_stats(ogl_plan* p, int64_t out[2]) {

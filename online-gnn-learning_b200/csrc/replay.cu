@@ -13,13 +13,16 @@ constexpr int kBlock = 256;
 
 __global__ void __launch_bounds__(kBlock) k_tree_write(double* __restrict__ value, int64_t cap, const int64_t* __restrict__ idx,
                                                        const double* __restrict__ val, int64_t n) {
+  // (indices outside [0, cap) are skipped in all three update kernels: the host mirrors raise before the call, as the reference's
+  // SegmentTree.__setitem__ asserts; a raw C-ABI caller gets no out-of-bounds write either)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    value[cap + idx[i]] = val[i];
+    if ((uint64_t)idx[i] < (uint64_t)cap) value[cap + idx[i]] = val[i];
 }
 
 // one level up: parent of every written leaf at height `level` (duplicates write identical values)
 __global__ void __launch_bounds__(kBlock) k_tree_level(double* value, int64_t cap, const int64_t* __restrict__ idx, int64_t n, int level) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if ((uint64_t)idx[i] >= (uint64_t)cap) continue;
     const int64_t node = (cap + idx[i]) >> level;
     value[node] = __dadd_rn(value[2 * node], value[2 * node + 1]);
   }
@@ -28,11 +31,13 @@ __global__ void __launch_bounds__(kBlock) k_tree_level(double* value, int64_t ca
 // small batches: one CTA walks all levels (block barrier + fence between levels)
 __global__ void __launch_bounds__(1024) k_tree_update_small(double* value, int64_t cap, const int64_t* __restrict__ idx,
                                                             const double* __restrict__ val, int64_t n, int levels) {
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) value[cap + idx[i]] = val[i];
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+    if ((uint64_t)idx[i] < (uint64_t)cap) value[cap + idx[i]] = val[i];
   __threadfence_block();
   __syncthreads();
   for (int level = 1; level <= levels; ++level) {
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      if ((uint64_t)idx[i] >= (uint64_t)cap) continue;
       const int64_t node = (cap + idx[i]) >> level;
       const double s = __dadd_rn(((volatile double*)value)[2 * node], ((volatile double*)value)[2 * node + 1]);
       ((volatile double*)value)[node] = s;

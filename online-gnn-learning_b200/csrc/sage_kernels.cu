@@ -11,6 +11,7 @@ constexpr int kBlock = 256;
 template <typename T> struct Vec;           // 16-byte vector of T
 template <> struct Vec<float> { static constexpr int N = 4; };
 template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
+template <> struct Vec<tf32_t> { static constexpr int N = 4; };
 
 __device__ __forceinline__ int dyn_count(const int32_t* n_dev, int n_max) { return n_dev ? min(*n_dev, n_max) : n_max; }
 __device__ __forceinline__ int pad128(int n, int n_max) { return min((n + 127) / 128 * 128, n_max); }
@@ -348,17 +349,26 @@ __global__ void __launch_bounds__(kBlock) k_unpad_copy(const float* __restrict__
 }
 
 // ================================ host wrappers ====================================================
-#define L2(K, grid, s, ...)                                              \
-  do {                                                                   \
-    if (bf16) OGL_LAUNCH((K<__nv_bfloat16>), grid, kBlock, 0, s, __VA_ARGS__); \
-    else OGL_LAUNCH((K<float>), grid, kBlock, 0, s, __VA_ARGS__);        \
+// mode: OGL_F32 (exact fp32), OGL_BF16, OGL_TF32 (fp32 storage, values rounded to TF32 where a GEMM operand is produced)
+#define L2(K, grid, s, ...)                                                                      \
+  do {                                                                                           \
+    if (mode == OGL_BF16) OGL_LAUNCH((K<__nv_bfloat16>), grid, kBlock, 0, s, __VA_ARGS__);       \
+    else if (mode == OGL_TF32) OGL_LAUNCH((K<tf32_t>), grid, kBlock, 0, s, __VA_ARGS__);         \
+    else OGL_LAUNCH((K<float>), grid, kBlock, 0, s, __VA_ARGS__);                                \
   } while (0)
+// the same with typed views of the void* arguments (T names the element type inside CALL)
+#define L2T(K, grid, s, CALL)                                                                    \
+  do {                                                                                           \
+    if (mode == OGL_BF16) { using T = __nv_bfloat16; OGL_LAUNCH((K<T>), grid, kBlock, 0, s, CALL); } \
+    else if (mode == OGL_TF32) { using T = tf32_t; OGL_LAUNCH((K<T>), grid, kBlock, 0, s, CALL); }   \
+    else { using T = float; OGL_LAUNCH((K<T>), grid, kBlock, 0, s, CALL); }                      \
+  } while (0)
+#define ARGS(...) __VA_ARGS__
 
-int feat_write(int bf16, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s) {
+int feat_write(int mode, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s) {
   if (n <= 0) return OGL_OK;
   const int grid = grid_for(n * 32, kBlock);
-  if (bf16) OGL_LAUNCH((k_feat_write<__nv_bfloat16>), grid, kBlock, 0, s, src, src_rows, n, F, (__nv_bfloat16*)dst, pitch, row0);
-  else OGL_LAUNCH((k_feat_write<float>), grid, kBlock, 0, s, src, src_rows, n, F, (float*)dst, pitch, row0);
+  L2T(k_feat_write, grid, s, ARGS(src, src_rows, n, F, (T*)dst, pitch, row0));
   return OGL_OK;
 }
 int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t* dst, int64_t row0, cudaStream_t s) {
@@ -366,39 +376,34 @@ int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t*
   OGL_LAUNCH(k_label_write, grid_for(n, kBlock), kBlock, 0, s, src, src_rows, n, dst, row0);
   return OGL_OK;
 }
-int gather_rows(int bf16, const void* table, int pitch, const int32_t* nodes, const int32_t* n_dev, int n_max, void* out, cudaStream_t s) {
+int gather_rows(int mode, const void* table, int pitch, const int32_t* nodes, const int32_t* n_dev, int n_max, void* out, cudaStream_t s) {
   const int grid = grid_for((int64_t)n_max * pitch / 8, kBlock, 16);
-  if (bf16) OGL_LAUNCH((k_gather_rows<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)table, pitch, nodes, n_dev, n_max, (__nv_bfloat16*)out);
-  else OGL_LAUNCH((k_gather_rows<float>), grid, kBlock, 0, s, (const float*)table, pitch, nodes, n_dev, n_max, (float*)out);
+  L2T(k_gather_rows, grid, s, ARGS((const T*)table, pitch, nodes, n_dev, n_max, (T*)out));
   return OGL_OK;
 }
-int segmax_fwd(int bf16, const void* hp, int pitch, const int32_t* edge_lid, int fanout, const int32_t* n_dst_dev, int n_dst_max, void* ng,
+int segmax_fwd(int mode, const void* hp, int pitch, const int32_t* edge_lid, int fanout, const int32_t* n_dst_dev, int n_dst_max, void* ng,
                uint8_t* arg, cudaStream_t s) {
   const int grid = grid_for((int64_t)n_dst_max * pitch / 8, kBlock, 16);
-  if (bf16) OGL_LAUNCH((k_segmax_fwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)hp, pitch, edge_lid, fanout, n_dst_dev, n_dst_max, (__nv_bfloat16*)ng, arg);
-  else OGL_LAUNCH((k_segmax_fwd<float>), grid, kBlock, 0, s, (const float*)hp, pitch, edge_lid, fanout, n_dst_dev, n_dst_max, (float*)ng, arg);
+  L2T(k_segmax_fwd, grid, s, ARGS((const T*)hp, pitch, edge_lid, fanout, n_dst_dev, n_dst_max, (T*)ng, arg));
   return OGL_OK;
 }
-int pool_bwd(int bf16, const void* dng, int pitch, const uint8_t* arg, const int32_t* rev_ptr, const int32_t* rev_edge, int fanout,
+int pool_bwd(int mode, const void* dng, int pitch, const uint8_t* arg, const int32_t* rev_ptr, const int32_t* rev_edge, int fanout,
              const int32_t* n_src_dev, int n_src_max, void* dhp, cudaStream_t s) {
-  const int grid = grid_for((int64_t)round_up(n_src_max, 128) * pitch / (bf16 ? 8 : 4), kBlock, 32);
-  if (bf16) OGL_LAUNCH((k_pool_bwd<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)dng, pitch, arg, rev_ptr, rev_edge, fanout, n_src_dev, n_src_max, (__nv_bfloat16*)dhp);
-  else OGL_LAUNCH((k_pool_bwd<float>), grid, kBlock, 0, s, (const float*)dng, pitch, arg, rev_ptr, rev_edge, fanout, n_src_dev, n_src_max, (float*)dhp);
+  const int grid = grid_for((int64_t)round_up(n_src_max, 128) * pitch / (mode == OGL_BF16 ? 8 : 4), kBlock, 32);
+  L2T(k_pool_bwd, grid, s, ARGS((const T*)dng, pitch, arg, rev_ptr, rev_edge, fanout, n_src_dev, n_src_max, (T*)dhp));
   return OGL_OK;
 }
 int64_t colsum_partial_elems(int n_max, int cols) { return ceil_div(n_max, kColRows) * (int64_t)cols; }
-int colsum(int bf16, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s) {
-  dim3 grid((unsigned)ceil_div(pitch / (bf16 ? 8 : 4), 32), (unsigned)ceil_div(n_max, kColRows));
-  if (bf16) OGL_LAUNCH((k_colsum_partial<__nv_bfloat16>), grid, kBlock, 0, s, (const __nv_bfloat16*)x, pitch, cols, n_dev, n_max, partial);
-  else OGL_LAUNCH((k_colsum_partial<float>), grid, kBlock, 0, s, (const float*)x, pitch, cols, n_dev, n_max, partial);
+int colsum(int mode, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s) {
+  dim3 grid((unsigned)ceil_div(pitch / (mode == OGL_BF16 ? 8 : 4), 32), (unsigned)ceil_div(n_max, kColRows));
+  L2T(k_colsum_partial, grid, s, ARGS((const T*)x, pitch, cols, n_dev, n_max, partial));
   OGL_LAUNCH(k_colsum_final, (unsigned)ceil_div(cols, 32), 1024, 0, s, partial, cols, n_dev, n_max, out, out2);
   return OGL_OK;
 }
-int xent(int bf16, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,
+int xent(int mode, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,
          int rows_buf, float scale, float* per_loss, void* dlogits, int ldd, int want_grad, cudaStream_t s) {
   const int grid = grid_for((int64_t)(rows_buf > n_max ? rows_buf : n_max) * 32, kBlock);
-  if (bf16) OGL_LAUNCH((k_xent<__nv_bfloat16>), grid, kBlock, 0, s, logits, ldl, C, labels, nodes, n_dev, n_max, rows_buf, scale, per_loss, (__nv_bfloat16*)dlogits, ldd, want_grad);
-  else OGL_LAUNCH((k_xent<float>), grid, kBlock, 0, s, logits, ldl, C, labels, nodes, n_dev, n_max, rows_buf, scale, per_loss, (float*)dlogits, ldd, want_grad);
+  L2T(k_xent, grid, s, ARGS(logits, ldl, C, labels, nodes, n_dev, n_max, rows_buf, scale, per_loss, (T*)dlogits, ldd, want_grad));
   return OGL_OK;
 }
 int sum_f32(const float* x, const int32_t* n_dev, int n_max, float* out, cudaStream_t s) {
@@ -409,23 +414,21 @@ int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, floa
   OGL_LAUNCH(k_adam, grid_for(n, kBlock), kBlock, 0, s, p, g, m, v, n, lr, b1, b2, eps, t_dev);
   return OGL_OK;
 }
-int adam_shadow(int bf16, float* p, const float* g, float* m, float* v, int64_t lo, int64_t hi, float lr, float b1, float b2, float eps,
+int adam_shadow(int mode, float* p, const float* g, float* m, float* v, int64_t lo, int64_t hi, float lr, float b1, float b2, float eps,
                 uint32_t* t_dev, const ShadowSeg* segs_dev, int n_segs, cudaStream_t s) {
   OGL_ARG(n_segs <= 48, "adam_shadow: too many weight segments");
   OGL_ARG(lo >= 0 && hi > lo, "adam_shadow: empty range");
   const int grid = grid_for(hi - lo, kBlock);
-  if (bf16) OGL_LAUNCH((k_adam_shadow<__nv_bfloat16>), grid, kBlock, 0, s, p, g, m, v, lo, hi, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
-  else OGL_LAUNCH((k_adam_shadow<float>), grid, kBlock, 0, s, p, g, m, v, lo, hi, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
+  L2(k_adam_shadow, grid, s, p, g, m, v, lo, hi, lr, b1, b2, eps, t_dev, segs_dev, n_segs);
   return OGL_OK;
 }
 int bump(uint32_t* a, uint32_t* b, cudaStream_t s) {
   OGL_LAUNCH(k_bump, 1, 1, 0, s, a, b);
   return OGL_OK;
 }
-int weight_shadow(int bf16, const float* w, int out, int in, void* ws, int pitch_in, void* wt, int pitch_out, cudaStream_t s) {
+int weight_shadow(int mode, const float* w, int out, int in, void* ws, int pitch_in, void* wt, int pitch_out, cudaStream_t s) {
   const int grid = grid_for((int64_t)out * pitch_in, kBlock);
-  if (bf16) OGL_LAUNCH((k_weight_shadow<__nv_bfloat16>), grid, kBlock, 0, s, w, out, in, (__nv_bfloat16*)ws, pitch_in, (__nv_bfloat16*)wt, pitch_out);
-  else OGL_LAUNCH((k_weight_shadow<float>), grid, kBlock, 0, s, w, out, in, (float*)ws, pitch_in, (float*)wt, pitch_out);
+  L2T(k_weight_shadow, grid, s, ARGS(w, out, in, (T*)ws, pitch_in, (T*)wt, pitch_out));
   return OGL_OK;
 }
 int unpad_copy(const float* src, int lds, int n_rows_max, const int32_t* n_dev, int cols, float* dst, cudaStream_t s) {

@@ -43,8 +43,18 @@ __global__ void __launch_bounds__(kBlock) k_sample(GraphView g, const int32_t* _
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_cast_nodes(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+// seed ids -> int32 rows.  An id outside [0, n_vertices) would index deg / row_start out of bounds: it is replaced by vertex 0
+// and reported through *err_flag (read back by ogl_plan_error_flags; DGL raises on such seeds)
+__global__ void __launch_bounds__(kBlock) k_cast_nodes(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n, int64_t n_vertices,
+                                                       uint32_t* __restrict__ err_flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = in[i];
+    if (v < 0 || v >= n_vertices) {
+      if (err_flag) atomicOr(err_flag, 1u);
+      v = 0;
+    }
+    out[i] = (int32_t)v;
+  }
 }
 
 // ---- to_block: direct-address first-appearance table ----------------------------------------
@@ -82,11 +92,11 @@ __global__ void __launch_bounds__(kBlock) k_tb_emit(const int32_t* __restrict__ 
                                                     int n_dst_max, int fanout, const int32_t* __restrict__ picked,
                                                     const int32_t* __restrict__ first, const int32_t* __restrict__ flags,
                                                     const int32_t* __restrict__ pos, const int32_t* __restrict__ n_new_dev,
-                                                    int32_t* __restrict__ src_nodes, int32_t* __restrict__ n_src_dev,
+                                                    int32_t* __restrict__ src_nodes, int32_t* __restrict__ n_src_dev, int n_src_max,
                                                     int32_t* __restrict__ edge_lid, int64_t ne_max) {
   const int n_dst = min(*n_dst_dev, n_dst_max);
   const int64_t ne = (int64_t)n_dst * fanout;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *n_src_dev = n_dst + *n_new_dev;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_src_dev = min(n_dst + *n_new_dev, n_src_max);
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_dst_max + ne_max; t += (int64_t)gridDim.x * blockDim.x) {
     if (t < n_dst_max) {
       if (t < n_dst) src_nodes[t] = dst_nodes[t];
@@ -98,7 +108,7 @@ __global__ void __launch_bounds__(kBlock) k_tb_emit(const int32_t* __restrict__ 
         if (g >= 0) {
           const int m = first[g];
           lid = m < n_dst ? m : n_dst + pos[m - n_dst];
-          if (flags[p]) src_nodes[n_dst + pos[p]] = g;
+          if (flags[p] && n_dst + pos[p] < n_src_max) src_nodes[n_dst + pos[p]] = g;      // (the plan sizes n_src_max so that this always holds)
         }
         edge_lid[p] = lid;
       } else {
@@ -159,7 +169,7 @@ int sample_hop(const GraphView& g, const int32_t* dst_nodes, const int32_t* n_ds
   return OGL_OK;
 }
 
-int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max) {
+int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max, int64_t rows_max) {
   ws->v_cap = v_cap;
   ws->ne_max = ne_max;
   OGL_CUDA(cudaMalloc(&ws->first, sizeof(int32_t) * v_cap));
@@ -167,9 +177,9 @@ int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max) {
   OGL_CUDA(cudaMalloc(&ws->pos, sizeof(int32_t) * (ne_max + 1)));
   const int64_t scan_n = (ne_max > v_cap ? ne_max : v_cap) + 2;
   OGL_CUDA(cudaMalloc(&ws->scan_scratch, sizeof(int32_t) * scan_scratch_elems(scan_n)));
-  ws->rev_cap = v_cap + 1;
+  ws->rev_cap = (rows_max > v_cap ? rows_max : v_cap) + 1;      // a frontier may exceed v_cap by the duplicates among its seeds
   OGL_CUDA(cudaMalloc(&ws->rev_cnt, sizeof(int32_t) * 2 * (size_t)ws->rev_cap));
-  OGL_CUDA(cudaMalloc(&ws->rev_scan_scratch, sizeof(int32_t) * scan_scratch_elems(v_cap + 2)));
+  OGL_CUDA(cudaMalloc(&ws->rev_scan_scratch, sizeof(int32_t) * scan_scratch_elems(ws->rev_cap + 1)));
   OGL_CUDA(cudaMalloc(&ws->n_new, sizeof(int32_t)));
   OGL_LAUNCH(k_fill_i32, grid_for(v_cap, kBlock), kBlock, 0, 0, ws->first, 0x7fffffff, v_cap);
   OGL_CUDA(cudaDeviceSynchronize());
@@ -189,13 +199,13 @@ int to_block(ToBlockWs* ws, const int32_t* dst_nodes, const int32_t* n_dst_dev, 
   OGL_LAUNCH(k_tb_flags, grid_for(ne_max, kBlock), kBlock, 0, s, n_dst_dev, n_dst_max, fanout, picked, ws->first, ws->flags, ne_max);
   OGL_TRY(exclusive_scan_i32(ws->flags, ws->pos, ne_max, ws->scan_scratch, ws->n_new, s));
   OGL_LAUNCH(k_tb_emit, grid_for(n_dst_max + ne_max, kBlock), kBlock, 0, s, dst_nodes, n_dst_dev, n_dst_max, fanout, picked, ws->first,
-             ws->flags, ws->pos, ws->n_new, src_nodes, n_src_dev, edge_lid, ne_max);
+             ws->flags, ws->pos, ws->n_new, src_nodes, n_src_dev, n_src_max, edge_lid, ne_max);
   OGL_LAUNCH(k_tb_reset, grid_for(n_src_max, kBlock), kBlock, 0, s, src_nodes, n_src_dev, n_src_max, ws->first);
   return OGL_OK;
 }
 
-int cast_nodes(const int64_t* in, int32_t* out, int64_t n, cudaStream_t s) {
-  if (n > 0) OGL_LAUNCH(k_cast_nodes, grid_for(n, kBlock), kBlock, 0, s, in, out, n);
+int cast_nodes(const int64_t* in, int32_t* out, int64_t n, int64_t n_vertices, uint32_t* err_flag, cudaStream_t s) {
+  if (n > 0) OGL_LAUNCH(k_cast_nodes, grid_for(n, kBlock), kBlock, 0, s, in, out, n, n_vertices, err_flag);
   return OGL_OK;
 }
 
@@ -276,7 +286,7 @@ extern "C" int ogl_sample_neighbors(ogl_graph* g, const int64_t* dst_dev, int64_
   cudaStream_t s = (cudaStream_t)stream;
   int32_t* tmp = nullptr;
   OGL_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * n, s));
-  int r = cast_nodes(dst_dev, tmp, n, s);
+  int r = cast_nodes(dst_dev, tmp, n, graph_view(g).n_vertices, nullptr, s);
   if (r == OGL_OK) r = sample_hop(graph_view(g), tmp, nullptr, (int)n, fanout, seed, nullptr, step, hop, out_src_dev, out_eid_dev, s);
   cudaFreeAsync(tmp, s);
   return r;

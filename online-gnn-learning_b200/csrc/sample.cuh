@@ -16,7 +16,7 @@ struct ToBlockWs {
   int64_t v_cap = 0, ne_max = 0;
 };
 
-int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max);
+int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max, int64_t rows_max);
 void to_block_free(ToBlockWs* ws);
 
 // picks for rows dst_nodes[0 .. *n_dst_dev) (n_dst_dev == nullptr: n_dst_max rows); step from step_dev if non-null
@@ -31,6 +31,6 @@ int to_block(ToBlockWs* ws, const int32_t* dst_nodes, const int32_t* n_dst_dev, 
 int reverse_edges(ToBlockWs* ws, const int32_t* edge_lid, const int32_t* n_dst_dev, int n_dst_max, int fanout, int n_src_max,
                   int32_t* rev_ptr, int32_t* rev_edge, cudaStream_t s);
 
-int cast_nodes(const int64_t* in, int32_t* out, int64_t n, cudaStream_t s);
+int cast_nodes(const int64_t* in, int32_t* out, int64_t n, int64_t n_vertices, uint32_t* err_flag, cudaStream_t s);
 
 }  // namespace ogl

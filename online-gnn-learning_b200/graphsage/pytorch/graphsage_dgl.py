@@ -28,6 +28,22 @@ class _Affine(nn.Module):
         nn.init.uniform_(self.bias, -bound, bound)
 
 
+def xavier_state_dict(in_feats, n_hidden, n_classes, n_layers, seed, dtype=torch.float32):
+    """seeded state_dict with the initialisation of DGL's SAGEConv.reset_parameters [recalled]: Xavier-uniform weights with
+    gain = calculate_gain('relu'), nn.Linear-default biases; keys as the reference's checkpoints (inference_optimized.py:135-139).
+    Drawn from one seeded generator in float64 so that CPU and GPU runs (bench.py's two arms) start from the same values."""
+    g = torch.Generator().manual_seed(seed)
+    dims = [(in_feats, n_hidden)] + [(n_hidden, n_hidden)] * (n_layers - 1) + [(n_hidden, n_classes)]
+    p = {}
+    for i, (fi, fo) in enumerate(dims):
+        for name, (o, k) in (("fc_pool", (fi, fi)), ("fc_self", (fo, fi)), ("fc_neigh", (fo, fi))):
+            a = math.sqrt(2.0) * math.sqrt(6.0 / (o + k))
+            p["layers.%d.%s.weight" % (i, name)] = ((torch.rand(o, k, generator=g, dtype=torch.float64) * 2 - 1) * a).to(dtype)
+            b = 1.0 / math.sqrt(k)
+            p["layers.%d.%s.bias" % (i, name)] = ((torch.rand(o, generator=g, dtype=torch.float64) * 2 - 1) * b).to(dtype)
+    return p
+
+
 class SAGEConv(nn.Module):
     """fc_pool: in->in, fc_self / fc_neigh: in->out.  out = fc_self(h_dst) + fc_neigh(max_nbr relu(fc_pool(h_src)))."""
 

@@ -87,6 +87,8 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
             plan.eval_step(graph.native, graph.features, chunk, logits_out=out[i:i + chunk.numel()])
         self._mark_pin_busy(seeds)
         host = out.cpu().numpy()
+        if plan.error_flags() & 1:
+            raise IndexError("a vertex id outside the graph was evaluated (DGL's NodeDataLoader raises on such ids)")
         return [host[i:i + self.batch_full] for i in range(0, n, self.batch_full)]
 
     # ---- one minibatch -----------------------------------------------------------------------------
@@ -180,8 +182,15 @@ class PrioritizedPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
         draws = [graph_util.draw_priority_train_nodes(self.batch_size) for _ in range(self.batch_per_timestep)]
         return [v for d in draws for v in d]
 
+    def _device_priorities(self):
+        """the on-GPU priority update feeds the raw per-vertex losses to the sum tree, which is what LossPriority computes
+        (generate_priority.py:7-9); Trend / Hybrid priorities keep per-vertex history on the host, so they always take the
+        reference's route through priority_strategy.get_priorities (pytorch/model.py:203-206, 250-253)"""
+        from ...prioritized_replay.generate_priority import LossPriority
+        return (not config.faithful()) and type(self.priority_strategy) is LossPriority
+
     def _push_priorities(self, graph_util, nodes, losses_dev):
-        if config.faithful():
+        if not self._device_priorities():
             pri = self.priority_strategy.get_priorities(nodes, losses_dev.cpu().numpy())
             graph_util.update_priorities(dict(zip(nodes, pri)))
         else:
@@ -201,7 +210,7 @@ class PrioritizedPytorchSupervisedGraphSage(PytorchSupervisedGraphSage):
             batch = max(n // self.batch_per_timestep, 1)
             self._fused_steps(graph, seeds, batch, per_vertex_out=per)
             nodes = np.asarray(subgraph_to_id[np.asarray(train_vertices, dtype=np.int64)]).tolist()
-            if config.faithful():
+            if not self._device_priorities():
                 # one read-back, then the reference's sequence of per-batch dict updates (the running min / max of the
                 # priority transform advances batch by batch, replay_buffer.py:110-130)
                 host = per.cpu().numpy()

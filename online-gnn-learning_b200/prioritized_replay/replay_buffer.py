@@ -61,10 +61,25 @@ class PrioritizedReplayBuffer(ReplayBuffer):
             print("PrioritizedBuffer init, alpha: ", self._alpha)
 
     def get_max_priority(self):
+        self._pull_dev_state()
         return self.max_val
 
     def get_min_priority(self):
+        self._pull_dev_state()
         return self.min_val
+
+    def _pull_dev_state(self):
+        """device-side updates (update_from_losses) advance the running min / max on the GPU only: bring them back (one 4-double
+        D2H copy) before any host-side reader or writer of that state runs, then let the host copy be the truth again"""
+        if self._dev_state is not None:
+            self.sync_state()
+            self._dev_state = None
+
+    def _check_room(self, n_new):
+        cap = self._it_sum.capacity
+        if self._next_idx + n_new > cap:
+            raise AssertionError("PrioritizedReplayBuffer: %d + %d entries exceed the tree capacity %d (the reference asserts "
+                                 "0 <= idx < capacity in SegmentTree.__setitem__)" % (self._next_idx, n_new, cap))
 
     # ---- host (dict) API: transform in Python floats, tree on the device -----------------------
     def _normalize(self, node_priority_dict):
@@ -96,6 +111,8 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         return out
 
     def add_all(self, node_priority_dict):
+        self._pull_dev_state()
+        self._check_room(len(node_priority_dict))
         logs = self._normalize(node_priority_dict)
         vals = self._leaf_values(logs, 0.00001)
         idx = []
@@ -106,15 +123,14 @@ class PrioritizedReplayBuffer(ReplayBuffer):
             idx.append(i)
         if idx:
             self._it_sum.set_many(idx, vals)
-        self._dev_state = None
 
     def update_priorities(self, d_priorities):
+        self._pull_dev_state()
         logs = self._normalize(d_priorities)
         vals = self._leaf_values(logs, 0.000001)
         idx = [self._key_to_idx[node] for node in logs]
         if idx:
             self._it_sum.set_many(idx, vals)
-        self._dev_state = None
 
     # ---- device API ---------------------------------------------------------------------------------
     def update_from_losses(self, nodes, losses_dev, adding=False):
@@ -123,6 +139,8 @@ class PrioritizedReplayBuffer(ReplayBuffer):
             self._dev_state = torch.tensor([self.min_val, self.max_val, self._min_priority, self._max_priority],
                                            dtype=torch.float64, device="cuda")
         if adding:
+            nodes = list(nodes)
+            self._check_room(len(nodes))
             idx = []
             for node in nodes:
                 self._key_to_idx[node] = self._next_idx
@@ -167,6 +185,7 @@ class PrioritizedReplayBuffer(ReplayBuffer):
     def increment_priorities(self, node, increment):
         if increment < 0:
             raise AssertionError("increment must be >= 0")
+        self._pull_dev_state()
         idx = self._key_to_idx[node]
         cur = self._it_sum[idx]
         if self._max_priority == -1:

@@ -12,11 +12,20 @@ class SumSegmentTree:
         self._capacity = capacity
         self._t = backend if backend is not None else _NativeTree(capacity)
 
+    @property
+    def capacity(self):
+        return self._capacity
+
     # batch leaf write (keys are unique per call: they come from a dict)
     def set_many(self, idx, val):
+        # the reference asserts 0 <= idx < capacity per write (segment_tree.py:71); the kernels take the indices as they come
+        if len(idx) and not (0 <= min(idx) and max(idx) < self._capacity):
+            raise AssertionError("index out of range")
         self._t.set(idx, val)
 
     def __setitem__(self, idx, val):
+        if not (0 <= idx < self._capacity):
+            raise AssertionError("index out of range")
         self._t.set([int(idx)], [float(val)])
 
     def __getitem__(self, idx):

@@ -13,12 +13,28 @@ Loss = CrossEntropyLoss(mean | none) on labels.flatten(), Adam(lr=1e-3)
 (pytorch/model.py:20-25,103-107).  PARITY UNPINNED against DGL (absent); the argmax tie
 rule (lowest edge slot wins) is this repo's specification.
 
-``quant='bf16'`` models the product's bf16 tensor-core path: every GEMM operand
-(activations, weights, activation gradients) is rounded to bf16 exactly where the
-product stores it, accumulation stays fp32/fp64.
+``quant='bf16'`` / ``quant='tf32'`` model the product's tensor-core paths: every GEMM operand
+(activations, weights, activation gradients) is rounded to bf16 / TF32 exactly where the
+product stores it, accumulation stays fp32/fp64.  ``quant=None`` is the reference's own fp32
+arithmetic (train/utils.py:63-64) -- the oracle every tolerance is stated against; the
+quantised variants only show that a kernel implements the arithmetic it claims.
 """
 import math
 import torch
+
+_QUANT = [None]          # rounding of the autograd functions below; set per call by forward()
+
+
+def round_tf32(x):
+    """nearest TF32 (10 explicit mantissa bits), ties away from zero -- PTX cvt.rna.tf32.f32"""
+    b = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32).to(x.dtype)
+
+
+def _round(x):
+    if _QUANT[0] == "tf32":
+        return round_tf32(x)
+    return x.to(torch.bfloat16).to(x.dtype)
 
 
 def xavier_params(in_feats, n_hidden, n_classes, n_layers, seed, dtype=torch.float32):
@@ -42,18 +58,18 @@ class _Q(torch.autograd.Function):
     (the product stores activation gradients once, in bf16)."""
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+        return _round(x)
 
     @staticmethod
     def backward(ctx, g):
-        return g.to(torch.bfloat16).to(g.dtype)
+        return _round(g)
 
 
 class _Qf(torch.autograd.Function):
     """Round forward only (weights / leaves: their gradients stay full precision)."""
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+        return _round(x)
 
     @staticmethod
     def backward(ctx, g):
@@ -68,7 +84,7 @@ class _Qb(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g.to(torch.bfloat16).to(g.dtype)
+        return _round(g)
 
 
 def segment_max(hp, edge_src, n_dst, fanout, arg=None):
@@ -100,11 +116,11 @@ def segment_max(hp, edge_src, n_dst, fanout, arg=None):
 
 
 def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, quant=None, arg=None):
-    q = _Q.apply if quant == "bf16" else (lambda t: t)
-    qf = _Qf.apply if quant == "bf16" else (lambda t: t)
+    q = _Q.apply if quant else (lambda t: t)
+    qf = _Qf.apply if quant else (lambda t: t)
     hp = q(torch.relu(x @ qf(Wp).t() + bp))
     neigh, arg = segment_max(hp, edge_src, n_dst, fanout, arg=arg)
-    if quant == "bf16":
+    if quant:
         neigh = _Qb.apply(neigh)
     out = x[:n_dst] @ qf(Ws).t() + neigh @ qf(Wn).t() + (bs + bn)
     if relu_out:
@@ -115,7 +131,9 @@ def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, qua
 def forward(params, x_in, blocks, quant=None):
     """blocks: list (input layer first) of dict(n_dst, edge_src[int64], fanout[, arg]).  x_in: features
     of blocks[0]'s src nodes.  Returns (logits, per-layer intermediates)."""
-    h = _Qf.apply(x_in) if quant == "bf16" else x_in
+    assert quant in (None, "bf16", "tf32")
+    _QUANT[0] = quant
+    h = _Qf.apply(x_in) if quant else x_in
     inter = []
     L = len(blocks)
     for i, b in enumerate(blocks):
@@ -129,7 +147,7 @@ def forward(params, x_in, blocks, quant=None):
 
 
 def xent(logits, labels, reduction="mean", quant=None):
-    if quant == "bf16":
+    if quant:
         logits = _Qb.apply(logits)
     return torch.nn.functional.cross_entropy(logits, labels.flatten(), reduction=reduction)
 

@@ -127,3 +127,28 @@ def test_draw_uniform_subset(n_pop, n):
             assert np.array_equal(got, ref)
         else:
             assert np.array_equal(np.sort(got), np.arange(n_pop))
+
+
+def test_duplicate_and_out_of_range_seeds_are_safe():
+    """DGL accepts duplicate seeds (every copy is a destination row of its own); on a small graph the v_cap clamp of the frontier
+    size must leave room for them.  Seed ids outside the graph raise the plan's error flag instead of reading out of bounds."""
+    import ogl_b200
+    rng = np.random.default_rng(3)
+    V, E = 300, 4000
+    g = ogl_b200.native.Graph(V, 2 * E)
+    g.insert_vertices(V)
+    g.insert_edges(torch.as_tensor(rng.integers(0, V, E)).cuda(), torch.as_tensor(rng.integers(0, V, E)).cuda(), symmetric=True)
+    plan = ogl_b200.native.Plan([8, 8, 8], [45, 45], 1024, V, mode=ogl_b200.OGL_F32, seed=1)
+    seeds = torch.as_tensor(np.concatenate([np.arange(V), rng.integers(0, V, 1024 - V)]).astype(np.int64)).cuda()   # 724 duplicates
+    plan.sample(g, seeds)
+    torch.cuda.synchronize()
+    n0, n1, n2 = (plan.level_nodes(lv).numel() for lv in range(3))
+    assert n0 == 1024 and n1 >= 1024 and n2 >= n1
+    assert torch.equal(plan.level_nodes(1)[:1024].long(), seeds)
+    lid = plan.block_edges(1)[0]
+    assert int(lid.max()) < n2 and plan.error_flags() == 0
+    bad = seeds.clone()
+    bad[5] = V + 7
+    bad[9] = -3
+    plan.sample(g, bad)
+    assert plan.error_flags() == 1 and plan.error_flags() == 0
