@@ -39,6 +39,7 @@ WORKLOADS = {
     "pubmed": dict(V=19717, E=44338, F=500, C=3, H=32, B=32, fanouts=[10, 10]),
 }
 EXCHANGE = ["peer"]
+IMPL = ["ours"]
 EXCHANGE_NAME = {"peer": "gradient sum over NVLink peer memory (P2P loads) fused with Adam in one kernel per bucket, no NCCL on the data path",
                  "nccl": "NCCL all-reduce + Adam"}
 NAMES = ("fc_pool.weight", "fc_pool.bias", "fc_self.weight", "fc_self.bias", "fc_neigh.weight", "fc_neigh.bias")
@@ -73,8 +74,13 @@ def gen_features(w, device, seed=2):
 
 
 def init_params(w, seed=0):
-    from oracle.sage import xavier_params          # parameter init only (same init for both arms)
-    return xavier_params(w["F"], w["H"], w["C"], 1, seed=seed)
+    """seeded Xavier init, the same values for both arms (the CPU arm takes the oracle's twin of the package's initialiser;
+    tests/test_host_logic.py checks the two are bit-identical)"""
+    if IMPL[0] == "reference":
+        from oracle.sage import xavier_params
+        return xavier_params(w["F"], w["H"], w["C"], 1, seed=seed)
+    from ogl_b200.graphsage.pytorch.graphsage_dgl import xavier_state_dict
+    return xavier_state_dict(w["F"], w["H"], w["C"], 1, seed=seed)
 
 
 def seed_batches(w, n_batches, rank, world, seed=4):
@@ -90,42 +96,56 @@ def seed_batches(w, n_batches, rank, world, seed=4):
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock, power and clock-event (throttle) reasons of one GPU, polled through NVML every ~2 ms on a background thread for
+    the whole run: the timed region of the default run is ~10-20 ms long, which `nvidia-smi -lms 100` cannot sample at all."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period=0.002):
+        self.rows, self.h, self.nv, self.period, self._stop = [], None, None, period, False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+                self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:                    # no NVML: the line says so instead of carrying an empty record
+            self.err = repr(e)[:200]
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons_fn(self.h)),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def window(self, t0, t1):
-        sm, smax, reasons = [], 0, set()
-        for t, line in self.rows:
-            if t < t0 - 0.05 or t > t1 + 0.15:
-                continue
-            p = [x.strip() for x in line.split(",")]
-            try:
-                sm.append(float(p[0]))
-                smax = max(smax, float(p[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
-                if v.lower().startswith("active"):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": getattr(self, "err", "NVML unavailable")}
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        reasons = set()
+        for r in rows:
+            for bit, name in self.BITS.items():
+                if r[2] & bit:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_min_mhz": min((r[1] for r in rows), default=None),
+                "sm_max_mhz": self.max_mhz, "power_w_max": max((r[3] for r in rows), default=None), "reasons": sorted(reasons),
+                "samples": len(rows), "period_ms": 1e3 * self.period, "source": "NVML polled in-process"}
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self._stop = True
 
 
 # ----------------------------------------------------------------------------------------- CPU path (oracle)
@@ -311,29 +331,60 @@ def aux_elliptic_pbr(n_snapshots=30, faithful=True):
         config.set_faithful(True)
 
 
-def aux_sampler_sweep(g, V, n_rows=1 << 20, fanout=25, iters=5):
+def aux_sampler_sweep(g, V, n_rows=1 << 20, fanout=25, iters=9):
     """config 5 flavour: the standalone uniform k-neighbour sampler over the resident Reddit-shaped CSR, 2^20 random
-    destination rows x 25 picks per launch (indices + edge ids out)"""
+    destination rows x 25 picks per launch (indices + edge ids out).  Every call is timed by itself (CUDA events) after 5
+    warm-up calls; min and median are reported."""
     from ogl_b200 import native
     gen = torch.Generator(device="cuda").manual_seed(9)
     dst = torch.randint(0, V, (n_rows,), generator=gen, device="cuda", dtype=torch.int64)
-    for _ in range(2):
-        native.sample_neighbors(g, dst, fanout, seed=3, step=0, hop=0)
+    for i in range(5):
+        native.sample_neighbors(g, dst, fanout, seed=3, step=i, hop=0)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    ms = []
     for i in range(iters):
-        native.sample_neighbors(g, dst, fanout, seed=3, step=i + 1, hop=0)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        native.sample_neighbors(g, dst, fanout, seed=3, step=10 + i, hop=0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
     picks = n_rows * fanout
     alg = n_rows * (8 + 4 + 8) + picks * 8 + picks * (4 + 8)            # row meta + (eid, src) entry reads + (src, eid) writes
-    return {"rows": n_rows, "fanout": fanout, "ms": ms, "picks_per_s": picks / (ms * 1e-3), "algorithmic_gbs": alg / (ms * 1e-3) / 1e9,
-            "sector_gbs": (n_rows * 64 + picks * 32 + picks * 12) / (ms * 1e-3) / 1e9,
-            "note": "includes the int64->int32 cast of the row list and a stream-ordered scratch allocation per call; sector_gbs counts "
-                    "every random read as the 32-byte DRAM sector it costs (row start + degree: 2 sectors per row; one 8-byte "
+    sect = n_rows * 64 + picks * 32 + picks * 12
+    med, best = float(np.median(ms)), float(min(ms))
+    return {"rows": n_rows, "fanout": fanout, "ms_median": med, "ms_min": best, "calls": iters, "picks_per_s": picks / (med * 1e-3),
+            "algorithmic_gbs": alg / (med * 1e-3) / 1e9, "sector_gbs": sect / (med * 1e-3) / 1e9, "sector_gbs_best": sect / (best * 1e-3) / 1e9,
+            "note": "includes the int64->int32 cast of the row list (stream-ordered scratch from a pool that keeps its memory); sector_gbs "
+                    "counts every random read as the 32-byte DRAM sector it costs (row start + degree: 2 sectors per row; one 8-byte "
                     "(edge id, source) entry: 1 sector per pick)"}
+
+
+def aux_snapshot_insert(g, V, n_snap=40, snap_edges=11461):
+    """the streaming regime the reference runs (settings/reddit.json: 57.3 M stream edges over 5000 snapshots = 11,461 stream edges
+    per evolve(), dynamic_graph_edge.py:190-218): one symmetrised snapshot appended to the LIVE 114.6 M-edge CSR per call.  Launch
+    bound, so microseconds per snapshot are reported beside edges/s."""
+    import ogl_b200
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    src = torch.randint(0, V, (n_snap + 5, snap_edges), generator=gen, device="cuda", dtype=torch.int64)
+    dst = torch.randint(0, V, (n_snap + 5, snap_edges), generator=gen, device="cuda", dtype=torch.int64)
+    for i in range(5):
+        g.insert_edges(src[i], dst[i], symmetric=True)
+    torch.cuda.synchronize()
+    us, l0 = [], ogl_b200.kernel_launches()
+    for i in range(5, n_snap + 5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        g.insert_edges(src[i], dst[i], symmetric=True)
+        e1.record()
+        torch.cuda.synchronize()
+        us.append((1e3 * e0.elapsed_time(e1), 1e6 * (time.perf_counter() - t0)))
+    dev_us = float(np.median([u[0] for u in us]))
+    return {"stream_edges_per_snapshot": snap_edges, "snapshots": n_snap, "us_per_snapshot_device_median": dev_us,
+            "us_per_snapshot_wall_median": float(np.median([u[1] for u in us])),
+            "launches_per_snapshot": (ogl_b200.kernel_launches() - l0) / n_snap, "stream_edges_per_s": snap_edges / (dev_us * 1e-6),
+            "algorithmic_gbs": 2 * snap_edges * 32 / (dev_us * 1e-6) / 1e9}
 
 
 def aux_arxiv_vertex_stream(n_snapshots=20):
@@ -443,63 +494,31 @@ def workload_config(w, name, world):
                         "2-layer GraphSAGE-pool, Adam" % (name, w["V"], w["E"], 2 * w["E"], w["F"], w["C"], w["H"], w["B"], w["fanouts"]),
             "global_batch": w["B"] * world, "parallelism": ("dp%d (replicated graph+features, two gradient buckets, %s, on a comm stream)" % (world, EXCHANGE_NAME.get(EXCHANGE[0], "?")) if world > 1 else "single GPU") +
                            "; sample+gather of step t+1 prefetched (second buffer set, own stream) under forward/backward of step t",
-            "l2": "inputs larger than L2: feature table %.0f MB + CSR %.0f MB resident, random row gathers; no explicit flush"
-                  % (w["V"] * ((w["F"] + 7) // 8 * 8) * 2 / 1e6, 2 * w["E"] * 8 * 1.5 / 1e6)}
+            "l2": "inputs larger than L2: feature table %.0f MB (fp32 storage of the tf32 mode; %.0f MB in bf16) + CSR %.0f MB resident, random "
+                  "row gathers; no explicit flush" % (w["V"] * ((w["F"] + 7) // 8 * 8) * 4 / 1e6, w["V"] * ((w["F"] + 7) // 8 * 8) * 2 / 1e6,
+                                                      2 * w["E"] * 8 * 1.5 / 1e6)}
 
 
-def run_ours(args, rank, world, local_rank):
+DTYPES = {"tf32": dict(es=4, note="fp32 storage with every GEMM operand rounded to TF32 where it is produced, tcgen05.mma.kind::tf32, fp32 accumulation"),
+          "bf16": dict(es=2, note="bf16 storage, tcgen05.mma.kind::f16, fp32 accumulation: the fast mode, a labelled DEVIATION from north_star's "
+                                  "rtol 1e-3 against the reference's fp32 path (see its `parity` block)")}
+
+
+def measure(dt, headline, args, w, rank, world, dev, dist, g, feats, labels, host, peaks, clocks):
+    """everything bench.py measures for one arithmetic mode `dt` on the resident graph: value (inputs in HBM), the stage table
+    (headline mode only), e2e (pinned host seeds in, loss out every step), the replica check (N > 1) and the parity leg (N = 1)"""
     import ogl_b200
     from ogl_b200 import native
-    w = WORKLOADS[args.workload]
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-
-    # ---- build the streaming graph by inserting the edge stream in snapshot batches (timed: edge inserts/s)
-    src, dst = gen_edges(w, dev)
-    V, E = w["V"], w["E"]
-    g = native.Graph(V, 2 * E)
-    g.insert_vertices(V)
-    chunk = max(1 << 14, min(1 << 21, E // 16))
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = ogl_b200.kernel_launches()
-    e0.record()
-    for a in range(0, E, chunk):
-        g.insert_edges(src[a:a + chunk], dst[a:a + chunk], symmetric=True)
-    e1.record()
-    torch.cuda.synchronize()
-    insert_ms = e0.elapsed_time(e1)
-    insert_launches = ogl_b200.kernel_launches() - launches0
-    assert g.num_edges == 2 * E
-    feats, labels = gen_features(w, dev)
-    mode = ogl_b200.OGL_BF16
+    V, B, K, W = w["V"], w["B"], args.steps, args.warmup
+    es = DTYPES[dt]["es"]
+    mode = {"tf32": ogl_b200.OGL_TF32, "bf16": ogl_b200.OGL_BF16}[dt]
     fs = native.Features(V, w["F"], mode)
     fs.write(0, feats, labels)
-    host_csr = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ip, ix, _ = g.export_csr(with_eids=False)
-        host_csr = (ip.cpu().numpy(), ix.cpu().numpy())
-        del ip, ix
-        feats_host, labels_host = feats.cpu(), labels.cpu()
-    del feats, src, dst
-    torch.cuda.empty_cache()
-
     params = init_params(w)
-    flat = torch.cat([params[f"layers.{i}.{n}"].reshape(-1).float() for i in range(2) for n in NAMES]).to(dev)
+    flat0 = torch.cat([params[f"layers.{i}.{n}"].reshape(-1).float() for i in range(2) for n in NAMES]).to(dev)
+    flat = flat0.clone()
     grad = torch.zeros_like(flat)
-    plan = native.Plan([w["F"], w["H"], w["C"]], w["fanouts"], w["B"], V, mode=mode, seed=11)
+    plan = native.Plan([w["F"], w["H"], w["C"]], w["fanouts"], B, V, mode=mode, seed=11)
     plan.bind_params(flat, grad)
     peer = None
     if world > 1 and args.exchange == "peer":
@@ -507,9 +526,8 @@ def run_ours(args, rank, world, local_rank):
         # the peer-visible allocation
         peer = ogl_b200.parallel.make_peer_exchange(plan, flat)
         grad = peer.grads
-    B = w["B"]
-    K, W = args.steps, args.warmup
-    batches = seed_batches(w, K + W, rank, world)
+    n_check = 3 if world > 1 else 0
+    batches = seed_batches(w, K + W + n_check, rank, world)
     dev_batches = [torch.as_tensor(b).to(dev) for b in batches]
     pin = [torch.as_tensor(b).pin_memory() for b in batches]
     loss_dev = torch.zeros(1, device=dev)
@@ -525,7 +543,7 @@ def run_ours(args, rank, world, local_rank):
 
     def run_steps(inputs, read_back, losses):
         """pipelined loop (ogl_b200.parallel.Pipeline): sample + gather of step t+1 (ogl_plan_prefetch, the plan's second buffer
-        set) overlap forward / backward of step t; N > 1 adds the bucketed gradient all-reduce + Adam on a comm stream.
+        set) overlap forward / backward of step t; N > 1 adds the bucketed gradient exchange + Adam on a comm stream.
         --no-pipeline: one fused (graph-replayed) ogl_plan_train_step per step."""
         if pipe is None:
             for s in inputs:
@@ -571,113 +589,277 @@ def run_ours(args, rank, world, local_rank):
         host_ms[0] = (time.perf_counter() - h0) * 1e3      # host time to ENQUEUE the steps (well below the device time = not host-bound)
         t1.record()
         barrier()
+        wall1 = time.time()
         ms = t0.elapsed_time(t1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, wall0, time.time(), losses
+        return ms, wall0, wall1, losses
 
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    # ---- N > 1: replicas stay bit-identical, and the N-rank run equals the same global batches trained on ONE rank
+    replicas = None
+    if world > 1:
+        chk = dev_batches[K + W:]
+        run_steps(chk, False, [])
+        torch.cuda.synchronize()
+        # 64-bit checksum of the raw parameter bits, compared across the ranks
+        cs = flat.view(torch.int32).to(torch.int64).sum().reshape(1)
+        every = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(every, cs)
+        same = all(int(e.item()) == int(every[0].item()) for e in every)
+        # rank 0 replays the n_check steps alone: for every step the shards of all ranks one after the other (same Philox step and
+        # row positions as rank r used), gradients summed in rank order, one Adam step -- with a plan of its own
+        all_seeds = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(world)]
+        replay_err = None
+        trained = flat.clone()
+        step_seeds = []
+        for sd in chk:
+            dist.all_gather(all_seeds, sd)
+            step_seeds.append([t.clone() for t in all_seeds])
+        if rank == 0:
+            f2, g2 = flat0.clone(), torch.zeros_like(flat0)
+            p2 = native.Plan([w["F"], w["H"], w["C"]], w["fanouts"], B, V, mode=mode, seed=11)
+            p2.bind_params(f2, g2)
+            acc = torch.zeros_like(g2)
+            for t, shards in enumerate(step_seeds):
+                acc.zero_()
+                for sd in shards:
+                    p2.set_step(t)
+                    p2.sample(g, sd)
+                    p2.forward(fs, want_logits=False)
+                    p2.loss_backward(fs, 1.0 / (B * world), want_per_vertex=False)
+                    acc += g2
+                g2.copy_(acc)
+                p2.adam_step()
+            torch.cuda.synchronize()
+            replay_err = float((f2 - trained).abs().max().item() / trained.abs().max().item())
+            del p2
+        replicas = {"replicas_bit_identical": bool(same), "checked_after_steps": n_check, "checksum": int(every[0].item()),
+                    "one_rank_replay_max_err_of_scale": replay_err,
+                    "note": "rank 0 replays the same global batches alone (all shards in rank order, summed gradients, one Adam step per step)"}
+        assert same, "data-parallel replicas diverged: %r" % [int(e.item()) for e in every]
+        # back to the initial state for the measurement
+        flat.copy_(flat0)
+        plan.refresh_params()
+        plan.reset_optimizer(0)
+        barrier()
+
     run_steps(dev_batches[:W], False, [])
-    # ---- value: inputs resident in HBM (the step's launch sequence is replayed as one CUDA graph)
+    # ---- value: inputs resident in HBM (the step's launch sequence is replayed as CUDA graphs)
     gs0 = plan.graph_stats()
-    ms_dev, wall0, wall1, _ = timed(dev_batches[W:], read_back=False)
+    l0 = ogl_b200.kernel_launches()
+    ms_dev, wall0, wall1, _ = timed(dev_batches[W:W + K], read_back=False)
     host_enqueue_ms = host_ms[0]
     gs1 = plan.graph_stats()
-    # ---- the same K steps once more with the library's per-stage CUDA events on (direct launches, no graph):
+    out = {"dtype": dt, "arithmetic": DTYPES[dt]["note"], "value": B * world * K / (ms_dev / 1e3), "ms_per_step": ms_dev / K,
+           "host_enqueue_ms_per_step": host_enqueue_ms / K, "replicas": replicas,
+           "cuda_graph": {"replays_in_timed_region": gs1["replays"] - gs0["replays"], "captures_in_timed_region": gs1["captures"] - gs0["captures"]},
+           "clocks": clocks.window(wall0, wall1) if clocks else None}
+    # ---- the same K steps once more with the library's per-stage CUDA events on (direct launches, no graph, no overlap):
     #      stage shares + the roofline of the dominant kernel
-    plan.profile(True)
-    l0 = ogl_b200.kernel_launches()
-    ms_prof, _, _, _ = timed(dev_batches[W:], read_back=False)
-    launches = ogl_b200.kernel_launches() - l0          # kernels per K steps (a graph replay launches the same kernels)
-    stages, level_sums, n_prof = plan.profile_read()
-    plan.profile(False)
+    stages = None
+    if headline:
+        plan.profile(True)
+        l0 = ogl_b200.kernel_launches()
+        ms_prof, _, _, _ = timed(dev_batches[W:W + K], read_back=False)
+        launches = ogl_b200.kernel_launches() - l0          # kernels per K steps (a graph replay launches the same kernels)
+        stages, level_sums, n_prof = plan.profile_read()
+        plan.profile(False)
+        out["gpu_launches"] = launches
+        out["cuda_graph"]["ms_per_step_direct_launch_profiled"] = ms_prof / K
     # ---- e2e: pinned host seeds -> H2D inside the call, loss D2H every step
     run_steps(pin[:W], False, [])
-    ms_e2e, _, wall2, losses = timed(pin[W:], read_back=True)
-    # clock samples (100 ms period) over the value + profiled + e2e regions: the same K steps back to back
-    clk = clocks.window(wall0, wall2) if clocks else None
+    ms_e2e, wall2, wall3, losses = timed(pin[W:W + K], read_back=True)
+    last_loss = None
+    if losses:
+        t = torch.tensor([losses[-1]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t)                              # the loss sum of the GLOBAL batch of the last step
+        last_loss = float(t.item()) / (B * world)
+    out["e2e"] = {"value": B * world * K / (ms_e2e / 1e3), "unit": "vertices/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4,
+                  "ms_per_step": ms_e2e / K,
+                  "api": "ogl_plan_prefetch(pinned host seeds of step t+1) + ogl_plan_step_finish(step t) + D2H copy of the step's loss into pinned memory every step (consumed by the host one step later)",
+                  "last_loss": last_loss, "clocks": clocks.window(wall2, wall3) if clocks else None}
+    if rank != 0:
+        return out
+
+    # ---- roofline of the dominant kernel (headline mode)
+    if headline:
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tc_sus, tc_burst = peaks.get("bf16_tflops_sustained", 1400.0), peaks.get("bf16_tflops", 1650.0)
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        if dt == "tf32":                                    # tcgen05 kind::tf32 issues at half the kind::f16 rate (1.125 vs 2.25 PFLOP/s nominal)
+            tc_sus, tc_burst, tc_nom = tc_sus / 2, tc_burst / 2, 1125.0
+            peak_src += ", bf16 figures / 2 for kind::tf32"
+        else:
+            tc_nom = 2250.0
+        lv = [x / max(n_prof, 1) for x in level_sums]                 # mean [B, N1, N0] per step
+        per = {k: v[0] / max(n_prof, 1) for k, v in stages.items()}   # ms per step per stage
+        total_stage_ms = sum(per.values())
+        # dominant kernel = the kernel family with the largest total share of the step; the roofline is quoted on its
+        # largest launch (FLOPs / bytes of that launch from the per-step node counts, duration from the stage events)
+        is_layer = lambda k: len(k) > 3 and k[0] == "l" and k[1].isdigit() and k[2] == "."
+
+        def family(k):
+            kind = k.split(".", 1)[1] if is_layer(k) else k.split(".")[0]
+            if kind in ("pool_gemm", "out_gemm", "dneigh_gemm", "dx_gemm"):
+                return "k_gemm_nt_tc"
+            if kind in ("dW_self", "dW_neigh", "dW_pool", "dW_group"):
+                return "k_gemm_tn_tc"
+            return {"pool_bwd": "k_pool_bwd", "segmax": "k_segmax_fwd", "gather": "k_gather_rows", "sample": "k_sample",
+                    "to_block": "k_tb_*", "rev_edges": "k_rev_*", "db_out": "k_colsum_*", "db_pool": "k_colsum_*"}.get(kind, kind)
+        fam = {}
+        for k in per:
+            fam.setdefault(family(k), []).append(k)
+        fam_ms = {f: sum(per[k] for k in ks) for f, ks in fam.items()}
+        top_family = max(fam_ms, key=fam_ms.get)
+        top = max(fam[top_family], key=per.get)
+        fl = stage_flops(top, w, lv) if is_layer(top) else None
+        by = stage_bytes(top, w, lv, es)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dt, {}).get(top)
+            if tr:
+                traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+        except Exception:
+            pass
+        common = {"kernel": top_family, "launch": top, "kernel_share_of_step": fam_ms[top_family] / total_stage_ms,
+                  "kernel_ms_per_step": fam_ms[top_family], "kernel_launches_per_step": len(fam[top_family]), "traffic": traffic,
+                  "ms_per_launch": per[top], "timed_by": "CUDA events recorded by the library around the launch, on the launch stream, "
+                                                         "kernel alone on the device (stages_mode)"}
+        if fl:
+            ach = fl / (per[top] * 1e-3) / 1e12
+            # a single ~0.1 ms kernel timed by itself runs in the burst regime (1965 MHz): `frac` is against the burst peak; the
+            # sustained figure (long back-to-back GEMMs, clocks settled ~1.3 GHz) and the data-sheet one are printed beside it
+            roof = dict(common, bound="tensor", achieved=ach, peak=tc_burst, unit="TFLOP/s", frac=ach / tc_burst, peak_source=peak_src + ", burst",
+                        peak_burst=tc_burst, frac_burst=ach / tc_burst, peak_sustained=tc_sus, frac_sustained=ach / tc_sus,
+                        flops_per_launch=fl, peak_nominal=tc_nom, frac_nominal=ach / tc_nom)
+            fam_fl = sum(stage_flops(k, w, lv) or 0.0 for k in fam[top_family])
+            roof["kernel_avg_tflops"] = fam_fl / (fam_ms[top_family] * 1e-3) / 1e12
+        elif by:
+            ach = by / (per[top] * 1e-3) / 1e9
+            roof = dict(common, bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src,
+                        bytes_per_launch=by, peak_nominal=8000.0, frac_nominal=ach / 8000.0)
+        else:
+            roof = dict(common, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None)
+        stage_table = {}
+        for k in sorted(per, key=per.get, reverse=True):
+            ent = {"ms": round(per[k], 4), "share": round(per[k] / total_stage_ms, 4)}
+            f_, b_ = (stage_flops(k, w, lv) if is_layer(k) else None), stage_bytes(k, w, lv, es)
+            if f_:
+                ent["tflops"] = round(f_ / (per[k] * 1e-3) / 1e12, 1)
+            if b_:
+                ent["gbs"] = round(b_ / (per[k] * 1e-3) / 1e9, 1)
+            stage_table[k] = ent
+        out["roofline"] = roof
+        out["stages"] = stage_table
+        out["stages_mode"] = ("direct launches with CUDA events around every stage, no CUDA graph, no side-stream / prefetch overlap: %.3f ms per "
+                              "step against %.3f ms for the graph-replayed, overlapped step that `value` times; shares and per-kernel rates come "
+                              "from this mode" % (ms_prof / K, ms_dev / K))
+        out["mean_level_counts"] = {"B": lv[0], "N1": lv[1], "N0": lv[2]}
+
+    # ---- parity leg (N = 1, untimed): ONE step of this mode at the trained weights against the unquantised fp64 oracle on the
+    #      same sampled blocks (oracle/parity.py; the oracle is the checker here, never the thing measured)
+    if host is not None and not args.no_parity:
+        from oracle import parity as opar
+        t0 = time.time()
+        seeds = batches[W]
+        sd = torch.as_tensor(seeds).to(dev)
+        plan.sample(g, sd)
+        logits = plan.forward(fs)
+        per_v, _ = plan.loss_backward(fs, 1.0 / B)
+        torch.cuda.synchronize()
+        cur = opar.dict_from_flat(flat.detach().cpu(), [w["F"], w["H"], w["C"]])
+        m = opar.compare_step(plan, cur, host["feats"], host["labels"], seeds, logits, per_v, grad, {"tf32": 2.0 ** -10, "bf16": 2.0 ** -8}[dt])
+        out["parity"] = opar.summary(m)
+        out["parity"]["seconds"] = round(time.time() - t0, 1)
+        out["parity"]["meets_rtol_1e-3"] = bool(m["logits"]["frac_outside"] == 0.0 and m["per_vertex_loss"]["frac_outside"] == 0.0 and
+                                                m["grad_frac_outside_pinned_max"] == 0.0)
+    del pipe, plan, fs
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import ogl_b200
+    from ogl_b200 import native
+    w = WORKLOADS[args.workload]
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- build the streaming graph by inserting the edge stream in snapshot batches (timed: edge inserts/s)
+    src, dst = gen_edges(w, dev)
+    V, E = w["V"], w["E"]
+    g = native.Graph(V, 2 * E + (1 << 20))               # (+ room for the snapshot-insert aux leg)
+    g.insert_vertices(V)
+    chunk = max(1 << 14, min(1 << 21, E // 16))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ogl_b200.kernel_launches()
+    e0.record()
+    for a in range(0, E, chunk):
+        g.insert_edges(src[a:a + chunk], dst[a:a + chunk], symmetric=True)
+    e1.record()
+    torch.cuda.synchronize()
+    insert_ms = e0.elapsed_time(e1)
+    insert_launches = ogl_b200.kernel_launches() - launches0
+    assert g.num_edges == 2 * E
+    feats, labels = gen_features(w, dev)
+    host = None
+    if rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_parity):
+        ip, ix, _ = g.export_csr(with_eids=False)
+        host = {"csr": (ip.cpu().numpy(), ix.cpu().numpy()), "feats": feats.cpu(), "labels": labels.cpu()}
+        del ip, ix
+    del src, dst
+    torch.cuda.empty_cache()
+
+    dts = [args.dtype]
+    if world == 1 and not args.no_alt:
+        dts.append("bf16" if args.dtype == "tf32" else "tf32")
+    res = {}
+    for i, dt in enumerate(dts):
+        res[dt] = measure(dt, i == 0, args, w, rank, world, dev, dist, g, feats, labels, host, peaks, clocks)
     if clocks:
         clocks.stop()
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    value = B * world * K / (ms_dev / 1e3)
-    e2e = B * world * K / (ms_e2e / 1e3)
-    lv = [x / max(n_prof, 1) for x in level_sums]                 # mean [B, N1, N0] per step
-    per = {k: v[0] / max(n_prof, 1) for k, v in stages.items()}   # ms per step per stage
-    total_stage_ms = sum(per.values())
-    # dominant kernel = the kernel family with the largest total share of the step; the roofline is quoted on its
-    # largest launch (FLOPs / bytes of that launch from the per-step node counts, duration from the stage events)
-    is_layer = lambda k: len(k) > 3 and k[0] == "l" and k[1].isdigit() and k[2] == "."
-    def family(k):
-        kind = k.split(".", 1)[1] if is_layer(k) else k.split(".")[0]
-        if kind in ("pool_gemm", "out_gemm", "dneigh_gemm", "dx_gemm"):
-            return "k_gemm_nt_tc"
-        if kind in ("dW_self", "dW_neigh", "dW_pool", "dW_group"):
-            return "k_gemm_tn_tc"
-        return {"pool_bwd": "k_pool_bwd", "segmax": "k_segmax_fwd", "gather": "k_gather_rows", "sample": "k_sample",
-                "to_block": "k_tb_*", "rev_edges": "k_rev_*", "db_out": "k_colsum_*", "db_pool": "k_colsum_*"}.get(kind, kind)
-    fam = {}
-    for k, v in per.items():
-        fam.setdefault(family(k), []).append(k)
-    fam_ms = {f: sum(per[k] for k in ks) for f, ks in fam.items()}
-    top_family = max(fam_ms, key=fam_ms.get)
-    top = max(fam[top_family], key=per.get)
-    fl = stage_flops(top, w, lv) if is_layer(top) else None
-    by = stage_bytes(top, w, lv)
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
-        if tr:
-            traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
-    except Exception:
-        pass
-    common = {"kernel": top_family, "launch": top, "kernel_share_of_step": fam_ms[top_family] / total_stage_ms,
-              "kernel_ms_per_step": fam_ms[top_family], "kernel_launches_per_step": len(fam[top_family]), "traffic": traffic,
-              "ms_per_launch": per[top]}
-    if fl:
-        ach = fl / (per[top] * 1e-3) / 1e12
-        roof = dict(common, bound="tensor", achieved=ach, peak=tc_peak, unit="TFLOP/s", frac=ach / tc_peak,
-                    peak_source=peak_src + ", sustained bf16", flops_per_launch=fl,
-                    peak_nominal=2250.0, frac_nominal=ach / 2250.0)          # B200 dense bf16 data-sheet figure beside the measured one
-        fam_fl = sum(stage_flops(k, w, lv) or 0.0 for k in fam[top_family])
-        roof["kernel_avg_tflops"] = fam_fl / (fam_ms[top_family] * 1e-3) / 1e12
-    elif by:
-        ach = by / (per[top] * 1e-3) / 1e9
-        roof = dict(common, bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src,
-                    bytes_per_launch=by, peak_nominal=8000.0, frac_nominal=ach / 8000.0)
-    else:
-        roof = dict(common, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None)
-    stage_table = {}
-    for k in sorted(per, key=per.get, reverse=True):
-        ent = {"ms": round(per[k], 4), "share": round(per[k] / total_stage_ms, 4)}
-        f_, b_ = (stage_flops(k, w, lv) if is_layer(k) else None), stage_bytes(k, w, lv)
-        if f_:
-            ent["tflops"] = round(f_ / (per[k] * 1e-3) / 1e12, 1)
-        if b_:
-            ent["gbs"] = round(b_ / (per[k] * 1e-3) / 1e9, 1)
-        stage_table[k] = ent
+    B, K, W = w["B"], args.steps, args.warmup
+    head = res[args.dtype]
 
     cpu = None
-    if host_csr is not None:
+    if host is not None and not args.no_cpu_baseline:
+        IMPL[0] = "reference"
         torch.set_num_threads(os.cpu_count() or 1)
-        path = CpuPath(w, host_csr[0], host_csr[1], feats_host, labels_host, params)
+        path = CpuPath(w, host["csr"][0], host["csr"][1], host["feats"], host["labels"], init_params(w))
+        IMPL[0] = "ours"
         cb = seed_batches(w, args.cpu_steps + 1, 0, 1, seed=5)
         el = time_cpu(path, cb, 1)
         cpu = {"value": B * args.cpu_steps / el, "unit": "vertices/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d full train steps (B=%d) of the same workload, oracle port (numpy sampler + torch-CPU fp32 SAGE-pool + Adam), %.1f s"
                          % (args.cpu_steps, B, el)}
-    aux = None
+    del feats
+    aux, snap = None, None
     if world == 1 and not args.no_aux:
         try:
             sweep = aux_sampler_sweep(g, V)
+            # the regime the reference runs: one snapshot of settings/reddit.json = 11,461 stream edges appended to the LIVE graph
+            snap = aux_snapshot_insert(g, V)
         except Exception as e:
             sweep = {"error": repr(e)[:300]}
-        del plan, g, fs
+        del g
         torch.cuda.empty_cache()
         try:
             aux = {"elliptic_pbr": aux_elliptic_pbr(faithful=True)}
@@ -689,18 +871,20 @@ def run_ours(args, rank, world, local_rank):
             aux["cached_inference"] = aux_cached_inference()
         except Exception as e:                       # the aux leg must never take the headline line with it
             aux = {"elliptic_pbr": {"error": repr(e)[:300]}}
-    line = {"metric": "graphsage_train_vertices_per_s", "value": value, "unit": "vertices/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": workload_config(w, args.workload, world),
-            "e2e": {"value": e2e, "unit": "vertices/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
-                    "api": "ogl_plan_prefetch(pinned host seeds of step t+1) + ogl_plan_step_finish(step t) + D2H copy of the step's loss into pinned memory every step (consumed by the host one step later)", "last_loss": losses[-1] / (B * world) if losses else None},
-            "host_enqueue_ms_per_step": host_enqueue_ms / K, "gpu_launches": launches, "cuda_graph": {"replays_in_timed_region": gs1["replays"] - gs0["replays"],
-                                                      "captures_in_timed_region": gs1["captures"] - gs0["captures"],
-                                                      "ms_per_step_direct_launch_profiled": ms_prof / K},
-            "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "mean_level_counts": {"B": lv[0], "N1": lv[1], "N0": lv[2]}, "stages": stage_table, "aux": aux,
+    alt = None
+    for dt in dts[1:]:
+        r = res[dt]
+        alt = {k: r[k] for k in ("dtype", "arithmetic", "value", "ms_per_step", "e2e", "parity", "clocks") if k in r}
+    line = {"metric": "graphsage_train_vertices_per_s", "value": head["value"], "unit": "vertices/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"],
+            "arithmetic": head["arithmetic"], "data": "synthetic", "config": workload_config(w, args.workload, world),
+            "e2e": head["e2e"], "parity": head.get("parity"), "replicas": head.get("replicas"),
+            "host_enqueue_ms_per_step": head["host_enqueue_ms_per_step"], "gpu_launches": head.get("gpu_launches"),
+            "cuda_graph": head["cuda_graph"], "clocks": head["clocks"], "roofline": head.get("roofline"), "cpu_baseline": cpu,
+            "mean_level_counts": head.get("mean_level_counts"), "stages": head.get("stages"), "stages_mode": head.get("stages_mode"),
+            "alt": alt, "aux": aux,
             "edge_insert": {"stream_edges_per_s": E / (insert_ms / 1e3), "ms": insert_ms, "batch_stream_edges": chunk, "launches": insert_launches,
-                            "algorithmic_gbs": 2 * E * (16 + 8 + 8) / (insert_ms / 1e3) / 1e9}}
+                            "algorithmic_gbs": 2 * E * (16 + 8 + 8) / (insert_ms / 1e3) / 1e9, "snapshot": snap}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -719,8 +903,14 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gradient exchange + Adam fused in one kernel over NVLink peer memory, or NCCL all-reduce + Adam")
     ap.add_argument("--no-pipeline", action="store_true", help="one fused ogl_plan_train_step per step instead of the prefetch pipeline")
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
+                    help="arithmetic of the headline line: tf32 meets north_star's rtol 1e-3 against the reference's fp32 path, bf16 is the "
+                         "faster labelled deviation (N = 1 prints the other one too, under `alt`)")
+    ap.add_argument("--no-alt", action="store_true", help="N = 1: do not measure the other arithmetic mode")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity leg (one step against the fp64 oracle, untimed)")
     args = ap.parse_args()
     EXCHANGE[0] = args.exchange
+    IMPL[0] = args.impl
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

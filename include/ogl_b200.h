@@ -123,6 +123,9 @@ int ogl_plan_bind_params(ogl_plan* p, float* params_dev, float* grads_dev, void*
 /* call after params were changed outside the library (load_state_dict) */
 int ogl_plan_refresh_params(ogl_plan* p, void* stream);
 int ogl_plan_set_step(ogl_plan* p, uint32_t step, void* stream);
+/* fresh optimiser state (Adam moments and step counter zeroed) and Philox step = philox_step: the reference's build_optimizer()
+ * constructs a new torch.optim.Adam (pytorch/model.py:22-25) */
+int ogl_plan_reset_optimizer(ogl_plan* p, uint32_t philox_step, void* stream);
 /* sticky device-side error flags since the last call (synchronises; clears them).  bit 0: a seed id outside [0, n_vertices) was
  * passed to a sampling / train / eval call -- it was replaced by vertex 0 so that no row metadata is read out of bounds (DGL's
  * NodeDataLoader raises on such ids, pytorch/model.py:128-131) */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "ogl_plan_refresh_params": (_i, [_vp, _vp]),
     "ogl_plan_set_step": (_i, [_vp, _u32, _vp]),
     "ogl_plan_error_flags": (_i, [_vp, C.POINTER(_u32)]),
+    "ogl_plan_reset_optimizer": (_i, [_vp, _u32, _vp]),
     "ogl_plan_sample": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ogl_plan_forward": (_i, [_vp, _vp, _vp, _vp]),
     "ogl_plan_loss_backward": (_i, [_vp, _vp, _f, _vp, _vp, _vp]),

@@ -329,6 +329,10 @@ class Plan:
         self.n_seeds = n
         self._stamp += 1
 
+    def reset_optimizer(self, philox_step=0):
+        """zero Adam's moments / step counter and set the Philox step (a fresh optimiser; replays of a run from its start)"""
+        check(lib.ogl_plan_reset_optimizer(self._h, int(philox_step) & 0xFFFFFFFF, _stream()))
+
     def error_flags(self):
         """sticky device error bits since the last call (bit 0: out-of-range seed id); synchronises"""
         v = C.c_uint32()

@@ -221,9 +221,12 @@ __device__ __forceinline__ void tmem_free(uint32_t base) {
 //   K-major : rows of 128 B (64 bf16 of the contraction), 8-row groups 1024 B apart (SBO); LBO unused (1)
 //   MN-major: 64-element (128 B) chunks of the M/N index, contraction rows 128 B apart, 8-row groups 1024 B
 //             apart (SBO), next 64-element chunk `lbo` bytes apart
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major 32-bit (tf32) operands exist in ONE layout only: SWIZZLE_128B_BASE32B = 1 at bits 61-63 -- 128-byte rows swizzled in
+//             32-byte units over groups of FOUR contraction rows (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); SBO = distance of the
+//             4-row groups (512 B for dense rows), LBO = distance of the 32-element chunks
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // instruction descriptor for kind::f16 / kind::tf32: D = f32 (bits 4-5 = 1), A / B format at bits 7-9 / 10-12 (1 = bf16,
 // 2 = tf32), majors at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28
@@ -754,7 +757,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       uint32_t accumulate = 0;
       // MN-major descriptors (LBO = distance between 128-byte-wide chunks of the M / N index, SBO = 8 contraction rows): one MMA
       // covers 16 (bf16) / 8 (tf32) contraction rows = 2048 / 1024 bytes = KSTEP in the 14-bit address field; kept branch-free
-      const uint64_t a_desc0 = smem_desc(smem_u32(a_stage(0)), CHUNK_BYTES, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), CHUNK_BYTES, 1024);
+      const uint64_t a_desc0 = smem_desc(smem_u32(a_stage(0)), CHUNK_BYTES, TF ? 512 : 1024, TF ? 1 : 2),
+                     b_desc0 = smem_desc(smem_u32(s.b(0)), CHUNK_BYTES, TF ? 512 : 1024, TF ? 1 : 2);
       const uint32_t acc1 = tmem_base + (uint32_t)BN_MAX;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.full[stage], phase);
@@ -890,14 +894,15 @@ int tc_init() {
 
 // 2-D bf16 (es = 2) or fp32 (es = 4) tensor [rows, cols] with row pitch ld (elements), box = box_cols x box_rows (box_cols * es
 // = 128 bytes), 128-byte swizzle
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int es = 2) {
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int es = 2,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   OGL_ARG(((uintptr_t)ptr & 15) == 0 && (ld * es) % 16 == 0, "gemm_tc: operand not 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)es};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows %lld cols %lld ld %lld box %dx%d", (int)r, (long long)rows,
@@ -1040,8 +1045,10 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
     OGL_ARG(g[i].m_dev == g[0].m_dev && g[i].m_max == g[0].m_max && g[i].tf32 == g[0].tf32,
             "gemm_tn_tc: grouped problems must contract over the same rows in the same arithmetic");
     TnProblem& q = p.pr[i];
-    OGL_TRY(make_map(&q.ta, g[i].a, g[i].m_max, g[i].n, g[i].lda, cw, cw, es));
-    OGL_TRY(make_map(&q.tb, g[i].b, g[i].m_max, g[i].k, g[i].ldb, cw, cw, es));
+    // (MN-major tf32 operands: the 32-byte-atom flavour of the 128-byte swizzle, see smem_desc)
+    const CUtensorMapSwizzle sw = tf ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    OGL_TRY(make_map(&q.ta, g[i].a, g[i].m_max, g[i].n, g[i].lda, cw, cw, es, sw));
+    OGL_TRY(make_map(&q.tb, g[i].b, g[i].m_max, g[i].k, g[i].ldb, cw, cw, es, sw));
     q.n = g[i].n;
     q.k = g[i].k;
     q.k_tiles = (g[i].k + BN_MAX - 1) / BN_MAX;

@@ -444,6 +444,20 @@ extern "C" int ogl_plan_set_step(ogl_plan* p, uint32_t step, void* stream) {
   return OGL_OK;
 }
 
+// a fresh optimiser: Adam moments and step counter zeroed, Philox step set (build_optimizer() of the reference constructs a new
+// torch.optim.Adam, pytorch/model.py:22-25); also what a replica needs to replay a run from its start
+extern "C" int ogl_plan_reset_optimizer(ogl_plan* p, uint32_t philox_step, void* stream) {
+  OGL_ARG(p, "ogl_plan_reset_optimizer: null");
+  OGL_ARG(!p->pend[0] && !p->pend[1], "ogl_plan_reset_optimizer: a prefetched minibatch is pending");
+  cudaStream_t s = (cudaStream_t)stream;
+  OGL_CUDA(cudaMemsetAsync(p->adam_m, 0, sizeof(float) * p->n_params, s));
+  OGL_CUDA(cudaMemsetAsync(p->adam_v, 0, sizeof(float) * p->n_params, s));
+  const uint32_t ctl[2] = {philox_step, 0u};
+  OGL_CUDA(cudaMemcpyAsync(p->ctl, ctl, sizeof(ctl), cudaMemcpyHostToDevice, s));
+  OGL_CUDA(cudaStreamSynchronize(s));
+  return OGL_OK;
+}
+
 __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 
 extern "C" int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_dev, int n_seeds, void* stream) {

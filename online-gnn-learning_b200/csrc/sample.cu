@@ -285,6 +285,21 @@ extern "C" int ogl_sample_neighbors(ogl_graph* g, const int64_t* dst_dev, int64_
   if (n == 0) return OGL_OK;
   cudaStream_t s = (cudaStream_t)stream;
   int32_t* tmp = nullptr;
+  {
+    // the int32 row list is stream-ordered scratch: keep the default pool from handing its memory back to the driver at every
+    // synchronisation (release threshold 0), which made single calls cost tens of milliseconds now and then
+    static bool pool_kept = false;
+    if (!pool_kept) {
+      int dev = 0;
+      cudaMemPool_t pool = nullptr;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      pool_kept = true;
+    }
+  }
   OGL_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * n, s));
   int r = cast_nodes(dst_dev, tmp, n, graph_view(g).n_vertices, nullptr, s);
   if (r == OGL_OK) r = sample_hop(graph_view(g), tmp, nullptr, (int)n, fanout, seed, nullptr, step, hop, out_src_dev, out_eid_dev, s);

@@ -9,11 +9,16 @@ same inputs.  What is reported, per tensor:
   rel_fro            ||a - b||_F / ||b||_F
   frac_outside       share of elements with |a - b| > rtol * |b| + rtol * max |b|   (rtol = 1e-3)
 
-and for the gradients twice: `free` = the oracle picks its own max-pool argmax, `routed` = the oracle's gradient is routed
-through the slots the DEVICE picked (after checking that every device slot attains the oracle's maximum within the mode's
-rounding).  The difference between the two is the max-pool's tie-breaking: when two neighbours' hp values differ by less than
-the mode's rounding the device may route the gradient to the other one -- a whole different input row for that (vertex,
-feature) pair, not a rounding error -- and `argmax_flip_frac` says how often that happened.
+and for the gradients twice.  GraphSAGE-pool is piecewise linear: which neighbour wins a max-pool and which ReLUs are on select
+a linear region, and the gradient JUMPS between regions.  A pre-activation that is zero within rounding error, or two
+neighbours that tie within rounding error, put the device and the oracle in neighbouring regions -- a whole different input
+row for that (vertex, feature) pair, not a rounding error; any two fp32 implementations (the reference on CPU and on GPU, say)
+differ the same way.  So:
+
+  grad_free     the oracle picks its own regions (includes the jumps; `argmax_flip_frac` / `relu_flip_frac` say how many)
+  grad_pinned   the oracle is evaluated in the DEVICE's region (its max-pool slots and ReLU on/off patterns), after checking that
+                every device choice is a valid one within the mode's rounding (`*_not_within_rounding` must be 0): what is left
+                is the arithmetic error proper
 """
 import numpy as np
 import torch
@@ -70,11 +75,20 @@ def compare_step(plan, params, feats_cpu, labels_cpu, seeds_cpu, logits_dev, per
     out = {"oracle": "oracle/sage.py, fp64, quant=None (the reference's fp32 path restated), same sampled blocks",
            "rtol": RTOL, "logits": tensor_err(logits_dev, logits_ref), "per_vertex_loss": tensor_err(per_dev, per_ref),
            "level_counts": [plan.level_nodes(lv).numel() for lv in range(L + 1)]}
-    # the device's argmax slots: each must attain the oracle's maximum within the mode's rounding
-    flips, not_max = [], []
+    # the device's argmax slots: each must attain the oracle's maximum within the mode's rounding; the device's ReLU patterns: a
+    # sign that differs from the oracle's must belong to a pre-activation that is zero within the mode's rounding
+    flips, not_max, relu_flips, relu_bad = [], [], [], []
     for l in range(L):
         h = L - 1 - l
         n_dst = plan.level_nodes(h).numel()
+        n_src = plan.level_nodes(h + 1).numel()
+        for name, pre, rows in (("hp", inter[l]["hp_pre"], n_src),) + ((("out", inter[l]["out_pre"], n_dst),) if l < L - 1 else ()):
+            cols = dims[l] if name == "hp" else dims[l + 1]
+            on = plan.tensor("%s%d" % (name, l), rows=rows)[:, :cols].float().cpu() > 0
+            differ = on != (pre > 0)
+            relu_flips.append(differ.double().mean().item())
+            relu_bad.append(int((differ & (pre.abs() > 4 * slot_tol * pre.abs().max())).sum()))
+            blocks[l]["mask_" + name] = on
         arg = plan.tensor("arg%d" % l, rows=n_dst)[:, :dims[l]].long().cpu()
         arg[arg == 255] = -1
         ref_arg = inter[l]["arg"]
@@ -94,7 +108,9 @@ def compare_step(plan, params, feats_cpu, labels_cpu, seeds_cpu, logits_dev, per
         blocks[l]["arg"] = arg
     out["argmax_flip_frac"] = flips
     out["argmax_not_a_max_within_rounding"] = not_max
-    # pass 2: the oracle's gradient through the device's routing
+    out["relu_flip_frac"] = relu_flips                       # [hp0, out0, hp1, ...]
+    out["relu_sign_not_within_rounding"] = relu_bad
+    # pass 2: the oracle evaluated in the device's linear region
     _, _, _, grads_routed, _ = osage.loss_and_grads(params, x_in, blocks, labels, quant=None, dtype=torch.float64)
     got = dict_from_flat(grad_dev.detach().double().cpu(), dims)
     gf, gr = {}, {}
@@ -102,10 +118,11 @@ def compare_step(plan, params, feats_cpu, labels_cpu, seeds_cpu, logits_dev, per
         gf[k] = tensor_err(got[k], grads_free[k])
         gr[k] = tensor_err(got[k], grads_routed[k])
     out["grad_free"] = gf
-    out["grad_routed"] = gr
+    out["grad_pinned"] = gr
     out["grad_rel_fro_free_max"] = max(v["rel_fro"] for v in gf.values())
-    out["grad_rel_fro_routed_max"] = max(v["rel_fro"] for v in gr.values())
-    out["grad_max_err_of_scale_routed_max"] = max(v["max_err_of_scale"] for v in gr.values())
+    out["grad_rel_fro_pinned_max"] = max(v["rel_fro"] for v in gr.values())
+    out["grad_max_err_of_scale_pinned_max"] = max(v["max_err_of_scale"] for v in gr.values())
+    out["grad_frac_outside_pinned_max"] = max(v["frac_outside"] for v in gr.values())
     return out
 
 
@@ -115,8 +132,10 @@ def summary(m):
             "logits_max_err_of_scale": m["logits"]["max_err_of_scale"], "logits_rel_fro": m["logits"]["rel_fro"],
             "logits_frac_outside_rtol": m["logits"]["frac_outside"],
             "loss_max_err_of_scale": m["per_vertex_loss"]["max_err_of_scale"],
-            "grad_rel_fro": {k: v["rel_fro"] for k, v in m["grad_free"].items()},
-            "grad_rel_fro_routed": {k: v["rel_fro"] for k, v in m["grad_routed"].items()},
-            "grad_rel_fro_max": m["grad_rel_fro_free_max"], "grad_rel_fro_routed_max": m["grad_rel_fro_routed_max"],
-            "grad_max_err_of_scale_routed_max": m["grad_max_err_of_scale_routed_max"],
-            "argmax_flip_frac": m["argmax_flip_frac"], "argmax_not_a_max_within_rounding": m["argmax_not_a_max_within_rounding"]}
+            "grad_rel_fro_free": {k: v["rel_fro"] for k, v in m["grad_free"].items()},
+            "grad_rel_fro_pinned": {k: v["rel_fro"] for k, v in m["grad_pinned"].items()},
+            "grad_rel_fro_free_max": m["grad_rel_fro_free_max"], "grad_rel_fro_pinned_max": m["grad_rel_fro_pinned_max"],
+            "grad_max_err_of_scale_pinned_max": m["grad_max_err_of_scale_pinned_max"],
+            "grad_frac_outside_rtol_pinned_max": m["grad_frac_outside_pinned_max"],
+            "argmax_flip_frac": m["argmax_flip_frac"], "argmax_not_a_max_within_rounding": m["argmax_not_a_max_within_rounding"],
+            "relu_flip_frac": m["relu_flip_frac"], "relu_sign_not_within_rounding": m["relu_sign_not_within_rounding"]}

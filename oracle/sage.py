@@ -115,17 +115,22 @@ def segment_max(hp, edge_src, n_dst, fanout, arg=None):
     return neigh, arg
 
 
-def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, quant=None, arg=None):
+def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, quant=None, arg=None, mask_hp=None, mask_out=None):
+    """``mask_hp`` / ``mask_out`` (bool, optional) replace the two ReLUs by a fixed on/off pattern: together with ``arg`` they pin
+    the piecewise-linear region in which the layer is evaluated (oracle/parity.py: the device's region, to compare gradients
+    without the jumps that a sign or an argmax decided inside rounding error causes)."""
     q = _Q.apply if quant else (lambda t: t)
     qf = _Qf.apply if quant else (lambda t: t)
-    hp = q(torch.relu(x @ qf(Wp).t() + bp))
+    hp_pre = x @ qf(Wp).t() + bp
+    hp = q(torch.relu(hp_pre) if mask_hp is None else torch.where(mask_hp, hp_pre, torch.zeros((), dtype=hp_pre.dtype)))
     neigh, arg = segment_max(hp, edge_src, n_dst, fanout, arg=arg)
     if quant:
         neigh = _Qb.apply(neigh)
-    out = x[:n_dst] @ qf(Ws).t() + neigh @ qf(Wn).t() + (bs + bn)
+    out_pre = x[:n_dst] @ qf(Ws).t() + neigh @ qf(Wn).t() + (bs + bn)
+    out = out_pre
     if relu_out:
-        out = q(torch.relu(out))
-    return out, dict(hp=hp, neigh=neigh, arg=arg)
+        out = q(torch.relu(out_pre) if mask_out is None else torch.where(mask_out, out_pre, torch.zeros((), dtype=out_pre.dtype)))
+    return out, dict(hp=hp, neigh=neigh, arg=arg, hp_pre=hp_pre.detach(), out_pre=out_pre.detach())
 
 
 def forward(params, x_in, blocks, quant=None):
@@ -140,7 +145,8 @@ def forward(params, x_in, blocks, quant=None):
         g = lambda n: params[f"layers.{i}.{n}"]
         h, it = sage_layer(h, b["n_dst"], b["edge_src"], b["fanout"],
                            g("fc_pool.weight"), g("fc_pool.bias"), g("fc_self.weight"), g("fc_self.bias"),
-                           g("fc_neigh.weight"), g("fc_neigh.bias"), relu_out=(i < L - 1), quant=quant, arg=b.get("arg"))
+                           g("fc_neigh.weight"), g("fc_neigh.bias"), relu_out=(i < L - 1), quant=quant, arg=b.get("arg"),
+                           mask_hp=b.get("mask_hp"), mask_out=b.get("mask_out"))
         it["out"] = h
         inter.append(it)
     return h, inter

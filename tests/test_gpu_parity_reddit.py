@@ -20,16 +20,19 @@ from oracle import sage as osage
 
 pytestmark = pytest.mark.gpu
 
-V, E, DIMS, FAN, B = 120000, 1500000, (602, 600, 41), (25, 10), 1024
+V, E, DIMS, FAN, B = 120000, 6000000, (602, 600, 41), (25, 10), 1024
 
 # mode -> (plan mode name, gemm_impl, rounding of a stored hp value, bounds)
-#   logits / loss: max |err| / scale;  grad_routed: rel. Frobenius with the oracle routed through the device's max-pool slots;
-#   grad_free: rel. Frobenius against the free-running oracle (includes the max-pool's tie-breaking, see oracle/parity.py)
+#   logits / loss: max |err| / scale;  grad_pinned: rel. Frobenius with the oracle evaluated in the device's linear region (its
+#   max-pool slots and ReLU patterns, each checked to be a valid choice within rounding);  grad_free: rel. Frobenius against the
+#   free-running oracle (includes the gradient's jumps between neighbouring regions, see oracle/parity.py)
 CASES = {
-    "fp32": dict(gemm_impl=1, slot_tol=2.0 ** -20, logits=1e-5, grad_routed=1e-5, grad_free=5e-3, outside=0.0),
-    "tf32": dict(gemm_impl=0, slot_tol=2.0 ** -10, logits=1e-3, grad_routed=1e-3, grad_free=1e-1, outside=0.0),
+    "fp32": dict(gemm_impl=1, slot_tol=2.0 ** -20, logits=1e-5, grad_pinned=1e-5, grad_free=5e-3, outside=0.0),
+    # tf32: every element of the logits, the losses and (pinned) every gradient within rtol 1e-3 (`outside` = 0); the relative
+    # Frobenius error of a TF32 GEMM chain is ~4e-4 per GEMM (two operands rounded at 2^-11), ~1e-3 after the five on the longest path
+    "tf32": dict(gemm_impl=0, slot_tol=2.0 ** -10, logits=1e-3, grad_pinned=1.5e-3, grad_free=1e-1, outside=0.0),
     # bf16 is a labelled DEVIATION from the 1e-3 target (bench.py prints its measured error beside the tf32 line)
-    "bf16": dict(gemm_impl=0, slot_tol=2.0 ** -8, logits=1e-2, grad_routed=1e-2, grad_free=3e-1, outside=0.5),
+    "bf16": dict(gemm_impl=0, slot_tol=2.0 ** -8, logits=1e-2, grad_pinned=1e-2, grad_free=3e-1, outside=0.5),
 }
 
 _world = {}
@@ -40,7 +43,7 @@ def world():
         import ogl_b200
         rng = np.random.default_rng(1)
         # degree-skewed endpoints (squared uniform) so that hubs and low-degree rows both occur
-        src = (rng.random(E) ** 2 * V).astype(np.int64)
+        src = (rng.random(E) ** 1.3 * V).astype(np.int64)
         dst = rng.integers(0, V, E).astype(np.int64)
         g = ogl_b200.native.Graph(V, 2 * E)
         g.insert_vertices(V)
@@ -75,11 +78,14 @@ def test_step_vs_unquantised_oracle_at_bench_shape(mode):
     n1, n0 = res["level_counts"][1], res["level_counts"][2]
     assert n0 > 80000 and n1 > 20000, "frontier too small to exercise the persistent GEMM loops: %r" % (res["level_counts"],)
     assert s["argmax_not_a_max_within_rounding"] == [0, 0], s["argmax_not_a_max_within_rounding"]
+    assert s["relu_sign_not_within_rounding"] == [0, 0, 0], s["relu_sign_not_within_rounding"]
     assert s["logits_max_err_of_scale"] <= c["logits"], s
     assert s["loss_max_err_of_scale"] <= c["logits"], s
     assert s["logits_frac_outside_rtol"] <= c["outside"], s
-    assert s["grad_rel_fro_routed_max"] <= c["grad_routed"], s
-    assert s["grad_rel_fro_max"] <= c["grad_free"], s
+    assert s["grad_rel_fro_pinned_max"] <= c["grad_pinned"], s
+    if mode != "bf16":
+        assert s["grad_frac_outside_rtol_pinned_max"] == 0.0 and s["grad_max_err_of_scale_pinned_max"] <= c["logits"], s
+    assert s["grad_rel_fro_free_max"] <= c["grad_free"], s
     if mode != "fp32":
         # the graph-replayed fused step on the same minibatch (same Philox step) reproduces the direct launches
         direct = grad.clone()

@@ -218,3 +218,24 @@ def test_pipeline_call_order_single_rank():
         ogl_b200.parallel.torch.cuda.Event = real_event
     assert calls == [("prefetch", "s0"), ("prefetch", "s1"), ("finish", 1.0 / 8, True), ("prefetch", "s2"), ("finish", 1.0 / 8, True),
                      ("finish", 1.0 / 8, True)]
+
+
+def test_package_initialiser_equals_the_oracle_twin():
+    """bench.py's two arms start from the same weights: the package's seeded Xavier initialiser and the oracle's are bit-identical"""
+    import torch
+    from oracle.sage import xavier_params
+    from ogl_b200.graphsage.pytorch.graphsage_dgl import xavier_state_dict
+    a, b = xavier_params(37, 16, 5, 2, seed=3), xavier_state_dict(37, 16, 5, 2, seed=3)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_oracle_tf32_rounding_matches_cvt_rna():
+    import torch
+    from oracle.sage import round_tf32
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -11 - 2 ** -20, -1.0 - 2 ** -11, 3.0e-30, 65504.0, 0.1])
+    r = round_tf32(x)
+    assert r[0] == 1.0 and r[1] == 1.0 + 2 ** -10 and r[2] == 1.0 and r[3] == -1.0 - 2 ** -10      # ties away from zero
+    assert bool(((r.view(torch.int32) & 0x1FFF) == 0).all())
+    assert float(((r - x).abs() / x.abs()).max()) <= 2 ** -11
