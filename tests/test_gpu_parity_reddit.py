@@ -84,7 +84,9 @@ def test_step_vs_unquantised_oracle_at_bench_shape(mode):
     assert s["logits_frac_outside_rtol"] <= c["outside"], s
     assert s["grad_rel_fro_pinned_max"] <= c["grad_pinned"], s
     if mode != "bf16":
-        assert s["grad_frac_outside_rtol_pinned_max"] == 0.0 and s["grad_max_err_of_scale_pinned_max"] <= c["logits"], s
+        assert s["grad_frac_outside_rtol_pinned_max"] == 0.0, s          # every gradient element within rtol * |b| + rtol * scale
+    if mode == "fp32":
+        assert s["grad_max_err_of_scale_pinned_max"] <= c["logits"], s
     assert s["grad_rel_fro_free_max"] <= c["grad_free"], s
     if mode != "fp32":
         # the graph-replayed fused step on the same minibatch (same Philox step) reproduces the direct launches
