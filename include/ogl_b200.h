@@ -111,6 +111,8 @@ typedef struct {
   int gemm_impl;         /* 0 = default for mode (tcgen05 for bf16 / tf32, SIMT for f32), 1 = force SIMT (tests) */
   uint64_t seed;         /* Philox key */
   float lr, beta1, beta2, eps;
+  float feat_drop;       /* SAGEConv(feat_drop=dropout), graphsage_dgl.py:41-46: dropout of every layer's input rows in training mode
+                            (train steps; ogl_plan_forward after ogl_plan_set_option("train_mode", 1)); 0 = off */
 } ogl_plan_config;
 
 int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg);
@@ -265,6 +267,13 @@ int ogl_sumtree_find(ogl_sumtree* t, const double* mass_dev, int64_t n, int64_t*
 int ogl_sumtree_sample_stratified(ogl_sumtree* t, const double* uniforms_dev, int64_t n, int64_t n_items,
                                   int64_t* out_idx_dev, void* stream);
 int ogl_sumtree_values(ogl_sumtree* t, const double** value_dev, int64_t* capacity);
+
+/* ------------------------------------------------------------------ evaluation metrics
+ * Replaces `output.argmax(axis=1)` + sklearn.metrics.confusion_matrix on the host (train/graphsage/model.py:83-86): the logits stay
+ * on the device, cm_dev[y * n_classes + argmax] is incremented per vertex (int64 [n_classes * n_classes + 1], caller-zeroed; the
+ * last slot counts labels outside [0, n_classes)).  The macro-F1 of :86 follows from the matrix. */
+int ogl_eval_confusion(const float* logits_dev, int ld, int64_t n, int n_classes, const int64_t* labels_dev, int64_t* cm_dev,
+                       void* stream);
 
 /* ------------------------------------------------------------------ dense GEMM (tests / bench) */
 /* C[M,N] (fp32, ldc) = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb), tcgen05 path */

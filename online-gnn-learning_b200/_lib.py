@@ -20,7 +20,7 @@ class OglError(RuntimeError):
 class PlanConfig(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("dims", C.c_int * 8), ("fanouts", C.c_int * 8), ("max_seeds", C.c_int),
                 ("v_cap", C.c_int64), ("mode", C.c_int), ("gemm_impl", C.c_int), ("seed", C.c_uint64),
-                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("feat_drop", C.c_float)]
 
 
 def _load():
@@ -111,6 +111,7 @@ SIGNATURES = {
     "ogl_sumtree_find": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "ogl_sumtree_sample_stratified": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "ogl_sumtree_values": (_i, [_vp, _pp, C.POINTER(_i64)]),
+    "ogl_eval_confusion": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),
     "ogl_gemm_bf16_nt": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "ogl_gemm_bf16_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ogl_gemm_bf16_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),

@@ -183,7 +183,7 @@ class Plan:
     """ogl_plan handle: sampler + L-layer GraphSAGE-pool + Adam over one workspace."""
 
     def __init__(self, dims, fanouts, max_seeds, v_cap, mode=OGL_BF16, seed=0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 gemm_impl=0):
+                 gemm_impl=0, feat_drop=0.0):
         L = len(fanouts)
         assert len(dims) == L + 1
         cfg = PlanConfig()
@@ -194,6 +194,7 @@ class Plan:
             cfg.fanouts[i] = int(f)
         cfg.max_seeds, cfg.v_cap, cfg.mode, cfg.gemm_impl, cfg.seed = int(max_seeds), int(v_cap), int(mode), int(gemm_impl), int(seed)
         cfg.lr, cfg.beta1, cfg.beta2, cfg.eps = lr, betas[0], betas[1], eps
+        cfg.feat_drop = float(feat_drop or 0.0)
         self._h = C.c_void_p()
         check(lib.ogl_plan_create(C.byref(self._h), C.byref(cfg)))
         self.dims, self.fanouts, self.L = list(dims), list(fanouts), L
@@ -574,3 +575,27 @@ def gemm_tf32_tn(a, b, n=None, k=None, workspace_elems=1 << 24):
     check(lib.ogl_gemm_tf32_tn(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), k, a.shape[0], n, k,
                                _ptr(ws), int(workspace_elems), _stream()))
     return c
+
+
+def eval_confusion(logits, labels, n_classes=None):
+    """int64 [C, C] confusion matrix (rows = label, columns = argmax of the logits, first maximum wins) of CUDA logits [n, C] and
+    int64 labels [n], computed on the device; labels outside [0, C) are skipped.  -> (cm CUDA tensor, n_skipped)"""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    C_ = logits.shape[1] if n_classes is None else int(n_classes)
+    lab = labels.to(device="cuda", dtype=torch.int64).reshape(-1).contiguous()
+    assert lab.numel() == logits.shape[0]
+    cm = torch.zeros(C_ * C_ + 1, dtype=torch.int64, device="cuda")
+    check(lib.ogl_eval_confusion(C.c_void_p(logits.data_ptr()), logits.stride(0), logits.shape[0], C_, _ptr(lab), _ptr(cm), _stream()))
+    return cm[:C_ * C_].view(C_, C_), cm[C_ * C_]
+
+
+def macro_f1_from_confusion(cm):
+    """(f1_macro, cm restricted to the classes present) exactly as sklearn computes them from (y_true, y_pred): the class set is
+    the union of the labels that occur in either; f1_c = 2 tp / (2 tp + fp + fn)"""
+    cm = np.asarray(cm, dtype=np.int64)
+    present = (cm.sum(0) + cm.sum(1)) > 0
+    sub = cm[present][:, present]
+    tp = np.diag(sub).astype(np.float64)
+    den = sub.sum(0) + sub.sum(1)
+    f1 = np.where(den > 0, 2 * tp / np.maximum(den, 1), 0.0)
+    return (float(f1.mean()) if len(f1) else 0.0), sub

@@ -20,6 +20,7 @@ struct GemmNT {
   const float* bias = nullptr;     // [n] fp32 (nullable)
   const float* bias2 = nullptr;    // second bias added too (fc_self.bias + fc_neigh.bias)
   int relu = 0;
+  float alpha = 1.f;               // scales the accumulated product before the bias (feat_drop's 1 / (1 - p) in the backward pass)
   const void* mask = nullptr;      // same shape/type as A-typed [m, ldmask]: out = mask>0 ? out : 0
   int ldmask = 0;
   void* c = nullptr;               // out_bf16 ? bf16 : f32

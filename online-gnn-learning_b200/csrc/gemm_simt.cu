@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_gemm_nt(GemmNT g) {
       if (gn >= g.n) continue;
       float v = 0.f;
       if (gm < m_dyn) {
-        v = acc[i][j];
+        v = acc[i][j] * g.alpha;
         if (g.bias) v += g.bias[gn];
         if (g.bias2) v += g.bias2[gn];
         if (g.relu) v = fmaxf(v, 0.f);

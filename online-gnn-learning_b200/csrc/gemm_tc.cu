@@ -289,6 +289,7 @@ struct NtParams {
   const float* bias;
   const float* bias2;
   int relu;
+  float alpha;
   const void* mask;             // operand-typed (bf16 | fp32) [m, ldmask]
   int ldmask;
   void* c;
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       const bool row_live = gm < m_dyn;
       const bool tile_live = mb * BM + BM <= m_dyn;
       const float relu_lo = p.relu ? 0.f : -INFINITY;
+      const float alpha = p.alpha;
       // bias slice of this tile -> shared (broadcast reads below); double-buffered with the accumulator
       float* bias_s = s.bias + acc * BN_MAX;
       for (int j = epi_tid; j < bn_tile; j += 256) {
@@ -489,16 +491,16 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + q * 4);
-              v[q * 4 + 0] = fmaxf(__uint_as_float(r[q * 4 + 0]) + b4.x, relu_lo);
-              v[q * 4 + 1] = fmaxf(__uint_as_float(r[q * 4 + 1]) + b4.y, relu_lo);
-              v[q * 4 + 2] = fmaxf(__uint_as_float(r[q * 4 + 2]) + b4.z, relu_lo);
-              v[q * 4 + 3] = fmaxf(__uint_as_float(r[q * 4 + 3]) + b4.w, relu_lo);
+              v[q * 4 + 0] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 0]), alpha, b4.x), relu_lo);
+              v[q * 4 + 1] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 1]), alpha, b4.y), relu_lo);
+              v[q * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 2]), alpha, b4.z), relu_lo);
+              v[q * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 3]), alpha, b4.w), relu_lo);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float x = 0.f;
-              if (row_live && gn0 + j < p.n) x = fmaxf(__uint_as_float(r[j]) + bias_s[c0 + j], relu_lo);
+              if (row_live && gn0 + j < p.n) x = fmaxf(fmaf(__uint_as_float(r[j]), alpha, bias_s[c0 + j]), relu_lo);
               v[j] = x;
             }
           }
@@ -561,16 +563,16 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + q * 4);
-                v[q * 4 + 0] = fmaxf(__uint_as_float(r[q * 4 + 0]) + b4.x, relu_lo);
-                v[q * 4 + 1] = fmaxf(__uint_as_float(r[q * 4 + 1]) + b4.y, relu_lo);
-                v[q * 4 + 2] = fmaxf(__uint_as_float(r[q * 4 + 2]) + b4.z, relu_lo);
-                v[q * 4 + 3] = fmaxf(__uint_as_float(r[q * 4 + 3]) + b4.w, relu_lo);
+                v[q * 4 + 0] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 0]), alpha, b4.x), relu_lo);
+                v[q * 4 + 1] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 1]), alpha, b4.y), relu_lo);
+                v[q * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 2]), alpha, b4.z), relu_lo);
+                v[q * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[q * 4 + 3]), alpha, b4.w), relu_lo);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float x = 0.f;
-                if (row_live && gn0 + j < p.n) x = fmaxf(__uint_as_float(r[j]) + bias_s[cc + j], relu_lo);
+                if (row_live && gn0 + j < p.n) x = fmaxf(fmaf(__uint_as_float(r[j]), alpha, bias_s[cc + j]), relu_lo);
                 v[j] = x;
               }
             }
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
                 for (int j = 0; j < 4; ++j) {
                   float x = 0.f;
                   if (row_live && gn0 + q * 4 + j < p.n) {
-                    x = __uint_as_float(r[q * 4 + j]) + bias_s[c0 + q * 4 + j];
+                    x = fmaf(__uint_as_float(r[q * 4 + j]), alpha, bias_s[c0 + q * 4 + j]);
                     if (p.relu) x = fmaxf(x, 0.f);
                   }
                   v[j] = x;
@@ -995,6 +997,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.bias = g.bias;
   p.bias2 = g.bias2;
   p.relu = g.relu;
+  p.alpha = g.alpha;
   p.mask = g.mask;
   p.ldmask = g.ldmask;
   p.c = g.c;

@@ -161,6 +161,7 @@ struct ogl_plan {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int skip_gather = 0;                   // step_finish: the input rows were already gathered by step_begin
+  int train_mode = 0;                    // feat_drop is applied by ogl_plan_forward (train steps set it; eval steps never)
   int adam_in_backward = 0;              // fused step with do_step: the backward pass runs Adam on all but the last gradient itself
   int64_t adam_done_from = 0;            // ... and leaves [0, adam_done_from) to ogl_plan_adam_step
   int tail_mode = 0;                     // backward: 0 = all, 1 = everything but the last weight-gradient GEMM (layer 0 fc_pool),
@@ -273,6 +274,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   OGL_ARG(cfg->n_layers >= 1 && cfg->n_layers <= 7, "ogl_plan_create: n_layers must be in [1,7]");
   OGL_ARG(cfg->max_seeds > 0 && cfg->v_cap > 0, "ogl_plan_create: max_seeds / v_cap must be positive");
   OGL_ARG(cfg->mode == OGL_F32 || cfg->mode == OGL_BF16 || cfg->mode == OGL_TF32, "ogl_plan_create: bad mode");
+  OGL_ARG(cfg->feat_drop >= 0.f && cfg->feat_drop < 1.f, "ogl_plan_create: feat_drop must be in [0, 1)");
   for (int i = 0; i <= cfg->n_layers; ++i) OGL_ARG(cfg->dims[i] > 0, "ogl_plan_create: dims[%d] must be positive", i);
   for (int i = 0; i < cfg->n_layers; ++i) OGL_ARG(cfg->fanouts[i] > 0 && cfg->fanouts[i] < 255, "ogl_plan_create: fanouts[%d] must be in [1,254]", i);
   ogl_plan* p = new ogl_plan();
@@ -502,9 +504,14 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
   // f == NULL: the input rows were supplied by ogl_plan_set_input
   if (f && !p->skip_gather)
     STAGE("gather", gather_rows(p->mode, f->table, f->pitch, p->nodes[L], p->counts + L, p->nmax[L], p->act[L], s));
+  const bool drop = p->train_mode && p->cfg.feat_drop > 0.f;
   for (int l = 0; l < L; ++l) {
     LayerBuf& lb = p->layer[l];
     const int h = L - 1 - l, sl = h + 1, dl = h;
+    // feat_drop: the layer's input rows are dropped out once, in place (they feed fc_pool, h_self and the weight gradients alike)
+    if (drop)
+      STAGE(nm("l%d.feat_drop", l).c_str(), feat_drop(p->mode, p->act[sl], lb.pin, lb.in, p->counts + sl, p->nmax[sl], p->cfg.feat_drop,
+                                                      p->cfg.seed, p->ctl + 1, l, s));
     GemmNT g1;
     g1.a[0] = p->act[sl]; g1.lda[0] = lb.pin; g1.b[0] = lb.wp; g1.ldb[0] = lb.pin; g1.k[0] = lb.in; g1.n_seg = 1;
     g1.bias = p->params + lb.o_bp; g1.relu = 1;
@@ -622,7 +629,8 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       d.a[1] = lb.dpre; d.lda[1] = lb.pout; d.b[1] = lb.wsT; d.ldb[1] = lb.pout; d.k[1] = lb.out; d.a_rows_dev[1] = p->counts + dl;
       d.a_rows_max[1] = round_up(p->nmax[dl], 128);
       d.n_seg = 2;
-      d.mask = p->act[sl]; d.ldmask = lb.pin;
+      d.mask = p->act[sl]; d.ldmask = lb.pin;      // (after feat_drop a dropped element is 0 as well: relu' and the keep mask in one)
+      if (p->train_mode && p->cfg.feat_drop > 0.f) d.alpha = 1.f / (1.f - p->cfg.feat_drop);
       d.c = prev.dpre; d.ldc = prev.pout; d.m_max = p->nmax[sl]; d.m_dev = p->counts + sl; d.n = lb.in;
       d.in_bf16 = p->bf16; d.out_bf16 = p->bf16; d.tf32 = p->tf32; d.out_tf32 = p->tf32;
       STAGE(nm("l%d.dx_gemm", l).c_str(), gemm_nt(p, d, s));
@@ -732,12 +740,15 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
     return rb;
   }
   p->skip_gather = (kind == 2 || kind == 3);
+  const int keep_mode = p->train_mode;
+  p->train_mode = 1;                             // a train step: feat_drop on (the reference calls model.train() first, pytorch/model.py:120)
   const int rf = ogl_plan_forward(p, f, nullptr, s);
   p->skip_gather = 0;
-  OGL_TRY(rf);
+  if (rf != OGL_OK) { p->train_mode = keep_mode; return rf; }
   p->tail_mode = (kind == 3) ? 1 : 0;
   p->adam_in_backward = (do_step && kind != 3) ? 1 : 0;
   const int rl = ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s);
+  p->train_mode = keep_mode;
   p->tail_mode = 0;
   p->adam_in_backward = 0;
   OGL_TRY(rl);
@@ -1025,6 +1036,7 @@ extern "C" int ogl_plan_set_option(ogl_plan* p, const char* name, int value) {
   if (strcmp(name, "cuda_graph") == 0) { p->use_graph = value ? 1 : 0; return OGL_OK; }
   if (strcmp(name, "side_stream") == 0) { p->use_side = value ? 1 : 0; return OGL_OK; }
   if (strcmp(name, "pipeline") == 0) { p->use_pipeline = value ? 1 : 0; return OGL_OK; }
+  if (strcmp(name, "train_mode") == 0) { p->train_mode = value ? 1 : 0; return OGL_OK; }
   set_error("ogl_plan_set_option: unknown option '%s'", name);
   return OGL_ERR_ARG;
 }
@@ -1053,7 +1065,11 @@ extern "C" int ogl_plan_eval_step(ogl_plan* p, ogl_graph* g, ogl_features* f, co
   const int64_t* sd = nullptr;
   OGL_TRY(stage_seeds(p, seeds, n_seeds, seeds_on_host, &sd, s));
   OGL_TRY(ogl_plan_sample(p, g, sd, n_seeds, stream));
-  OGL_TRY(ogl_plan_forward(p, f, logits_dev, stream));
+  const int keep_mode = p->train_mode;
+  p->train_mode = 0;                             // evaluation: no dropout (model.eval(), pytorch/model.py:41)
+  const int rfw = ogl_plan_forward(p, f, logits_dev, stream);
+  p->train_mode = keep_mode;
+  OGL_TRY(rfw);
   if (per_vertex_loss_dev) OGL_TRY(plan_loss(p, f, 1.f, 0, per_vertex_loss_dev, nullptr, s));
   OGL_TRY(bump(p->ctl, nullptr, s));
   return OGL_OK;

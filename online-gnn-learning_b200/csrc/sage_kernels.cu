@@ -54,6 +54,32 @@ __global__ void __launch_bounds__(kBlock) k_gather_rows(const T* __restrict__ ta
   }
 }
 
+// ---- feat_drop: dropout of a layer's input rows, in place (training mode) ----------------------------------------------------
+// graphsage_dgl.py:41-46 hands `dropout` to SAGEConv(feat_drop=...): the layer input is dropped ONCE and the same dropped rows
+// feed h_self and fc_pool.  keep(r, c) = philox4x32_10(counter = (c >> 2, r, 0xD0 + layer, optimiser step), key = seed)[c & 3]
+// >= p * 2^32; kept values are scaled by 1 / (1 - p) (torch.nn.Dropout).  oracle/sage.py:dropout_keep is the numpy twin.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_feat_drop(T* __restrict__ x, int pitch, int cols, const int32_t* __restrict__ n_dev, int n_max,
+                                                      uint32_t thresh, float scale, uint2 key, const uint32_t* __restrict__ step_dev,
+                                                      uint32_t layer) {
+  const int n = dyn_count(n_dev, n_max);
+  const int qpr = (cols + 3) >> 2;
+  const uint32_t step = *step_dev;
+  const int64_t total = (int64_t)n * qpr;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / qpr), q = (int)(t % qpr);
+    const uint4 w = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)r, 0xD0u + layer, step), key);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = q * 4 + i;
+      if (c < cols) {
+        T* at = x + (int64_t)r * pitch + c;
+        *at = from_f32<T>(pick4(w, i) >= thresh ? to_f32<T>(*at) * scale : 0.f);
+      }
+    }
+  }
+}
+
 // ---- segment max over the fixed-fanout block (ELL layout), first-slot-wins argmax -----------------
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_segmax_fwd(const T* __restrict__ hp, int pitch, const int32_t* __restrict__ edge_lid, int fanout,
@@ -381,6 +407,17 @@ int gather_rows(int mode, const void* table, int pitch, const int32_t* nodes, co
   L2T(k_gather_rows, grid, s, ARGS((const T*)table, pitch, nodes, n_dev, n_max, (T*)out));
   return OGL_OK;
 }
+int feat_drop(int mode, void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float p, uint64_t seed, const uint32_t* step_dev,
+              int layer, cudaStream_t s) {
+  if (!(p > 0.f)) return OGL_OK;
+  OGL_ARG(p < 1.f, "feat_drop: dropout probability must be in [0, 1)");
+  const uint32_t thresh = (uint32_t)fmin(4294967295.0, floor((double)p * 4294967296.0));
+  const float scale = 1.f / (1.f - p);
+  const uint2 key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  const int grid = grid_for((int64_t)n_max * ((cols + 3) / 4), kBlock, 16);
+  L2T(k_feat_drop, grid, s, ARGS((T*)x, pitch, cols, n_dev, n_max, thresh, scale, key, step_dev, (uint32_t)layer));
+  return OGL_OK;
+}
 int segmax_fwd(int mode, const void* hp, int pitch, const int32_t* edge_lid, int fanout, const int32_t* n_dst_dev, int n_dst_max, void* ng,
                uint8_t* arg, cudaStream_t s) {
   const int grid = grid_for((int64_t)n_dst_max * pitch / 8, kBlock, 16);
@@ -437,3 +474,43 @@ int unpad_copy(const float* src, int lds, int n_rows_max, const int32_t* n_dev, 
 }
 
 }  // namespace ogl
+
+// ---- evaluation metrics on the device (train/graphsage/model.py:60-95: argmax -> confusion matrix -> macro-F1) -----------------
+// one warp per vertex: argmax over the C logits with numpy's tie rule (first maximum), one atomic into cm[label][pred].
+// Labels outside [0, C) (the "unknown" -1 of Elliptic) are skipped and counted in cm[C * C].
+namespace ogl {
+__global__ void __launch_bounds__(kBlock) k_eval_confusion(const float* __restrict__ logits, int ld, int64_t n, int C,
+                                                           const int64_t* __restrict__ labels, unsigned long long* __restrict__ cm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const float* l = logits + r * ld;
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      const float x = l[c];
+      if (x > best || (arg == 0x7fffffff && !(x < best))) { best = x; arg = c; }      // strict >: the first maximum of this lane
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) {
+      const int64_t y = labels[r];
+      if (y >= 0 && y < C && arg < C) atomicAdd(&cm[y * C + arg], 1ull);
+      else atomicAdd(&cm[(int64_t)C * C], 1ull);
+    }
+  }
+}
+}  // namespace ogl
+
+extern "C" int ogl_eval_confusion(const float* logits_dev, int ld, int64_t n, int n_classes, const int64_t* labels_dev,
+                                  int64_t* cm_dev, void* stream) {
+  OGL_TRY(ogl::require_device());
+  OGL_ARG(n >= 0 && n_classes > 0 && ld >= n_classes && cm_dev && (n == 0 || (logits_dev && labels_dev)), "ogl_eval_confusion: bad arguments");
+  if (n == 0) return OGL_OK;
+  OGL_LAUNCH(ogl::k_eval_confusion, ogl::grid_for(n * 32, ogl::kBlock), ogl::kBlock, 0, stream, logits_dev, ld, n, n_classes, labels_dev,
+             (unsigned long long*)cm_dev);
+  return OGL_OK;
+}

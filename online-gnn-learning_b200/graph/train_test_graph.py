@@ -74,10 +74,20 @@ class TrainTestGraph:
         g = self.temporal_graph.get_graph()
         nbrs = {source_node: 1 * self.scale}
         for _ in range(depth):
+            # ONE neighbourhood query per hop for the whole frontier (ogl_graph_gather_rows: the in-edge rows of all frontier
+            # vertices, each in edge-id order) + one degree query for the distinct predecessors; the float accumulation below then
+            # runs in the reference's dict order
+            keys = list(nbrs.keys())
+            offsets, src = g.native.gather_rows(np.asarray(keys, dtype=np.int64))
+            offsets, src = offsets.cpu().numpy(), src.cpu().numpy()
+            uniq = np.unique(src)
+            # out-degree == in-degree: every stream of the reference is symmetrised (DeviceGraph.out_degree)
+            out_deg = dict(zip(uniq.tolist(), g.native.row_degrees(uniq).cpu().tolist())) if len(uniq) else {}
             tmp = {}
-            for k, v in nbrs.items():
-                for nbr in g.predecessors(k).tolist():
-                    w = (1 / g.out_degree(nbr)) * v * self.scale
+            for i, k in enumerate(keys):
+                v = nbrs[k]
+                for nbr in src[offsets[i]:offsets[i + 1]].tolist():
+                    w = (1 / out_deg[nbr]) * v * self.scale
                     if nbr in tmp:
                         tmp[nbr] = min(tmp[nbr] + w, 1)
                     else:

@@ -67,16 +67,29 @@ class SupervisedGraphSage:
         subgraph_to_id = graph_util.get_subgraph_to_original_map()
         graph = graph_util.get_graph()
         vertices = np.asarray(id_to_subgraph[batch_nids], dtype=np.int64)
-        chunks = self._run_custom_eval(graph, subgraph_to_id, id_to_subgraph, vertices)
-        if len(chunks) == 0:
-            return None
-        logits = np.concatenate(chunks)
-        if len(logits) == 0:
-            return None
-        labels = graph.ndata["target"][torch.as_tensor(vertices, device="cuda")].reshape(-1).cpu().numpy()
-        pred = logits.argmax(axis=1)
-        cm = sklearn.metrics.confusion_matrix(labels, pred)
-        f1 = f1_score(labels, pred, average="macro")
+        device_eval = getattr(self, "_eval_logits_device", None)
+        if device_eval is not None and type(self)._run_custom_eval is getattr(type(self), "_base_run_custom_eval", None):
+            # logits never leave the GPU: argmax + confusion matrix in one kernel (ogl_eval_confusion), C x C int64 come back and
+            # the macro-F1 follows from the matrix exactly as sklearn derives it from (labels, predictions) (reference :83-86)
+            from .._native import eval_confusion, macro_f1_from_confusion
+            logits_dev = device_eval(graph, vertices)
+            if logits_dev is None or logits_dev.shape[0] == 0:
+                return None
+            labels_dev = graph.ndata["target"][torch.as_tensor(vertices, device="cuda")].reshape(-1)
+            cm_dev, _ = eval_confusion(logits_dev, labels_dev)
+            f1, cm = macro_f1_from_confusion(cm_dev.cpu().numpy())
+        else:
+            # a subclass overrode the reference's hook (returns host chunks): the reference's own host path
+            chunks = self._run_custom_eval(graph, subgraph_to_id, id_to_subgraph, vertices)
+            if len(chunks) == 0:
+                return None
+            logits = np.concatenate(chunks)
+            if len(logits) == 0:
+                return None
+            labels = graph.ndata["target"][torch.as_tensor(vertices, device="cuda")].reshape(-1).cpu().numpy()
+            pred = logits.argmax(axis=1)
+            cm = sklearn.metrics.confusion_matrix(labels, pred)
+            f1 = f1_score(labels, pred, average="macro")
         if path:
             with open(path, "a+") as f:
                 f.write(self.get_model() + ";" + str(f1) + ";" + str(self.delay) + ";" + str([int(x) for r in cm for x in r]) + "\n")

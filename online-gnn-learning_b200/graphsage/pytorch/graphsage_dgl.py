@@ -4,7 +4,7 @@ SAGEConv('pool') it imports at :3).
 Same constructor, same state_dict keys (`layers.{i}.{fc_pool,fc_self,fc_neigh}.{weight,bias}`,
 cf. inference_optimized.py:135-139), but all parameters are views into ONE flat fp32 buffer that the
 C library's fused kernels (csrc/plan.cu) read and update in place.  `edge_feats` / `pool_feats` are
-accepted and ignored exactly like the reference (graphsage_dgl.py:41-46).
+accepted and ignored exactly like the reference (graphsage_dgl.py:41-46); `dropout` is SAGEConv's feat_drop.
 """
 import math
 
@@ -78,8 +78,9 @@ class GraphSAGE(nn.Module):
     def __init__(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout, aggregator_type,
                  edge_feats=None, pool_feats=None):
         super().__init__()
-        if dropout not in (0, 0.0, None):
-            raise NotImplementedError("every settings/*.json of the reference uses dropout 0; feat_drop is not built")
+        # `dropout` becomes SAGEConv(feat_drop=dropout) (reference :41-46): dropout of every layer's input in training mode, done by
+        # the plan with a Philox-keyed mask (csrc/sage_kernels.cu: k_feat_drop)
+        self.dropout = float(dropout or 0.0)
         self.dims = [in_feats] + [n_hidden] * n_layers + [n_classes]
         self.layers = nn.ModuleList()
         for i in range(len(self.dims) - 1):
@@ -143,7 +144,8 @@ class GraphSAGE(nn.Module):
         key = (id(graph), tuple(hop_fanouts), int(max_seeds), graph.mode, gemm_impl)
         plan = self._plans.get(key)
         if plan is None:
-            plan = Plan(self.dims, hop_fanouts, max_seeds, graph.v_cap, mode=graph.mode, seed=config.seed(), gemm_impl=gemm_impl)
+            plan = Plan(self.dims, hop_fanouts, max_seeds, graph.v_cap, mode=graph.mode, seed=config.seed(), gemm_impl=gemm_impl,
+                        feat_drop=self.dropout)
             plan.bind_params(self._flat, self._flat_grad)
             plan._version = self._version
             self._plans[key] = plan
@@ -168,4 +170,5 @@ class GraphSAGE(nn.Module):
         if plan._version != self._version:
             plan.refresh_params()
             plan._version = self._version
+        plan.set_option("train_mode", int(self.training))      # feat_drop only in training mode, like nn.Dropout
         return _SageFn.apply(x, self, plan, *list(self._ordered_params()))

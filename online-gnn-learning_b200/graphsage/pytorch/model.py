@@ -73,12 +73,13 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
         return self._pin[:v.numel()]
 
     # ---- evaluation (reference :39-71) -------------------------------------------------------------
-    def _run_custom_eval(self, graph, subgraph_to_id, id_to_subgraph, test_vertices):
+    def _eval_logits_device(self, graph, test_vertices):
+        """eval-mode forward over `test_vertices` in batch_full chunks; logits [n, C] stay on the device"""
         self.graphsage_model.eval()
         seeds = self._host_seeds(test_vertices)
         n = seeds.numel()
         if n == 0:
-            return []
+            return None
         plan = self._eval_plan(graph)
         C = self.graphsage_model.dims[-1]
         out = torch.empty(n, C, dtype=torch.float32, device="cuda")
@@ -86,10 +87,20 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
             chunk = seeds[i:i + self.batch_full]
             plan.eval_step(graph.native, graph.features, chunk, logits_out=out[i:i + chunk.numel()])
         self._mark_pin_busy(seeds)
-        host = out.cpu().numpy()
-        if plan.error_flags() & 1:
+        if plan.error_flags() & 1:                       # (synchronises: evaluation reads its result back right after anyway)
             raise IndexError("a vertex id outside the graph was evaluated (DGL's NodeDataLoader raises on such ids)")
-        return [host[i:i + self.batch_full] for i in range(0, n, self.batch_full)]
+        return out
+
+    def _run_custom_eval(self, graph, subgraph_to_id, id_to_subgraph, test_vertices):
+        """the reference's hook (:39-71): a list of host arrays [<= batch_full, C].  _evaluate_vertices itself uses
+        _eval_logits_device + the on-GPU confusion matrix and only falls back to this hook when a subclass overrides it."""
+        out = self._eval_logits_device(graph, test_vertices)
+        if out is None:
+            return []
+        host = out.cpu().numpy()
+        return [host[i:i + self.batch_full] for i in range(0, host.shape[0], self.batch_full)]
+
+    _base_run_custom_eval = _run_custom_eval
 
     # ---- one minibatch -----------------------------------------------------------------------------
     def _fused_step(self, graph, seeds, per_vertex_out=None, loss_sum_out=None):
@@ -126,9 +137,25 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
             self._fused_step(graph, tail, per_vertex_out=None if per_vertex_out is None else per_vertex_out[n_full * batch:])
 
     def train_step(self, graph, blocks, input_nodes, seeds, subgraph_to_id):
-        """DGL-style signature of the reference (:77-107).  The blocks only identify the minibatch: the fused
-        kernels re-derive it from the same Philox counters, so this is one fused step on `seeds`."""
-        self._fused_step(graph, seeds.to("cuda", torch.int64).contiguous())
+        """DGL-style signature of the reference (:77-107): one optimiser step on the minibatch `blocks` describes.  Blocks that were
+        sampled by this trainer's own train plan and are still current (NodeDataLoader(..., plan=self._train_plan(graph))) are
+        trained AS GIVEN -- forward, loss, backward and Adam run over the neighbourhoods those blocks hold; any other blocks
+        (another plan's, or stale ones) cannot be replayed, so a fresh minibatch is sampled for `seeds` and the call says so."""
+        plan = self._train_plan(graph)
+        seeds = seeds.to("cuda", torch.int64).contiguous()
+        blk = blocks[0] if blocks else None
+        if blk is not None and getattr(blk, "_plan", None) is plan and getattr(blk, "_stamp", None) == plan._stamp and \
+                plan.n_seeds == seeds.numel():
+            plan.set_option("train_mode", 1)
+            plan.forward(graph.features, want_logits=False)
+            plan.loss_backward(graph.features, 1.0 / seeds.numel(), want_per_vertex=False)
+            plan.set_option("train_mode", 0)
+            plan.adam_step()
+            self.graphsage_model.mark_updated(plan)
+            self._last_plan = plan
+            return "trained on the given blocks"
+        self._fused_step(graph, seeds)
+        return "resampled"
 
     def _batches(self, vertices, batch):
         seeds = self._host_seeds(vertices)

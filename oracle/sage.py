@@ -115,12 +115,28 @@ def segment_max(hp, edge_src, n_dst, fanout, arg=None):
     return neigh, arg
 
 
-def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, quant=None, arg=None, mask_hp=None, mask_out=None):
+def dropout_keep(n_rows, n_cols, p, seed, step, layer):
+    """keep mask [n_rows, n_cols] (bool) of the product's feat_drop (csrc/sage_kernels.cu: k_feat_drop):
+    keep(r, c) = philox4x32_10(counter = (c >> 2, r, 0xD0 + layer, optimiser step), key = seed)[c & 3] >= floor(p * 2^32)"""
+    import numpy as np
+    from .philox import philox4x32, split_seed
+    k0, k1 = split_seed(seed)
+    q = (n_cols + 3) // 4
+    w = philox4x32(np.arange(q, dtype=np.uint64)[None, :], np.arange(n_rows, dtype=np.uint64)[:, None], 0xD0 + layer, step, k0, k1)
+    words = np.stack(w, axis=-1).reshape(n_rows, 4 * q)[:, :n_cols]
+    thresh = min(4294967295, int(math.floor(float(np.float32(p)) * 4294967296.0)))
+    return torch.from_numpy(words.astype(np.int64) >= thresh)
+
+
+def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, quant=None, arg=None, mask_hp=None, mask_out=None, drop=None):
     """``mask_hp`` / ``mask_out`` (bool, optional) replace the two ReLUs by a fixed on/off pattern: together with ``arg`` they pin
     the piecewise-linear region in which the layer is evaluated (oracle/parity.py: the device's region, to compare gradients
     without the jumps that a sign or an argmax decided inside rounding error causes)."""
     q = _Q.apply if quant else (lambda t: t)
     qf = _Qf.apply if quant else (lambda t: t)
+    if drop is not None:                       # SAGEConv's feat_drop: (keep mask, 1 / (1 - p)) on the layer input, once
+        keep, scale = drop
+        x = q(torch.where(keep, x * scale, torch.zeros((), dtype=x.dtype)))
     hp_pre = x @ qf(Wp).t() + bp
     hp = q(torch.relu(hp_pre) if mask_hp is None else torch.where(mask_hp, hp_pre, torch.zeros((), dtype=hp_pre.dtype)))
     neigh, arg = segment_max(hp, edge_src, n_dst, fanout, arg=arg)
@@ -146,7 +162,7 @@ def forward(params, x_in, blocks, quant=None):
         h, it = sage_layer(h, b["n_dst"], b["edge_src"], b["fanout"],
                            g("fc_pool.weight"), g("fc_pool.bias"), g("fc_self.weight"), g("fc_self.bias"),
                            g("fc_neigh.weight"), g("fc_neigh.bias"), relu_out=(i < L - 1), quant=quant, arg=b.get("arg"),
-                           mask_hp=b.get("mask_hp"), mask_out=b.get("mask_out"))
+                           mask_hp=b.get("mask_hp"), mask_out=b.get("mask_out"), drop=b.get("drop"))
         it["out"] = h
         inter.append(it)
     return h, inter

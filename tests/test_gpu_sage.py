@@ -437,3 +437,49 @@ def test_multi_step_call_equals_single_steps():
     close(runs[0][1], runs[1][1], 1e-4, "per-vertex losses")
     close(runs[0][2], runs[1][2], 1e-4, "loss sums")
     close(runs[0][1].view(5, 32).sum(1), runs[0][2], 1e-5, "loss sum == sum of per-vertex losses")
+
+
+@pytest.mark.parametrize("mode,gemm_impl,rtol", [("fp32", 1, 1e-5), ("tf32", 0, 2e-3), ("bf16", 0, 2e-2)])
+def test_feat_drop_matches_the_oracle_mask(mode, gemm_impl, rtol):
+    """SAGEConv(feat_drop=p) (graphsage_dgl.py:41-46): every layer's input is dropped once in training mode with the Philox-keyed
+    mask of oracle/sage.py:dropout_keep, scaled by 1 / (1 - p); evaluation is untouched"""
+    p_drop = 0.3
+    c = Case(dims=(48, 24, 5), fanouts=(6, 4), n_seeds=96, mode=mode, gemm_impl=gemm_impl)
+    plan = c.ogl.native.Plan(c.dims, c.fanouts, 96, c.V, mode=c.mode, seed=11, gemm_impl=gemm_impl, feat_drop=p_drop)
+    grad = torch.zeros_like(c.flat)
+    plan.bind_params(c.flat, grad)
+    c.plan = plan
+    seeds_dev = torch.as_tensor(c.seeds).cuda()
+    # evaluation mode: identical to a plan without dropout
+    plan.sample(c.g, seeds_dev)
+    logits_eval = plan.forward(c.f)
+    _, _, logits_ref, _, _ = c.run_oracle()
+    close(logits_eval, logits_ref, rtol, "eval-mode logits")
+    # training mode (optimiser step 0)
+    plan.set_option("train_mode", 1)
+    plan.sample(c.g, seeds_dev)
+    logits = plan.forward(c.f)
+    per, _ = plan.loss_backward(c.f, 1.0 / len(c.seeds))
+    x_in, blocks = c.oracle_blocks()
+    for l, b in enumerate(blocks):
+        n_src = c.plan.level_nodes(c.L - l).numel()
+        keep = osage.dropout_keep(n_src, c.dims[l], p_drop, 11, 0, l)
+        assert 0.6 < keep.double().mean().item() < 0.8
+        b["drop"] = (keep, 1.0 / (1.0 - float(np.float32(p_drop))))
+    labels = c.labels[torch.as_tensor(c.seeds)]
+    _, per_ref, logits_ref2, grads_ref, _ = osage.loss_and_grads(c.params, x_in, blocks, labels, quant=c.quant, dtype=torch.float64)
+    assert (logits_ref2 - logits_ref).abs().max().item() > 0.05           # dropout did something
+    close(logits, logits_ref2, rtol, "train-mode logits")
+    close(per, per_ref, rtol, "train-mode losses")
+    got = dict_from_flat(grad, c.dims)
+    for k, v in grads_ref.items():
+        if mode == "fp32":
+            close(got[k], v, rtol, "grad " + k)
+        else:
+            close_bf16_grad(got[k], v, "grad " + k)
+    # the fused train step applies it too (same optimiser step -> same mask)
+    plan.set_option("train_mode", 0)
+    plan.set_step(0)
+    per2 = torch.empty(len(c.seeds), device="cuda")
+    plan.train_step(c.g, c.f, seeds_dev, loss_scale=1.0 / len(c.seeds), do_step=False, per_vertex_out=per2)
+    close(per2, per, 1e-5 if mode == "fp32" else 1e-4, "fused step losses")

@@ -135,3 +135,46 @@ def test_vertex_stream_training_and_next_snapshot_eval(tmp_path):
         assert os.path.getsize(out) > 0
     finally:
         ttg.SIZE_BUFFER = old
+
+
+def test_train_step_honours_the_blocks_it_is_given():
+    """the reference's train_step(graph, blocks, input_nodes, seeds, ...) trains on the minibatch the loader produced
+    (pytorch/model.py:77-107): blocks sampled by the trainer's own plan are trained as given, stale / foreign blocks are resampled"""
+    import ogl_b200
+    from ogl_b200.sampling import MultiLayerNeighborSampler, NodeDataLoader
+    ogl_b200.config.set_precision("fp32")
+    try:
+        V, E, F, C, H = 700, 6000, 10, 3, 12
+        src, dst, x, y = _planted(V, E, F, C, seed=3)
+        dg = ogl_b200.DeviceGraph(V, 2 * E, F)
+        dg.add_nodes(V, {"feat": x, "target": y})
+        dg.add_edges(src, dst, symmetric=True)
+        GraphSAGE, RandomT, _, _, _, act = ogl_b200.init(ogl_b200.Lib_supported.PYTORCH, True, -1)
+        torch.manual_seed(1)
+        model = GraphSAGE(F, H, C, 1, act, 0, "pool").cuda()
+        t = RandomT(model, 1, 32, y, 5, cuda=True, batch_full=64, n_workers=0)
+        t.build_optimizer()
+        plan = t._train_plan(dg)
+        loader = NodeDataLoader(dg, np.arange(64), MultiLayerNeighborSampler([5, 5]), batch_size=32, plan=plan)
+        it = iter(loader)
+        input_nodes, seeds, blocks = next(it)
+        before = model._flat.clone()
+        frontier = plan.level_nodes(2).clone()
+        # the oracle's loss gradient on exactly these blocks = the direction Adam's first step takes
+        assert t.train_step(dg, blocks, input_nodes, seeds, None) == "trained on the given blocks"
+        assert torch.equal(plan.level_nodes(2), frontier), "the given minibatch was resampled"
+        step1 = model._flat - before
+        assert float(step1.abs().max()) > 0
+        from oracle import sage as osage
+        params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        ob = [dict(n_dst=b.number_of_dst_nodes(), edge_src=b._lid.long().cpu(), fanout=b.fanout) for b in blocks]
+        p0 = {k: before[o:o + v.numel()].view(v.shape).cpu() for (k, v), o in zip(params.items(), np.cumsum([0] + [v.numel() for v in params.values()])[:-1])}
+        _, _, _, gref, _ = osage.loss_and_grads(p0, torch.as_tensor(x)[input_nodes.cpu()], ob, torch.as_tensor(y)[seeds.cpu()].flatten(), dtype=torch.float64)
+        gflat = torch.cat([gref[k].reshape(-1) for k in params])
+        big = gflat.abs() > 1e-3 * gflat.abs().max()
+        assert bool((torch.sign(step1.cpu().double()[big]) == -torch.sign(gflat[big])).all()), "first Adam step is not along -grad of the given blocks"
+        # stale blocks (the plan has sampled another minibatch since) are not replayable
+        next(it)
+        assert t.train_step(dg, blocks, input_nodes, seeds, None) == "resampled"
+    finally:
+        ogl_b200.config.set_precision("bf16")
