@@ -280,6 +280,153 @@ __global__ void __launch_bounds__(1024) k_fix_big(const int32_t* __restrict__ to
   }
 }
 
+// ---- the streaming regime: one snapshot = ONE kernel ------------------------------------------------------------------------
+// The reference appends ~10^4 edges per evolve() (settings/reddit.json: 57.3 M stream edges over 5000 snapshots,
+// dynamic_graph_edge.py:190-218).  At that size the seven-kernel sequence above is pure launch latency (nine launches and two
+// memsets for < 1 MB of traffic), so batches of <= kFuseMaxEdges directed edges run through one cooperative kernel whose phases
+// are separated by a grid barrier in global memory: count -> need (+ capacity / id check: on failure nothing is changed and the
+// host takes the general path) -> reserve + relocate (one warp per touched row) -> place -> order the tails (one warp per row;
+// tails beyond kMedTail are left to k_fix_big).  Same results as the general path, bit for bit (rows end in edge-id order).
+constexpr int kFuseMaxEdges = 1 << 16;
+constexpr int kFuseWarpCopyMax = 1 << 14;
+
+__device__ __forceinline__ void grid_barrier(GraphCtl* ctl, unsigned int n_blocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    volatile unsigned int* gen = &ctl->bar_gen;
+    const unsigned int g = *gen;
+    if (atomicAdd(&ctl->bar_count, 1u) == n_blocks - 1) {
+      ctl->bar_count = 0;
+      __threadfence();
+      atomicAdd(&ctl->bar_gen, 1u);
+    } else {
+      while (*gen == g) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlock) k_insert_fused(BatchEdges b, int32_t* __restrict__ add, int32_t* __restrict__ touched,
+                                                         int64_t* __restrict__ row_start, int32_t* __restrict__ deg, int32_t* __restrict__ cap,
+                                                         int32_t* __restrict__ tail_len, unsigned long long* __restrict__ adj,
+                                                         MoveJob* __restrict__ jobs, int* __restrict__ n_jobs, int jobs_cap,
+                                                         int32_t* __restrict__ large, GraphCtl* ctl, int64_t n_vertices, uint32_t eid_base,
+                                                         long long pool_cap) {
+  __shared__ unsigned long long keys[kBlock / 32][kMedTail];
+  const int64_t tot = b.total();
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int gwarp = (int)(tid >> 5), nwarps = (int)(nthreads >> 5);
+  // ---- 1: per-row counts of the batch, list of touched rows
+  for (int64_t i = tid; i < tot; i += nthreads) {
+    int64_t s, d;
+    b.get(i, s, d);
+    if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) { ctl->bad_id = 1; continue; }
+    if (atomicAdd(&add[d], 1) == 0) touched[atomicAdd(&ctl->n_touched, 1)] = (int32_t)d;
+  }
+  grid_barrier(ctl, gridDim.x);
+  const int nt = ctl->n_touched;
+  // ---- 2: pool slots the batch needs; bail out untouched if they are not there (or an id was bad)
+  {
+    unsigned long long local = 0;
+    for (int t = (int)tid; t < nt; t += (int)nthreads) {
+      const int v = touched[t];
+      const int need = deg[v] + add[v];
+      if (need > cap[v]) local += (unsigned long long)grow_cap(need);
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&ctl->need, local);
+  }
+  grid_barrier(ctl, gridDim.x);
+  if (ctl->bad_id || (long long)(ctl->pool_top + ctl->need) > pool_cap) {
+    for (int t = (int)tid; t < nt; t += (int)nthreads) add[touched[t]] = 0;
+    if (tid == 0) ctl->overflow = 1;
+    return;                                        // (uniform: every CTA reads the same values after the barrier)
+  }
+  // ---- 3: claim tails; rows without slack move to the pool top with doubled capacity (one warp per touched row)
+  for (int q = gwarp; q < nt; q += nwarps) {
+    const int v = touched[q];
+    const int a = add[v], d = deg[v];
+    if (lane == 0) tail_len[q] = a;
+    const int need = d + a;
+    if (need > cap[v]) {
+      const int nc = grow_cap(need);
+      unsigned long long off = 0;
+      if (lane == 0) off = atomicAdd(&ctl->pool_top, (unsigned long long)nc);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      const int64_t old = row_start[v];
+      if (d <= kFuseWarpCopyMax) {
+        for (int i = lane; i < d; i += 32) adj[off + i] = adj[old + i];
+      } else if (lane == 0) {
+        jobs[jobs_cap - 1 - atomicAdd(n_jobs + 1, 1)] = MoveJob{(long long)old, (long long)off, d, 0};     // a hub row: every CTA helps below
+      }
+      __syncwarp();
+      if (lane == 0) {
+        row_start[v] = (int64_t)off;
+        cap[v] = nc;
+        atomicAdd(&ctl->relocations, 1ull);
+      }
+    }
+  }
+  grid_barrier(ctl, gridDim.x);
+  // ---- 4: hub rows queued above (they write [new, new + deg), the placement below writes behind that: no conflict)
+  {
+    const int nb = n_jobs[1];
+    for (int q = 0; q < nb; ++q) {
+      const MoveJob j = jobs[jobs_cap - 1 - q];
+      for (int64_t i = tid; i < j.len; i += nthreads) adj[j.to + i] = adj[j.from + i];
+    }
+  }
+  // ---- 5: place every edge in a slot of its row's tail (arbitrary order inside the tail)
+  for (int64_t i = tid; i < tot; i += nthreads) {
+    int64_t s, d;
+    b.get(i, s, d);
+    const int p = atomicSub(&add[d], 1) - 1;        // add[] is back at zero when this phase ends
+    adj[row_start[d] + deg[d] + p] = ((unsigned long long)(eid_base + (uint32_t)i) << 32) | (uint32_t)s;
+  }
+  grid_barrier(ctl, gridDim.x);
+  // ---- 6: every tail into ascending edge-id order, then the degrees (one warp per touched row)
+  unsigned long long* sk = keys[w];
+  for (int q = gwarp; q < nt; q += nwarps) {
+    const int v = touched[q];
+    const int L = tail_len[q];
+    const int64_t base = row_start[v] + deg[v];
+    if (L <= 1) {
+      if (lane == 0 && L == 1) deg[v] += 1;
+    } else if (L <= 32) {
+      const unsigned long long ent = lane < L ? adj[base + lane] : ~0ull;
+      const uint32_t e = (uint32_t)(ent >> 32);
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+        rank += (j < L && ej < e) ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane < L) adj[base + rank] = ent;
+      __syncwarp();
+      if (lane == 0) deg[v] += L;
+    } else if (L <= kMedTail) {
+      int P = 64;
+      while (P < L) P <<= 1;
+      for (int i = lane; i < P; i += 32) sk[i] = i < L ? adj[base + i] : ~0ull;
+      __syncwarp();
+      for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < P; i += 32) bitonic_step(sk, i, j, k);
+          __syncwarp();
+        }
+      for (int i = lane; i < L; i += 32) adj[base + i] = sk[i];
+      __syncwarp();
+      if (lane == 0) deg[v] += L;
+    } else if (lane == 0) {
+      large[atomicAdd(&ctl->n_large, 1)] = q;       // ordered by k_fix_big, launched by the host when the count is not zero
+    }
+  }
+}
+
 // ---- compaction / growth: rewrite all rows into a fresh pool ---------------------------------
 __global__ void __launch_bounds__(kBlock) k_newcap(const int32_t* __restrict__ deg, const int32_t* __restrict__ add,
                                                    int32_t* __restrict__ newcap, int64_t n) {
@@ -400,6 +547,7 @@ struct ogl_graph {
   int64_t p_v = 0, p_e = 0;
   int64_t pool_used_host = 0, relocations = 0, compactions = 0;
   uint64_t generation = 1;
+  int fuse_small = 1;                    // snapshot-sized batches go through the single cooperative kernel (OGL_INSERT_FUSED=0: off)
 };
 
 static int graph_alloc_pool(ogl_graph* g, int64_t cap) {
@@ -415,6 +563,7 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
   OGL_ARG(v_cap < 0x7fffffffLL, "ogl_graph_create: v_cap must fit int32");
   ogl_graph* g = new ogl_graph();
   g->v_cap = v_cap;
+  if (const char* e = getenv("OGL_INSERT_FUSED")) g->fuse_small = atoi(e) != 0;
   g->batch_cap = 1 << 21;
   const int64_t pool = e_cap_directed * 3 + 1024;   // slack rows (x2) + relocation holes
   int r = graph_alloc_pool(g, pool);
@@ -497,12 +646,57 @@ static int graph_rebuild_pool(ogl_graph* g, int64_t extra, cudaStream_t s) {
   return OGL_OK;
 }
 
+// one snapshot-sized batch through the single cooperative kernel; *done = 0 when the pool has no room (the general path rebuilds it)
+static int graph_insert_fused(ogl_graph* g, const BatchEdges& b, int64_t tot, cudaStream_t s, int* done) {
+  static int max_blocks = 0;
+  if (max_blocks == 0) {
+    int per_sm = 0;
+    OGL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_insert_fused, kBlock, 0));
+    max_blocks = per_sm * sm_count();
+    if (max_blocks < 1) max_blocks = -1;
+  }
+  *done = 0;
+  if (max_blocks < 0) return OGL_OK;
+  int grid = (int)ceil_div(tot, 2 * kBlock);
+  if (grid < 8) grid = 8;
+  if (grid > 64) grid = 64;                       // a barrier over few CTAs is cheap; 64 x 256 threads cover 2^16 edges in 4 rounds
+  if (grid > max_blocks) grid = max_blocks;
+  OGL_CUDA(cudaMemsetAsync(&g->ctl->n_touched, 0, sizeof(GraphCtl) - offsetof(GraphCtl, n_touched), s));
+  OGL_CUDA(cudaMemsetAsync(g->n_jobs, 0, 2 * sizeof(int), s));
+  BatchEdges bb = b;
+  int64_t nv = g->n_vertices;
+  uint32_t eid_base = (uint32_t)g->n_edges;
+  long long pool_cap = g->pool_cap;
+  void* args[] = {&bb, &g->add, &g->touched, &g->row_start, &g->deg, &g->cap, &g->tail_len, &g->adj, &g->jobs, &g->n_jobs, &g->jobs_cap,
+                  &g->large, &g->ctl, &nv, &eid_base, &pool_cap};
+  OGL_CUDA(cudaLaunchCooperativeKernel((const void*)k_insert_fused, dim3((unsigned)grid), dim3(kBlock), args, 0, s));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  OGL_CUDA(cudaMemcpyAsync(g->h_ctl, g->ctl, sizeof(GraphCtl), cudaMemcpyDeviceToHost, s));
+  OGL_CUDA(cudaStreamSynchronize(s));
+  if (g->h_ctl->bad_id) {                         // (the kernel changed nothing)
+    set_error("ogl_graph_insert_edges: vertex id out of range [0, %lld) (call insert_vertices first)", (long long)g->n_vertices);
+    return OGL_ERR_ARG;
+  }
+  if (g->h_ctl->overflow) return OGL_OK;
+  if (g->h_ctl->n_large > 0)
+    OGL_LAUNCH(k_fix_big, sm_count() * 2, 1024, kBigTail * sizeof(unsigned long long), s, g->touched, g->tail_len, g->row_start, g->deg,
+               g->adj, g->scr, g->large, g->ctl);
+  g->n_edges += tot;
+  *done = 1;
+  return OGL_OK;
+}
+
 static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_t* dst_dev, int64_t n, int symmetric, cudaStream_t s) {
   BatchEdges b{src_dev, dst_dev, n, symmetric};
   const int64_t tot = symmetric ? 2 * n : n;
   if (g->n_edges + tot > 0xffffffffLL) {
     set_error("ogl_graph_insert_edges: edge ids exceed 32 bits");
     return OGL_ERR_CAPACITY;
+  }
+  if (tot <= kFuseMaxEdges && g->fuse_small) {
+    int done = 0;
+    OGL_TRY(graph_insert_fused(g, b, tot, s, &done));
+    if (done) return OGL_OK;
   }
   // reset the per-batch counters (pool_top / relocations persist)
   OGL_CUDA(cudaMemsetAsync(&g->ctl->n_touched, 0, sizeof(GraphCtl) - offsetof(GraphCtl, n_touched), s));

@@ -226,3 +226,44 @@ def test_predecessors_and_change_propagation():
         for k, val in tmp.items():
             nbrs[k] = max(nbrs[k], val) if k in nbrs else val
     assert got == nbrs
+
+
+def test_fused_snapshot_insert_equals_general_path(monkeypatch):
+    """snapshot-sized batches run through ONE cooperative kernel (k_insert_fused); the result must be the general multi-kernel
+    path's, bit for bit: same CSR, same edge ids -- including a hub row of > 2^14 edges that relocates inside a small batch (queued
+    copy swept by all CTAs), tails of every size class, a bad id (nothing changes) and pool exhaustion (fallback + rebuild)"""
+    import ogl_b200
+    V = 4000
+    rng = np.random.default_rng(11)
+    hub = 5
+    # a big first batch makes vertex 5 a hub (general path), then 60 snapshots of 3000 stream edges, 20 % of them on the hub
+    first = (rng.integers(0, V, 70000).astype(np.int64), np.full(70000, hub, dtype=np.int64))
+    snaps = []
+    for k in range(60):
+        s = rng.integers(0, V, 3000).astype(np.int64)
+        d = np.where(rng.random(3000) < 0.2, hub, (rng.random(3000) ** 3 * V).astype(np.int64)).astype(np.int64)
+        snaps.append((s, d))
+    out = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("OGL_INSERT_FUSED", fused)
+        dg = ogl_b200.native.Graph(V, 600000)
+        dg.insert_vertices(V)
+        dg.insert_edges(torch.as_tensor(first[0]).cuda(), torch.as_tensor(first[1]).cuda(), symmetric=False)
+        launches = ogl_b200.kernel_launches()
+        for s, d in snaps:
+            dg.insert_edges(torch.as_tensor(s).cuda(), torch.as_tensor(d).cuda(), symmetric=True)
+        per_snapshot = (ogl_b200.kernel_launches() - launches) / len(snaps)
+        bad = torch.as_tensor(np.array([1, 2, V + 3], dtype=np.int64)).cuda()
+        with pytest.raises(Exception):
+            dg.insert_edges(bad, bad, symmetric=True)
+        s, d = snaps[0]
+        dg.insert_edges(torch.as_tensor(s).cuda(), torch.as_tensor(d).cuda(), symmetric=True)      # still usable after the error
+        out.append([t.cpu() for t in dg.export_csr()] + [per_snapshot, dg.stats()["relocations"]])
+    for a, b in zip(out[0][:3], out[1][:3]):
+        assert torch.equal(a, b)
+    assert out[0][3] <= 2.1 and out[1][3] >= 9, (out[0][3], out[1][3])          # launches per snapshot: fused vs general
+    assert out[0][4] == out[1][4] and out[0][4] > 0
+    es = np.concatenate([first[0]] + [np.concatenate([s, d]) for s, d in snaps] + [np.concatenate(snaps[0])])
+    ed = np.concatenate([first[1]] + [np.concatenate([d, s]) for s, d in snaps] + [np.concatenate(snaps[0][::-1])])
+    dg2 = dg
+    _check(dg2, es, ed, V)
