@@ -285,8 +285,7 @@ __global__ void __launch_bounds__(1024) k_fix_big(const int32_t* __restrict__ to
 // dynamic_graph_edge.py:190-218).  At that size the seven-kernel sequence above is pure launch latency (nine launches and two
 // memsets for < 1 MB of traffic), so batches of <= kFuseMaxEdges directed edges run through one cooperative kernel whose phases
 // are separated by a grid barrier in global memory: count -> need (+ capacity / id check: on failure nothing is changed and the
-// host takes the general path) -> reserve + relocate (one warp per touched row) -> place -> order the tails (one warp per row;
-// tails beyond kMedTail are left to k_fix_big).  Same results as the general path, bit for bit (rows end in edge-id order).
+// host takes the general path) -> reserve + relocate -> place -> order the tails (tails beyond kMedTail are left to k_fix_big).  Same results as the general path, bit for bit (rows end in edge-id order).
 constexpr int kFuseMaxEdges = 1 << 16;
 constexpr int kFuseWarpCopyMax = 1 << 14;
 
@@ -308,12 +307,28 @@ __device__ __forceinline__ void grid_barrier(GraphCtl* ctl, unsigned int n_block
   __syncthreads();
 }
 
+// what the host needs to know about a fused insert, written by the kernel straight into pinned host memory (the host spins on
+// `seq` instead of paying a D2H copy + stream synchronisation per snapshot)
+struct FusedStatus { volatile unsigned int seq; volatile int bad_id, overflow, n_large; };
+
+__device__ __forceinline__ void fused_finish(GraphCtl* ctl, int* n_jobs, FusedStatus* st, unsigned int seq, int failed) {
+  // every CTA is past its last read of the per-batch counters (grid barrier before this): publish, then leave them zeroed for
+  // the next call (n_large stays for k_fix_big when it is not zero; the host clears it after that launch)
+  st->bad_id = ctl->bad_id;
+  st->overflow = failed;
+  st->n_large = ctl->n_large;
+  ctl->n_touched = 0; ctl->bad_id = 0; ctl->n_med = 0; ctl->n_small = 0; ctl->overflow = 0; ctl->need = 0; ctl->scratch_top = 0;
+  n_jobs[0] = 0; n_jobs[1] = 0;
+  __threadfence_system();
+  st->seq = seq;
+}
+
 __global__ void __launch_bounds__(kBlock) k_insert_fused(BatchEdges b, int32_t* __restrict__ add, int32_t* __restrict__ touched,
                                                          int64_t* __restrict__ row_start, int32_t* __restrict__ deg, int32_t* __restrict__ cap,
                                                          int32_t* __restrict__ tail_len, unsigned long long* __restrict__ adj,
                                                          MoveJob* __restrict__ jobs, int* __restrict__ n_jobs, int jobs_cap,
                                                          int32_t* __restrict__ large, GraphCtl* ctl, int64_t n_vertices, uint32_t eid_base,
-                                                         long long pool_cap) {
+                                                         long long pool_cap, FusedStatus* status, unsigned int seq) {
   __shared__ unsigned long long keys[kBlock / 32][kMedTail];
   const int64_t tot = b.total();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -342,31 +357,62 @@ __global__ void __launch_bounds__(kBlock) k_insert_fused(BatchEdges b, int32_t* 
   grid_barrier(ctl, gridDim.x);
   if (ctl->bad_id || (long long)(ctl->pool_top + ctl->need) > pool_cap) {
     for (int t = (int)tid; t < nt; t += (int)nthreads) add[touched[t]] = 0;
-    if (tid == 0) ctl->overflow = 1;
-    return;                                        // (uniform: every CTA reads the same values after the barrier)
+    grid_barrier(ctl, gridDim.x);                  // (uniform: every CTA read the same values after the barrier above)
+    if (tid == 0) fused_finish(ctl, n_jobs, status, seq, 1);
+    return;
   }
-  // ---- 3: claim tails; rows without slack move to the pool top with doubled capacity (one warp per touched row)
-  for (int q = gwarp; q < nt; q += nwarps) {
-    const int v = touched[q];
-    const int a = add[v], d = deg[v];
-    if (lane == 0) tail_len[q] = a;
-    const int need = d + a;
-    if (need > cap[v]) {
-      const int nc = grow_cap(need);
-      unsigned long long off = 0;
-      if (lane == 0) off = atomicAdd(&ctl->pool_top, (unsigned long long)nc);
-      off = __shfl_sync(0xffffffffu, off, 0);
-      const int64_t old = row_start[v];
-      if (d <= kFuseWarpCopyMax) {
-        for (int i = lane; i < d; i += 32) adj[off + i] = adj[old + i];
-      } else if (lane == 0) {
-        jobs[jobs_cap - 1 - atomicAdd(n_jobs + 1, 1)] = MoveJob{(long long)old, (long long)off, d, 0};     // a hub row: every CTA helps below
-      }
-      __syncwarp();
-      if (lane == 0) {
+  // ---- 3: claim tails; rows without slack move to the pool top with doubled capacity.  One THREAD per touched row (the row
+  //         metadata is a chain of dependent loads: a warp per row would serialise ~60 of them); a row that must move more than
+  //         kThreadCopyMax entries is then copied by its whole warp, hub rows are queued for every CTA
+  for (int q0 = (int)(tid - lane); q0 < nt; q0 += (int)nthreads) {
+    const int q = q0 + lane;
+    int d = 0, nc = 0;
+    int64_t old = 0;
+    unsigned long long off = 0;
+    bool warp_copy = false;
+    if (q < nt) {
+      const int v = touched[q];
+      const int a = add[v];
+      d = deg[v];
+      tail_len[q] = a;
+      const int need = d + a;
+      if (need > cap[v]) {
+        nc = grow_cap(need);
+        off = atomicAdd(&ctl->pool_top, (unsigned long long)nc);
+        old = row_start[v];
+        if (d <= kThreadCopyMax) {
+          for (int i = 0; i < d; ++i) adj[off + i] = adj[old + i];
+        } else if (d <= kFuseWarpCopyMax) {
+          warp_copy = true;
+        } else {
+          jobs[jobs_cap - 1 - atomicAdd(n_jobs + 1, 1)] = MoveJob{(long long)old, (long long)off, d, 0};   // a hub row: every CTA helps below
+        }
         row_start[v] = (int64_t)off;
         cap[v] = nc;
-        atomicAdd(&ctl->relocations, 1ull);
+      }
+    }
+    const unsigned moved = __ballot_sync(0xffffffffu, nc > 0);
+    if (lane == 0 && moved) atomicAdd(&ctl->relocations, (unsigned long long)__popc(moved));
+    unsigned todo = __ballot_sync(0xffffffffu, warp_copy);
+    while (todo) {
+      const int src_lane = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int dd = __shfl_sync(0xffffffffu, d, src_lane);
+      const long long from = __shfl_sync(0xffffffffu, (long long)old, src_lane);
+      const unsigned long long to = __shfl_sync(0xffffffffu, off, src_lane);
+      // eight independent loads in flight per lane (a plain copy loop is one L2 round trip per 32 entries)
+      for (int i0 = 0; i0 < dd; i0 += 256) {
+        unsigned long long u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = i0 + k * 32 + lane;
+          u[k] = i < dd ? adj[from + i] : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = i0 + k * 32 + lane;
+          if (i < dd) adj[to + i] = u[k];
+        }
       }
     }
   }
@@ -387,44 +433,56 @@ __global__ void __launch_bounds__(kBlock) k_insert_fused(BatchEdges b, int32_t* 
     adj[row_start[d] + deg[d] + p] = ((unsigned long long)(eid_base + (uint32_t)i) << 32) | (uint32_t)s;
   }
   grid_barrier(ctl, gridDim.x);
-  // ---- 6: every tail into ascending edge-id order, then the degrees (one warp per touched row)
+  // ---- 6: every tail into ascending edge-id order, then the degrees.  One thread per touched row again: tails of one edge (the
+  //         common case) are finished by the thread; longer ones are ordered by the whole warp, one after the other
   unsigned long long* sk = keys[w];
-  for (int q = gwarp; q < nt; q += nwarps) {
-    const int v = touched[q];
-    const int L = tail_len[q];
-    const int64_t base = row_start[v] + deg[v];
-    if (L <= 1) {
-      if (lane == 0 && L == 1) deg[v] += 1;
-    } else if (L <= 32) {
-      const unsigned long long ent = lane < L ? adj[base + lane] : ~0ull;
-      const uint32_t e = (uint32_t)(ent >> 32);
-      int rank = 0;
+  for (int q0 = (int)(tid - lane); q0 < nt; q0 += (int)nthreads) {
+    const int q = q0 + lane;
+    int v = 0, L = 0;
+    int64_t base = 0;
+    if (q < nt) {
+      v = touched[q];
+      L = tail_len[q];
+      base = row_start[v] + deg[v];
+      if (L == 1) deg[v] += 1;
+      else if (L > kMedTail) large[atomicAdd(&ctl->n_large, 1)] = q;      // ordered by k_fix_big, launched by the host when the count is not zero
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, L > 1 && L <= kMedTail);
+    while (todo) {
+      const int src_lane = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int Lw = __shfl_sync(0xffffffffu, L, src_lane);
+      const int vw = __shfl_sync(0xffffffffu, v, src_lane);
+      const long long bw = __shfl_sync(0xffffffffu, (long long)base, src_lane);
+      if (Lw <= 32) {
+        const unsigned long long ent = lane < Lw ? adj[bw + lane] : ~0ull;
+        const uint32_t e = (uint32_t)(ent >> 32);
+        int rank = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
-        rank += (j < L && ej < e) ? 1 : 0;
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+          rank += (j < Lw && ej < e) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane < Lw) adj[bw + rank] = ent;
+      } else {
+        int P = 64;
+        while (P < Lw) P <<= 1;
+        for (int i = lane; i < P; i += 32) sk[i] = i < Lw ? adj[bw + i] : ~0ull;
+        __syncwarp();
+        for (int k = 2; k <= P; k <<= 1)
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P; i += 32) bitonic_step(sk, i, j, k);
+            __syncwarp();
+          }
+        for (int i = lane; i < Lw; i += 32) adj[bw + i] = sk[i];
       }
       __syncwarp();
-      if (lane < L) adj[base + rank] = ent;
-      __syncwarp();
-      if (lane == 0) deg[v] += L;
-    } else if (L <= kMedTail) {
-      int P = 64;
-      while (P < L) P <<= 1;
-      for (int i = lane; i < P; i += 32) sk[i] = i < L ? adj[base + i] : ~0ull;
-      __syncwarp();
-      for (int k = 2; k <= P; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = lane; i < P; i += 32) bitonic_step(sk, i, j, k);
-          __syncwarp();
-        }
-      for (int i = lane; i < L; i += 32) adj[base + i] = sk[i];
-      __syncwarp();
-      if (lane == 0) deg[v] += L;
-    } else if (lane == 0) {
-      large[atomicAdd(&ctl->n_large, 1)] = q;       // ordered by k_fix_big, launched by the host when the count is not zero
+      if (lane == 0) deg[vw] += Lw;
     }
   }
+  grid_barrier(ctl, gridDim.x);
+  if (tid == 0) fused_finish(ctl, n_jobs, status, seq, 0);
 }
 
 // ---- compaction / growth: rewrite all rows into a fresh pool ---------------------------------
@@ -548,6 +606,9 @@ struct ogl_graph {
   int64_t pool_used_host = 0, relocations = 0, compactions = 0;
   uint64_t generation = 1;
   int fuse_small = 1;                    // snapshot-sized batches go through the single cooperative kernel (OGL_INSERT_FUSED=0: off)
+  void* h_status = nullptr;              // pinned: FusedStatus written by the fused kernel
+  unsigned int fused_seq = 0;
+  int fused_dirty = 0;                   // per-batch device counters may be non-zero (the fused kernel expects and leaves them zero)
 };
 
 static int graph_alloc_pool(ogl_graph* g, int64_t cap) {
@@ -591,6 +652,8 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
   A(g->total_dev, sizeof(int64_t));
 #undef A
   OGL_CUDA(cudaMallocHost(&g->h_ctl, sizeof(GraphCtl)));
+  OGL_CUDA(cudaMallocHost(&g->h_status, 64));
+  memset(g->h_status, 0, 64);
   OGL_CUDA(cudaFuncSetAttribute(k_fix_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBigTail * sizeof(unsigned long long))));
   OGL_CUDA(cudaMemset(g->row_start, 0, sizeof(int64_t) * v_cap));
   OGL_CUDA(cudaMemset(g->deg, 0, sizeof(int32_t) * v_cap));
@@ -608,6 +671,7 @@ extern "C" int ogl_graph_destroy(ogl_graph* g) {
                   g->p_indptr, g->p_indices, g->p_eids};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (g->h_ctl) cudaFreeHost(g->h_ctl);
+  if (g->h_status) cudaFreeHost(g->h_status);
   delete g;
   return OGL_OK;
 }
@@ -657,30 +721,44 @@ static int graph_insert_fused(ogl_graph* g, const BatchEdges& b, int64_t tot, cu
   }
   *done = 0;
   if (max_blocks < 0) return OGL_OK;
-  int grid = (int)ceil_div(tot, 2 * kBlock);
+  int grid = (int)ceil_div(tot, kBlock);          // about one edge / one touched row per thread, at most one CTA per SM
   if (grid < 8) grid = 8;
-  if (grid > 64) grid = 64;                       // a barrier over few CTAs is cheap; 64 x 256 threads cover 2^16 edges in 4 rounds
+  if (grid > sm_count()) grid = sm_count();
   if (grid > max_blocks) grid = max_blocks;
-  OGL_CUDA(cudaMemsetAsync(&g->ctl->n_touched, 0, sizeof(GraphCtl) - offsetof(GraphCtl, n_touched), s));
-  OGL_CUDA(cudaMemsetAsync(g->n_jobs, 0, 2 * sizeof(int), s));
+  if (g->fused_dirty) {                           // the general path (or k_fix_big) left per-batch counters behind
+    OGL_CUDA(cudaMemsetAsync(&g->ctl->n_touched, 0, sizeof(GraphCtl) - offsetof(GraphCtl, n_touched), s));
+    OGL_CUDA(cudaMemsetAsync(g->n_jobs, 0, 2 * sizeof(int), s));
+    g->fused_dirty = 0;
+  }
   BatchEdges bb = b;
   int64_t nv = g->n_vertices;
   uint32_t eid_base = (uint32_t)g->n_edges;
   long long pool_cap = g->pool_cap;
+  FusedStatus* st = (FusedStatus*)g->h_status;
+  unsigned int seq = ++g->fused_seq;
   void* args[] = {&bb, &g->add, &g->touched, &g->row_start, &g->deg, &g->cap, &g->tail_len, &g->adj, &g->jobs, &g->n_jobs, &g->jobs_cap,
-                  &g->large, &g->ctl, &nv, &eid_base, &pool_cap};
+                  &g->large, &g->ctl, &nv, &eid_base, &pool_cap, &st, &seq};
   OGL_CUDA(cudaLaunchCooperativeKernel((const void*)k_insert_fused, dim3((unsigned)grid), dim3(kBlock), args, 0, s));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  OGL_CUDA(cudaMemcpyAsync(g->h_ctl, g->ctl, sizeof(GraphCtl), cudaMemcpyDeviceToHost, s));
-  OGL_CUDA(cudaStreamSynchronize(s));
-  if (g->h_ctl->bad_id) {                         // (the kernel changed nothing)
+  // the kernel's last act is to write its status into pinned host memory: spin on the sequence number (a launch failure or a
+  // device fault shows up as an error of the stream query, never as an endless wait)
+  for (unsigned spins = 0; st->seq != seq; ++spins) {
+    if ((spins & 0x3ff) == 0x3ff) {
+      const cudaError_t qe = cudaStreamQuery(s);
+      if (qe != cudaSuccess && qe != cudaErrorNotReady) OGL_CUDA(qe);
+      if (qe == cudaSuccess && st->seq != seq) OGL_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  if (st->bad_id) {                               // (the kernel changed nothing)
     set_error("ogl_graph_insert_edges: vertex id out of range [0, %lld) (call insert_vertices first)", (long long)g->n_vertices);
     return OGL_ERR_ARG;
   }
-  if (g->h_ctl->overflow) return OGL_OK;
-  if (g->h_ctl->n_large > 0)
+  if (st->overflow) return OGL_OK;
+  if (st->n_large > 0) {
     OGL_LAUNCH(k_fix_big, sm_count() * 2, 1024, kBigTail * sizeof(unsigned long long), s, g->touched, g->tail_len, g->row_start, g->deg,
                g->adj, g->scr, g->large, g->ctl);
+    g->fused_dirty = 1;
+  }
   g->n_edges += tot;
   *done = 1;
   return OGL_OK;
@@ -699,6 +777,7 @@ static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_
     if (done) return OGL_OK;
   }
   // reset the per-batch counters (pool_top / relocations persist)
+  g->fused_dirty = 1;
   OGL_CUDA(cudaMemsetAsync(&g->ctl->n_touched, 0, sizeof(GraphCtl) - offsetof(GraphCtl, n_touched), s));
   OGL_LAUNCH(k_count, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->touched, g->ctl, g->n_vertices);
   OGL_LAUNCH(k_need, grid_for(tot, kBlock), kBlock, 0, s, g->touched, g->add, g->deg, g->cap, g->ctl);
