@@ -99,6 +99,12 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {     // descriptor fetch off the first load's critical path
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// L2 prefetch of a tensor box (no shared memory involved): the producers run these a few stages AHEAD of the loads.  The ring
+// holds 160-192 KB per SM, which at the 2-3 us a DRAM miss costs under load covers less than the tensor pipe consumes; a box that
+// is already in L2 when its load is issued comes back in ~0.7 us
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -298,6 +304,7 @@ struct NtParams {
   int out_f32_tma;              // TF kernels: fp32 output through TMA stores (activations), rounded to TF32 if round_out
   int round_out;
   int zero_tail;
+  int prefetch;                 // k-blocks the A operand is prefetched into L2 ahead of its load (0: off)
   int debug;                    // perf experiments (OGL_GEMM_DBG): 1 = epilogue drains the accumulator without storing
 };
 
@@ -354,6 +361,26 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       uint32_t phase = 0;
       // bytes landing per stage on the barrier the MMA issuer waits on (pair mode: both CTAs' boxes, on the leader's)
       const uint32_t tx = CG == 2 ? (uint32_t)(2 * (A_STAGE_BYTES + (p.bn / 2) * 128)) : (uint32_t)(A_STAGE_BYTES + p.bn * 128);
+      // prefetch cursor: the A boxes (activations: they stream from DRAM; the weights are L2-resident anyway) of the position
+      // p.prefetch k-blocks ahead of the load, across segment and tile boundaries
+      int pt = unit, pseg = 0, pkb = 0;
+      auto pf_settle = [&]() {                       // first live (tile, segment, k-block) at or after the cursor
+        while (pt < total_tiles) {
+          while (pseg < p.n_seg) {
+            if ((pt / p.n_tiles) * CG * BM < rows_valid[pseg] && pkb < (p.k[pseg] + BKE - 1) / BKE) return;
+            ++pseg; pkb = 0;
+          }
+          pseg = 0; pkb = 0; pt += n_units;
+        }
+      };
+      auto pf_issue = [&]() {
+        pf_settle();
+        if (pt < total_tiles) {
+          tma_prefetch_2d(&p.ta[pseg], pkb * BKE, ((pt / p.n_tiles) * CG + rank) * BM);
+          ++pkb;
+        }
+      };
+      for (int i = 0; i < p.prefetch; ++i) pf_issue();
       for (int t = unit; t < total_tiles; t += n_units) {
         const int mt = t / p.n_tiles, nb = t % p.n_tiles;
         const int mb = mt * CG + rank;
@@ -362,6 +389,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
           if (mt * CG * BM >= rows_valid[seg]) continue;          // (pair-uniform: decided on the pair's first row)
           const int nkb = (p.k[seg] + BKE - 1) / BKE;
           for (int kb = 0; kb < nkb; ++kb) {
+            if (p.prefetch) pf_issue();
             mbar_wait(&s.empty[stage], phase ^ 1);
             if (CG == 2) {
               if (rank == 0) mbar_expect_tx(&s.full[stage], tx);
@@ -673,6 +701,7 @@ struct TnParams {
   int n_prob;
   int total_tiles, splits;
   int use_tma_store;
+  int prefetch;                  // contraction blocks both operands are prefetched into L2 ahead of their loads (0: off)
   const int32_t* m_dev;
   int m_max;
 };
@@ -740,7 +769,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)((n_chunks_a + n_chunks_b) * CHUNK_BYTES);
+      auto pf = [&](int kb) {                      // both operands are activations streaming from DRAM
+        for (int c = 0; c < n_chunks_a; ++c) tma_prefetch_2d(&q.ta, row0 + c * CW, kb * BKR);
+        for (int c = 0; c < n_chunks_b; ++c) tma_prefetch_2d(&q.tb, kt * BN_MAX + c * CW, kb * BKR);
+      };
+      for (int kb = kb0; kb < min(kb1, kb0 + p.prefetch); ++kb) pf(kb);
       for (int kb = kb0; kb < kb1; ++kb) {
+        if (p.prefetch && kb + p.prefetch < kb1) pf(kb + p.prefetch);
         mbar_wait(&s.empty[stage], phase ^ 1);
         mbar_expect_tx(&s.full[stage], tx);
         for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(a_stage(stage) + c * CHUNK_BYTES, &q.ta, &s.full[stage], row0 + c * CW, kb * BKR);
@@ -1009,9 +1044,11 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.round_out = g.out_tf32;
   p.zero_tail = g.zero_tail;
   {
-    static int dbg = -1;
+    static int dbg = -1, pfd = -1;
     if (dbg < 0) { const char* e = getenv("OGL_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    if (pfd < 0) { const char* e = getenv("OGL_GEMM_PF_NT"); pfd = e ? atoi(e) : 0; }      // (measured: prefetches cost TMA issue slots, slower)
     p.debug = dbg;
+    p.prefetch = pfd;
   }
   OGL_ARG(!(g.mask && !(g.out_bf16 || p.out_f32_tma)), "gemm_nt_tc: the mask epilogue is implemented for the TMA-store outputs only");
   if (g.out_bf16) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 64, 32));
@@ -1019,7 +1056,8 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   OGL_ARG(g.ldc % 8 == 0 && ((uintptr_t)g.c & 15) == 0, "gemm_nt_tc: output pitch must be a multiple of 8 elements");
   OGL_ARG(!g.mask || (g.ldmask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0), "gemm_nt_tc: mask pitch must be a multiple of 8 elements");
   if (cg == 2) {
-    const int pairs = (int)(super_tiles < sm_count() / 2 ? super_tiles : sm_count() / 2);
+    int pairs = (int)(super_tiles < sm_count() / 2 ? super_tiles : sm_count() / 2);
+    if (const char* e = getenv("OGL_NT_MAXPAIRS")) pairs = pairs < atoi(e) ? pairs : atoi(e);      // experiments: is the kernel bound per SM or chip-wide?
     if (tf) OGL_TRY(launch_gemm(k_gemm_nt_tc<2, 1>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
     else OGL_TRY(launch_gemm(k_gemm_nt_tc<2, 0>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
     return OGL_OK;
@@ -1063,6 +1101,7 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
   p.total_tiles = tiles;
   // one CTA per SM and exactly one wave: tiles * splits <= #SMs (150 CTAs on 148 SMs would run as two waves)
   int splits = sm_count() / tiles;
+  if (const char* e = getenv("OGL_TN_MAXCTAS")) splits = atoi(e) / tiles > 0 ? (splits < atoi(e) / tiles ? splits : atoi(e) / tiles) : 1;
   const int by_rows = (int)ceil_div(g[0].m_max, 4 * cw);          // at least 4 contraction blocks per split
   if (splits > by_rows) splits = by_rows;
   float* ws = g[0].partial;
@@ -1094,6 +1133,11 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
     }
   }
   p.use_tma_store = staged ? 1 : 0;
+  {
+    static int pfd = -1;
+    if (pfd < 0) { const char* e = getenv("OGL_GEMM_PF_TN"); pfd = e ? atoi(e) : 0; }
+    p.prefetch = pfd;
+  }
   if (tf) OGL_TRY(launch_gemm(k_gemm_tn_tc<1>, tiles * splits, THREADS, SMEM_TN, 1, p, s));
   else OGL_TRY(launch_gemm(k_gemm_tn_tc<0>, tiles * splits, THREADS, SMEM_TN, 1, p, s));
   if (staged) return reduce_splits_group(rg, s);

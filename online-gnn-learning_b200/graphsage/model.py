@@ -57,8 +57,9 @@ class SupervisedGraphSage:
         new_vertices, labelled = temporal_graph.get_added_vertices(delta)
         test = np.array(new_vertices)[np.asarray(labelled, dtype=bool)]
         if len(test) < at_least:
-            with open(path, "a+") as f:
-                f.write(self.get_model() + ";;;\n")
+            if path:
+                with open(path, "a+") as f:
+                    f.write(self.get_model() + ";;;\n")
             return None
         return self._evaluate_vertices(temporal_graph, path, test)
 

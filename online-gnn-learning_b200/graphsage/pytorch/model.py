@@ -11,7 +11,7 @@ import os
 import numpy as np
 import torch
 
-from ... import config, utils
+from ... import config, parallel, utils
 from ...sampling import MultiLayerNeighborSampler, NodeDataLoader
 from ..model import SupervisedGraphSage
 
@@ -105,6 +105,8 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
     # ---- one minibatch -----------------------------------------------------------------------------
     def _fused_step(self, graph, seeds, per_vertex_out=None, loss_sum_out=None):
         plan = self._train_plan(graph)
+        if parallel.world() > 1:
+            return self._dp_steps(graph, plan, seeds, seeds.numel(), per_vertex_out)
         plan.train_step(graph.native, graph.features, seeds, loss_scale=1.0 / seeds.numel(), do_step=True,
                         per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
         self.graphsage_model.mark_updated(plan)
@@ -122,6 +124,8 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
         n = seeds.numel()
         n_full = n // batch
         plan = self._train_plan(graph)
+        if parallel.world() > 1:
+            return self._dp_steps(graph, plan, seeds, batch, per_vertex_out)
         if os.environ.get("OGL_NO_MULTISTEP"):                     # A/B switch: one C call per minibatch
             for i in range(0, n, batch):
                 self._fused_step(graph, seeds[i:i + batch], per_vertex_out=None if per_vertex_out is None else per_vertex_out[i:i + batch])
@@ -135,6 +139,45 @@ class PytorchSupervisedGraphSage(SupervisedGraphSage):
         if n > n_full * batch:
             tail = seeds[n_full * batch:]
             self._fused_step(graph, tail, per_vertex_out=None if per_vertex_out is None else per_vertex_out[n_full * batch:])
+
+    def _dp_steps(self, graph, plan, seeds, batch, per_vertex_out):
+        """data-parallel twin of the loop above (one process per GPU, torchrun): every rank holds the same graph, model
+        and -- because the choosers run on identically seeded RNGs -- the same `seeds`; of each minibatch a rank trains its
+        contiguous shard (parallel.shard) with the loss scaled by 1 / global minibatch size, the flat gradients are summed over
+        the ranks (NCCL all-reduce, bucketed and overlapped by parallel.Pipeline) and every replica takes the same Adam step.
+        Per-vertex losses (PBR) are all-gathered so that every rank applies identical priority updates."""
+        w = parallel.world()
+        if getattr(self, "_dp_pipe_plan", None) is not plan:
+            self._dp_pipe = parallel.Pipeline(plan, graph.native, graph.features, self.graphsage_model._flat_grad, batch)
+            self._dp_pipe_plan = plan
+        pipe = self._dp_pipe
+        n = seeds.numel()
+        jobs = []                                                  # (global lo, global hi, local lo, local hi)
+        for lo in range(0, n, batch):
+            hi = min(lo + batch, n)
+            if hi - lo >= w:
+                sl = parallel.shard(range(lo, hi))
+                jobs.append((lo, hi, sl[0], sl[-1] + 1))
+            else:                                                  # fewer seeds than ranks: every rank trains all of them, scaled by 1 / w
+                jobs.append((lo, hi, lo, hi))
+        per_local = None
+        if per_vertex_out is not None:
+            per_local = torch.empty(sum(j[3] - j[2] for j in jobs), dtype=torch.float32, device="cuda")
+        pipe.begin(seeds[jobs[0][2]:jobs[0][3]])
+        off = 0
+        for i, (lo, hi, a, b) in enumerate(jobs):
+            nxt = seeds[jobs[i + 1][2]:jobs[i + 1][3]] if i + 1 < len(jobs) else None
+            scale = 1.0 / (hi - lo) if hi - lo >= w else 1.0 / ((hi - lo) * w)
+            pipe.finish(nxt, per_vertex_out=None if per_local is None else per_local[off:off + b - a], scale=scale)
+            off += b - a
+        pipe.flush()
+        self.graphsage_model.mark_updated(plan)
+        self._last_plan = plan
+        self._mark_pin_busy(seeds)
+        if per_vertex_out is not None:
+            pos = torch.cat([torch.arange(a, b, device="cuda") for (_, _, a, b) in jobs])
+            all_pos, all_loss = parallel.allgather_losses(pos, per_local)
+            per_vertex_out[all_pos] = all_loss
 
     def train_step(self, graph, blocks, input_nodes, seeds, subgraph_to_id):
         """DGL-style signature of the reference (:77-107): one optimiser step on the minibatch `blocks` describes.  Blocks that were

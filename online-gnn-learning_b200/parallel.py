@@ -112,12 +112,22 @@ class Pipeline:
         self.plan.prefetch(self.graph, self.features, seeds)
         self._begun += 1
 
-    def finish(self, next_seeds=None, per_vertex_out=None, loss_sum_out=None):
+    def finish(self, next_seeds=None, per_vertex_out=None, loss_sum_out=None, scale=None):
+        """scale: loss scale of THIS step (1 / its global batch) when it differs from the pipeline's (a ragged last minibatch)"""
         assert self._begun > 0, "Pipeline.finish() without begin()"
         if next_seeds is not None and self._begun < 2:
             self.begin(next_seeds)                       # enqueued first: overlaps this step's forward / backward
         self._begun -= 1
         main = torch.cuda.current_stream()
+        keep_scale = self.scale
+        if scale is not None:
+            self.scale = float(scale)
+        try:
+            self._finish(main, per_vertex_out, loss_sum_out)
+        finally:
+            self.scale = keep_scale
+
+    def _finish(self, main, per_vertex_out, loss_sum_out):
         if self.w == 1:
             self.plan.step_finish(self.features, self.scale, do_step=True, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
             return

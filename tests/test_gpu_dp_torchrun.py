@@ -29,3 +29,17 @@ def test_two_rank_bench_replicas_identical_and_equal_to_one_rank(exchange):
     # so the replay is compared at a few lr, not at fp32 resolution
     assert rep["one_rank_replay_max_err_of_scale"] <= 5e-2, rep
     assert 0.0 < line["e2e"]["last_loss"] < 20.0
+
+
+def test_drop_in_trainers_data_parallel():
+    """the four trainers of the reference's API under torchrun: shards of every minibatch per rank, gradient all-reduce, PBR's
+    (vertex, loss) all-gather -- replicas (weights and priority trees) identical after every timestep, models learn"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "dp_trainers_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["replicas_identical"] is True and res["world"] == 2
+    assert res["f1"]["random"] > 0.5 and res["f1"]["prioritized"] > 0.5, res

@@ -41,7 +41,8 @@ def parse(argv=None):
     # extensions (not in the reference)
     ap.add_argument("--path", help="dataset directory (overrides settings/<dataset>.json)")
     ap.add_argument("--max_timesteps", type=int, help="stop after N snapshots")
-    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--precision", choices=["bf16", "tf32", "fp32"], default="bf16",
+                    help="arithmetic of the dense path: bf16 (fastest), tf32 (tensor cores, rtol 1e-3 vs the reference's fp32), fp32 (exact, SIMT)")
     ap.add_argument("--fast_choosers", action="store_true", help="on-GPU counter-RNG draws / proportional PBR instead of the literal reference choosers")
     args = ap.parse_args(argv)
     custom = {k: v for k, v in vars(args).items() if v is not None}
@@ -59,6 +60,19 @@ def run(args, data):
 
     if not data["cuda"]:
         raise SystemExit("ogl_b200 is the `--cuda` path of the reference; pass --cuda (there is no CPU fallback)")
+    # data-parallel run: `torchrun --nproc-per-node N train ...` -- one process per GPU, replicated graph / model / choosers (same
+    # seeds on every rank), every minibatch sharded over the ranks, gradients summed over NCCL (ogl_b200.parallel)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        data["gpu"] = local
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        torch.manual_seed(1)                 # torch.randperm of the offline / no-rehearsal policies must agree across the ranks
+        if dist.get_rank() != 0:
+            data["save_result"] = None       # rank 0 writes the CSV; the replicas evaluate the same numbers
     config.set_precision(data["precision"])
     config.set_faithful(not data["fast_choosers"])
     print("init")
