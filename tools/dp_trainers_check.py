@@ -35,12 +35,12 @@ def main():
     gu = ttg.TrainTestGraph(dyn, split=0.15, start_prior_alpha=4, end_prior_alpha=50, scale=1, max_priority=10)
     mk = lambda: GraphSAGE(F, H, C, 1, act, 0, "pool").cuda()
     kw = dict(cuda=True, batch_full=128, n_workers=0)
-    trainers = [RandomT(mk(), 6, 32, y, 5, **kw), PrioT(mk(), 6, 32, y, 5, ogl_b200.LossPriority(), full_pass=2, **kw),
-                NoRehT(mk(), 6, 32, y, 5, **kw), FullT(mk(), 1, 32, y, 5, **kw)]
+    trainers = [RandomT(mk(), 25, 32, y, 5, **kw), PrioT(mk(), 25, 32, y, 5, ogl_b200.LossPriority(), full_pass=2, **kw),
+                NoRehT(mk(), 25, 32, y, 5, **kw), FullT(mk(), 1, 32, y, 5, **kw)]
     for t in trainers:
         t.build_optimizer()
     ok, f1 = True, {}
-    for step in range(8):
+    for step in range(10):
         for t in trainers:
             t.train_timestep(gu)
         for t in trainers:
