@@ -62,6 +62,9 @@ int ogl_graph_insert_vertices(ogl_graph* g, int64_t n, void* stream);
  * (dynamic_graph_edge.py:214-215). */
 int ogl_graph_insert_edges(ogl_graph* g, const int64_t* src_dev, const int64_t* dst_dev, int64_t n,
                            int symmetric, void* stream);
+/* a shard of a destination-range-partitioned CSR: its rows are local, the source ids stored in them
+ * global -- sources are then accepted in [0, n_sources) instead of [0, number of local vertices) (0 restores the default) */
+int ogl_graph_set_source_bound(ogl_graph* g, int64_t n_sources);
 int ogl_graph_insert_edges_host(ogl_graph* g, const int64_t* src_host, const int64_t* dst_host, int64_t n,
                                 int symmetric, void* stream);
 /* vertex streams: load the parent graph once (ids already relabelled to arrival rank,

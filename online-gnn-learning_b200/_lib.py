@@ -45,6 +45,7 @@ SIGNATURES = {
     "ogl_graph_destroy": (_i, [_vp]),
     "ogl_graph_insert_vertices": (_i, [_vp, _i64, _vp]),
     "ogl_graph_insert_edges": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "ogl_graph_set_source_bound": (_i, [_vp, _i64]),
     "ogl_graph_insert_edges_host": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "ogl_graph_load_parent": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "ogl_graph_set_active_prefix": (_i, [_vp, _i64, _vp]),

@@ -82,6 +82,10 @@ class Graph:
         check(lib.ogl_graph_insert_edges_host(self._h, ps, pd, int(n), int(symmetric), _stream()))
         torch.cuda.current_stream().synchronize()   # host buffers may be released by the caller
 
+    def set_source_bound(self, n_sources):
+        """accept source ids in [0, n_sources): a destination-range shard stores global source ids in its local rows"""
+        check(lib.ogl_graph_set_source_bound(self._h, int(n_sources)))
+
     def load_parent(self, indptr, indices, eids):
         ip, ix, ei = _dev(indptr, torch.int64), _dev(indices, torch.int64), _dev(eids, torch.int64)
         check(lib.ogl_graph_load_parent(self._h, _ptr(ip), _ptr(ix), _ptr(ei), ip.numel() - 1, _stream()))

@@ -40,12 +40,12 @@ struct BatchEdges {
 };
 
 __global__ void __launch_bounds__(kBlock) k_count(BatchEdges b, int32_t* __restrict__ add, int32_t* __restrict__ touched,
-                                                  GraphCtl* ctl, int64_t n_vertices) {
+                                                  GraphCtl* ctl, int64_t n_vertices, int64_t n_sources) {
   const int64_t tot = b.total();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t s, d;
     b.get(i, s, d);
-    if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) { ctl->bad_id = 1; continue; }
+    if (s < 0 || d < 0 || s >= n_sources || d >= n_vertices) { ctl->bad_id = 1; continue; }
     int old = atomicAdd(&add[d], 1);
     if (old == 0) touched[atomicAdd(&ctl->n_touched, 1)] = (int32_t)d;
   }
@@ -129,12 +129,12 @@ __global__ void __launch_bounds__(kBlock) k_move_jobs(const MoveJob* __restrict_
 // claim a slot in the row tail (arbitrary order inside the batch; fixed up by k_fix)
 __global__ void __launch_bounds__(kBlock) k_place(BatchEdges b, int32_t* __restrict__ add, const int64_t* __restrict__ row_start,
                                                   const int32_t* __restrict__ deg, unsigned long long* __restrict__ adj,
-                                                  uint32_t eid_base, int64_t n_vertices) {
+                                                  uint32_t eid_base, int64_t n_vertices, int64_t n_sources) {
   const int64_t tot = b.total();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t s, d;
     b.get(i, s, d);
-    if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) continue;
+    if (s < 0 || d < 0 || s >= n_sources || d >= n_vertices) continue;
     const int p = atomicSub(&add[d], 1) - 1;      // add[] returns to zero by the end of the kernel
     const int64_t at = row_start[d] + deg[d] + p;
     adj[at] = ((unsigned long long)(eid_base + (uint32_t)i) << 32) | (uint32_t)s;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kBlock) k_insert_fused(BatchEdges b, int32_t* 
                                                          int32_t* __restrict__ tail_len, unsigned long long* __restrict__ adj,
                                                          MoveJob* __restrict__ jobs, int* __restrict__ n_jobs, int jobs_cap,
                                                          int32_t* __restrict__ large, GraphCtl* ctl, int64_t n_vertices, uint32_t eid_base,
-                                                         long long pool_cap, FusedStatus* status, unsigned int seq) {
+                                                         long long pool_cap, FusedStatus* status, unsigned int seq, int64_t n_sources) {
   __shared__ unsigned long long keys[kBlock / 32][kMedTail];
   const int64_t tot = b.total();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kBlock) k_insert_fused(BatchEdges b, int32_t* 
   for (int64_t i = tid; i < tot; i += nthreads) {
     int64_t s, d;
     b.get(i, s, d);
-    if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) { ctl->bad_id = 1; continue; }
+    if (s < 0 || d < 0 || s >= n_sources || d >= n_vertices) { ctl->bad_id = 1; continue; }
     if (atomicAdd(&add[d], 1) == 0) touched[atomicAdd(&ctl->n_touched, 1)] = (int32_t)d;
   }
   grid_barrier(ctl, gridDim.x);
@@ -605,6 +605,8 @@ struct ogl_graph {
   int64_t p_v = 0, p_e = 0;
   int64_t pool_used_host = 0, relocations = 0, compactions = 0;
   uint64_t generation = 1;
+  int64_t src_bound = 0;                 // sources may be any id in [0, src_bound) (0: the graph's own vertex count): a shard of a
+                                         // destination-range-partitioned CSR stores GLOBAL source ids in its local rows
   int fuse_small = 1;                    // snapshot-sized batches go through the single cooperative kernel (OGL_INSERT_FUSED=0: off)
   void* h_status = nullptr;              // pinned: FusedStatus written by the fused kernel
   unsigned int fused_seq = 0;
@@ -732,12 +734,13 @@ static int graph_insert_fused(ogl_graph* g, const BatchEdges& b, int64_t tot, cu
   }
   BatchEdges bb = b;
   int64_t nv = g->n_vertices;
+  int64_t ns = g->src_bound > 0 ? g->src_bound : g->n_vertices;
   uint32_t eid_base = (uint32_t)g->n_edges;
   long long pool_cap = g->pool_cap;
   FusedStatus* st = (FusedStatus*)g->h_status;
   unsigned int seq = ++g->fused_seq;
   void* args[] = {&bb, &g->add, &g->touched, &g->row_start, &g->deg, &g->cap, &g->tail_len, &g->adj, &g->jobs, &g->n_jobs, &g->jobs_cap,
-                  &g->large, &g->ctl, &nv, &eid_base, &pool_cap, &st, &seq};
+                  &g->large, &g->ctl, &nv, &eid_base, &pool_cap, &st, &seq, &ns};
   OGL_CUDA(cudaLaunchCooperativeKernel((const void*)k_insert_fused, dim3((unsigned)grid), dim3(kBlock), args, 0, s));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   // the kernel's last act is to write its status into pinned host memory: spin on the sequence number (a launch failure or a
@@ -779,7 +782,8 @@ static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_
   // reset the per-batch counters (pool_top / relocations persist)
   g->fused_dirty = 1;
   OGL_CUDA(cudaMemsetAsync(&g->ctl->n_touched, 0, sizeof(GraphCtl) - offsetof(GraphCtl, n_touched), s));
-  OGL_LAUNCH(k_count, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->touched, g->ctl, g->n_vertices);
+  const int64_t n_src = g->src_bound > 0 ? g->src_bound : g->n_vertices;
+  OGL_LAUNCH(k_count, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->touched, g->ctl, g->n_vertices, n_src);
   OGL_LAUNCH(k_need, grid_for(tot, kBlock), kBlock, 0, s, g->touched, g->add, g->deg, g->cap, g->ctl);
   OGL_CUDA(cudaMemcpyAsync(g->h_ctl, g->ctl, sizeof(GraphCtl), cudaMemcpyDeviceToHost, s));
   OGL_CUDA(cudaStreamSynchronize(s));
@@ -800,7 +804,7 @@ static int graph_insert_chunk(ogl_graph* g, const int64_t* src_dev, const int64_
              g->n_jobs, g->jobs_cap, g->ctl);
   OGL_LAUNCH(k_move_jobs, sm_count() * 8, kBlock, 0, s, g->jobs, g->n_jobs, g->jobs_cap, g->adj);
   OGL_LAUNCH(k_place, grid_for(tot, kBlock), kBlock, 0, s, b, g->add, g->row_start, g->deg, g->adj,
-             (uint32_t)g->n_edges, g->n_vertices);
+             (uint32_t)g->n_edges, g->n_vertices, n_src);
   OGL_LAUNCH(k_fix, tgrid, kBlock, 0, s, g->touched, g->tail_len, g->deg, g->small, g->med, g->large, g->ctl);
   OGL_LAUNCH(k_fix_small, wgrid, kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj, g->small, g->ctl);
   OGL_LAUNCH(k_fix_med, grid_for((int64_t)nt * 4, kBlock, 4), kBlock, 0, s, g->touched, g->tail_len, g->row_start, g->deg, g->adj,
@@ -841,6 +845,12 @@ extern "C" int ogl_graph_insert_edges(ogl_graph* g, const int64_t* src_dev, cons
 }
 extern "C" int ogl_graph_insert_edges_host(ogl_graph* g, const int64_t* src_host, const int64_t* dst_host, int64_t n, int symmetric, void* stream) {
   return graph_insert(g, src_host, dst_host, n, symmetric, 1, stream);
+}
+
+extern "C" int ogl_graph_set_source_bound(ogl_graph* g, int64_t n_sources) {
+  OGL_ARG(g && n_sources >= 0 && n_sources < 0xffffffffLL, "ogl_graph_set_source_bound: bad arguments");
+  g->src_bound = n_sources;
+  return OGL_OK;
 }
 
 extern "C" int ogl_graph_compact(ogl_graph* g, void* stream) {

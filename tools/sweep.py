@@ -83,9 +83,13 @@ def run_sharded(E, batch, hbm_peak, rank, world):
     perm = torch.randperm(V, generator=torch.Generator(device="cuda").manual_seed(1), device="cuda")     # same scatter on every rank
     graph = native.Graph(max(v_local, 1), int(2.6 * E / world) + (1 << 22))
     graph.insert_vertices(max(v_local, 1))
+    graph.set_source_bound(V)                         # local rows, global source ids
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     ms_route = ms_insert = 0.0
     per_rank_batch = batch // world
+    warm = torch.zeros(world, dtype=torch.int64, device="cuda")          # communicator set-up outside the timed region
+    dist.all_to_all_single(torch.empty_like(warm), warm)
+    torch.cuda.synchronize()
     for a in range(0, E, batch):
         n = min(per_rank_batch, max(0, (min(batch, E - a) + world - 1) // world))
         u = perm[torch.searchsorted(cdf, torch.rand(n, generator=gen, device="cuda")).clamp_(max=V - 1)]
