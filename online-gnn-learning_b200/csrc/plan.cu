@@ -164,6 +164,7 @@ struct ogl_plan {
   int train_mode = 0;                    // feat_drop is applied by ogl_plan_forward (train steps set it; eval steps never)
   int adam_in_backward = 0;              // fused step with do_step: the backward pass runs Adam on all but the last gradient itself
   int64_t adam_done_from = 0;            // ... and leaves [0, adam_done_from) to ogl_plan_adam_step
+  int tail_part = 0, tail_parts = 1;     // tail_mode 2: the last weight-gradient GEMM in `tail_parts` pieces of 256 output rows each
   int tail_mode = 0;                     // backward: 0 = all, 1 = everything but the last weight-gradient GEMM (layer 0 fc_pool),
                                          // 2 = only that GEMM (data-parallel: its predecessors' gradients are already on the wire)
   int in_train_step = 0;                 // set by the fused train step: sampling may defer the reverse edge lists to the side stream
@@ -180,9 +181,10 @@ struct ogl_plan {
     int kind;            // 0 = whole step, 1 = step_begin (sample + gather), 2 = step_finish (forward .. Adam),
                          // 3 = step_finish minus the last weight-gradient GEMM, 4 = that GEMM
     int parity;          // which of the two minibatch buffer sets the captured pointers belong to
+    int part, parts;     // kind 4: piece of the last weight-gradient GEMM
     bool operator==(const StepKey& o) const {
       return g == o.g && f == o.f && per == o.per && loss == o.loss && g_gen == o.g_gen && n_seeds == o.n_seeds && do_step == o.do_step &&
-             loss_scale == o.loss_scale && kind == o.kind && parity == o.parity;
+             loss_scale == o.loss_scale && kind == o.kind && parity == o.parity && part == o.part && parts == o.parts;
     }
   };
   struct StepGraph { StepKey key; cudaGraphExec_t exec; uint64_t last_use; };
@@ -570,7 +572,17 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     return tp;
   };
   if (p->tail_mode == 2) {                        // only dWp of layer 0 (its dhp was left in place by the tail_mode 1 pass)
-    STAGE("l0.dW_pool", gemm_tn(p, dw_pool(0), s));
+    GemmTN tp = dw_pool(0);
+    if (p->tail_parts > 1) {
+      // one piece of 256 output rows: data-parallel runs exchange piece i over NVLink while piece i + 1 is computed, so that only
+      // the last (smallest) piece's exchange is exposed at the end of the step
+      const int r0 = p->tail_part * 256, r1 = std::min(tp.n, r0 + 256);
+      OGL_ARG(r0 < tp.n, "ogl_plan_step_finish_tail: part %d of %d is empty", p->tail_part, p->tail_parts);
+      tp.a = (const char*)tp.a + (size_t)r0 * p->es;
+      tp.c = tp.c + (int64_t)r0 * tp.ldc;
+      tp.n = r1 - r0;
+    }
+    STAGE("l0.dW_pool", gemm_tn(p, tp, s));
     return OGL_OK;
   }
   OGL_TRY(join_side(p, s));                      // reverse edge lists built on the side stream during sampling
@@ -761,7 +773,8 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
 static int run_step(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step,
                     float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
   if (!p->use_graph || p->prof_on) return step_body(p, kind, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s);
-  const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, g ? graph_generation(g) : 0, n_seeds, do_step, loss_scale, kind, p->parity};
+  const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, g ? graph_generation(g) : 0, n_seeds, do_step, loss_scale, kind, p->parity,
+                              kind == 4 ? p->tail_part : 0, kind == 4 ? p->tail_parts : 1};
   ogl_plan::StepGraph* hit = nullptr;
   for (auto& sg : p->step_graphs)
     if (sg.key == key) { hit = &sg; break; }
@@ -777,7 +790,7 @@ static int run_step(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_
     const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     OGL_CUDA(ei);
-    if (p->step_graphs.size() >= 16) {          // evict the least recently used
+    if (p->step_graphs.size() >= 24) {          // evict the least recently used
       size_t lru = 0;
       for (size_t i = 1; i < p->step_graphs.size(); ++i)
         if (p->step_graphs[i].last_use < p->step_graphs[lru].last_use) lru = i;
@@ -1000,6 +1013,24 @@ extern "C" int ogl_plan_step_finish_head(ogl_plan* p, ogl_features* f, float los
   OGL_ARG(p && f && p->params && (p->n_seeds > 0 || p->pend[0]), "ogl_plan_step_finish_head: no step begun / parameters not bound");
   if (p->pend[0]) OGL_TRY(consume_prefetched(p, p->pend_n[0], (cudaStream_t)stream));   // (released by _tail)
   return run_step(p, 3, nullptr, f, p->n_seeds, loss_scale, 0, per_vertex_loss_dev, loss_sum_dev, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_plan_step_finish_tail_part(ogl_plan* p, ogl_features* f, int part, int n_parts, void* stream) {
+  OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish_tail: no step begun / parameters not bound");
+  OGL_ARG(n_parts >= 1 && part >= 0 && part < n_parts && (n_parts - 1) * 256 < p->cfg.dims[0],
+          "ogl_plan_step_finish_tail_part: part %d of %d (pieces are 256 rows of the %d x %d gradient)", part, n_parts, p->cfg.dims[0], p->cfg.dims[0]);
+  cudaStream_t s = (cudaStream_t)stream;
+  p->tail_part = part; p->tail_parts = n_parts;
+  const int r4 = run_step(p, 4, nullptr, f, p->n_seeds, 0.f, 0, nullptr, nullptr, s);
+  p->tail_part = 0; p->tail_parts = 1;
+  if (part + 1 < n_parts) return r4;              // (the minibatch is released by the last piece)
+  advance_prefetched(p);
+  OGL_TRY(r4);
+  if (p->prof_on && p->prof_steps < kProfSteps) {
+    OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
+    p->prof_steps++;
+  }
+  return OGL_OK;
 }
 
 extern "C" int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream) {

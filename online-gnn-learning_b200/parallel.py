@@ -102,6 +102,10 @@ class Pipeline:
         self.scale = 1.0 / float(global_batch)
         self.w = world()
         self.comm = torch.cuda.Stream() if self.w > 1 else None
+        import os
+        pieces = getattr(plan, "tail_pieces", [None])
+        self.tail_pieces = len(pieces) if int(os.environ.get("OGL_DP_TAIL_PIECES", "1")) else 1
+        self.ev_piece = [torch.cuda.Event() for _ in range(len(pieces))] if self.w > 1 else []
         self.ev_bwd = torch.cuda.Event()
         self.ev_head = torch.cuda.Event()
         self.ev_adam = torch.cuda.Event()
@@ -146,6 +150,19 @@ class Pipeline:
                 self.plan.peer_adam(self.peer, n0, n, last=False)     # P2P sum + Adam of bucket 1, beside the tail GEMM
             else:
                 allreduce_grads(self.flat_grad[n0:])
+        if self.peer is not None and self.tail_pieces > 1:
+            # the last weight-gradient GEMM in pieces of 256 gradient rows: piece i is exchanged (and its Adam done) while piece
+            # i + 1 is computed, so only the last, smallest piece's exchange is exposed before the next step's forward pass
+            pieces = self.plan.tail_pieces
+            for i, (lo, hi) in enumerate(pieces):
+                self.plan.step_finish_tail(self.features, part=i, n_parts=len(pieces))
+                self.ev_piece[i].record(main)
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(self.ev_piece[i])
+                    self.plan.peer_adam(self.peer, lo, hi, last=(i + 1 == len(pieces)))
+            self.ev_adam.record(self.comm)
+            self._adam_pending = True
+            return
         self.plan.step_finish_tail(self.features)
         self.ev_bwd.record(main)
         with torch.cuda.stream(self.comm):

@@ -483,3 +483,28 @@ def test_feat_drop_matches_the_oracle_mask(mode, gemm_impl, rtol):
     per2 = torch.empty(len(c.seeds), device="cuda")
     plan.train_step(c.g, c.f, seeds_dev, loss_scale=1.0 / len(c.seeds), do_step=False, per_vertex_out=per2)
     close(per2, per, 1e-5 if mode == "fp32" else 1e-4, "fused step losses")
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_tail_gemm_in_pieces_equals_whole(mode):
+    """the last weight-gradient GEMM issued in pieces of 256 gradient rows (data-parallel runs exchange piece i while piece i + 1 is
+    computed) writes the same gradient as the single launch"""
+    outs = []
+    for pieces in (False, True):
+        c = Case(V=3000, E=20000, dims=(600, 64, 5), fanouts=(6, 4), n_seeds=64, mode=mode, gemm_impl=0)
+        sd = torch.as_tensor(c.seeds).cuda()
+        c.plan.step_begin(c.g, c.f, sd)
+        c.plan.step_finish_head(c.f, 1.0 / 64)
+        if pieces:
+            ps = c.plan.tail_pieces
+            assert ps == [(0, 256 * 600), (256 * 600, 512 * 600), (512 * 600, 600 * 600)]
+            for i in range(len(ps)):
+                c.plan.step_finish_tail(c.f, part=i, n_parts=len(ps))
+        else:
+            c.plan.step_finish_tail(c.f)
+        torch.cuda.synchronize()
+        outs.append(c.grad.clone())
+    g0, g1 = outs
+    assert float(g0[:600 * 600].abs().max()) > 0
+    # different split counts over the rows -> a different (still fixed) summation order of the fp32 partials
+    close(g1, g0, 1e-5, "gradient, pieces vs whole")
