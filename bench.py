@@ -521,7 +521,8 @@ def measure(dt, headline, args, w, rank, world, dev, dist, g, feats, labels, hos
     plan = native.Plan([w["F"], w["H"], w["C"]], w["fanouts"], B, V, mode=mode, seed=11)
     plan.bind_params(flat, grad)
     peer = None
-    if world > 1 and args.exchange == "peer":
+    force_split = world == 1 and bool(os.environ.get("OGL_DP_FORCE_SPLIT"))
+    if (world > 1 and args.exchange == "peer") or force_split:
         # gradient exchange + Adam as ONE kernel per bucket over NVLink peer memory (csrc/peer.cu); the gradient buffer moves into
         # the peer-visible allocation
         peer = ogl_b200.parallel.make_peer_exchange(plan, flat)
@@ -536,7 +537,7 @@ def measure(dt, headline, args, w, rank, world, dev, dist, g, feats, labels, hos
         # local sample / forward / backward -> (N > 1: one NCCL all-reduce of the flat gradient) -> fused Adam
         ogl_b200.parallel.train_step(plan, g, fs, seeds, B * world, grad, loss_sum_out=loss_dev)
 
-    pipe = ogl_b200.parallel.Pipeline(plan, g, fs, grad, B * world, peer=peer) if not args.no_pipeline else None
+    pipe = ogl_b200.parallel.Pipeline(plan, g, fs, grad, B * world, peer=peer, force_split=force_split) if not args.no_pipeline else None
     loss_slots = [torch.zeros(1, device=dev) for _ in range(2)]
     loss_host = torch.zeros(2, 1).pin_memory()
     loss_evs = [torch.cuda.Event(), torch.cuda.Event()]

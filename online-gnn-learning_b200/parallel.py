@@ -92,7 +92,7 @@ class Pipeline:
     bucket + Adam run on a communication stream; forward(t+1) waits for Adam(t).  Same arithmetic as the unpipelined loop
     (no stale gradients, same Philox step per minibatch)."""
 
-    def __init__(self, plan, graph, features, flat_grad, global_batch, peer=None):
+    def __init__(self, plan, graph, features, flat_grad, global_batch, peer=None, force_split=False):
         """peer: a native.Peer from make_peer_exchange -> the gradient exchange + Adam is ONE kernel per bucket over NVLink peer
         memory (no NCCL on the data path); None -> NCCL all-reduce + ogl_plan_adam_step"""
         self.plan, self.graph, self.features, self.flat_grad = plan, graph, features, flat_grad
@@ -100,11 +100,15 @@ class Pipeline:
         if peer is not None:
             assert flat_grad.data_ptr() == peer.grads.data_ptr(), "the plan must be bound to the peer group's gradient buffer"
         self.scale = 1.0 / float(global_batch)
-        self.w = world()
+        # force_split (experiments): run the data-parallel launch structure (head | bucket exchange | tail | bucket exchange) on ONE
+        # rank with a one-rank peer group -- what the structure itself costs, without NVLink traffic or waiting for other ranks
+        self.w = max(world(), 2) if force_split else world()
         self.comm = torch.cuda.Stream() if self.w > 1 else None
         import os
         pieces = getattr(plan, "tail_pieces", [None])
-        self.tail_pieces = len(pieces) if int(os.environ.get("OGL_DP_TAIL_PIECES", "1")) else 1
+        # measured on 2 and 8 B200 (tf32, Reddit shape): exchanging the last gradient in 256-row pieces is SLOWER (1.135 vs 1.014 ms
+        # at 8 GPUs: three GEMM prologues, three reduces and three box-wide barriers cost more than the exposed exchange they hide)
+        self.tail_pieces = len(pieces) if int(os.environ.get("OGL_DP_TAIL_PIECES", "0")) else 1
         self.ev_piece = [torch.cuda.Event() for _ in range(len(pieces))] if self.w > 1 else []
         self.ev_bwd = torch.cuda.Event()
         self.ev_head = torch.cuda.Event()
