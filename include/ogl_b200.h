@@ -173,6 +173,11 @@ int ogl_plan_step_finish(ogl_plan* p, ogl_features* f, float loss_scale, int do_
 int ogl_plan_step_finish_head(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev, float* loss_sum_dev,
                               void* stream);
 int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream);
+/* data-parallel finish in ONE launch sequence (one CUDA graph per step): forward .. backward with the gradient exchange over NVLink
+ * peer memory and Adam as nodes of the same graph -- all gradients but layer 0's fc_pool.weight are exchanged beside the last
+ * weight-gradient GEMM, that one after it.  The plan's gradient buffer must be `peer`'s (ogl_peer_buffer). */
+int ogl_plan_step_finish_dp(ogl_plan* p, ogl_peer* peer, ogl_features* f, float loss_scale, float* per_vertex_loss_dev,
+                            float* loss_sum_dev, void* stream);
 /* the same GEMM in n_parts pieces of 256 output rows (piece `part` writes gradient rows [256 part, 256 part + 256) of layer 0's
  * fc_pool.weight): a data-parallel caller exchanges piece i while piece i + 1 is computed */
 int ogl_plan_step_finish_tail_part(ogl_plan* p, ogl_features* f, int part, int n_parts, void* stream);

@@ -313,6 +313,10 @@ class Plan:
         check(lib.ogl_plan_step_finish(self._h, features._h, float(loss_scale), int(do_step), _ptr(per_vertex_out), _ptr(loss_sum_out),
                                        _stream()))
 
+    def step_finish_dp(self, peer, features, loss_scale, per_vertex_out=None, loss_sum_out=None):
+        """data-parallel finish in one launch sequence: forward .. backward + the peer-memory gradient exchange + Adam"""
+        check(lib.ogl_plan_step_finish_dp(self._h, peer._h, features._h, float(loss_scale), _ptr(per_vertex_out), _ptr(loss_sum_out), _stream()))
+
     def step_finish_head(self, features, loss_scale, per_vertex_out=None, loss_sum_out=None):
         """forward + loss + backward except the last weight-gradient GEMM (layer 0 fc_pool.weight)"""
         check(lib.ogl_plan_step_finish_head(self._h, features._h, float(loss_scale), _ptr(per_vertex_out), _ptr(loss_sum_out), _stream()))

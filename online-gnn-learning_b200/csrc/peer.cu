@@ -25,7 +25,10 @@ namespace {
 
 constexpr int kMaxWorld = 8;
 constexpr int kFlagWords = 64;                    // per rank: arrive[8] | pad | done[8] | pad | cta counter
-constexpr int kArrive = 0, kDone = 16, kCounter = 32, kCounter2 = 33, kGathered = 40;
+constexpr int kArrive = 0, kDone = 16, kCounter = 32, kCounter2 = 33, kEpoch = 34, kGathered = 40;
+// kEpoch: exchanges this rank has completed.  The kernels take their epoch from this word (every CTA of a launch reads it before the
+// launch's last CTA advances it), not from a kernel argument: an exchange can then sit inside a captured CUDA graph that is
+// replayed every step
 constexpr long long kSpinLimit = 20000000000ll;   // ~10 s of SM clocks: a missing peer traps instead of hanging the box
 
 struct PeerView {
@@ -83,12 +86,13 @@ __device__ __forceinline__ void shadow_one(int64_t i, float pi, const ShadowSeg*
 // the whole range from its local gsum -- (W - 1) / W remote loads + stores per element instead of W - 1 loads.  All CTAs of the
 // grid are resident (<= 1 per SM): the second barrier is grid-wide.
 template <typename T, bool TWO_SHOT>
-__global__ void __launch_bounds__(256) k_peer_sum_adam(const PeerView pv, uint32_t epoch, int64_t lo, int64_t hi, float* __restrict__ p,
+__global__ void __launch_bounds__(256) k_peer_sum_adam(const PeerView pv, int64_t lo, int64_t hi, float* __restrict__ p,
                                                        float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2, float eps,
                                                        const uint32_t* __restrict__ t_dev, const ShadowSeg* __restrict__ segs, int n_segs,
                                                        float* __restrict__ reduced_out) {
   __shared__ ShadowSeg ss[48];
   for (int i = threadIdx.x; i < n_segs; i += blockDim.x) ss[i] = segs[i];
+  const uint32_t epoch = *((volatile const uint32_t*)(pv.flags[pv.rank] + kEpoch)) + 1u;
   // ---- arrive: my gradients are final (stream order) -> tell every peer, then wait for every peer
   if (blockIdx.x == 0 && threadIdx.x < pv.world) {
     __threadfence_system();
@@ -189,14 +193,16 @@ __global__ void __launch_bounds__(256) k_peer_sum_adam(const PeerView pv, uint32
     const uint32_t old = atomicAdd(counter, 1u);
     if (old == gridDim.x - 1) {
       *counter = 0;
+      pv.flags[pv.rank][kEpoch] = epoch;           // (every CTA of this launch has read the old value: they have all finished)
       __threadfence_system();
       for (int r = 0; r < W; ++r) st_release_sys(pv.flags[r] + kDone + pv.rank, epoch);
     }
   }
 }
 
-__global__ void k_peer_wait_done(const uint32_t* my_flags, int world, uint32_t epoch) {
-  if (threadIdx.x < world) spin_until(my_flags + kDone + threadIdx.x, epoch);
+__global__ void k_peer_wait_done(const uint32_t* my_flags, int world) {
+  const uint32_t epoch = *((volatile const uint32_t*)(my_flags + kEpoch));      // exchanges this rank has completed
+  if (epoch != 0 && threadIdx.x < world) spin_until(my_flags + kDone + threadIdx.x, epoch);
 }
 
 }  // namespace
@@ -214,7 +220,6 @@ struct ogl_peer {
   void* peer_base[kMaxWorld] = {};      // mapped peers (own slot = base)
   int opened[kMaxWorld] = {};
   int connected = 0;
-  uint32_t epoch = 0;                   // exchanges issued so far (the same sequence on every rank)
   PeerView view;
 };
 
@@ -305,9 +310,12 @@ extern "C" int ogl_peer_buffer(ogl_peer* p, float** grads_dev) {
 
 extern "C" int ogl_peer_wait_readers(ogl_peer* p, void* stream) {
   OGL_ARG(p && p->connected, "ogl_peer_wait_readers: not connected");
-  if (p->epoch == 0) return OGL_OK;
-  OGL_LAUNCH(k_peer_wait_done, 1, 32, 0, stream, p->view.flags[p->rank], p->world, p->epoch);
+  OGL_LAUNCH(k_peer_wait_done, 1, 32, 0, stream, p->view.flags[p->rank], p->world);
   return OGL_OK;
+}
+
+namespace ogl {
+int peer_wait_readers(ogl_peer* p, cudaStream_t s) { return ogl_peer_wait_readers(p, s); }
 }
 
 namespace ogl {
@@ -318,7 +326,6 @@ int peer_sum_adam(ogl_peer* p, const PeerAdamArgs& a, int64_t lo, int64_t hi, cu
           (long long)hi, (long long)p->n_floats);
   OGL_ARG(a.grads == (const float*)p->base, "ogl_plan_peer_adam: the plan's gradient buffer is not this peer group's buffer");
   OGL_ARG(a.n_segs <= 48, "ogl_plan_peer_adam: too many weight segments");
-  p->epoch += 1;
   // at most 2 CTAs per SM: 2 KB of shared memory and 78 registers per thread, so the whole grid is resident NEXT to the
   // weight-gradient GEMM it overlaps (that kernel leaves ~35 KB of shared memory and 4/5 of the registers free)
   const int64_t quads = (hi - lo + 3) / 4;
@@ -328,7 +335,7 @@ int peer_sum_adam(ogl_peer* p, const PeerAdamArgs& a, int64_t lo, int64_t hi, cu
   const bool two = p->two_shot && p->world > 1;
   if (two && grid > sm_count()) grid = sm_count();          // grid-wide barrier inside: every CTA resident
 #define OGL_PEER_LAUNCH(T, TWO)                                                                                                          \
-  OGL_LAUNCH((k_peer_sum_adam<T, TWO>), grid, 256, 0, s, p->view, p->epoch, lo, hi, a.params, a.m, a.v, a.lr, a.b1, a.b2, a.eps, a.t_dev, \
+  OGL_LAUNCH((k_peer_sum_adam<T, TWO>), grid, 256, 0, s, p->view, lo, hi, a.params, a.m, a.v, a.lr, a.b1, a.b2, a.eps, a.t_dev, \
              a.segs, a.n_segs, a.reduced_out)
   if (a.mode == OGL_BF16) {
     if (two) OGL_PEER_LAUNCH(__nv_bfloat16, true);

@@ -19,5 +19,7 @@ struct PeerAdamArgs {
 };
 
 int peer_sum_adam(ogl_peer* p, const PeerAdamArgs& a, int64_t lo, int64_t hi, cudaStream_t s);
+// enqueue: wait until every peer has finished reading this rank's gradients of the previous exchange
+int peer_wait_readers(ogl_peer* p, cudaStream_t s);
 
 }  // namespace ogl

@@ -164,6 +164,7 @@ struct ogl_plan {
   int train_mode = 0;                    // feat_drop is applied by ogl_plan_forward (train steps set it; eval steps never)
   int adam_in_backward = 0;              // fused step with do_step: the backward pass runs Adam on all but the last gradient itself
   int64_t adam_done_from = 0;            // ... and leaves [0, adam_done_from) to ogl_plan_adam_step
+  ogl_peer* dp_peer = nullptr;           // step kind 5: the peer group of the data-parallel finish being enqueued / captured
   int tail_part = 0, tail_parts = 1;     // tail_mode 2: the last weight-gradient GEMM in `tail_parts` pieces of 256 output rows each
   int tail_mode = 0;                     // backward: 0 = all, 1 = everything but the last weight-gradient GEMM (layer 0 fc_pool),
                                          // 2 = only that GEMM (data-parallel: its predecessors' gradients are already on the wire)
@@ -695,6 +696,14 @@ extern "C" int ogl_plan_adam_step(ogl_plan* p, void* stream) {
 
 // data-parallel twin of ogl_plan_adam_step: gradients [lo, hi) are summed over the ranks of `peer` through NVLink peer memory inside
 // the Adam kernel (peer.cu).  `last` != 0 on the final bucket of a step: the Adam step counter advances after it.
+static int peer_adam_range(ogl_plan* p, ogl_peer* peer, int64_t lo, int64_t hi, float* reduced_out_dev, cudaStream_t s) {
+  PeerAdamArgs a;
+  a.mode = p->mode; a.params = p->params; a.grads = p->grads; a.m = p->adam_m; a.v = p->adam_v;
+  a.lr = p->cfg.lr; a.b1 = p->cfg.beta1; a.b2 = p->cfg.beta2; a.eps = p->cfg.eps;
+  a.t_dev = p->ctl + 1; a.segs = p->shadow_segs; a.n_segs = p->n_shadow_segs; a.reduced_out = reduced_out_dev;
+  return peer_sum_adam(peer, a, lo, hi, s);
+}
+
 extern "C" int ogl_plan_peer_adam(ogl_plan* p, ogl_peer* peer, int64_t lo, int64_t hi, int last, float* reduced_out_dev, void* stream) {
   OGL_ARG(p && p->params && peer, "ogl_plan_peer_adam: parameters not bound / null peer group");
   OGL_ARG(lo >= 0 && hi <= p->n_params, "ogl_plan_peer_adam: range outside the %lld parameters", (long long)p->n_params);
@@ -751,6 +760,41 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
     p->tail_mode = 0;
     return rb;
   }
+  if (kind == 5) {
+    // the whole data-parallel finish as ONE launch sequence (one CUDA graph per step): the split form (head graph | exchange kernel
+    // | tail graph | exchange kernel on a communication stream, with events between them) costs ~80 us of launch / dependency latency
+    // per step even on a single rank; here the exchanges are nodes of the same graph as the GEMMs they overlap.
+    //   peers have read my previous gradients -> forward -> loss -> backward without the last weight-gradient GEMM
+    //   -> [side: exchange + Adam of everything but layer 0's fc_pool.weight]  ||  [main: that GEMM]
+    //   -> exchange + Adam of fc_pool.weight -> optimiser step counter
+    ogl_peer* peer = p->dp_peer;
+    OGL_ARG(peer && p->use_side, "ogl_plan_step_finish_dp: needs a peer group and the side stream");
+    OGL_TRY(peer_wait_readers(peer, s));
+    p->skip_gather = 1;
+    const int keep_mode = p->train_mode;
+    p->train_mode = 1;
+    int r = ogl_plan_forward(p, f, nullptr, s);
+    p->skip_gather = 0;
+    if (r == OGL_OK) {
+      p->tail_mode = 1;
+      r = ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s);
+      p->tail_mode = 0;
+    }
+    p->train_mode = keep_mode;
+    OGL_TRY(r);
+    const int64_t n0 = p->layer[0].o_bp;            // = in * in: layer 0's fc_pool.weight leads the flat buffers
+    OGL_CUDA(cudaEventRecord(p->ev_fork, s));
+    OGL_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    if (p->n_params > n0) OGL_TRY(peer_adam_range(p, peer, n0, p->n_params, nullptr, p->side));
+    OGL_CUDA(cudaEventRecord(p->ev_join, p->side));
+    p->tail_mode = 2;
+    r = plan_backward_layers(p, s);
+    p->tail_mode = 0;
+    OGL_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+    OGL_TRY(r);
+    OGL_TRY(peer_adam_range(p, peer, 0, n0, nullptr, s));
+    return bump(nullptr, p->ctl + 1, s);
+  }
   p->skip_gather = (kind == 2 || kind == 3);
   const int keep_mode = p->train_mode;
   p->train_mode = 1;                             // a train step: feat_drop on (the reference calls model.train() first, pytorch/model.py:120)
@@ -773,7 +817,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
 static int run_step(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step,
                     float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
   if (!p->use_graph || p->prof_on) return step_body(p, kind, g, f, n_seeds, loss_scale, do_step, per_vertex_loss_dev, loss_sum_dev, s);
-  const ogl_plan::StepKey key{g, f, per_vertex_loss_dev, loss_sum_dev, g ? graph_generation(g) : 0, n_seeds, do_step, loss_scale, kind, p->parity,
+  const ogl_plan::StepKey key{kind == 5 ? (const void*)p->dp_peer : (const void*)g, f, per_vertex_loss_dev, loss_sum_dev, g ? graph_generation(g) : 0, n_seeds, do_step, loss_scale, kind, p->parity,
                               kind == 4 ? p->tail_part : 0, kind == 4 ? p->tail_parts : 1};
   ogl_plan::StepGraph* hit = nullptr;
   for (auto& sg : p->step_graphs)
@@ -1039,6 +1083,25 @@ extern "C" int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* str
   const int r4 = run_step(p, 4, nullptr, f, p->n_seeds, 0.f, 0, nullptr, nullptr, s);
   advance_prefetched(p);
   OGL_TRY(r4);
+  if (p->prof_on && p->prof_steps < kProfSteps) {
+    OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
+    p->prof_steps++;
+  }
+  return OGL_OK;
+}
+
+// data-parallel finish: forward .. backward with the gradient exchange over NVLink peer memory and Adam inside the same launch
+// sequence (step kind 5).  The plan's gradient buffer must be the peer group's (ogl_peer_buffer).
+extern "C" int ogl_plan_step_finish_dp(ogl_plan* p, ogl_peer* peer, ogl_features* f, float loss_scale, float* per_vertex_loss_dev,
+                                       float* loss_sum_dev, void* stream) {
+  OGL_ARG(p && peer && f && p->params && (p->n_seeds > 0 || p->pend[0]), "ogl_plan_step_finish_dp: no step begun / parameters not bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->pend[0]) OGL_TRY(consume_prefetched(p, p->pend_n[0], s));
+  p->dp_peer = peer;
+  const int r5 = run_step(p, 5, nullptr, f, p->n_seeds, loss_scale, 1, per_vertex_loss_dev, loss_sum_dev, s);
+  p->dp_peer = nullptr;
+  advance_prefetched(p);
+  OGL_TRY(r5);
   if (p->prof_on && p->prof_steps < kProfSteps) {
     OGL_CUDA(cudaMemcpyAsync(p->prof_counts_host + 8 * p->prof_steps, p->counts, sizeof(int32_t) * (p->L + 1), cudaMemcpyDeviceToHost, s));
     p->prof_steps++;

@@ -105,6 +105,7 @@ class Pipeline:
         self.w = max(world(), 2) if force_split else world()
         self.comm = torch.cuda.Stream() if self.w > 1 else None
         import os
+        self.split_launch = bool(int(os.environ.get("OGL_DP_SPLIT_LAUNCH", "0")))      # the older form: head | exchange | tail | exchange
         pieces = getattr(plan, "tail_pieces", [None])
         # measured on 2 and 8 B200 (tf32, Reddit shape): exchanging the last gradient in 256-row pieces is SLOWER (1.135 vs 1.014 ms
         # at 8 GPUs: three GEMM prologues, three reduces and three box-wide barriers cost more than the exposed exchange they hide)
@@ -138,6 +139,10 @@ class Pipeline:
     def _finish(self, main, per_vertex_out, loss_sum_out):
         if self.w == 1:
             self.plan.step_finish(self.features, self.scale, do_step=True, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
+            return
+        if self.peer is not None and not self.split_launch and hasattr(self.plan, "step_finish_dp"):
+            # one launch sequence (one CUDA graph) per step, the exchanges inside it (ogl_plan_step_finish_dp)
+            self.plan.step_finish_dp(self.peer, self.features, self.scale, per_vertex_out=per_vertex_out, loss_sum_out=loss_sum_out)
             return
         if self._adam_pending:
             main.wait_event(self.ev_adam)                # weights (and the gradient buffer) of the previous step are settled

@@ -70,3 +70,41 @@ def test_peer_adam_single_rank_equals_adam_step():
     torch.cuda.synchronize()
     # same Adam arithmetic; the gradients differ only by the summation order of the reverse edge lists
     assert (a.flat - b.flat).abs().max().item() <= 1e-4 * b.flat.abs().max().item()
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_one_graph_data_parallel_finish_two_ranks(mode):
+    """ogl_plan_step_finish_dp: forward .. backward + both gradient exchanges + Adam as ONE captured launch sequence per rank (the
+    exchange kernels take their epoch from device memory, so the graph is replayed every step).  Two ranks in this process, each
+    on its own stream: the weights must equal Adam on the summed gradients, and the replicas each other bit for bit."""
+    from ogl_b200 import native
+    W, B = 2, 64
+    kw = dict(dims=(300, 32, 5), fanouts=(6, 4), n_seeds=B, mode=mode, gemm_impl=0)
+    ranks = [Case(**kw) for _ in range(W)]
+    ref = Case(**kw)
+    n = ref.plan.n_params
+    peers = [native.Peer(r, W, n) for r in range(W)]
+    native.Peer.connect_local(peers)
+    for c, p in zip(ranks, peers):
+        c.plan.bind_params(c.flat, p.grads)
+    rng = np.random.default_rng(4)
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    for step in range(4):
+        seeds = [torch.as_tensor(rng.permutation(ranks[0].V - 40)[:B].astype(np.int64)).cuda() for _ in range(W)]
+        torch.cuda.synchronize()
+        for r, c in enumerate(ranks):
+            with torch.cuda.stream(streams[r]):
+                c.plan.step_begin(c.g, c.f, seeds[r])
+                c.plan.step_finish_dp(peers[r], c.f, 1.0 / (W * B))
+        torch.cuda.synchronize()
+        want = peers[0].grads.clone()
+        for r in range(1, W):
+            want += peers[r].grads
+        ref.grad.copy_(want)
+        ref.plan.adam_step()
+        for r, c in enumerate(ranks):
+            err = (c.flat - ref.flat).abs().max().item()
+            assert err <= 1e-6 * ref.flat.abs().max().item(), "rank %d, step %d: weights differ from Adam on the summed gradient: %g" % (r, step, err)
+        assert torch.equal(ranks[0].flat, ranks[1].flat)
+    st = ranks[0].plan.graph_stats()
+    assert st["captures"] <= 3 and st["replays"] >= 8, st          # begin + finish graphs captured once, replayed every step
