@@ -148,6 +148,75 @@ __global__ void __launch_bounds__(kBlock) k_rev_fill(const int32_t* __restrict__
   }
 }
 
+// The fill above claims slots with atomics, so a row's entries land in arbitrary order -- and k_pool_bwd would sum a source row's
+// gradient contributions in a different order from run to run.  Every row is therefore put into ascending entry order
+// ((destination << 8) | slot = sampling order): one thread per row (most rows hold 1-3 entries and are finished by their thread),
+// rows of up to kRevWarpMax entries by their warp (rank by counting through shared memory), longer ones by a whole CTA.
+constexpr int kRevThreadMax = 8, kRevWarpMax = 1024;
+__global__ void __launch_bounds__(kBlock) k_rev_sort(const int32_t* __restrict__ rev_ptr, int32_t* __restrict__ rev_edge,
+                                                     const int32_t* __restrict__ n_src_dev, int n_src_max, int32_t* __restrict__ long_rows) {
+  __shared__ int32_t buf[kBlock / 32][kRevWarpMax];
+  const int n = n_src_dev ? min(*n_src_dev, n_src_max) : n_src_max;      // (rows beyond the live count are empty)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nthreads = gridDim.x * blockDim.x;
+  for (int r0 = blockIdx.x * blockDim.x + threadIdx.x - lane; r0 < n; r0 += nthreads) {
+    const int r = r0 + lane;
+    int a = 0, len = 0;
+    if (r < n) {
+      a = rev_ptr[r];
+      len = rev_ptr[r + 1] - a;
+      if (len > 1 && len <= kRevThreadMax) {                 // insertion sort in registers
+        int32_t e[kRevThreadMax];
+#pragma unroll
+        for (int i = 0; i < kRevThreadMax; ++i) e[i] = i < len ? rev_edge[a + i] : 0x7fffffff;
+#pragma unroll
+        for (int i = 1; i < kRevThreadMax; ++i)
+#pragma unroll
+          for (int j = i; j > 0; --j)
+            if (e[j] < e[j - 1]) { const int32_t t = e[j]; e[j] = e[j - 1]; e[j - 1] = t; }
+#pragma unroll
+        for (int i = 0; i < kRevThreadMax; ++i)
+          if (i < len) rev_edge[a + i] = e[i];
+      } else if (len > kRevWarpMax) {
+        long_rows[1 + atomicAdd(long_rows, 1)] = r;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, len > kRevThreadMax && len <= kRevWarpMax);
+    while (todo) {
+      const int src_lane = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int aw = __shfl_sync(0xffffffffu, a, src_lane), lw = __shfl_sync(0xffffffffu, len, src_lane);
+      for (int i = lane; i < lw; i += 32) buf[w][i] = rev_edge[aw + i];
+      __syncwarp();
+      for (int i = lane; i < lw; i += 32) {
+        const int32_t e = buf[w][i];
+        int rank = 0;
+        for (int j = 0; j < lw; ++j) rank += buf[w][j] < e ? 1 : 0;      // entries of a row are distinct
+        rev_edge[aw + rank] = e;
+      }
+      __syncwarp();
+    }
+  }
+}
+// rows beyond kRevWarpMax entries (one source picked > 1024 times inside one block: extreme hubs only): one CTA per row
+__global__ void __launch_bounds__(1024) k_rev_sort_long(const int32_t* __restrict__ rev_ptr, int32_t* __restrict__ rev_edge,
+                                                        int32_t* __restrict__ long_rows, int32_t* __restrict__ copy) {
+  const int nl = long_rows[0];
+  for (int q = blockIdx.x; q < nl; q += gridDim.x) {
+    const int r = long_rows[1 + q];
+    const int a = rev_ptr[r], len = rev_ptr[r + 1] - a;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) copy[a + i] = rev_edge[a + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const int32_t e = copy[a + i];
+      int rank = 0;
+      for (int j = 0; j < len; ++j) rank += copy[a + j] < e ? 1 : 0;
+      rev_edge[a + rank] = e;
+    }
+    __syncthreads();
+  }
+}
+
 int reverse_edges(ToBlockWs* ws, const int32_t* edge_lid, const int32_t* n_dst_dev, int n_dst_max, int fanout, int n_src_max,
                   int32_t* rev_ptr, int32_t* rev_edge, cudaStream_t s) {
   const int64_t ne_max = (int64_t)n_dst_max * fanout;
@@ -157,6 +226,12 @@ int reverse_edges(ToBlockWs* ws, const int32_t* edge_lid, const int32_t* n_dst_d
   OGL_TRY(exclusive_scan_i32(ws->rev_cnt, rev_ptr, (int64_t)n_src_max + 1, ws->rev_scan_scratch, nullptr, s));   // own scratch: may run beside to_block
   OGL_LAUNCH(k_rev_fill, grid_for(ne_max, kBlock), kBlock, 0, s, edge_lid, n_dst_dev, n_dst_max, fanout, rev_ptr, ws->rev_cnt + ws->rev_cap,
              rev_edge);
+  // canonical (ascending) order inside every row: the backward pass is then bit-reproducible.  Rows beyond the live source count
+  // are empty (their counters are zero), so the pass simply covers all n_src_max rows
+  OGL_CUDA(cudaMemsetAsync(ws->rev_sort_scratch, 0, sizeof(int32_t), s));
+  OGL_LAUNCH(k_rev_sort, grid_for(n_src_max, kBlock, 16), kBlock, 0, s, rev_ptr, rev_edge, (const int32_t*)nullptr, n_src_max,
+             ws->rev_sort_scratch);
+  OGL_LAUNCH(k_rev_sort_long, 32, 1024, 0, s, rev_ptr, rev_edge, ws->rev_sort_scratch, ws->rev_sort_scratch + (ws->ne_max / kRevWarpMax + 8));
   return OGL_OK;
 }
 
@@ -180,6 +255,7 @@ int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max, int64_t rows_max
   ws->rev_cap = (rows_max > v_cap ? rows_max : v_cap) + 1;      // a frontier may exceed v_cap by the duplicates among its seeds
   OGL_CUDA(cudaMalloc(&ws->rev_cnt, sizeof(int32_t) * 2 * (size_t)ws->rev_cap));
   OGL_CUDA(cudaMalloc(&ws->rev_scan_scratch, sizeof(int32_t) * scan_scratch_elems(ws->rev_cap + 1)));
+  OGL_CUDA(cudaMalloc(&ws->rev_sort_scratch, sizeof(int32_t) * (size_t)(ne_max / kRevWarpMax + 8 + ne_max + 8)));
   OGL_CUDA(cudaMalloc(&ws->n_new, sizeof(int32_t)));
   OGL_LAUNCH(k_fill_i32, grid_for(v_cap, kBlock), kBlock, 0, 0, ws->first, 0x7fffffff, v_cap);
   OGL_CUDA(cudaDeviceSynchronize());
@@ -187,7 +263,7 @@ int to_block_init(ToBlockWs* ws, int64_t v_cap, int64_t ne_max, int64_t rows_max
 }
 
 void to_block_free(ToBlockWs* ws) {
-  cudaFree(ws->first); cudaFree(ws->flags); cudaFree(ws->pos); cudaFree(ws->scan_scratch); cudaFree(ws->n_new); cudaFree(ws->rev_cnt); cudaFree(ws->rev_scan_scratch);
+  cudaFree(ws->first); cudaFree(ws->flags); cudaFree(ws->pos); cudaFree(ws->scan_scratch); cudaFree(ws->n_new); cudaFree(ws->rev_cnt); cudaFree(ws->rev_scan_scratch); cudaFree(ws->rev_sort_scratch);
   *ws = ToBlockWs();
 }
 

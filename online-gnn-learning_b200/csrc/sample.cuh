@@ -12,6 +12,7 @@ struct ToBlockWs {
   int32_t* n_new = nullptr;
   int32_t* rev_cnt = nullptr;       // [2 * rev_cap]: per-source counters, then fill cursors
   int32_t* rev_scan_scratch = nullptr;
+  int32_t* rev_sort_scratch = nullptr;   // [ne_max + 2]: [0] = number of long rows, [1 ..] their ids, then a copy buffer
   int64_t rev_cap = 0;
   int64_t v_cap = 0, ne_max = 0;
 };

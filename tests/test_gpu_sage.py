@@ -508,3 +508,37 @@ def test_tail_gemm_in_pieces_equals_whole(mode):
     assert float(g0[:600 * 600].abs().max()) > 0
     # different split counts over the rows -> a different (still fixed) summation order of the fp32 partials
     close(g1, g0, 1e-5, "gradient, pieces vs whole")
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_train_step_is_bit_reproducible(mode):
+    """reverse edge lists are put into canonical order after the atomic fill, so the max-pool backward sums every source row's
+    contributions in the same order on every run: two runs from the same state give bit-identical gradients and weights -- on a
+    graph with hub sources that are picked > 1024 times in one block (CTA-wide ordering), tens of times (warp) and a few times"""
+    import ogl_b200
+    V, E, B = 4000, 60000, 500
+    rng = np.random.default_rng(2)
+    src = np.where(rng.random(E) < 0.5, rng.integers(0, 4, E), rng.integers(0, V, E)).astype(np.int64)
+    dst = rng.integers(0, V, E).astype(np.int64)
+    runs = []
+    for _ in range(2):
+        g = ogl_b200.native.Graph(V, 2 * E)
+        g.insert_vertices(V)
+        g.insert_edges(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), symmetric=False)
+        m = {"bf16": ogl_b200.OGL_BF16, "tf32": ogl_b200.OGL_TF32}[mode]
+        f = ogl_b200.native.Features(V, 40, m)
+        gen = torch.Generator().manual_seed(0)
+        f.write(0, torch.randn(V, 40, generator=gen).cuda(), torch.randint(0, 5, (V,), generator=gen).cuda())
+        params = osage.xavier_params(40, 24, 5, 1, seed=1)
+        flat = flat_from_dict(params, 2).cuda()
+        grad = torch.zeros_like(flat)
+        plan = ogl_b200.native.Plan([40, 24, 5], [10, 10], B, V, mode=m, seed=3)
+        plan.bind_params(flat, grad)
+        seeds = torch.arange(100, 100 + B, dtype=torch.int64).cuda()
+        for _step in range(3):
+            plan.train_step(g, f, seeds, loss_scale=1.0 / B, do_step=True)
+        torch.cuda.synchronize()
+        rp = plan.block_edges(1)
+        runs.append((flat.clone(), grad.clone()))
+    assert torch.equal(runs[0][1], runs[1][1]), "gradients differ between two identical runs"
+    assert torch.equal(runs[0][0], runs[1][0]), "weights differ between two identical runs"
