@@ -48,9 +48,10 @@ constexpr int SMEM_NT2 = RING2_BYTES + STORE_BYTES + BIAS_BYTES + TAIL_BYTES;
 // TN kernel: its epilogue starts after the last MMA has retired, so its staging boxes alias the (then idle) operand ring
 constexpr int SMEM_TN = RING_BYTES + TAIL_BYTES;
 static_assert(SMEM_NT1 <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
-constexpr int THREADS = 192;     // TN kernel: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
-constexpr int THREADS_NT = 320;  // NT kernel: the same roles with EIGHT epilogue warps (two per TMEM lane quarter, each taking
-                                 // every other 64-column box) so that draining a tile stays well below the tile's MMA time
+constexpr int THREADS = 288;     // TN kernel: warps 0, 6 (A halves) and 7, 8 (B halves) TMA producers, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
+constexpr int THREADS_NT = 384;  // NT kernel: the same roles with EIGHT epilogue warps (two per TMEM lane quarter, each taking
+                                 // every other 64-column box) so that draining a tile stays well below the tile's MMA time,
+                                 // and a second TMA producer (warp 10; see k_gemm_nt_tc)
 
 // ------------------------------------------------------------------ PTX wrappers ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -305,6 +306,7 @@ struct NtParams {
   int round_out;
   int zero_tail;
   int prefetch;                 // k-blocks the A operand is prefetched into L2 ahead of its load (0: off)
+  int loader;                   // 3: two TMA producers (warp 0: A boxes, warp 10: B boxes), 0: one
   int debug;                    // perf experiments (OGL_GEMM_DBG): 1 = epilogue drains the accumulator without storing
 };
 
@@ -337,7 +339,9 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
     if (p.out_bf16 || p.out_f32_tma) prefetch_tensormap(&p.tc);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    s.tmem_slot[2] = 0;                            // the A producer's progress counter (read by the L2 prefetcher)
+    // full[]: loader 0: one TMA producer; 3: two TMA producers (A | B), one expect_tx arrival each
+    for (int i = 0; i < NST; ++i) { mbar_init(&s.full[i], p.loader == 3 ? 2 : 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -354,57 +358,75 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   pdl_trigger();                         // a GEMM behind this one cannot share an SM with it (shared memory): it takes each SM as this
                                          // kernel's CTA leaves it, instead of waiting for the whole grid
 
-  if (warp == 0) {
-    // ===== TMA producer (in pair mode: in both CTAs, each for its own shared memory) =====
-    if (lane == 0 && !(p.debug & 2)) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // bytes landing per stage on the barrier the MMA issuer waits on (pair mode: both CTAs' boxes, on the leader's)
-      const uint32_t tx = CG == 2 ? (uint32_t)(2 * (A_STAGE_BYTES + (p.bn / 2) * 128)) : (uint32_t)(A_STAGE_BYTES + p.bn * 128);
-      // prefetch cursor: the A boxes (activations: they stream from DRAM; the weights are L2-resident anyway) of the position
-      // p.prefetch k-blocks ahead of the load, across segment and tile boundaries
-      int pt = unit, pseg = 0, pkb = 0;
-      auto pf_settle = [&]() {                       // first live (tile, segment, k-block) at or after the cursor
-        while (pt < total_tiles) {
-          while (pseg < p.n_seg) {
-            if ((pt / p.n_tiles) * CG * BM < rows_valid[pseg] && pkb < (p.k[pseg] + BKE - 1) / BKE) return;
-            ++pseg; pkb = 0;
-          }
-          pseg = 0; pkb = 0; pt += n_units;
+  // ===== TMA producers (in pair mode: in both CTAs, each for its own shared memory) =====
+  // One thread's TMA copies are served at ~30 B/clk however many are in flight; copies issued by threads of DIFFERENT warps are
+  // served in parallel (tools/exp/ingest_probe.cu: 30.4 B/clk from one issuing thread, 60.7 from two).  The kernel needs ~64 B/clk
+  // to keep the tensor pipe fed, so the A and the B boxes of a stage are issued by two producers (warp 0 and warp 10), each with
+  // its own expect_tx arrival on the stage's full barrier.  which: 0 = A and B (single producer), 1 = A only, 2 = B only.
+  // which: 0 = A and B (single producer), 1 = A only, 2 = B only, 3 = no loads at all: L2 PREFETCHES of the A boxes p.prefetch
+  // k-blocks ahead of the loads (warp 11).  The A operand streams from DRAM; a miss costs 2-3 us under load, and the ring's 160 KB
+  // then sustain only ~32 B/clk per SM (Little's law) -- a box that is already in L2 when its load is issued comes back in ~0.7 us.
+  // The prefetcher paces itself on a progress counter in shared memory that the A producer advances once per stage: it stays at
+  // most p.prefetch k-blocks ahead and ends with its cursor (no barrier wait that could outlive the producers).
+  auto tma_producer = [&](int which) {
+    int stage = 0;
+    uint32_t phase = 0;
+    // prefetch cursor: (tile, segment, k-block) of the position p.prefetch k-blocks ahead, across segment and tile boundaries
+    int pt = unit, pseg = 0, pkb = 0;
+    auto pf_issue = [&]() {
+      while (pt < total_tiles) {                    // settle on the first live position at or after the cursor
+        bool found = false;
+        while (pseg < p.n_seg) {
+          if ((pt / p.n_tiles) * CG * BM < rows_valid[pseg] && pkb < (p.k[pseg] + BKE - 1) / BKE) { found = true; break; }
+          ++pseg; pkb = 0;
         }
-      };
-      auto pf_issue = [&]() {
-        pf_settle();
-        if (pt < total_tiles) {
-          tma_prefetch_2d(&p.ta[pseg], pkb * BKE, ((pt / p.n_tiles) * CG + rank) * BM);
-          ++pkb;
-        }
-      };
-      for (int i = 0; i < p.prefetch; ++i) pf_issue();
-      for (int t = unit; t < total_tiles; t += n_units) {
-        const int mt = t / p.n_tiles, nb = t % p.n_tiles;
-        const int mb = mt * CG + rank;
-        const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
-        for (int seg = 0; seg < p.n_seg; ++seg) {
-          if (mt * CG * BM >= rows_valid[seg]) continue;          // (pair-uniform: decided on the pair's first row)
-          const int nkb = (p.k[seg] + BKE - 1) / BKE;
-          for (int kb = 0; kb < nkb; ++kb) {
-            if (p.prefetch) pf_issue();
-            mbar_wait(&s.empty[stage], phase ^ 1);
-            if (CG == 2) {
-              if (rank == 0) mbar_expect_tx(&s.full[stage], tx);
-              tma_load_2d_pair(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
-              tma_load_2d_pair(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX + rank * (bn_tile / 2));
-            } else {
-              mbar_expect_tx(&s.full[stage], tx);
-              tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
-              tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX);
-            }
-            if (++stage == NST) { stage = 0; phase ^= 1; }
+        if (found) break;
+        pseg = 0; pkb = 0; pt += n_units;
+      }
+      if (pt < total_tiles) {
+        tma_prefetch_2d(&p.ta[pseg], pkb * BKE, ((pt / p.n_tiles) * CG + rank) * BM);
+        ++pkb;
+      }
+    };
+    volatile int* prog = (volatile int*)(s.tmem_slot + 2);          // k-blocks the A producer has issued so far
+    if (which == 3) {
+      for (int n_pf = 0; pt < total_tiles; ++n_pf) {
+        while (n_pf - *prog >= p.prefetch) __nanosleep(64);
+        pf_issue();
+      }
+      return;
+    }
+    int n_issued = 0;
+    // bytes this producer lands per stage on the barrier the MMA issuer waits on (pair mode: both CTAs' boxes, on the leader's)
+    const uint32_t tx_a = (uint32_t)(CG * A_STAGE_BYTES);
+    const uint32_t tx_b = CG == 2 ? (uint32_t)(2 * (p.bn / 2) * 128) : (uint32_t)(p.bn * 128);
+    const uint32_t tx = which == 0 ? tx_a + tx_b : (which == 1 ? tx_a : tx_b);
+    for (int t = unit; t < total_tiles; t += n_units) {
+      const int mt = t / p.n_tiles, nb = t % p.n_tiles;
+      const int mb = mt * CG + rank;
+      const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
+      for (int seg = 0; seg < p.n_seg; ++seg) {
+        if (mt * CG * BM >= rows_valid[seg]) continue;          // (pair-uniform: decided on the pair's first row)
+        const int nkb = (p.k[seg] + BKE - 1) / BKE;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&s.empty[stage], phase ^ 1);
+          if (which != 2) *prog = ++n_issued;
+          if (CG == 2) {
+            if (rank == 0) mbar_expect_tx(&s.full[stage], tx);
+            if (which != 2) tma_load_2d_pair(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
+            if (which != 1) tma_load_2d_pair(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX + rank * (bn_tile / 2));
+          } else {
+            mbar_expect_tx(&s.full[stage], tx);
+            if (which != 2) tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
+            if (which != 1) tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX);
           }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
+  };
+  if (warp == 0) {
+    if (lane == 0 && !(p.debug & 2) && (p.loader == 0 || p.loader == 3)) tma_producer(p.loader == 3 ? 1 : 0);
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer (pair mode: the leader CTA only) =====
@@ -458,6 +480,13 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       }
     }
     __syncwarp();
+  } else if (warp >= 10) {
+    // ===== second TMA producer (warp 10) =====
+    if (p.loader == 3) {
+      if (warp == 10 && lane == 0 && !(p.debug & 2)) tma_producer(2);      // the second TMA producer: the B boxes
+      if (warp == 11 && lane == 0 && !(p.debug & 2) && p.prefetch > 0) tma_producer(3);      // the L2 prefetcher of the A boxes
+      __syncwarp();
+    }
   } else {
     // ===== epilogue: TMEM -> registers -> bias / ReLU / mask -> swizzled smem box -> TMA store =====
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
@@ -752,7 +781,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
     if (p.use_tma_store) prefetch_tensormap(&q.tout);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TN_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < TN_STAGES; ++i) { mbar_init(&s.full[i], 4); mbar_init(&s.empty[i], 1); }      // (four producers)
     mbar_init(&s.acc_full[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -764,25 +793,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   auto a_stage = [&](int i) { return smem_raw + i * TN_A_STAGE_BYTES; };
   pdl_wait();
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)((n_chunks_a + n_chunks_b) * CHUNK_BYTES);
-      auto pf = [&](int kb) {                      // both operands are activations streaming from DRAM
-        for (int c = 0; c < n_chunks_a; ++c) tma_prefetch_2d(&q.ta, row0 + c * CW, kb * BKR);
-        for (int c = 0; c < n_chunks_b; ++c) tma_prefetch_2d(&q.tb, kt * BN_MAX + c * CW, kb * BKR);
-      };
-      for (int kb = kb0; kb < min(kb1, kb0 + p.prefetch); ++kb) pf(kb);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        if (p.prefetch && kb + p.prefetch < kb1) pf(kb + p.prefetch);
-        mbar_wait(&s.empty[stage], phase ^ 1);
-        mbar_expect_tx(&s.full[stage], tx);
-        for (int c = 0; c < n_chunks_a; ++c) tma_load_2d(a_stage(stage) + c * CHUNK_BYTES, &q.ta, &s.full[stage], row0 + c * CW, kb * BKR);
-        for (int c = 0; c < n_chunks_b; ++c) tma_load_2d(s.b(stage) + c * CHUNK_BYTES, &q.tb, &s.full[stage], kt * BN_MAX + c * CW, kb * BKR);
-        if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
-      }
+  // FOUR TMA producers (see k_gemm_nt_tc: copies issued by ONE thread are served at ~30 B/clk -- and, for the 4 KB boxes of the
+  // tf32 flavour, at a fixed cost per box -- while those of different warps are served in parallel): warps 0 / 6 load the first /
+  // second half of the A chunks of a stage, warps 7 / 8 of the B chunks; each makes its own expect_tx arrival on the full barrier
+  auto tma_producer = [&](int which, int part) {    // which: 1 = A chunks, 2 = B chunks; part: 0 / 1 = first / second half of them
+    int stage = 0;
+    uint32_t phase = 0;
+    constexpr int HALF = NCH_A / 2;
+    const int n_all = which == 1 ? n_chunks_a : n_chunks_b;
+    const int c0 = part * HALF, c1 = min(n_all, c0 + HALF);
+    const uint32_t tx = (uint32_t)(max(c1 - c0, 0) * CHUNK_BYTES);
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&s.empty[stage], phase ^ 1);
+      mbar_expect_tx(&s.full[stage], tx);
+      if (which == 1)
+        for (int c = c0; c < c1; ++c) tma_load_2d(a_stage(stage) + c * CHUNK_BYTES, &q.ta, &s.full[stage], row0 + c * CW, kb * BKR);
+      else
+        for (int c = c0; c < c1; ++c) tma_load_2d(s.b(stage) + c * CHUNK_BYTES, &q.tb, &s.full[stage], kt * BN_MAX + c * CW, kb * BKR);
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
     }
+  };
+  if (warp == 0 || warp >= 6) {
+    if (lane == 0) tma_producer(warp == 0 || warp == 6 ? 1 : 2, warp == 0 || warp == 7 ? 0 : 1);
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
@@ -1044,9 +1076,13 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.round_out = g.out_tf32;
   p.zero_tail = g.zero_tail;
   {
-    static int dbg = -1, pfd = -1;
+    static int dbg = -1, pfd = -1, ldr = -1;
     if (dbg < 0) { const char* e = getenv("OGL_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
-    if (pfd < 0) { const char* e = getenv("OGL_GEMM_PF_NT"); pfd = e ? atoi(e) : 0; }      // (measured: prefetches cost TMA issue slots, slower)
+    if (ldr < 0) { const char* e = getenv("OGL_GEMM_LOADER"); ldr = e ? atoi(e) : 3; }
+    if (ldr != 0) ldr = 3;
+    p.loader = ldr;
+    // (measured, tf32 fc_pool GEMM: 140 us without the prefetcher, 150 us with it 12 k-blocks ahead -- off by default)
+    if (pfd < 0) { const char* e = getenv("OGL_GEMM_PF_NT"); pfd = e ? atoi(e) : 0; }
     p.debug = dbg;
     p.prefetch = pfd;
   }
