@@ -662,6 +662,7 @@ extern "C" int ogl_graph_create(ogl_graph** out, int64_t v_cap, int64_t e_cap_di
   OGL_CUDA(cudaMemset(g->cap, 0, sizeof(int32_t) * v_cap));
   OGL_CUDA(cudaMemset(g->add, 0, sizeof(int32_t) * v_cap));
   OGL_CUDA(cudaMemset(g->ctl, 0, sizeof(GraphCtl)));
+  OGL_CUDA(cudaMemset(g->n_jobs, 0, 2 * sizeof(int)));      // (the fused insert expects and leaves the per-batch counters zero)
   *out = g;
   return OGL_OK;
 }
