@@ -494,12 +494,15 @@ def workload_config(w, name, world):
                         "2-layer GraphSAGE-pool, Adam" % (name, w["V"], w["E"], 2 * w["E"], w["F"], w["C"], w["H"], w["B"], w["fanouts"]),
             "global_batch": w["B"] * world, "parallelism": ("dp%d (replicated graph+features, two gradient buckets, %s, on a comm stream)" % (world, EXCHANGE_NAME.get(EXCHANGE[0], "?")) if world > 1 else "single GPU") +
                            "; sample+gather of step t+1 prefetched (second buffer set, own stream) under forward/backward of step t",
-            "l2": "inputs larger than L2: feature table %.0f MB (fp32 storage of the tf32 mode; %.0f MB in bf16) + CSR %.0f MB resident, random "
+            "l2": "inputs larger than L2: feature table %.0f MB in the tf32 mode (fp32 storage), %.0f MB in fp16 / bf16, + CSR %.0f MB resident, random "
                   "row gathers; no explicit flush" % (w["V"] * ((w["F"] + 7) // 8 * 8) * 4 / 1e6, w["V"] * ((w["F"] + 7) // 8 * 8) * 2 / 1e6,
                                                       2 * w["E"] * 8 * 1.5 / 1e6)}
 
 
-DTYPES = {"tf32": dict(es=4, note="fp32 storage with every GEMM operand rounded to TF32 where it is produced, tcgen05.mma.kind::tf32, fp32 accumulation"),
+DTYPES = {"fp16": dict(es=2, note="fp16 storage (ten explicit mantissa bits, as TF32) with static loss scaling: activation gradients are stored times a "
+                                  "power of two derived from 1 / global batch and every weight / bias gradient is unscaled exactly where it is "
+                                  "written in fp32; tcgen05.mma.kind::f16, fp32 accumulation, fp32 master weights and Adam"),
+          "tf32": dict(es=4, note="fp32 storage with every GEMM operand rounded to TF32 where it is produced, tcgen05.mma.kind::tf32, fp32 accumulation"),
           "bf16": dict(es=2, note="bf16 storage, tcgen05.mma.kind::f16, fp32 accumulation: the fast mode, a labelled DEVIATION from north_star's "
                                   "rtol 1e-3 against the reference's fp32 path (see its `parity` block)")}
 
@@ -511,7 +514,7 @@ def measure(dt, headline, args, w, rank, world, dev, dist, g, feats, labels, hos
     from ogl_b200 import native
     V, B, K, W = w["V"], w["B"], args.steps, args.warmup
     es = DTYPES[dt]["es"]
-    mode = {"tf32": ogl_b200.OGL_TF32, "bf16": ogl_b200.OGL_BF16}[dt]
+    mode = {"tf32": ogl_b200.OGL_TF32, "bf16": ogl_b200.OGL_BF16, "fp16": ogl_b200.OGL_FP16}[dt]
     fs = native.Features(V, w["F"], mode)
     fs.write(0, feats, labels)
     params = init_params(w)
@@ -778,7 +781,7 @@ def measure(dt, headline, args, w, rank, world, dev, dist, g, feats, labels, hos
             torch.cuda.synchronize()
             cur = opar.dict_from_flat(flat.detach().cpu(), [w["F"], w["H"], w["C"]])
             m = opar.compare_step(plan, cur, host["feats"], host["labels"], seeds, logits, per_v, grad,
-                                  {"tf32": 2.0 ** -10, "bf16": 2.0 ** -8}[dt])
+                                  {"tf32": 2.0 ** -10, "fp16": 2.0 ** -10, "bf16": 2.0 ** -8}[dt])
             r = opar.summary(m)
             r["weights"] = label
             r["logits_scale"] = m["logits"]["scale"]
@@ -841,7 +844,7 @@ def run_ours(args, rank, world, local_rank):
 
     dts = [args.dtype]
     if world == 1 and not args.no_alt:
-        dts.append("bf16" if args.dtype == "tf32" else "tf32")
+        dts += [d for d in ("fp16", "tf32", "bf16") if d != args.dtype]
     res = {}
     for i, dt in enumerate(dts):
         res[dt] = measure(dt, i == 0, args, w, rank, world, dev, dist, g, feats, labels, host, peaks, clocks)
@@ -886,10 +889,10 @@ def run_ours(args, rank, world, local_rank):
             aux["cached_inference"] = aux_cached_inference()
         except Exception as e:                       # the aux leg must never take the headline line with it
             aux = {"elliptic_pbr": {"error": repr(e)[:300]}}
-    alt = None
+    alt = []
     for dt in dts[1:]:
         r = res[dt]
-        alt = {k: r[k] for k in ("dtype", "arithmetic", "value", "ms_per_step", "e2e", "parity", "parity_trained", "clocks") if k in r}
+        alt.append({k: r[k] for k in ("dtype", "arithmetic", "value", "ms_per_step", "e2e", "parity", "parity_trained", "clocks") if k in r})
     line = {"metric": "graphsage_train_vertices_per_s", "value": head["value"], "unit": "vertices/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"],
             "arithmetic": head["arithmetic"], "data": "synthetic", "config": workload_config(w, args.workload, world),
@@ -897,7 +900,7 @@ def run_ours(args, rank, world, local_rank):
             "host_enqueue_ms_per_step": head["host_enqueue_ms_per_step"], "gpu_launches": head.get("gpu_launches"),
             "cuda_graph": head["cuda_graph"], "clocks": head["clocks"], "roofline": head.get("roofline"), "cpu_baseline": cpu,
             "mean_level_counts": head.get("mean_level_counts"), "stages": head.get("stages"), "stages_mode": head.get("stages_mode"),
-            "alt": alt, "aux": aux,
+            "alt": alt or None, "aux": aux,
             "edge_insert": {"stream_edges_per_s": E / (insert_ms / 1e3), "ms": insert_ms, "batch_stream_edges": chunk, "launches": insert_launches,
                             "algorithmic_gbs": 2 * E * (16 + 8 + 8) / (insert_ms / 1e3) / 1e9, "snapshot": snap}}
     print(json.dumps(line), flush=True)
@@ -918,10 +921,11 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gradient exchange + Adam fused in one kernel over NVLink peer memory, or NCCL all-reduce + Adam")
     ap.add_argument("--no-pipeline", action="store_true", help="one fused ogl_plan_train_step per step instead of the prefetch pipeline")
-    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
-                    help="arithmetic of the headline line: tf32 meets north_star's rtol 1e-3 against the reference's fp32 path, bf16 is the "
-                         "faster labelled deviation (N = 1 prints the other one too, under `alt`)")
-    ap.add_argument("--no-alt", action="store_true", help="N = 1: do not measure the other arithmetic mode")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "tf32", "bf16"],
+                    help="arithmetic of the headline line: fp16 (loss-scaled) and tf32 meet north_star's rtol 1e-3 against the reference's fp32 "
+                         "path -- fp16 stores half the bytes and issues at twice the tensor rate; bf16 is as fast as fp16 but a labelled deviation "
+                         "(N = 1 prints the other modes too, under `alt`)")
+    ap.add_argument("--no-alt", action="store_true", help="N = 1: do not measure the other arithmetic modes")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity leg (one step against the fp64 oracle, untimed)")
     args = ap.parse_args()
     EXCHANGE[0] = args.exchange

@@ -37,8 +37,12 @@ typedef struct ogl_peer ogl_peer;         /* one rank's end of the NVLink peer-m
 /* arithmetic mode of the dense path.  OGL_F32: fp32 storage, SIMT FFMA GEMMs (exact; rtol 1e-5 against the fp32 reference path).
  * OGL_BF16: bf16 storage, tcgen05 kind::f16 GEMMs with fp32 accumulation (fastest; ~2^-9 per stored value).
  * OGL_TF32: fp32 storage with every GEMM operand rounded to TF32 where it is produced, tcgen05 kind::tf32 GEMMs with fp32
- *           accumulation -- the tensor-core mode that meets rtol 1e-3 against the reference's fp32 path (utils.py:63-64). */
-enum { OGL_F32 = 0, OGL_BF16 = 1, OGL_TF32 = 2 };
+ *           accumulation -- the tensor-core mode that meets rtol 1e-3 against the reference's fp32 path (utils.py:63-64).
+ * OGL_FP16: fp16 storage (the same 10 explicit mantissa bits as TF32 in half the bytes), tcgen05 kind::f16 GEMMs with fp32
+ *           accumulation, STATIC LOSS SCALING: activation gradients are stored times a power of two chosen from the loss scale
+ *           (so that they sit in fp16's normal range) and every weight / bias gradient is unscaled, exactly, where it is written
+ *           in fp32.  TF32's error at bf16's speed; stored values must stay below 65504 (standardised features). */
+enum { OGL_F32 = 0, OGL_BF16 = 1, OGL_TF32 = 2, OGL_FP16 = 3 };
 enum { OGL_OK = 0, OGL_ERR_CUDA = -1, OGL_ERR_ARG = -2, OGL_ERR_CAPACITY = -3, OGL_ERR_NODEVICE = -4 };
 
 const char* ogl_last_error(void);
@@ -110,8 +114,8 @@ typedef struct {
   int fanouts[8];        /* fanouts[0] at the seeds hop, [1] next hop out, ... */
   int max_seeds;
   int64_t v_cap;
-  int mode;              /* OGL_F32 | OGL_BF16 | OGL_TF32 */
-  int gemm_impl;         /* 0 = default for mode (tcgen05 for bf16 / tf32, SIMT for f32), 1 = force SIMT (tests) */
+  int mode;              /* OGL_F32 | OGL_BF16 | OGL_TF32 | OGL_FP16 */
+  int gemm_impl;         /* 0 = default for mode (tcgen05 for bf16 / tf32 / fp16, SIMT for f32), 1 = force SIMT (tests) */
   uint64_t seed;         /* Philox key */
   float lr, beta1, beta2, eps;
   float feat_drop;       /* SAGEConv(feat_drop=dropout), graphsage_dgl.py:41-46: dropout of every layer's input rows in training mode
@@ -305,6 +309,13 @@ int ogl_gemm_tf32_nt_ex(const float* a_dev, int lda, const float* b_dev, int ldb
                         int tma_out, const float* bias_dev, int relu, const float* mask_dev, int ldmask, int cg, void* stream);
 int ogl_gemm_tf32_tn(const float* a_dev, int lda, const float* b_dev, int ldb, float* c_dev, int ldc,
                      int m, int n, int k, float* workspace_dev, int64_t workspace_elems, void* stream);
+/* the fp16 flavour (mode OGL_FP16: tcgen05 kind::f16 on fp16 operands -- TF32's 10 mantissa bits in half the bytes).  out_f16: fp16
+ * output through TMA stores, optional fp16 mask (out = mask > 0 ? out : 0); alpha scales the weight-gradient output (the plan
+ * passes 1 / loss scale: activation gradients are stored times a power of two) */
+int ogl_gemm_f16_nt_ex(const void* a_dev, int lda, const void* b_dev, int ldb, void* c_dev, int ldc, int m, int n, int k,
+                       int out_f16, const float* bias_dev, int relu, const void* mask_dev, int ldmask, int cg, void* stream);
+int ogl_gemm_f16_tn(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc,
+                    int m, int n, int k, float alpha, float* workspace_dev, int64_t workspace_elems, void* stream);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus

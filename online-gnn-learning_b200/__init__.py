@@ -2,7 +2,7 @@
 `--backend pytorch --cuda`).  Host code is Python/PyTorch plumbing over hand-written sm_100a kernels
 reached through the C ABI in include/ogl_b200.h; there is no CPU or eager fallback."""
 from . import config                                  # noqa: F401
-from ._lib import OGL_F32, OGL_BF16, OGL_TF32, OglError, LIB_PATH, kernel_launches          # noqa: F401
+from ._lib import OGL_F32, OGL_BF16, OGL_TF32, OGL_FP16, OglError, LIB_PATH, kernel_launches          # noqa: F401
 from . import _native as native                       # noqa: F401
 from . import utils, sampling, parallel, inference    # noqa: F401
 from .utils import Lib_supported, init                # noqa: F401

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libogl_b200.so")
 
-OGL_F32, OGL_BF16, OGL_TF32 = 0, 1, 2
+OGL_F32, OGL_BF16, OGL_TF32, OGL_FP16 = 0, 1, 2, 3
 
 
 class OglError(RuntimeError):
@@ -120,6 +120,8 @@ SIGNATURES = {
     "ogl_gemm_bf16_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "ogl_gemm_tf32_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "ogl_gemm_tf32_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "ogl_gemm_f16_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "ogl_gemm_f16_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i64, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

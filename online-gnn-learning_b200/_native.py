@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import lib, check, PlanConfig, OGL_F32, OGL_BF16, OGL_TF32, kernel_launches  # noqa: F401
+from ._lib import lib, check, PlanConfig, OGL_F32, OGL_BF16, OGL_TF32, OGL_FP16, kernel_launches  # noqa: F401
 
 
 def _stream():
@@ -32,7 +32,7 @@ class _CAI:
 
 
 _TYPESTR = {torch.float32: ("<f4", 4), torch.int32: ("<i4", 4), torch.int64: ("<i8", 8), torch.uint8: ("|u1", 1),
-            torch.float64: ("<f8", 8), torch.bfloat16: ("<i2", 2)}
+            torch.float64: ("<f8", 8), torch.bfloat16: ("<i2", 2), torch.float16: ("<f2", 2)}
 
 
 def wrap_device(ptr, shape, dtype, pitch=None):
@@ -203,7 +203,7 @@ class Plan:
         check(lib.ogl_plan_create(C.byref(self._h), C.byref(cfg)))
         self.dims, self.fanouts, self.L = list(dims), list(fanouts), L
         self.max_seeds, self.v_cap, self.mode = int(max_seeds), int(v_cap), int(mode)
-        self.dtype = torch.bfloat16 if mode == OGL_BF16 else torch.float32
+        self.dtype = {OGL_BF16: torch.bfloat16, OGL_FP16: torch.float16}.get(mode, torch.float32)
         self.n_params = int(lib.ogl_plan_param_count(self._h))
         self._params = self._grads = None
         self.n_seeds = 0
@@ -400,7 +400,7 @@ class Plan:
     def tensor(self, name, rows=None):
         p, r, pt, eb = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
         check(lib.ogl_plan_tensor(self._h, name.encode(), C.byref(p), C.byref(r), C.byref(pt), C.byref(eb)))
-        dt = {1: torch.uint8, 2: torch.bfloat16, 4: torch.float32}[eb.value]
+        dt = {1: torch.uint8, 2: self.dtype, 4: torch.float32}[eb.value]
         return wrap_device(p.value, (rows if rows is not None else r.value, pt.value), dt)
 
 
@@ -592,6 +592,34 @@ def gemm_tf32_tn(a, b, n=None, k=None, workspace_elems=1 << 24):
     ws = torch.empty(workspace_elems, dtype=torch.float32, device="cuda") if workspace_elems else None
     check(lib.ogl_gemm_tf32_tn(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), k, a.shape[0], n, k,
                                _ptr(ws), int(workspace_elems), _stream()))
+    return c
+
+
+def gemm_f16_nt_ex(a, b, k=None, out_f16=True, bias=None, relu=False, mask=None, cg=0):
+    """C[M,N] = act(A[M,:k] @ B[N,:k]^T + bias) on the tcgen05 kind::f16 path with fp16 operands (mode OGL_FP16)"""
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and a.is_cuda and b.is_cuda
+    a, b = a.contiguous(), b.contiguous()
+    k = a.shape[1] if k is None else int(k)
+    ldc = (b.shape[0] + 7) // 8 * 8
+    c = torch.empty(a.shape[0], ldc, dtype=torch.float16 if out_f16 else torch.float32, device="cuda")
+    if mask is not None:
+        mask = mask.contiguous()
+        assert mask.dtype == torch.float16
+    check(lib.ogl_gemm_f16_nt_ex(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), ldc, a.shape[0], b.shape[0], k, int(out_f16),
+                                 _ptr(bias), int(relu), _ptr(mask), mask.shape[1] if mask is not None else 0, int(cg), _stream()))
+    return c[:, :b.shape[0]]
+
+
+def gemm_f16_tn(a, b, n=None, k=None, alpha=1.0, workspace_elems=1 << 24):
+    """C[N,K] fp32 = alpha * A[M,:n]^T @ B[M,:k] on the tcgen05 kind::f16 path with fp16 MN-major operands"""
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and a.is_cuda and b.is_cuda and a.shape[0] == b.shape[0]
+    a, b = a.contiguous(), b.contiguous()
+    n = a.shape[1] if n is None else int(n)
+    k = b.shape[1] if k is None else int(k)
+    c = torch.empty(n, k, dtype=torch.float32, device="cuda")
+    ws = torch.empty(workspace_elems, dtype=torch.float32, device="cuda") if workspace_elems else None
+    check(lib.ogl_gemm_f16_tn(_ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), k, a.shape[0], n, k, float(alpha),
+                              _ptr(ws), int(workspace_elems), _stream()))
     return c
 
 

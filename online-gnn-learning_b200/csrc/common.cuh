@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -101,6 +102,9 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+// mode OGL_FP16: fp16 storage (10 explicit mantissa bits, like TF32; overflow gives inf on purpose -- it must be loud)
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
 // mode OGL_TF32: fp32 storage whose VALUE is rounded to TF32 (10 explicit mantissa bits, round to nearest) wherever a GEMM
 // operand is produced, so that tcgen05.mma.kind::tf32 -- which drops the low 13 mantissa bits of what it reads -- sees it exactly
@@ -113,5 +117,9 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 template <> __device__ __forceinline__ float to_f32<tf32_t>(tf32_t v) { return v.v; }
 template <> __device__ __forceinline__ tf32_t from_f32<tf32_t>(float v) { return tf32_t{round_tf32(v)}; }
+
+// element bytes / elements per 16-byte vector of a mode's storage type
+static inline int mode_is_16bit(int mode) { return mode == OGL_BF16 || mode == OGL_FP16; }
+static inline int mode_vec(int mode) { return mode_is_16bit(mode) ? 8 : 4; }
 
 }  // namespace ogl

@@ -1,4 +1,4 @@
-// Dense GEMM entry points of the GraphSAGE-pool path (SIMT fp32-accumulate + tcgen05 bf16 / tf32).
+// Dense GEMM entry points of the GraphSAGE-pool path (SIMT fp32-accumulate + tcgen05 bf16 / fp16 / tf32).
 #pragma once
 #include "common.cuh"
 
@@ -28,7 +28,8 @@ struct GemmNT {
   int m_max = 0;                   // static row bound (grid size)
   const int32_t* m_dev = nullptr;  // dynamic row count on device (nullptr: m_max)
   int n = 0;
-  int in_bf16 = 0, out_bf16 = 0;
+  int in_bf16 = 0, out_bf16 = 0;   // 16-bit operands / output ...
+  int f16 = 0;                     // ... which are fp16 instead of bf16 (mode OGL_FP16)
   int tf32 = 0;                    // mode OGL_TF32: operands are fp32 holding TF32-rounded values (tcgen05 kind::tf32 / exact on the SIMT path)
   int out_tf32 = 0;                // ... and the fp32 output is rounded to TF32 too (it is a later GEMM's operand)
   int zero_tail = 1;               // write zeros to rows [m, round_up(m, 128)) (contraction padding for later TN GEMMs)
@@ -45,8 +46,10 @@ struct GemmTN {
   int n = 0, k = 0;
   int m_max = 0;
   const int32_t* m_dev = nullptr;
-  int in_bf16 = 0;
+  int in_bf16 = 0;           // 16-bit operands ...
+  int f16 = 0;               // ... which are fp16 instead of bf16 (mode OGL_FP16)
   int tf32 = 0;              // operands are fp32 holding TF32-rounded values
+  float alpha = 1.f;         // C = alpha * A^T B (mode OGL_FP16: undoes the loss scale carried by the activation gradients)
   float* partial = nullptr;  // split workspace [splits, n, k]
   int64_t partial_elems = 0;
 };
@@ -62,7 +65,7 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s);
 
 // deterministic reduction of the split partials of up to 4 problems in one launch: c = sum over z (ascending) of partial[z]
 struct ReduceGroup {
-  struct Problem { const float* partial; float* c; int n, k, ldp, ldc; } pr[4];
+  struct Problem { const float* partial; float* c; int n, k, ldp, ldc; float alpha; } pr[4];
   int count, splits;
 };
 int reduce_splits_group(const ReduceGroup& g, cudaStream_t s);

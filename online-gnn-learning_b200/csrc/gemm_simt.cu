@@ -131,12 +131,13 @@ __global__ void __launch_bounds__(256) k_gemm_tn(GemmTN g, int rows_per_split, f
 }
 
 // deterministic reduction of the split partials: c[n, ldc] = sum_z partial[z][n][k] (z ascending)
-__global__ void __launch_bounds__(256) k_reduce_splits(const float* __restrict__ partial, int splits, int n, int k, float* __restrict__ c, int ldc) {
+__global__ void __launch_bounds__(256) k_reduce_splits(const float* __restrict__ partial, int splits, int n, int k, float* __restrict__ c, int ldc,
+                                                       float alpha) {
   const int64_t total = (int64_t)n * k;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + i];
-    c[(i / k) * ldc + (i % k)] = s;
+    c[(i / k) * ldc + (i % k)] = s * alpha;
   }
 }
 
@@ -170,10 +171,11 @@ __global__ void __launch_bounds__(256) k_reduce_splits_group(const ReduceGroup g
       acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
     }
     float* dst = q.c + r * q.ldc + col;
-    dst[0] = acc.x;
-    if (col + 1 < q.k) dst[1] = acc.y;
-    if (col + 2 < q.k) dst[2] = acc.z;
-    if (col + 3 < q.k) dst[3] = acc.w;
+    const float al = q.alpha;
+    dst[0] = acc.x * al;
+    if (col + 1 < q.k) dst[1] = acc.y * al;
+    if (col + 2 < q.k) dst[2] = acc.z * al;
+    if (col + 3 < q.k) dst[3] = acc.w * al;
   }
 }
 
@@ -193,14 +195,16 @@ int reduce_splits_ld(const float* partial, int splits, int n, int k, int ldp, fl
   return OGL_OK;
 }
 
-int reduce_splits(const float* partial, int splits, int n, int k, float* c, int ldc, cudaStream_t s) {
-  OGL_LAUNCH(k_reduce_splits, grid_for((int64_t)n * k, 256), 256, 0, s, partial, splits, n, k, c, ldc);
+int reduce_splits(const float* partial, int splits, int n, int k, float* c, int ldc, cudaStream_t s, float alpha) {
+  OGL_LAUNCH(k_reduce_splits, grid_for((int64_t)n * k, 256), 256, 0, s, partial, splits, n, k, c, ldc, alpha);
   return OGL_OK;
 }
 
 int gemm_nt_simt(const GemmNT& g, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(g.n, BN), (unsigned)ceil_div(g.m_max, BM));
-  if (g.in_bf16 && g.out_bf16) OGL_LAUNCH((k_gemm_nt<__nv_bfloat16, __nv_bfloat16>), grid, 256, 0, s, g);
+  if (g.in_bf16 && g.f16 && g.out_bf16) OGL_LAUNCH((k_gemm_nt<__half, __half>), grid, 256, 0, s, g);
+  else if (g.in_bf16 && g.f16) OGL_LAUNCH((k_gemm_nt<__half, float>), grid, 256, 0, s, g);
+  else if (g.in_bf16 && g.out_bf16) OGL_LAUNCH((k_gemm_nt<__nv_bfloat16, __nv_bfloat16>), grid, 256, 0, s, g);
   else if (g.in_bf16) OGL_LAUNCH((k_gemm_nt<__nv_bfloat16, float>), grid, 256, 0, s, g);
   else if (!g.out_bf16 && g.out_tf32) OGL_LAUNCH((k_gemm_nt<float, tf32_t>), grid, 256, 0, s, g);
   else if (!g.out_bf16) OGL_LAUNCH((k_gemm_nt<float, float>), grid, 256, 0, s, g);
@@ -220,9 +224,10 @@ int gemm_tn_simt(const GemmTN& g, cudaStream_t s) {
   int rows_per_split = (int)ceil_div(g.m_max, splits);
   rows_per_split = (rows_per_split + BK - 1) / BK * BK;
   dim3 grid((unsigned)ceil_div(g.k, BN), (unsigned)ceil_div(g.n, BM), (unsigned)splits);
-  if (g.in_bf16) OGL_LAUNCH((k_gemm_tn<__nv_bfloat16>), grid, 256, 0, s, g, rows_per_split, g.partial, per);
+  if (g.in_bf16 && g.f16) OGL_LAUNCH((k_gemm_tn<__half>), grid, 256, 0, s, g, rows_per_split, g.partial, per);
+  else if (g.in_bf16) OGL_LAUNCH((k_gemm_tn<__nv_bfloat16>), grid, 256, 0, s, g, rows_per_split, g.partial, per);
   else OGL_LAUNCH((k_gemm_tn<float>), grid, 256, 0, s, g, rows_per_split, g.partial, per);
-  return reduce_splits(g.partial, splits, g.n, g.k, g.c, g.ldc, s);
+  return reduce_splits(g.partial, splits, g.n, g.k, g.c, g.ldc, s, g.alpha);
 }
 
 }  // namespace ogl

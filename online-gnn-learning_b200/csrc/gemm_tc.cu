@@ -1,6 +1,8 @@
-// tcgen05 / TMA / TMEM GEMMs of the GraphSAGE-pool path (bf16 or tf32 operands, fp32 accumulation in tensor memory).
-// Template parameter TF = 1 selects tcgen05.mma.kind::tf32 on fp32 operands (mode OGL_TF32): a 128-byte swizzle row then holds 32
-// contraction elements instead of 64 and one MMA contracts 8 instead of 16, so stages, descriptors and barriers are byte-identical.
+// tcgen05 / TMA / TMEM GEMMs of the GraphSAGE-pool path (bf16, fp16 or tf32 operands, fp32 accumulation in tensor memory).
+// Template parameter KIND: 0 = bf16, 2 = fp16 (both tcgen05.mma.kind::f16; only the operand-format field of the instruction
+// descriptor and the epilogue's pack / mask conversions differ), 1 = tcgen05.mma.kind::tf32 on fp32 operands (mode OGL_TF32; `TF`
+// inside the kernels): a 128-byte swizzle row then holds 32 contraction elements instead of 64 and one MMA contracts 8 instead of
+// 16, so stages, descriptors and barriers are byte-identical.
 //
 // Two warp-specialised kernels, both with 128 x <=256 output tiles, 64-deep contraction stages moved by TMA
 // (SWIZZLE_128B) into a 4-stage shared-memory ring, one elected thread issuing tcgen05.mma (UMMA 128 x N x 16,
@@ -235,10 +237,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
-// instruction descriptor for kind::f16 / kind::tf32: D = f32 (bits 4-5 = 1), A / B format at bits 7-9 / 10-12 (1 = bf16,
-// 2 = tf32), majors at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28
-__device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major, int tf32 = 0) {
-  const uint32_t fmt = tf32 ? 2u : 1u;
+// instruction descriptor for kind::f16 / kind::tf32: D = f32 (bits 4-5 = 1), A / B format at bits 7-9 / 10-12 (kind::f16: 0 = fp16,
+// 1 = bf16; kind::tf32: 2 = tf32), majors at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+// kind: the kernels' KIND (0 = bf16, 1 = tf32, 2 = fp16)
+__device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major, int kind = 0) {
+  const uint32_t fmt = kind == 1 ? 2u : (kind == 2 ? 0u : 1u);
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
@@ -278,9 +281,19 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* base, int n_stages = STAGES
   return s;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+template <int KIND>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {          // two outputs in the 16-bit storage type of KIND
+  if constexpr (KIND == 2) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+template <int KIND>
+__device__ __forceinline__ bool positive16(uint16_t bits) {              // value > 0 (NaN: false), bf16 and fp16 alike
+  return (bits & 0x8000u) == 0 && (bits & 0x7fffu) != 0 && (bits & 0x7fffu) <= (KIND == 2 ? 0x7c00u : 0x7f80u);
 }
 
 // ------------------------------------------------------------------ NT kernel --------------------
@@ -314,8 +327,9 @@ struct NtParams {
 // tile: each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues UMMA M = 256 that reads
 // both halves, each CTA keeps the accumulator of its own rows in its own TMEM and runs its own epilogue.  Per CTA a
 // k-block then moves 32 KB instead of 48 KB through L2 -> SM, the limiter of the single-CTA kernel.
-template <int CG, int TF>
+template <int CG, int KIND>
 __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_constant__ NtParams p) {
+  constexpr int TF = KIND == 1 ? 1 : 0;
   constexpr int NST = CG == 2 ? STAGES2 : STAGES;
   constexpr int BKE = TF ? 32 : 64;               // contraction elements per stage = one 128-byte swizzle row
   constexpr int KI = TF ? 8 : 16;                 // contraction elements per tcgen05.mma
@@ -440,7 +454,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       for (int t = unit; t < total_tiles; t += n_units) {
         const int mt = t / p.n_tiles, nb = t % p.n_tiles;
         const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
-        const uint32_t idesc = instr_desc(BM * CG, bn_tile, 0, 0, TF);
+        const uint32_t idesc = instr_desc(BM * CG, bn_tile, 0, 0, KIND);
         mbar_wait(&s.acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN_MAX);
@@ -637,20 +651,20 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const uint4 raw = *reinterpret_cast<const uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4));
-                const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+                const uint16_t* mv = reinterpret_cast<const uint16_t*>(&raw);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  if (!(__bfloat162float(mv[j]) > 0.f)) v[q * 8 + j] = 0.f;
+                  if (!positive16<KIND>(mv[j])) v[q * 8 + j] = 0.f;
               }
             }
             // row `lane` of the box, 16-byte chunk (half*4 + q) XOR-swizzled like TMA's SWIZZLE_128B
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o;
-              o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              o.x = pack16<KIND>(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack16<KIND>(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack16<KIND>(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack16<KIND>(v[q * 8 + 6], v[q * 8 + 7]);
               *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = o;
             }
           }
@@ -731,6 +745,7 @@ struct TnParams {
   int total_tiles, splits;
   int use_tma_store;
   int prefetch;                  // contraction blocks both operands are prefetched into L2 ahead of their loads (0: off)
+  float alpha_direct;            // output scale of the un-staged single-split store (staged partials are scaled by the reduce)
   const int32_t* m_dev;
   int m_max;
 };
@@ -743,8 +758,9 @@ constexpr int TN_STAGES = 3;
 constexpr int TN_A_STAGE_BYTES = 2 * A_STAGE_BYTES;   // two 128-row sub-tiles, each two 64-row chunks of 8 KB
 static_assert(TN_STAGES * (TN_A_STAGE_BYTES + B_STAGE_BYTES) == RING_BYTES, "TN ring size mismatch");
 
-template <int TF>
+template <int KIND>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant__ TnParams p) {
+  constexpr int TF = KIND == 1 ? 1 : 0;
   // a TMA box = CW output-index elements (128 bytes) x BKR contraction rows; bf16: 64 x 64 (8 KB), tf32: 32 x 32 (4 KB).  Stages
   // hold the same bytes either way: 256 output rows of A + up to 256 of B over BKR contraction rows = 32 KB + 32 KB
   constexpr int CW = TF ? 32 : 64;
@@ -822,7 +838,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
       uint32_t phase = 0;
       // M is always issued as 128: when only part of a sub-tile's chunks was loaded its upper accumulator rows hold
       // products with stale shared memory and are never stored (rows >= n)
-      const uint32_t idesc = instr_desc(BM, bn_tile, 1, 1, TF);
+      const uint32_t idesc = instr_desc(BM, bn_tile, 1, 1, KIND);
       uint32_t accumulate = 0;
       // MN-major descriptors (LBO = distance between 128-byte-wide chunks of the M / N index, SBO = 8 contraction rows): one MMA
       // covers 16 (bf16) / 8 (tf32) contraction rows = 2048 / 1024 bytes = KSTEP in the 14-bit address field; kept branch-free
@@ -911,7 +927,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
             const int gk0 = kt * BN_MAX + c0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (gk0 + j < q.k) orow[gk0 + j] = __uint_as_float(r[j]);
+              if (gk0 + j < q.k) orow[gk0 + j] = __uint_as_float(r[j]) * p.alpha_direct;
           }
         }
       }
@@ -951,8 +967,11 @@ int tc_init() {
       cudaFuncSetAttribute(k_gemm_nt_tc<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT2) != cudaSuccess ||
       cudaFuncSetAttribute(k_gemm_nt_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT1) != cudaSuccess ||
       cudaFuncSetAttribute(k_gemm_nt_tc<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT2) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_nt_tc<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT1) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_nt_tc<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_NT2) != cudaSuccess ||
       cudaFuncSetAttribute(k_gemm_tn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess ||
-      cudaFuncSetAttribute(k_gemm_tn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess) {
+      cudaFuncSetAttribute(k_gemm_tn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess ||
+      cudaFuncSetAttribute(k_gemm_tn_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TN) != cudaSuccess) {
     cudaGetLastError();
     g_tc_state = -1;
     return -1;
@@ -964,13 +983,14 @@ int tc_init() {
 // 2-D bf16 (es = 2) or fp32 (es = 4) tensor [rows, cols] with row pitch ld (elements), box = box_cols x box_rows (box_cols * es
 // = 128 bytes), 128-byte swizzle
 int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int es = 2,
-             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int f16 = 0) {
   OGL_ARG(((uintptr_t)ptr & 15) == 0 && (ld * es) % 16 == 0, "gemm_tc: operand not 16-byte aligned (ptr %p, ld %lld)", ptr, (long long)ld);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)es};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(map, es == 2 ? (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1037,7 +1057,8 @@ static int launch_gemm(Kernel kernel, int grid, int block, int smem, int cluster
 
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   OGL_ARG(tc_init() == 1, "gemm_nt_tc: tcgen05 path unavailable (driver lacks cuTensorMapEncodeTiled?)");
-  OGL_ARG((g.in_bf16 != 0) != (g.tf32 != 0), "gemm_nt_tc: bf16 or tf32 operands only");
+  OGL_ARG((g.in_bf16 != 0) != (g.tf32 != 0), "gemm_nt_tc: 16-bit or tf32 operands only");
+  OGL_ARG(!(g.f16 && g.tf32), "gemm_nt_tc: f16 goes with 16-bit operands");
   OGL_ARG(!(g.tf32 && g.out_bf16), "gemm_nt_tc: tf32 operands give fp32 output");
   OGL_ARG(g.n > 0 && g.m_max > 0 && g.n_seg >= 1 && g.n_seg <= 2, "gemm_nt_tc: bad shape");
   const int tf = g.tf32 ? 1 : 0;
@@ -1056,8 +1077,8 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     p.k[i] = g.k[i];
     p.a_rows_dev[i] = g.a_rows_dev[i];
     const int64_t a_rows = g.a_rows_max[i] > 0 ? g.a_rows_max[i] : g.m_max;      // rows that exist in segment i's A buffer
-    OGL_TRY(make_map(&p.ta[i], g.a[i], a_rows, g.k[i], g.lda[i], bke, BM, es));
-    OGL_TRY(make_map(&p.tb[i], g.b[i], g.n, g.k[i], g.ldb[i], bke, cg == 2 ? p.bn / 2 : p.bn, es));
+    OGL_TRY(make_map(&p.ta[i], g.a[i], a_rows, g.k[i], g.lda[i], bke, BM, es, CU_TENSOR_MAP_SWIZZLE_128B, g.f16));
+    OGL_TRY(make_map(&p.tb[i], g.b[i], g.n, g.k[i], g.ldb[i], bke, cg == 2 ? p.bn / 2 : p.bn, es, CU_TENSOR_MAP_SWIZZLE_128B, g.f16));
   }
   p.m_dev = g.m_dev;
   p.m_max = g.m_max;
@@ -1087,7 +1108,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     p.prefetch = pfd;
   }
   OGL_ARG(!(g.mask && !(g.out_bf16 || p.out_f32_tma)), "gemm_nt_tc: the mask epilogue is implemented for the TMA-store outputs only");
-  if (g.out_bf16) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 64, 32));
+  if (g.out_bf16) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 64, 32, 2, CU_TENSOR_MAP_SWIZZLE_128B, g.f16));
   if (p.out_f32_tma) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 32, 32, 4));
   OGL_ARG(g.ldc % 8 == 0 && ((uintptr_t)g.c & 15) == 0, "gemm_nt_tc: output pitch must be a multiple of 8 elements");
   OGL_ARG(!g.mask || (g.ldmask % 8 == 0 && ((uintptr_t)g.mask & 15) == 0), "gemm_nt_tc: mask pitch must be a multiple of 8 elements");
@@ -1095,12 +1116,14 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     int pairs = (int)(super_tiles < sm_count() / 2 ? super_tiles : sm_count() / 2);
     if (const char* e = getenv("OGL_NT_MAXPAIRS")) pairs = pairs < atoi(e) ? pairs : atoi(e);      // experiments: is the kernel bound per SM or chip-wide?
     if (tf) OGL_TRY(launch_gemm(k_gemm_nt_tc<2, 1>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
+    else if (g.f16) OGL_TRY(launch_gemm(k_gemm_nt_tc<2, 2>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
     else OGL_TRY(launch_gemm(k_gemm_nt_tc<2, 0>, 2 * pairs, THREADS_NT, SMEM_NT2, 2, p, s));
     return OGL_OK;
   }
   const int64_t tiles = ceil_div(g.m_max, BM) * p.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (tf) return launch_gemm(k_gemm_nt_tc<1, 1>, grid, THREADS_NT, SMEM_NT1, 1, p, s);
+  if (g.f16) return launch_gemm(k_gemm_nt_tc<1, 2>, grid, THREADS_NT, SMEM_NT1, 1, p, s);
   return launch_gemm(k_gemm_nt_tc<1, 0>, grid, THREADS_NT, SMEM_NT1, 1, p, s);
 }
 
@@ -1119,13 +1142,13 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
   int64_t per_total = 0;
   for (int i = 0; i < count; ++i) {
     OGL_ARG((g[i].in_bf16 || g[i].tf32) && g[i].n > 0 && g[i].k > 0 && g[i].m_max > 0, "gemm_tn_tc: bad arguments");
-    OGL_ARG(g[i].m_dev == g[0].m_dev && g[i].m_max == g[0].m_max && g[i].tf32 == g[0].tf32,
+    OGL_ARG(g[i].m_dev == g[0].m_dev && g[i].m_max == g[0].m_max && g[i].tf32 == g[0].tf32 && g[i].f16 == g[0].f16,
             "gemm_tn_tc: grouped problems must contract over the same rows in the same arithmetic");
     TnProblem& q = p.pr[i];
     // (MN-major tf32 operands: the 32-byte-atom flavour of the 128-byte swizzle, see smem_desc)
     const CUtensorMapSwizzle sw = tf ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-    OGL_TRY(make_map(&q.ta, g[i].a, g[i].m_max, g[i].n, g[i].lda, cw, cw, es, sw));
-    OGL_TRY(make_map(&q.tb, g[i].b, g[i].m_max, g[i].k, g[i].ldb, cw, cw, es, sw));
+    OGL_TRY(make_map(&q.ta, g[i].a, g[i].m_max, g[i].n, g[i].lda, cw, cw, es, sw, g[i].f16));
+    OGL_TRY(make_map(&q.tb, g[i].b, g[i].m_max, g[i].k, g[i].ldb, cw, cw, es, sw, g[i].f16));
     q.n = g[i].n;
     q.k = g[i].k;
     q.k_tiles = (g[i].k + BN_MAX - 1) / BN_MAX;
@@ -1164,17 +1187,19 @@ int gemm_tn_tc_group(const GemmTN* g, int count, cudaStream_t s) {
       q.out = ws + off;
       q.split_stride = per;
       OGL_TRY(make_map_f32_3d(&q.tout, q.out, g[i].k, g[i].n, splits, q.ldo));
-      rg.pr[i] = {q.out, g[i].c, g[i].n, g[i].k, q.ldo, g[i].ldc};
+      rg.pr[i] = {q.out, g[i].c, g[i].n, g[i].k, q.ldo, g[i].ldc, g[i].alpha};
       off += (int64_t)splits * per;
     }
   }
   p.use_tma_store = staged ? 1 : 0;
+  p.alpha_direct = g[0].alpha;
   {
     static int pfd = -1;
     if (pfd < 0) { const char* e = getenv("OGL_GEMM_PF_TN"); pfd = e ? atoi(e) : 0; }
     p.prefetch = pfd;
   }
   if (tf) OGL_TRY(launch_gemm(k_gemm_tn_tc<1>, tiles * splits, THREADS, SMEM_TN, 1, p, s));
+  else if (g[0].f16) OGL_TRY(launch_gemm(k_gemm_tn_tc<2>, tiles * splits, THREADS, SMEM_TN, 1, p, s));
   else OGL_TRY(launch_gemm(k_gemm_tn_tc<0>, tiles * splits, THREADS, SMEM_TN, 1, p, s));
   if (staged) return reduce_splits_group(rg, s);
   return OGL_OK;
@@ -1236,6 +1261,30 @@ extern "C" int ogl_gemm_tf32_tn(const float* a_dev, int lda, const float* b_dev,
   OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_tf32_tn: bad arguments");
   GemmTN g;
   g.a = a_dev; g.lda = lda; g.b = b_dev; g.ldb = ldb; g.c = c_dev; g.ldc = ldc; g.n = n; g.k = k; g.m_max = m; g.tf32 = 1;
+  g.partial = workspace_dev; g.partial_elems = workspace_dev ? workspace_elems : 0;
+  return gemm_tn_tc(g, (cudaStream_t)stream);
+}
+
+// fp16 flavour (mode OGL_FP16: tcgen05 kind::f16 with fp16 operands; tests / bench).  mask (fp16, [m, ldmask]): out = mask > 0 ? out : 0;
+// alpha scales the weight-gradient output (the plan passes 1 / loss scale there)
+extern "C" int ogl_gemm_f16_nt_ex(const void* a_dev, int lda, const void* b_dev, int ldb, void* c_dev, int ldc, int m, int n, int k,
+                                  int out_f16, const float* bias_dev, int relu, const void* mask_dev, int ldmask, int cg, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_f16_nt_ex: bad arguments");
+  GemmNT g;
+  g.a[0] = a_dev; g.lda[0] = lda; g.b[0] = b_dev; g.ldb[0] = ldb; g.k[0] = k; g.n_seg = 1;
+  g.c = c_dev; g.ldc = ldc; g.m_max = m; g.n = n; g.in_bf16 = 1; g.f16 = 1; g.out_bf16 = out_f16; g.zero_tail = 0;
+  g.bias = bias_dev; g.relu = relu; g.force_cg = cg; g.mask = mask_dev; g.ldmask = ldmask;
+  return gemm_nt_tc(g, (cudaStream_t)stream);
+}
+
+extern "C" int ogl_gemm_f16_tn(const void* a_dev, int lda, const void* b_dev, int ldb, float* c_dev, int ldc, int m, int n, int k,
+                               float alpha, float* workspace_dev, int64_t workspace_elems, void* stream) {
+  OGL_TRY(require_device());
+  OGL_ARG(a_dev && b_dev && c_dev && m > 0 && n > 0 && k > 0, "ogl_gemm_f16_tn: bad arguments");
+  GemmTN g;
+  g.a = a_dev; g.lda = lda; g.b = b_dev; g.ldb = ldb; g.c = c_dev; g.ldc = ldc; g.n = n; g.k = k; g.m_max = m; g.in_bf16 = 1; g.f16 = 1;
+  g.alpha = alpha;
   g.partial = workspace_dev; g.partial_elems = workspace_dev ? workspace_elems : 0;
   return gemm_tn_tc(g, (cudaStream_t)stream);
 }

@@ -340,6 +340,9 @@ int peer_sum_adam(ogl_peer* p, const PeerAdamArgs& a, int64_t lo, int64_t hi, cu
   if (a.mode == OGL_BF16) {
     if (two) OGL_PEER_LAUNCH(__nv_bfloat16, true);
     else OGL_PEER_LAUNCH(__nv_bfloat16, false);
+  } else if (a.mode == OGL_FP16) {
+    if (two) OGL_PEER_LAUNCH(__half, true);
+    else OGL_PEER_LAUNCH(__half, false);
   } else if (a.mode == OGL_TF32) {
     if (two) OGL_PEER_LAUNCH(tf32_t, true);
     else OGL_PEER_LAUNCH(tf32_t, false);

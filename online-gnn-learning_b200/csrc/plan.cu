@@ -9,6 +9,7 @@
 #include "gemm.cuh"
 #include "sage_kernels.cuh"
 #include "peer.cuh"
+#include <cmath>
 #include <vector>
 #include <string>
 
@@ -20,7 +21,7 @@ static inline int pitch_of(int d) { return round_up(d, 8); }
 struct ogl_features {
   int64_t v_cap = 0;
   int F = 0, pitch = 0, mode = 0;
-  void* table = nullptr;      // [v_cap, pitch] f32 | bf16
+  void* table = nullptr;      // [v_cap, pitch] in the mode's storage type (fp32 | bf16 | fp16)
   int32_t* labels = nullptr;  // [v_cap]
   float* stage_f = nullptr;   // host-source staging
   int64_t* stage_l = nullptr;
@@ -29,10 +30,11 @@ struct ogl_features {
 
 extern "C" int ogl_features_create(ogl_features** out, int64_t v_cap, int n_feats, int mode) {
   OGL_TRY(require_device());
-  OGL_ARG(out && v_cap > 0 && n_feats > 0 && (mode == OGL_F32 || mode == OGL_BF16 || mode == OGL_TF32), "ogl_features_create: bad arguments");
+  OGL_ARG(out && v_cap > 0 && n_feats > 0 && (mode == OGL_F32 || mode == OGL_BF16 || mode == OGL_TF32 || mode == OGL_FP16),
+          "ogl_features_create: bad arguments");
   ogl_features* f = new ogl_features();
   f->v_cap = v_cap; f->F = n_feats; f->pitch = pitch_of(n_feats); f->mode = mode;
-  const size_t es = mode == OGL_BF16 ? 2 : 4;
+  const size_t es = mode_is_16bit(mode) ? 2 : 4;
   OGL_CUDA(cudaMalloc(&f->table, es * (size_t)v_cap * f->pitch));
   OGL_CUDA(cudaMemset(f->table, 0, es * (size_t)v_cap * f->pitch));
   OGL_CUDA(cudaMalloc(&f->labels, sizeof(int32_t) * v_cap));
@@ -110,7 +112,8 @@ struct LayerBuf {
 struct ogl_plan {
   ogl_plan_config cfg;
   int L = 0;
-  int bf16 = 0, tf32 = 0, mode = 0;      // mode = cfg.mode (OGL_F32 | OGL_BF16 | OGL_TF32); bf16 / tf32 = mode == ...
+  int bf16 = 0, tf32 = 0, mode = 0;      // mode = cfg.mode; bf16 = 16-bit storage (OGL_BF16 or OGL_FP16), tf32 = mode == OGL_TF32
+  int fp16 = 0;                          // mode == OGL_FP16: the 16-bit storage is fp16 and activation gradients carry a loss scale
   size_t es = 4;
   std::vector<int> nmax;                 // [L+1]
   std::vector<int32_t*> nodes;           // [L+1]
@@ -160,6 +163,8 @@ struct ogl_plan {
   int use_side = 1;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float head_loss_scale = 0.f;           // loss scale of the last ogl_plan_step_finish_head (its tail must unscale by the same)
+  float grad_scale = 1.f;                // mode OGL_FP16: the loss scale the stored activation gradients of the current backward pass carry
   int skip_gather = 0;                   // step_finish: the input rows were already gathered by step_begin
   int train_mode = 0;                    // feat_drop is applied by ogl_plan_forward (train steps set it; eval steps never)
   int adam_in_backward = 0;              // fused step with do_step: the backward pass runs Adam on all but the last gradient itself
@@ -276,7 +281,7 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   OGL_ARG(out && cfg, "ogl_plan_create: null");
   OGL_ARG(cfg->n_layers >= 1 && cfg->n_layers <= 7, "ogl_plan_create: n_layers must be in [1,7]");
   OGL_ARG(cfg->max_seeds > 0 && cfg->v_cap > 0, "ogl_plan_create: max_seeds / v_cap must be positive");
-  OGL_ARG(cfg->mode == OGL_F32 || cfg->mode == OGL_BF16 || cfg->mode == OGL_TF32, "ogl_plan_create: bad mode");
+  OGL_ARG(cfg->mode == OGL_F32 || cfg->mode == OGL_BF16 || cfg->mode == OGL_TF32 || cfg->mode == OGL_FP16, "ogl_plan_create: bad mode");
   OGL_ARG(cfg->feat_drop >= 0.f && cfg->feat_drop < 1.f, "ogl_plan_create: feat_drop must be in [0, 1)");
   for (int i = 0; i <= cfg->n_layers; ++i) OGL_ARG(cfg->dims[i] > 0, "ogl_plan_create: dims[%d] must be positive", i);
   for (int i = 0; i < cfg->n_layers; ++i) OGL_ARG(cfg->fanouts[i] > 0 && cfg->fanouts[i] < 255, "ogl_plan_create: fanouts[%d] must be in [1,254]", i);
@@ -284,7 +289,8 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   p->cfg = *cfg;
   const int L = p->L = cfg->n_layers;
   p->mode = cfg->mode;
-  p->bf16 = cfg->mode == OGL_BF16;
+  p->bf16 = mode_is_16bit(cfg->mode);
+  p->fp16 = cfg->mode == OGL_FP16;
   p->tf32 = cfg->mode == OGL_TF32;
   p->es = p->bf16 ? 2 : 4;
   p->nmax.resize(L + 1);
@@ -519,7 +525,7 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
     g1.a[0] = p->act[sl]; g1.lda[0] = lb.pin; g1.b[0] = lb.wp; g1.ldb[0] = lb.pin; g1.k[0] = lb.in; g1.n_seg = 1;
     g1.bias = p->params + lb.o_bp; g1.relu = 1;
     g1.c = lb.hp; g1.ldc = lb.pin; g1.m_max = p->nmax[sl]; g1.m_dev = p->counts + sl; g1.n = lb.in;
-    g1.in_bf16 = p->bf16; g1.out_bf16 = p->bf16; g1.tf32 = p->tf32; g1.out_tf32 = p->tf32;
+    g1.in_bf16 = p->bf16; g1.out_bf16 = p->bf16; g1.f16 = p->fp16; g1.tf32 = p->tf32; g1.out_tf32 = p->tf32;
     STAGE(nm("l%d.pool_gemm", l).c_str(), gemm_nt(p, g1, s));
     STAGE(nm("l%d.segmax", l).c_str(),
           segmax_fwd(p->mode, lb.hp, lb.pin, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], lb.neigh, lb.arg, s));
@@ -528,7 +534,7 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
     g2.a[1] = lb.neigh; g2.lda[1] = lb.pin; g2.b[1] = lb.wn; g2.ldb[1] = lb.pin; g2.k[1] = lb.in; g2.n_seg = 2;
     g2.bias = p->params + lb.o_bs; g2.bias2 = p->params + lb.o_bn; g2.relu = (l < L - 1);
     g2.c = p->act[dl]; g2.ldc = lb.pout; g2.m_max = p->nmax[dl]; g2.m_dev = p->counts + dl; g2.n = lb.out;
-    g2.in_bf16 = p->bf16; g2.out_bf16 = (l < L - 1) ? p->bf16 : 0; g2.tf32 = p->tf32; g2.out_tf32 = (l < L - 1) ? p->tf32 : 0;
+    g2.in_bf16 = p->bf16; g2.out_bf16 = (l < L - 1) ? p->bf16 : 0; g2.f16 = p->fp16; g2.tf32 = p->tf32; g2.out_tf32 = (l < L - 1) ? p->tf32 : 0;
     STAGE(nm("l%d.out_gemm", l).c_str(), gemm_nt(p, g2, s));
   }
   if (logits_dev)
@@ -536,8 +542,25 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
   return OGL_OK;
 }
 
+// Static loss scaling of mode OGL_FP16.  The activation gradients (dlogits and everything the backward pass derives from it) are
+// STORED times gs = 2^k, k chosen from the caller's loss scale (1 / global batch) so that the largest |dlogits| element is in
+// [32, 64): values down to 1e-6 of it stay in fp16's normal range, and there are ten binades of headroom to 65504.  Every fp32
+// result that leaves the backward pass -- the weight gradients (the TN GEMMs' reduce) and the bias gradients (column sums) -- is
+// multiplied by 1 / gs where it is written; a power of two, so the unscaling is exact and Adam, the peer exchange and the
+// gradient readers see true gradients.
+static float grad_scale_for(const ogl_plan* p, float loss_scale) {
+  if (!p->fp16) return 1.f;
+  const float a = fabsf(loss_scale);
+  if (!(a > 0.f) || !std::isfinite(a)) return 1.f;
+  int e = 0;
+  frexpf(64.f / a, &e);                 // 64 / a = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, e - 1);            // 2^floor(log2(64 / a)):  a * gs in (32, 64]
+}
+
 static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
   const int L = p->L;
+  p->grad_scale = want_grad ? grad_scale_for(p, scale) : 1.f;
+  scale *= p->grad_scale;
   LayerBuf& last = p->layer[L - 1];
   float* per = per_vertex_loss_dev ? per_vertex_loss_dev : p->per_loss;
   STAGE("xent", xent(p->mode, (const float*)p->act[0], last.pout, p->cfg.dims[L], f->labels, p->nodes[0], p->counts, p->nmax[0],
@@ -568,7 +591,8 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     const int sl = L - l;
     GemmTN tp;
     tp.a = lb.dhp; tp.lda = lb.pin; tp.n = lb.in; tp.b = p->act[sl]; tp.ldb = lb.pin; tp.k = lb.in;
-    tp.c = p->grads + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16; tp.tf32 = p->tf32;
+    tp.c = p->grads + lb.o_wp; tp.ldc = lb.in; tp.m_max = p->nmax[sl]; tp.m_dev = p->counts + sl; tp.in_bf16 = p->bf16; tp.f16 = p->fp16; tp.tf32 = p->tf32;
+    tp.alpha = 1.f / p->grad_scale;
     tp.partial = p->tn_partial; tp.partial_elems = p->tn_partial_elems;
     return tp;
   };
@@ -605,19 +629,21 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     if (l + 1 < L) grp[ng++] = dw_pool(l + 1);
     GemmTN t;
     t.a = lb.dpre; t.lda = lb.pout; t.n = lb.out; t.b = p->act[sl]; t.ldb = lb.pin; t.k = lb.in;
-    t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16; t.tf32 = p->tf32;
+    t.c = G + lb.o_ws; t.ldc = lb.in; t.m_max = p->nmax[dl]; t.m_dev = p->counts + dl; t.in_bf16 = p->bf16; t.f16 = p->fp16; t.tf32 = p->tf32;
+    t.alpha = 1.f / p->grad_scale;
     grp[ng++] = t;
     t.b = lb.neigh; t.c = G + lb.o_wn;
     grp[ng++] = t;
     for (int i = 0; i < ng; ++i) { grp[i].partial = ov ? p->tn_partial2 : p->tn_partial; grp[i].partial_elems = p->tn_partial_elems; }
     STAGE_ON(ss, nm("l%d.dW_group", l).c_str(), gemm_tn_group(p, grp, ng, ss));
     STAGE_ON(ss, nm("l%d.db_out", l).c_str(), colsum(p->mode, lb.dpre, lb.pout, lb.out, p->counts + dl, p->nmax[dl],
-                                                     ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bs, G + lb.o_bn, ss));
+                                                     ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bs, G + lb.o_bn, ss,
+                                                     1.f / p->grad_scale));
     // dneigh = dpre Wn
     GemmNT n1;
     n1.a[0] = lb.dpre; n1.lda[0] = lb.pout; n1.b[0] = lb.wnT; n1.ldb[0] = lb.pout; n1.k[0] = lb.out; n1.n_seg = 1;
     n1.c = lb.dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
-    n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.tf32 = p->tf32; n1.out_tf32 = p->tf32; n1.zero_tail = 0;
+    n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.f16 = p->fp16; n1.tf32 = p->tf32; n1.out_tf32 = p->tf32; n1.zero_tail = 0;
     n1.mask = lb.neigh; n1.ldmask = lb.pin;        // relu'(hp) at the argmax: neigh[d, f] == hp[src(arg), f]
     STAGE(nm("l%d.dneigh_gemm", l).c_str(), gemm_nt(p, n1, s));
     // fc_pool bias gradient: every dng[d, f] lands in exactly one source row, so colsum(dhp) == colsum(dng).  Side stream too (behind the
@@ -627,7 +653,8 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       OGL_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     }
     STAGE_ON(ss, nm("l%d.db_pool", l).c_str(), colsum(p->mode, lb.dng, lb.pin, lb.in, p->counts + dl, p->nmax[dl],
-                                                      ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bp, nullptr, ss));
+                                                      ov ? p->colsum_partial2 : p->colsum_partial, G + lb.o_bp, nullptr, ss,
+                                                      1.f / p->grad_scale));
     // max-pool backward as a gather over the reverse edge lists
     STAGE(nm("l%d.pool_bwd", l).c_str(), pool_bwd(p->mode, lb.dng, lb.pin, lb.arg, p->rev_ptr[h], p->rev_edge[h], p->cfg.fanouts[h],
                                                   p->counts + sl, p->nmax[sl], lb.dhp, s));
@@ -645,7 +672,7 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
       d.mask = p->act[sl]; d.ldmask = lb.pin;      // (after feat_drop a dropped element is 0 as well: relu' and the keep mask in one)
       if (p->train_mode && p->cfg.feat_drop > 0.f) d.alpha = 1.f / (1.f - p->cfg.feat_drop);
       d.c = prev.dpre; d.ldc = prev.pout; d.m_max = p->nmax[sl]; d.m_dev = p->counts + sl; d.n = lb.in;
-      d.in_bf16 = p->bf16; d.out_bf16 = p->bf16; d.tf32 = p->tf32; d.out_tf32 = p->tf32;
+      d.in_bf16 = p->bf16; d.out_bf16 = p->bf16; d.f16 = p->fp16; d.tf32 = p->tf32; d.out_tf32 = p->tf32;
       STAGE(nm("l%d.dx_gemm", l).c_str(), gemm_nt(p, d, s));
     }
   }
@@ -677,7 +704,10 @@ extern "C" int ogl_plan_backward(ogl_plan* p, const float* dlogits_dev, void* st
   cudaStream_t s = (cudaStream_t)stream;
   LayerBuf& last = p->layer[p->L - 1];
   const int n = p->n_seeds;
-  OGL_TRY(feat_write(p->mode, dlogits_dev, nullptr, n, last.out, last.dpre, last.pout, 0, s));
+  // (mode OGL_FP16: the caller's fp32 dlogits carry no scale of their own; a fixed 2^12 puts 1 / batch-sized values into fp16's
+  // normal range with the same headroom as the fused loss)
+  p->grad_scale = p->fp16 ? 4096.f : 1.f;
+  OGL_TRY(feat_write(p->mode, dlogits_dev, nullptr, n, last.out, last.dpre, last.pout, 0, s, p->grad_scale));
   const int np = round_up(n, 128);
   if (np > n) OGL_CUDA(cudaMemsetAsync((char*)last.dpre + p->es * (size_t)n * last.pout, 0, p->es * (size_t)(np - n) * last.pout, s));
   return plan_backward_layers(p, s);
@@ -755,6 +785,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
     return join_side(p, s);                       // a captured graph must rejoin its forked stream
   }
   if (kind == 4) {
+    p->grad_scale = grad_scale_for(p, loss_scale);
     p->tail_mode = 2;
     const int rb = plan_backward_layers(p, s);
     p->tail_mode = 0;
@@ -1056,6 +1087,7 @@ extern "C" int ogl_plan_step_finish_head(ogl_plan* p, ogl_features* f, float los
                                          void* stream) {
   OGL_ARG(p && f && p->params && (p->n_seeds > 0 || p->pend[0]), "ogl_plan_step_finish_head: no step begun / parameters not bound");
   if (p->pend[0]) OGL_TRY(consume_prefetched(p, p->pend_n[0], (cudaStream_t)stream));   // (released by _tail)
+  p->head_loss_scale = loss_scale;               // the tail (step kind 4) unscales its weight gradient by the same loss scale
   return run_step(p, 3, nullptr, f, p->n_seeds, loss_scale, 0, per_vertex_loss_dev, loss_sum_dev, (cudaStream_t)stream);
 }
 
@@ -1065,7 +1097,7 @@ extern "C" int ogl_plan_step_finish_tail_part(ogl_plan* p, ogl_features* f, int 
           "ogl_plan_step_finish_tail_part: part %d of %d (pieces are 256 rows of the %d x %d gradient)", part, n_parts, p->cfg.dims[0], p->cfg.dims[0]);
   cudaStream_t s = (cudaStream_t)stream;
   p->tail_part = part; p->tail_parts = n_parts;
-  const int r4 = run_step(p, 4, nullptr, f, p->n_seeds, 0.f, 0, nullptr, nullptr, s);
+  const int r4 = run_step(p, 4, nullptr, f, p->n_seeds, p->head_loss_scale, 0, nullptr, nullptr, s);
   p->tail_part = 0; p->tail_parts = 1;
   if (part + 1 < n_parts) return r4;              // (the minibatch is released by the last piece)
   advance_prefetched(p);
@@ -1080,7 +1112,7 @@ extern "C" int ogl_plan_step_finish_tail_part(ogl_plan* p, ogl_features* f, int 
 extern "C" int ogl_plan_step_finish_tail(ogl_plan* p, ogl_features* f, void* stream) {
   OGL_ARG(p && f && p->params && p->n_seeds > 0, "ogl_plan_step_finish_tail: no step begun / parameters not bound");
   cudaStream_t s = (cudaStream_t)stream;
-  const int r4 = run_step(p, 4, nullptr, f, p->n_seeds, 0.f, 0, nullptr, nullptr, s);
+  const int r4 = run_step(p, 4, nullptr, f, p->n_seeds, p->head_loss_scale, 0, nullptr, nullptr, s);
   advance_prefetched(p);
   OGL_TRY(r4);
   if (p->prof_on && p->prof_steps < kProfSteps) {

@@ -11,6 +11,7 @@ constexpr int kBlock = 256;
 template <typename T> struct Vec;           // 16-byte vector of T
 template <> struct Vec<float> { static constexpr int N = 4; };
 template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
+template <> struct Vec<__half> { static constexpr int N = 8; };
 template <> struct Vec<tf32_t> { static constexpr int N = 4; };
 
 __device__ __forceinline__ int dyn_count(const int32_t* n_dev, int n_max) { return n_dev ? min(*n_dev, n_max) : n_max; }
@@ -19,14 +20,14 @@ __device__ __forceinline__ int pad128(int n, int n_max) { return min((n + 127) /
 // ---- feature store -------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_feat_write(const float* __restrict__ src, const int64_t* __restrict__ src_rows, int64_t n, int F,
-                                                       T* __restrict__ dst, int pitch, int64_t row0) {
-  // one warp per row; fp32 -> T, zero the pad columns
+                                                       T* __restrict__ dst, int pitch, int64_t row0, float scale) {
+  // one warp per row; fp32 -> T (times `scale`: the loss scale of mode OGL_FP16 when the rows are gradients), zero the pad columns
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
     const float* s = src + (src_rows ? src_rows[r] : r) * (int64_t)F;
     T* d = dst + (row0 + r) * (int64_t)pitch;
-    for (int c = lane; c < pitch; c += 32) d[c] = from_f32<T>(c < F ? s[c] : 0.f);
+    for (int c = lane; c < pitch; c += 32) d[c] = from_f32<T>(c < F ? s[c] * scale : 0.f);
   }
 }
 
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kBlock) k_colsum_partial(const T* __restrict__
   }
 }
 __global__ void __launch_bounds__(1024) k_colsum_final(const float* __restrict__ partial, int cols, const int32_t* __restrict__ n_dev,
-                                                       int n_max, float* __restrict__ out, float* __restrict__ out2) {
+                                                       int n_max, float* __restrict__ out, float* __restrict__ out2, float alpha) {
   __shared__ float sm[32][33];
   const int n = dyn_count(n_dev, n_max);
   const int chunks = (n + kColRows - 1) / kColRows;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(1024) k_colsum_final(const float* __restrict__
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 32; ++w) t += sm[w][lane];
+    t *= alpha;                                   // (mode OGL_FP16: undoes the loss scale, a power of two)
     out[c] = t;
     if (out2) out2[c] = t;
   }
@@ -375,10 +377,11 @@ __global__ void __launch_bounds__(kBlock) k_unpad_copy(const float* __restrict__
 }
 
 // ================================ host wrappers ====================================================
-// mode: OGL_F32 (exact fp32), OGL_BF16, OGL_TF32 (fp32 storage, values rounded to TF32 where a GEMM operand is produced)
+// mode: OGL_F32 (exact fp32), OGL_BF16, OGL_FP16, OGL_TF32 (fp32 storage, values rounded to TF32 where a GEMM operand is produced)
 #define L2(K, grid, s, ...)                                                                      \
   do {                                                                                           \
     if (mode == OGL_BF16) OGL_LAUNCH((K<__nv_bfloat16>), grid, kBlock, 0, s, __VA_ARGS__);       \
+    else if (mode == OGL_FP16) OGL_LAUNCH((K<__half>), grid, kBlock, 0, s, __VA_ARGS__);         \
     else if (mode == OGL_TF32) OGL_LAUNCH((K<tf32_t>), grid, kBlock, 0, s, __VA_ARGS__);         \
     else OGL_LAUNCH((K<float>), grid, kBlock, 0, s, __VA_ARGS__);                                \
   } while (0)
@@ -386,15 +389,17 @@ __global__ void __launch_bounds__(kBlock) k_unpad_copy(const float* __restrict__
 #define L2T(K, grid, s, CALL)                                                                    \
   do {                                                                                           \
     if (mode == OGL_BF16) { using T = __nv_bfloat16; OGL_LAUNCH((K<T>), grid, kBlock, 0, s, CALL); } \
+    else if (mode == OGL_FP16) { using T = __half; OGL_LAUNCH((K<T>), grid, kBlock, 0, s, CALL); }   \
     else if (mode == OGL_TF32) { using T = tf32_t; OGL_LAUNCH((K<T>), grid, kBlock, 0, s, CALL); }   \
     else { using T = float; OGL_LAUNCH((K<T>), grid, kBlock, 0, s, CALL); }                      \
   } while (0)
 #define ARGS(...) __VA_ARGS__
 
-int feat_write(int mode, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s) {
+int feat_write(int mode, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s,
+               float scale) {
   if (n <= 0) return OGL_OK;
   const int grid = grid_for(n * 32, kBlock);
-  L2T(k_feat_write, grid, s, ARGS(src, src_rows, n, F, (T*)dst, pitch, row0));
+  L2T(k_feat_write, grid, s, ARGS(src, src_rows, n, F, (T*)dst, pitch, row0, scale));
   return OGL_OK;
 }
 int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t* dst, int64_t row0, cudaStream_t s) {
@@ -426,15 +431,16 @@ int segmax_fwd(int mode, const void* hp, int pitch, const int32_t* edge_lid, int
 }
 int pool_bwd(int mode, const void* dng, int pitch, const uint8_t* arg, const int32_t* rev_ptr, const int32_t* rev_edge, int fanout,
              const int32_t* n_src_dev, int n_src_max, void* dhp, cudaStream_t s) {
-  const int grid = grid_for((int64_t)round_up(n_src_max, 128) * pitch / (mode == OGL_BF16 ? 8 : 4), kBlock, 32);
+  const int grid = grid_for((int64_t)round_up(n_src_max, 128) * pitch / mode_vec(mode), kBlock, 32);
   L2T(k_pool_bwd, grid, s, ARGS((const T*)dng, pitch, arg, rev_ptr, rev_edge, fanout, n_src_dev, n_src_max, (T*)dhp));
   return OGL_OK;
 }
 int64_t colsum_partial_elems(int n_max, int cols) { return ceil_div(n_max, kColRows) * (int64_t)cols; }
-int colsum(int mode, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s) {
-  dim3 grid((unsigned)ceil_div(pitch / (mode == OGL_BF16 ? 8 : 4), 32), (unsigned)ceil_div(n_max, kColRows));
+int colsum(int mode, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s,
+           float alpha) {
+  dim3 grid((unsigned)ceil_div(pitch / mode_vec(mode), 32), (unsigned)ceil_div(n_max, kColRows));
   L2T(k_colsum_partial, grid, s, ARGS((const T*)x, pitch, cols, n_dev, n_max, partial));
-  OGL_LAUNCH(k_colsum_final, (unsigned)ceil_div(cols, 32), 1024, 0, s, partial, cols, n_dev, n_max, out, out2);
+  OGL_LAUNCH(k_colsum_final, (unsigned)ceil_div(cols, 32), 1024, 0, s, partial, cols, n_dev, n_max, out, out2, alpha);
   return OGL_OK;
 }
 int xent(int mode, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,

@@ -22,7 +22,8 @@ __device__ __forceinline__ float adam_math(float gi, float& mi, float& vi, float
 }
 #endif
 
-int feat_write(int mode, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s);
+int feat_write(int mode, const float* src, const int64_t* src_rows, int64_t n, int F, void* dst, int pitch, int64_t row0, cudaStream_t s,
+               float scale = 1.f);
 int label_write(const int64_t* src, const int64_t* src_rows, int64_t n, int32_t* dst, int64_t row0, cudaStream_t s);
 int gather_rows(int mode, const void* table, int pitch, const int32_t* nodes, const int32_t* n_dev, int n_max, void* out, cudaStream_t s);
 // in-place dropout of a layer's input rows (no-op for p == 0); step_dev = the optimiser step counter
@@ -33,7 +34,9 @@ int segmax_fwd(int mode, const void* hp, int pitch, const int32_t* edge_lid, int
 int pool_bwd(int mode, const void* dng, int pitch, const uint8_t* arg, const int32_t* rev_ptr, const int32_t* rev_edge, int fanout,
              const int32_t* n_src_dev, int n_src_max, void* dhp, cudaStream_t s);
 int64_t colsum_partial_elems(int n_max, int cols);
-int colsum(int mode, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s);
+// out (and out2) = alpha * column sums
+int colsum(int mode, const void* x, int pitch, int cols, const int32_t* n_dev, int n_max, float* partial, float* out, float* out2, cudaStream_t s,
+           float alpha = 1.f);
 int xent(int mode, const float* logits, int ldl, int C, const int32_t* labels, const int32_t* nodes, const int32_t* n_dev, int n_max,
          int rows_buf, float scale, float* per_loss, void* dlogits, int ldd, int want_grad, cudaStream_t s);
 int sum_f32(const float* x, const int32_t* n_dev, int n_max, float* out, cudaStream_t s);
@@ -44,7 +47,7 @@ int adam_shadow(int mode, float* p, const float* g, float* m, float* v, int64_t 
 int bump(uint32_t* a, uint32_t* b, cudaStream_t s);
 int weight_shadow(int mode, const float* w, int out, int in, void* ws, int pitch_in, void* wt, int pitch_out, cudaStream_t s);
 int unpad_copy(const float* src, int lds, int n_rows_max, const int32_t* n_dev, int cols, float* dst, cudaStream_t s);
-int reduce_splits(const float* partial, int splits, int n, int k, float* c, int ldc, cudaStream_t s);
+int reduce_splits(const float* partial, int splits, int n, int k, float* c, int ldc, cudaStream_t s, float alpha = 1.f);
 int reduce_splits_ld(const float* partial, int splits, int n, int k, int ldp, float* c, int ldc, cudaStream_t s);
 
 }  // namespace ogl

@@ -13,9 +13,11 @@ Loss = CrossEntropyLoss(mean | none) on labels.flatten(), Adam(lr=1e-3)
 (pytorch/model.py:20-25,103-107).  PARITY UNPINNED against DGL (absent); the argmax tie
 rule (lowest edge slot wins) is this repo's specification.
 
-``quant='bf16'`` / ``quant='tf32'`` model the product's tensor-core paths: every GEMM operand
-(activations, weights, activation gradients) is rounded to bf16 / TF32 exactly where the
-product stores it, accumulation stays fp32/fp64.  ``quant=None`` is the reference's own fp32
+``quant='bf16'`` / ``quant='tf32'`` / ``quant='fp16'`` model the product's tensor-core paths: every GEMM
+operand (activations, weights, activation gradients) is rounded to bf16 / TF32 / fp16 exactly where the
+product stores it, accumulation stays fp32/fp64.  fp16 also models the product's static loss scaling
+(csrc/plan.cu: grad_scale_for): activation gradients are rounded AS STORED, i.e. times a power of two
+chosen from the loss scale, so that the rounding grid (and fp16's subnormal range) is the device's.  ``quant=None`` is the reference's own fp32
 arithmetic (train/utils.py:63-64) -- the oracle every tolerance is stated against; the
 quantised variants only show that a kernel implements the arithmetic it claims.
 """
@@ -23,6 +25,16 @@ import math
 import torch
 
 _QUANT = [None]          # rounding of the autograd functions below; set per call by forward()
+_GSCALE = [1.0]          # quant='fp16': the power of two the stored activation gradients carry (set by loss_and_grads)
+
+
+def grad_scale_for(loss_scale):
+    """csrc/plan.cu: grad_scale_for -- 2^floor(log2(64 / loss_scale)): the largest |dlogits| element is stored in (32, 64]"""
+    a = abs(float(loss_scale))
+    if not (a > 0.0) or math.isinf(a):
+        return 1.0
+    m, e = math.frexp(64.0 / a)
+    return math.ldexp(1.0, e - 1)
 
 
 def round_tf32(x):
@@ -34,7 +46,16 @@ def round_tf32(x):
 def _round(x):
     if _QUANT[0] == "tf32":
         return round_tf32(x)
+    if _QUANT[0] == "fp16":
+        return x.to(torch.float16).to(x.dtype)
     return x.to(torch.bfloat16).to(x.dtype)
+
+
+def _round_grad(g):
+    """an activation gradient as the product stores it (fp16: times the loss scale, see _GSCALE)"""
+    if _QUANT[0] == "fp16" and _GSCALE[0] != 1.0:
+        return _round(g * _GSCALE[0]) / _GSCALE[0]
+    return _round(g)
 
 
 def xavier_params(in_feats, n_hidden, n_classes, n_layers, seed, dtype=torch.float32):
@@ -62,7 +83,7 @@ class _Q(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return _round(g)
+        return _round_grad(g)
 
 
 class _Qf(torch.autograd.Function):
@@ -84,7 +105,7 @@ class _Qb(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return _round(g)
+        return _round_grad(g)
 
 
 def segment_max(hp, edge_src, n_dst, fanout, arg=None):
@@ -152,7 +173,7 @@ def sage_layer(x, n_dst, edge_src, fanout, Wp, bp, Ws, bs, Wn, bn, relu_out, qua
 def forward(params, x_in, blocks, quant=None):
     """blocks: list (input layer first) of dict(n_dst, edge_src[int64], fanout[, arg]).  x_in: features
     of blocks[0]'s src nodes.  Returns (logits, per-layer intermediates)."""
-    assert quant in (None, "bf16", "tf32")
+    assert quant in (None, "bf16", "tf32", "fp16")
     _QUANT[0] = quant
     h = _Qf.apply(x_in) if quant else x_in
     inter = []
@@ -177,6 +198,7 @@ def xent(logits, labels, reduction="mean", quant=None):
 def loss_and_grads(params, x_in, blocks, labels, quant=None, dtype=torch.float32):
     """One fwd+bwd.  Returns (loss_mean, per_vertex_loss, logits, grads dict, intermediates)."""
     p = {k: v.detach().to(dtype).requires_grad_(True) for k, v in params.items()}
+    _GSCALE[0] = grad_scale_for(1.0 / max(1, labels.numel())) if quant == "fp16" else 1.0      # loss = per.mean()
     logits, inter = forward(p, x_in.to(dtype), blocks, quant=quant)
     per = xent(logits, labels, "none", quant=quant)
     loss = per.mean()

@@ -114,3 +114,47 @@ def test_nt_persistent_loop_many_tiles_per_cta():
     ref = torch.relu(a[:, :k].float() @ b[:, :k].float().t() + bias)
     err = (got - ref).abs()
     assert bool((err <= 2 ** -8 * ref.abs() + 1e-3 * ref.abs().max()).all()), "max err %.3e" % err.max().item()
+
+
+# ---- tcgen05 kind::f16 with fp16 operands (mode OGL_FP16): products of fp16 values are exact in fp32, so -- like the tf32 flavour -- the
+# result differs from the fp64 product of the same operands only by the fp32 accumulation
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(128, 16, 16), (128, 256, 512), (100, 24, 50), (1000, 602, 602), (2500, 600, 1204), (26000, 41, 600),
+                                   (1, 8, 8), (129, 257, 65), (40000, 602, 602)])
+def test_gemm_nt_tcgen05_fp16(m, n, k, cg):
+    from ogl_b200 import native
+    torch.manual_seed(m + n + k)
+    ld = (k + 7) // 8 * 8
+    a = torch.full((m, ld), 1000.0, dtype=torch.float16, device="cuda")      # poisoned pad columns
+    b = torch.full((n, ld), 1000.0, dtype=torch.float16, device="cuda")
+    a[:, :k] = torch.randn(m, k, device="cuda")
+    b[:, :k] = torch.randn(n, k, device="cuda")
+    bias = torch.randn(n, device="cuda")
+    ref = a[:, :k].double() @ b[:, :k].double().t()
+    got = native.gemm_f16_nt_ex(a, b, k=k, out_f16=False, cg=cg)           # fp32 output (the logits epilogue)
+    _check_tf32(got, ref, k, "NT fp16 %dx%dx%d cg%d" % (m, n, k, cg))
+    # activation epilogue: bias + ReLU + fp16 mask (positive / zero / negative / -0 entries), fp16 output through TMA stores
+    mask = torch.randn(m, (n + 7) // 8 * 8, device="cuda")
+    mask[::3] = 0.0
+    mask[1::7] = -0.0
+    mask = mask.half()
+    got2 = native.gemm_f16_nt_ex(a, b, k=k, out_f16=True, bias=bias, relu=True, mask=mask, cg=cg)
+    assert got2.dtype == torch.float16
+    ref2 = torch.relu(ref + bias.double()) * (mask[:, :n].float() > 0)
+    err = (got2.double() - ref2).abs()
+    assert bool((err <= 2 ** -11 * ref2.abs() + 1e-6 * (k ** 0.5 + 8) * ref.abs().max() + 2 ** -25).all()), "fp16 activation epilogue: max err %.3e" % err.max().item()
+
+
+@pytest.mark.parametrize("m,n,k,ws", [(64, 64, 64, 1 << 22), (1000, 602, 602, 1 << 24), (100, 41, 600, 1 << 22), (5000, 600, 41, 1 << 22),
+                                      (30000, 602, 602, 1 << 24), (200, 24, 50, 1 << 22), (1000, 602, 602, 0), (1, 8, 8, 0)])
+def test_gemm_tn_tcgen05_fp16(m, n, k, ws):
+    """the weight-gradient shape with the unscaling factor of the loss-scaled backward pass (alpha = 2^-7: exact)"""
+    from ogl_b200 import native
+    torch.manual_seed(m + n + k)
+    ldn, ldk = (n + 7) // 8 * 8, (k + 7) // 8 * 8
+    a = torch.full((m, ldn), 1000.0, dtype=torch.float16, device="cuda")
+    b = torch.full((m, ldk), 1000.0, dtype=torch.float16, device="cuda")
+    a[:, :n] = torch.randn(m, n, device="cuda")
+    b[:, :k] = torch.randn(m, k, device="cuda")
+    got = native.gemm_f16_tn(a, b, n=n, k=k, alpha=2.0 ** -7, workspace_elems=ws)
+    _check_tf32(got, (a[:, :n].double().t() @ b[:, :k].double()) * 2.0 ** -7, m, "TN fp16 %dx%dx%d" % (m, n, k))

@@ -71,8 +71,8 @@ class Case:
         src = rng.integers(0, V - isolated, E).astype(np.int64)
         dst = rng.integers(0, V - isolated, E).astype(np.int64)
         self.V, self.dims, self.fanouts, self.L = V, list(dims), list(fanouts), len(fanouts)
-        self.mode = {"bf16": ogl_b200.OGL_BF16, "tf32": ogl_b200.OGL_TF32}.get(mode, ogl_b200.OGL_F32)
-        self.quant = mode if mode in ("bf16", "tf32") else None
+        self.mode = {"bf16": ogl_b200.OGL_BF16, "tf32": ogl_b200.OGL_TF32, "fp16": ogl_b200.OGL_FP16}.get(mode, ogl_b200.OGL_F32)
+        self.quant = mode if mode in ("bf16", "tf32", "fp16") else None
         self.g = ogl_b200.native.Graph(V, 2 * E)
         self.g.insert_vertices(V)
         self.g.insert_edges(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), symmetric=True)
@@ -104,7 +104,7 @@ class Case:
         return osage.loss_and_grads(self.params, x_in, blocks, labels, quant=self.quant, dtype=dtype)
 
 
-@pytest.mark.parametrize("mode,rtol,rtol_store", [("fp32", 1e-5, 1e-5), ("bf16", 1e-3, 2 ** -8), ("tf32", 2e-4, 2 ** -10)])
+@pytest.mark.parametrize("mode,rtol,rtol_store", [("fp32", 1e-5, 1e-5), ("bf16", 1e-3, 2 ** -8), ("tf32", 2e-4, 2 ** -10), ("fp16", 2e-4, 2 ** -10)])
 @pytest.mark.parametrize("dims,fanouts", [((50, 24, 5), (6, 4)), ((166, 64, 2), (9, 9)), ((33, 7), (5,)), ((20, 16, 16, 3), (3, 3, 2))])
 def test_forward_backward_parity_simt(mode, rtol, rtol_store, dims, fanouts):
     c = Case(dims=dims, fanouts=fanouts, mode=mode, gemm_impl=1)
@@ -135,7 +135,7 @@ def test_forward_backward_parity_simt(mode, rtol, rtol_store, dims, fanouts):
             close(got[k], v, rtol * (3 if mode != "fp32" else 1), "grad " + k)
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32", "fp16"])
 @pytest.mark.parametrize("dims,fanouts,n_seeds", [((50, 24, 5), (6, 4), 96), ((166, 256, 2), (9, 9), 64), ((602, 600, 41), (10, 5), 300),
                                                   ((33, 7), (5,), 40), ((128, 32, 32, 40), (4, 3, 2), 50)])
 def test_forward_backward_parity_tcgen05(dims, fanouts, n_seeds, mode):
@@ -439,7 +439,7 @@ def test_multi_step_call_equals_single_steps():
     close(runs[0][1].view(5, 32).sum(1), runs[0][2], 1e-5, "loss sum == sum of per-vertex losses")
 
 
-@pytest.mark.parametrize("mode,gemm_impl,rtol", [("fp32", 1, 1e-5), ("tf32", 0, 2e-3), ("bf16", 0, 2e-2)])
+@pytest.mark.parametrize("mode,gemm_impl,rtol", [("fp32", 1, 1e-5), ("tf32", 0, 2e-3), ("fp16", 0, 2e-3), ("bf16", 0, 2e-2)])
 def test_feat_drop_matches_the_oracle_mask(mode, gemm_impl, rtol):
     """SAGEConv(feat_drop=p) (graphsage_dgl.py:41-46): every layer's input is dropped once in training mode with the Philox-keyed
     mask of oracle/sage.py:dropout_keep, scaled by 1 / (1 - p); evaluation is untouched"""
@@ -485,7 +485,7 @@ def test_feat_drop_matches_the_oracle_mask(mode, gemm_impl, rtol):
     close(per2, per, 1e-5 if mode == "fp32" else 1e-4, "fused step losses")
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32", "fp16"])
 def test_tail_gemm_in_pieces_equals_whole(mode):
     """the last weight-gradient GEMM issued in pieces of 256 gradient rows (data-parallel runs exchange piece i while piece i + 1 is
     computed) writes the same gradient as the single launch"""
@@ -510,7 +510,7 @@ def test_tail_gemm_in_pieces_equals_whole(mode):
     close(g1, g0, 1e-5, "gradient, pieces vs whole")
 
 
-@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32", "fp16"])
 def test_train_step_is_bit_reproducible(mode):
     """reverse edge lists are put into canonical order after the atomic fill, so the max-pool backward sums every source row's
     contributions in the same order on every run: two runs from the same state give bit-identical gradients and weights -- on a
@@ -525,7 +525,7 @@ def test_train_step_is_bit_reproducible(mode):
         g = ogl_b200.native.Graph(V, 2 * E)
         g.insert_vertices(V)
         g.insert_edges(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), symmetric=False)
-        m = {"bf16": ogl_b200.OGL_BF16, "tf32": ogl_b200.OGL_TF32}[mode]
+        m = {"bf16": ogl_b200.OGL_BF16, "tf32": ogl_b200.OGL_TF32, "fp16": ogl_b200.OGL_FP16}[mode]
         f = ogl_b200.native.Features(V, 40, m)
         gen = torch.Generator().manual_seed(0)
         f.write(0, torch.randn(V, 40, generator=gen).cuda(), torch.randint(0, 5, (V,), generator=gen).cuda())
