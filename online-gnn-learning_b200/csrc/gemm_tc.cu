@@ -135,6 +135,26 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One elected lane of a CONVERGED warp (CUTLASS's elect_one_sync).  The producer and MMA warps run their loops with all 32 lanes
+// and warp-uniform values and predicate only the asynchronous instructions with this: UTMALDG / UTCHMMA take their descriptors,
+// coordinates and addresses from UNIFORM registers, and for code the compiler sees as thread-divergent (`if (lane == 0) { ... }`)
+// it wraps every such instruction in a waterfall loop (ELECT + seven R2UR.BROADCAST + branch, ~140 clocks per MMA measured with
+// the loads and the epilogue switched off -- more than the 128 clocks a 256 x 256 x 16 MMA takes, and ~500 per 16 KB TMA box:
+// the "30 B/clk per issuing thread" of tools/exp/ingest_probe.cu).  With uniform control flow the operands stay in uniform
+// registers and an issue costs a few clocks.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// a value the compiler can prove warp-uniform (lane 0's copy): loads from global / shared memory and inline-asm outputs are not
+__device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- cta_group::2 (CTA pair) variants ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -335,18 +355,18 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   constexpr int KI = TF ? 8 : 16;                 // contraction elements per tcgen05.mma
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemLayout s = carve(smem_raw, NST, CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES, CG == 2 ? RING2_BYTES : RING_BYTES);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;          // CTA rank inside the pair
+  const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? uniform((int)cluster_ctarank()) : 0;          // CTA rank inside the pair
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-  const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
+  const int m_dyn = uniform(p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max);
   const int m_pad = p.zero_tail ? min((m_dyn + 127) / 128 * 128, p.m_max) : m_dyn;
   const int m_tiles = ((m_pad + BM - 1) / BM + CG - 1) / CG;      // row blocks of CG * 128 rows
   const int total_tiles = m_tiles * p.n_tiles;
   int rows_valid[2];
-  rows_valid[0] = p.a_rows_dev[0] ? min(*p.a_rows_dev[0], m_dyn) : m_dyn;
-  rows_valid[1] = p.n_seg > 1 ? (p.a_rows_dev[1] ? min(*p.a_rows_dev[1], m_dyn) : m_dyn) : 0;
+  rows_valid[0] = uniform(p.a_rows_dev[0] ? min(*p.a_rows_dev[0], m_dyn) : m_dyn);
+  rows_valid[1] = uniform(p.n_seg > 1 ? (p.a_rows_dev[1] ? min(*p.a_rows_dev[1], m_dyn) : m_dyn) : 0);
 
   if (threadIdx.x == 32) {                        // (a lane of the MMA warp: off the barrier-initialising thread)
     for (int i = 0; i < p.n_seg; ++i) { prefetch_tensormap(&p.ta[i]); prefetch_tensormap(&p.tb[i]); }
@@ -367,7 +387,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   __syncthreads();
   if (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before any remote arrive / TMA completes on them
   tc_fence_after();
-  const uint32_t tmem_base = *s.tmem_slot;
+  const uint32_t tmem_base = uniform(*s.tmem_slot);
   pdl_wait();                            // operands (and the output buffer's previous readers) belong to the preceding kernel
   pdl_trigger();                         // a GEMM behind this one cannot share an SM with it (shared memory): it takes each SM as this
                                          // kernel's CTA leaves it, instead of waiting for the whole grid
@@ -382,9 +402,8 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   // then sustain only ~32 B/clk per SM (Little's law) -- a box that is already in L2 when its load is issued comes back in ~0.7 us.
   // The prefetcher paces itself on a progress counter in shared memory that the A producer advances once per stage: it stays at
   // most p.prefetch k-blocks ahead and ends with its cursor (no barrier wait that could outlive the producers).
-  auto tma_producer = [&](int which) {
-    int stage = 0;
-    uint32_t phase = 0;
+  // (run by ONE lane of warp 11) the L2 prefetcher of the A boxes: paces itself on the A producer's progress counter
+  auto l2_prefetcher = [&]() {
     // prefetch cursor: (tile, segment, k-block) of the position p.prefetch k-blocks ahead, across segment and tile boundaries
     int pt = unit, pseg = 0, pkb = 0;
     auto pf_issue = [&]() {
@@ -403,13 +422,16 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       }
     };
     volatile int* prog = (volatile int*)(s.tmem_slot + 2);          // k-blocks the A producer has issued so far
-    if (which == 3) {
-      for (int n_pf = 0; pt < total_tiles; ++n_pf) {
-        while (n_pf - *prog >= p.prefetch) __nanosleep(64);
-        pf_issue();
-      }
-      return;
+    for (int n_pf = 0; pt < total_tiles; ++n_pf) {
+      while (n_pf - *prog >= p.prefetch) __nanosleep(64);
+      pf_issue();
     }
+  };
+  // (run by ALL lanes of a producer warp, converged; the copies themselves are issued by the elected lane)
+  auto tma_producer = [&](int which) {
+    int stage = 0;
+    uint32_t phase = 0;
+    volatile int* prog = (volatile int*)(s.tmem_slot + 2);
     int n_issued = 0;
     // bytes this producer lands per stage on the barrier the MMA issuer waits on (pair mode: both CTAs' boxes, on the leader's)
     const uint32_t tx_a = (uint32_t)(CG * A_STAGE_BYTES);
@@ -424,27 +446,31 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
         const int nkb = (p.k[seg] + BKE - 1) / BKE;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&s.empty[stage], phase ^ 1);
-          if (which != 2) *prog = ++n_issued;
-          if (CG == 2) {
-            if (rank == 0) mbar_expect_tx(&s.full[stage], tx);
-            if (which != 2) tma_load_2d_pair(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
-            if (which != 1) tma_load_2d_pair(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX + rank * (bn_tile / 2));
-          } else {
-            mbar_expect_tx(&s.full[stage], tx);
-            if (which != 2) tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
-            if (which != 1) tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX);
+          ++n_issued;
+          if (elect_one()) {
+            if (which != 2 && p.prefetch > 0) *prog = n_issued;
+            if (CG == 2) {
+              if (rank == 0) mbar_expect_tx(&s.full[stage], tx);
+              if (which != 2) tma_load_2d_pair(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
+              if (which != 1) tma_load_2d_pair(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX + rank * (bn_tile / 2));
+            } else {
+              mbar_expect_tx(&s.full[stage], tx);
+              if (which != 2) tma_load_2d(s.a(stage), &p.ta[seg], &s.full[stage], kb * BKE, mb * BM);
+              if (which != 1) tma_load_2d(s.b(stage), &p.tb[seg], &s.full[stage], kb * BKE, nb * BN_MAX);
+            }
           }
+          __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   };
   if (warp == 0) {
-    if (lane == 0 && !(p.debug & 2) && (p.loader == 0 || p.loader == 3)) tma_producer(p.loader == 3 ? 1 : 0);
+    if (!(p.debug & 2)) tma_producer(p.loader == 3 ? 1 : 0);
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer (pair mode: the leader CTA only) =====
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer (pair mode: the leader CTA only): the whole warp runs the loop, the elected lane issues =====
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -471,25 +497,31 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
             const uint64_t ad = a_desc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
             const uint64_t bd = b_desc0 + (uint64_t)(stage * (b_stage_bytes >> 4));
             const int k_left = K - kb * BKE;
-            if (k_left >= BKE) {
-              tc_mma<CG, TF>(d_tmem, ad, bd, idesc, accumulate);
-              tc_mma<CG, TF>(d_tmem, ad + 2, bd + 2, idesc, 1);
-              tc_mma<CG, TF>(d_tmem, ad + 4, bd + 4, idesc, 1);
-              tc_mma<CG, TF>(d_tmem, ad + 6, bd + 6, idesc, 1);
-            } else {
-              const int n_ki = (k_left + KI - 1) / KI;
-              for (int ki = 0; ki < n_ki; ++ki) tc_mma<CG, TF>(d_tmem, ad + 2 * ki, bd + 2 * ki, idesc, ki ? 1u : accumulate);
+            if (elect_one()) {
+              if (k_left >= BKE) {
+                tc_mma<CG, TF>(d_tmem, ad, bd, idesc, accumulate);
+                tc_mma<CG, TF>(d_tmem, ad + 2, bd + 2, idesc, 1);
+                tc_mma<CG, TF>(d_tmem, ad + 4, bd + 4, idesc, 1);
+                tc_mma<CG, TF>(d_tmem, ad + 6, bd + 6, idesc, 1);
+              } else {
+                const int n_ki = (k_left + KI - 1) / KI;
+                for (int ki = 0; ki < n_ki; ++ki) tc_mma<CG, TF>(d_tmem, ad + 2 * ki, bd + 2 * ki, idesc, ki ? 1u : accumulate);
+              }
+              if (!(p.debug & 2)) {
+                if (CG == 2) tc_commit_pair(&s.empty[stage]);
+                else tc_commit(&s.empty[stage]);
+              }
             }
+            __syncwarp();
             accumulate = 1;
-            if (!(p.debug & 2)) {
-              if (CG == 2) tc_commit_pair(&s.empty[stage]);
-              else tc_commit(&s.empty[stage]);
-            }
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
-        if (CG == 2) tc_commit_pair(&s.acc_full[acc]);
-        else tc_commit(&s.acc_full[acc]);
+        if (elect_one()) {
+          if (CG == 2) tc_commit_pair(&s.acc_full[acc]);
+          else tc_commit(&s.acc_full[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -497,8 +529,8 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   } else if (warp >= 10) {
     // ===== second TMA producer (warp 10) =====
     if (p.loader == 3) {
-      if (warp == 10 && lane == 0 && !(p.debug & 2)) tma_producer(2);      // the second TMA producer: the B boxes
-      if (warp == 11 && lane == 0 && !(p.debug & 2) && p.prefetch > 0) tma_producer(3);      // the L2 prefetcher of the A boxes
+      if (warp == 10 && !(p.debug & 2)) tma_producer(2);      // the second TMA producer: the B boxes
+      if (warp == 11 && lane == 0 && !(p.debug & 2) && p.prefetch > 0) l2_prefetcher();      // the L2 prefetcher of the A boxes
       __syncwarp();
     }
   } else {
@@ -771,7 +803,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout s = carve(smem_raw, TN_STAGES, B_STAGE_BYTES, RING_BYTES, true);
   s.b0 = smem_raw + TN_STAGES * TN_A_STAGE_BYTES;     // (carve assumes 16 KB A stages)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
 
   const int gtile = blockIdx.x % p.total_tiles;
   const int z = blockIdx.x / p.total_tiles;
@@ -781,7 +813,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   const int tile = gtile - q.tile0;
   const int nb = tile / q.k_tiles, kt = tile % q.k_tiles;
   const int row0 = nb * TN_ROWS;
-  const int m_dyn = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
+  const int m_dyn = uniform(p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max);
   // contraction range of this split, in 64-row blocks (rows in [m_dyn, round_up(m_dyn, 64)) are zero: zero-tail rule)
   const int blocks_total = (m_dyn + BKR - 1) / BKR;
   const int per = (blocks_total + p.splits - 1) / p.splits;
@@ -805,7 +837,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s.tmem_slot;
+  const uint32_t tmem_base = uniform(*s.tmem_slot);
   auto a_stage = [&](int i) { return smem_raw + i * TN_A_STAGE_BYTES; };
   pdl_wait();
 
@@ -821,19 +853,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
     const uint32_t tx = (uint32_t)(max(c1 - c0, 0) * CHUNK_BYTES);
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&s.empty[stage], phase ^ 1);
-      mbar_expect_tx(&s.full[stage], tx);
-      if (which == 1)
-        for (int c = c0; c < c1; ++c) tma_load_2d(a_stage(stage) + c * CHUNK_BYTES, &q.ta, &s.full[stage], row0 + c * CW, kb * BKR);
-      else
-        for (int c = c0; c < c1; ++c) tma_load_2d(s.b(stage) + c * CHUNK_BYTES, &q.tb, &s.full[stage], kt * BN_MAX + c * CW, kb * BKR);
+      if (elect_one()) {                             // (all lanes run the loop, see elect_one)
+        mbar_expect_tx(&s.full[stage], tx);
+        if (which == 1)
+          for (int c = c0; c < c1; ++c) tma_load_2d(a_stage(stage) + c * CHUNK_BYTES, &q.ta, &s.full[stage], row0 + c * CW, kb * BKR);
+        else
+          for (int c = c0; c < c1; ++c) tma_load_2d(s.b(stage) + c * CHUNK_BYTES, &q.tb, &s.full[stage], kt * BN_MAX + c * CW, kb * BKR);
+      }
+      __syncwarp();
       if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
     }
   };
   if (warp == 0 || warp >= 6) {
-    if (lane == 0) tma_producer(warp == 0 || warp == 6 ? 1 : 2, warp == 0 || warp == 7 ? 0 : 1);
+    tma_producer(warp == 0 || warp == 6 ? 1 : 2, warp == 0 || warp == 7 ? 0 : 1);
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       // M is always issued as 128: when only part of a sub-tile's chunks was loaded its upper accumulator rows hold
@@ -851,6 +886,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
         const uint64_t ad = a_desc0 + (uint64_t)(stage * (TN_A_STAGE_BYTES >> 4));
         const uint64_t ad1 = ad + (uint64_t)(A_STAGE_BYTES >> 4);              // second 128-row sub-tile
         const uint64_t bd = b_desc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
+        if (elect_one()) {
         if (n_sub == 2) {
           tc_mma<1, TF>(tmem_base, ad, bd, idesc, accumulate);
           tc_mma<1, TF>(acc1, ad1, bd, idesc, accumulate);
@@ -866,11 +902,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
           tc_mma<1, TF>(tmem_base, ad + 2 * KSTEP, bd + 2 * KSTEP, idesc, 1);
           tc_mma<1, TF>(tmem_base, ad + 3 * KSTEP, bd + 3 * KSTEP, idesc, 1);
         }
-        accumulate = 1;
         tc_commit(&s.empty[stage]);
+        }
+        __syncwarp();
+        accumulate = 1;
         if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&s.acc_full[0]);
+      if (elect_one()) tc_commit(&s.acc_full[0]);
+      __syncwarp();
     }
     __syncwarp();
   } else {
