@@ -43,10 +43,14 @@ constexpr int SMEM_NT1 = RING_BYTES + STORE_BYTES + BIAS_BYTES + TAIL_BYTES;
 // 16 KB of A + 16 KB of B per CTA.  FIVE stages (160 KB): together with the staging boxes the CTA then leaves ~33 KB of
 // the SM's shared memory free, so the small kernels of the side / prefetch streams (sampling, to_block, scans, column sums;
 // all <= 9 KB) can be resident next to it instead of waiting for the GEMM to leave the SM
-constexpr int STAGES2 = 5;
+#ifndef OGL_NT_STAGES2
+#define OGL_NT_STAGES2 5
+#endif
+constexpr int STAGES2 = OGL_NT_STAGES2;
 constexpr int B2_STAGE_BYTES = (BN_MAX / 2) * BK * 2;    // 16 KB
 constexpr int RING2_BYTES = STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES);
 constexpr int SMEM_NT2 = RING2_BYTES + STORE_BYTES + BIAS_BYTES + TAIL_BYTES;
+static_assert(SMEM_NT2 <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 // TN kernel: its epilogue starts after the last MMA has retired, so its staging boxes alias the (then idle) operand ring
 constexpr int SMEM_TN = RING_BYTES + TAIL_BYTES;
 static_assert(SMEM_NT1 <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
@@ -340,6 +344,8 @@ struct NtParams {
   int zero_tail;
   int prefetch;                 // k-blocks the A operand is prefetched into L2 ahead of its load (0: off)
   int loader;                   // 3: two TMA producers (warp 0: A boxes, warp 10: B boxes), 0: one
+  int order;                    // tile order of a unit: 0 = round robin over all (row block, column tile) pairs, 1 = row-block major
+                                //   (the column tiles of one row block back to back on the same unit: its A block is re-read from L2)
   int debug;                    // perf experiments (OGL_GEMM_DBG): 1 = epilogue drains the accumulator without storing
 };
 
@@ -364,6 +370,17 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
   const int m_pad = p.zero_tail ? min((m_dyn + 127) / 128 * 128, p.m_max) : m_dyn;
   const int m_tiles = ((m_pad + BM - 1) / BM + CG - 1) / CG;      // row blocks of CG * 128 rows
   const int total_tiles = m_tiles * p.n_tiles;
+  // i-th tile of this unit -> (row block mt, column tile nb); false past the unit's last tile
+  auto tile_at = [&](int i, int& mt, int& nb) -> bool {
+    if (p.order == 0) {
+      const int t = unit + i * n_units;
+      if (t >= total_tiles) return false;
+      mt = t / p.n_tiles; nb = t % p.n_tiles;
+      return true;
+    }
+    mt = unit + (i / p.n_tiles) * n_units; nb = i % p.n_tiles;
+    return mt < m_tiles;
+  };
   int rows_valid[2];
   rows_valid[0] = uniform(p.a_rows_dev[0] ? min(*p.a_rows_dev[0], m_dyn) : m_dyn);
   rows_valid[1] = uniform(p.n_seg > 1 ? (p.a_rows_dev[1] ? min(*p.a_rows_dev[1], m_dyn) : m_dyn) : 0);
@@ -437,8 +454,8 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
     const uint32_t tx_a = (uint32_t)(CG * A_STAGE_BYTES);
     const uint32_t tx_b = CG == 2 ? (uint32_t)(2 * (p.bn / 2) * 128) : (uint32_t)(p.bn * 128);
     const uint32_t tx = which == 0 ? tx_a + tx_b : (which == 1 ? tx_a : tx_b);
-    for (int t = unit; t < total_tiles; t += n_units) {
-      const int mt = t / p.n_tiles, nb = t % p.n_tiles;
+    int mt, nb;
+    for (int it = 0; tile_at(it, mt, nb); ++it) {
       const int mb = mt * CG + rank;
       const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
       for (int seg = 0; seg < p.n_seg; ++seg) {
@@ -477,8 +494,8 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       uint32_t acc_phase = 0;
       const int b_stage_bytes = CG == 2 ? B2_STAGE_BYTES : B_STAGE_BYTES;
       const uint64_t a_desc0 = smem_desc(smem_u32(s.a(0)), 16, 1024), b_desc0 = smem_desc(smem_u32(s.b(0)), 16, 1024);
-      for (int t = unit; t < total_tiles; t += n_units) {
-        const int mt = t / p.n_tiles, nb = t % p.n_tiles;
+      int mt, nb;
+      for (int it = 0; tile_at(it, mt, nb); ++it) {
         const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
         const uint32_t idesc = instr_desc(BM * CG, bn_tile, 0, 0, KIND);
         mbar_wait(&s.acc_empty[acc], acc_phase ^ 1);
@@ -542,8 +559,9 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t boxes_issued = 0;
-    for (int t = unit; t < total_tiles; t += n_units) {
-      const int mb = (t / p.n_tiles) * CG + rank, nb = t % p.n_tiles;
+    int mt_e, nb;
+    for (int it = 0; tile_at(it, mt_e, nb); ++it) {
+      const int mb = mt_e * CG + rank;
       const int bn_tile = (nb == p.n_tiles - 1) ? ((p.n - nb * BN_MAX + 15) / 16 * 16) : p.bn;
       const int gm = mb * BM + quarter * 32 + lane;
       const bool row_store = gm < m_pad;
@@ -568,23 +586,21 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       if (p.debug & 1) {
         // nothing: measures the load + MMA pipeline alone
       } else if (TF && p.out_f32_tma) {
-        // fp32 activations of the tf32 mode: one 32 x 32 fp32 box (32 rows of 128 bytes) per step, TF32-rounded, TMA store
+        // fp32 activations of the tf32 mode: one 32 x 32 fp32 box (32 rows of 128 bytes) per step, TF32-rounded, TMA store.
+        // The box leaves through ONE staging buffer per warp, so whatever does not need the buffer goes first: the mask rows are
+        // requested from global memory, the accumulator is read and (without a mask) finished in registers BEFORE the warp waits for
+        // the previous box's store to have read the buffer
         for (int c0 = parity * 32; c0 < bn_tile; c0 += 64) {
-          if (boxes_issued >= 1) {
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
-          }
-          if (p.mask) {                            // 32 x 32 fp32 mask box staged with coalesced 512-byte warp loads (see the bf16 path)
+          uint4 mreg[8];
+          if (p.mask) {                            // 32 x 32 fp32 mask box through coalesced 512-byte warp loads (see the 16-bit path)
             const int rbase = mb * BM + quarter * 32, cbase = nb * BN_MAX + c0 + (lane & 7) * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + (lane >> 3);
-              uint4 mraw = make_uint4(0u, 0u, 0u, 0u);
+              mreg[i] = make_uint4(0u, 0u, 0u, 0u);
               if (rbase + r < m_dyn && cbase < p.ldmask)
-                mraw = __ldg(reinterpret_cast<const uint4*>((const float*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
-              *reinterpret_cast<uint4*>(buf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = mraw;
+                mreg[i] = __ldg(reinterpret_cast<const uint4*>((const float*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
             }
-            __syncwarp();
           }
           uint32_t r[32];
           tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + c0), r);
@@ -607,7 +623,21 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
               v[j] = x;
             }
           }
+          if (p.round_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          }
+          if (boxes_issued >= 1) {                 // this warp's previous store has finished reading the staging box
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
           if (p.mask) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r_ = i * 4 + (lane >> 3);
+              *reinterpret_cast<uint4*>(buf + r_ * 128 + (((lane & 7) ^ (r_ & 7)) << 4)) = mreg[i];
+            }
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 mv = *reinterpret_cast<const float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4));
@@ -617,50 +647,44 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
               if (!(mv.w > 0.f)) v[q * 4 + 3] = 0.f;
             }
           }
-          if (p.round_out) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-          }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&p.tc, buf, nb * BN_MAX + c0, mb * BM + quarter * 32);
             tma_store_commit();
           }
+          __syncwarp();
           ++boxes_issued;
         }
       } else if (!TF && p.out_bf16) {
+        // 16-bit activations: one 32 x 64 box (32 rows of 128 bytes) per step.  As above, everything that does not need the warp's
+        // single staging buffer is done before the wait for the previous store: the mask rows are requested, and without a mask both
+        // halves of the box are read from TMEM, finished and packed in registers first
         for (int c0 = parity * 64; c0 < bn_tile; c0 += 128) {
-          if (boxes_issued >= 1) {                 // this warp's previous store has finished reading the staging box
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
-          }
+          const int n_half = (c0 + 32 < bn_tile) ? 2 : 1;      // columns >= bn_tile >= ldc are clipped by the TMA store
+          uint4 mreg[8];
           if (p.mask) {
-            // the 32 x 64 mask box of this warp goes through the staging buffer first: 8 fully coalesced 512-byte
-            // warp loads (4 rows x 128 B each) instead of 32-sector row-per-thread loads; same XOR swizzle, and each
-            // thread later overwrites only the chunks of its own row that it has already consumed
+            // the 32 x 64 mask box of this warp goes through the staging buffer: 8 fully coalesced 512-byte warp loads (4 rows x
+            // 128 B each) instead of 32-sector row-per-thread loads; same XOR swizzle, and each thread later overwrites only the
+            // chunks of its own row that it has already consumed
             const int rbase = mb * BM + quarter * 32, cbase = nb * BN_MAX + c0 + (lane & 7) * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + (lane >> 3);
-              uint4 mraw = make_uint4(0u, 0u, 0u, 0u);
+              mreg[i] = make_uint4(0u, 0u, 0u, 0u);
               if (rbase + r < m_dyn && cbase < p.ldmask)
-                mraw = __ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
-              *reinterpret_cast<uint4*>(buf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = mraw;
+                mreg[i] = __ldg(reinterpret_cast<const uint4*>((const uint16_t*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
             }
-            __syncwarp();
           }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          // one half (32 columns) of the box: accumulator -> alpha, bias, ReLU -> v[]
+          auto half_values = [&](int half, float (&v)[32]) {
             const int cc = c0 + half * 32;
-            if (cc >= bn_tile) break;              // columns >= bn_tile >= ldc are clipped by the TMA store
             uint32_t r[32];
             tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + cc), r);
             const int gn0 = nb * BN_MAX + cc;
-            float v[32];
             if (tile_live && gn0 + 32 <= p.n) {
               // interior chunk (every row live, every column < n): branch-free, bias through 16-byte shared loads
 #pragma unroll
@@ -679,35 +703,77 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
                 v[j] = x;
               }
             }
-            if (p.mask) {                          // mask box staged in `buf` (coalesced loads, see above)
+          };
+          auto pack4 = [&](const float (&v)[32], int q) {
+            uint4 o;
+            o.x = pack16<KIND>(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack16<KIND>(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack16<KIND>(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack16<KIND>(v[q * 8 + 6], v[q * 8 + 7]);
+            return o;
+          };
+          // row `lane` of the box, 16-byte chunk (half*4 + q) XOR-swizzled like TMA's SWIZZLE_128B
+          if (!p.mask) {
+            uint4 o[8];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 raw = *reinterpret_cast<const uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4));
-                const uint16_t* mv = reinterpret_cast<const uint16_t*>(&raw);
+            for (int half = 0; half < 2; ++half) {
+              if (half < n_half) {
+                float v[32];
+                half_values(half, v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (!positive16<KIND>(mv[j])) v[q * 8 + j] = 0.f;
+                for (int q = 0; q < 4; ++q) o[half * 4 + q] = pack4(v, q);
               }
             }
-            // row `lane` of the box, 16-byte chunk (half*4 + q) XOR-swizzled like TMA's SWIZZLE_128B
+            if (boxes_issued >= 1) {               // this warp's previous store has finished reading the staging box
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack16<KIND>(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack16<KIND>(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack16<KIND>(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack16<KIND>(v[q * 8 + 6], v[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = o;
+            for (int half = 0; half < 2; ++half)
+              if (half < n_half) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = o[half * 4 + q];
+              }
+          } else {
+            if (boxes_issued >= 1) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r_ = i * 4 + (lane >> 3);
+              *reinterpret_cast<uint4*>(buf + r_ * 128 + (((lane & 7) ^ (r_ & 7)) << 4)) = mreg[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              if (half < n_half) {
+                float v[32];
+                half_values(half, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 raw = *reinterpret_cast<const uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4));
+                  const uint16_t* mv = reinterpret_cast<const uint16_t*>(&raw);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (!positive16<KIND>(mv[j])) v[q * 8 + j] = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = pack4(v, q);
+              }
             }
           }
           fence_async_smem();
           __syncwarp();
           // rows >= m_pad of the tile receive zeros (never read: consumers stop at the padded count); rows >= m_max
           // and columns >= ldc are clipped by the tensor map
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_2d(&p.tc, buf, nb * BN_MAX + c0, mb * BM + quarter * 32);
             tma_store_commit();
           }
+          __syncwarp();
           ++boxes_issued;
         }
       } else {
@@ -1136,7 +1202,9 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   p.round_out = g.out_tf32;
   p.zero_tail = g.zero_tail;
   {
-    static int dbg = -1, pfd = -1, ldr = -1;
+    static int dbg = -1, pfd = -1, ldr = -1, ord = -1;
+    if (ord < 0) { const char* e = getenv("OGL_NT_ORDER"); ord = e ? atoi(e) : 0; }
+    p.order = ord;
     if (dbg < 0) { const char* e = getenv("OGL_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     if (ldr < 0) { const char* e = getenv("OGL_GEMM_LOADER"); ldr = e ? atoi(e) : 3; }
     if (ldr != 0) ldr = 3;
@@ -1144,7 +1212,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     // (measured, tf32 fc_pool GEMM: 140 us without the prefetcher, 150 us with it 12 k-blocks ahead -- off by default)
     if (pfd < 0) { const char* e = getenv("OGL_GEMM_PF_NT"); pfd = e ? atoi(e) : 0; }
     p.debug = dbg;
-    p.prefetch = pfd;
+    p.prefetch = ord == 0 ? pfd : 0;      // (the prefetcher's cursor follows the round-robin order)
   }
   OGL_ARG(!(g.mask && !(g.out_bf16 || p.out_f32_tma)), "gemm_nt_tc: the mask epilogue is implemented for the TMA-store outputs only");
   if (g.out_bf16) OGL_TRY(make_map(&p.tc, g.c, g.m_max, g.ldc, g.ldc, 64, 32, 2, CU_TENSOR_MAP_SWIZZLE_128B, g.f16));
