@@ -586,21 +586,23 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
       if (p.debug & 1) {
         // nothing: measures the load + MMA pipeline alone
       } else if (TF && p.out_f32_tma) {
-        // fp32 activations of the tf32 mode: one 32 x 32 fp32 box (32 rows of 128 bytes) per step, TF32-rounded, TMA store.
-        // The box leaves through ONE staging buffer per warp, so whatever does not need the buffer goes first: the mask rows are
-        // requested from global memory, the accumulator is read and (without a mask) finished in registers BEFORE the warp waits for
-        // the previous box's store to have read the buffer
+        // fp32 activations of the tf32 mode: one 32 x 32 fp32 box (32 rows of 128 bytes) per step, TF32-rounded, TMA store
         for (int c0 = parity * 32; c0 < bn_tile; c0 += 64) {
-          uint4 mreg[8];
-          if (p.mask) {                            // 32 x 32 fp32 mask box through coalesced 512-byte warp loads (see the 16-bit path)
+          if (boxes_issued >= 1) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          if (p.mask) {                            // 32 x 32 fp32 mask box staged with coalesced 512-byte warp loads (see the bf16 path)
             const int rbase = mb * BM + quarter * 32, cbase = nb * BN_MAX + c0 + (lane & 7) * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + (lane >> 3);
-              mreg[i] = make_uint4(0u, 0u, 0u, 0u);
+              uint4 mraw = make_uint4(0u, 0u, 0u, 0u);
               if (rbase + r < m_dyn && cbase < p.ldmask)
-                mreg[i] = __ldg(reinterpret_cast<const uint4*>((const float*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
+                mraw = __ldg(reinterpret_cast<const uint4*>((const float*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
+              *reinterpret_cast<uint4*>(buf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = mraw;
             }
+            __syncwarp();
           }
           uint32_t r[32];
           tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + c0), r);
@@ -623,21 +625,7 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
               v[j] = x;
             }
           }
-          if (p.round_out) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-          }
-          if (boxes_issued >= 1) {                 // this warp's previous store has finished reading the staging box
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
-          }
           if (p.mask) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r_ = i * 4 + (lane >> 3);
-              *reinterpret_cast<uint4*>(buf + r_ * 128 + (((lane & 7) ^ (r_ & 7)) << 4)) = mreg[i];
-            }
-            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 mv = *reinterpret_cast<const float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4));
@@ -646,6 +634,10 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
               if (!(mv.z > 0.f)) v[q * 4 + 2] = 0.f;
               if (!(mv.w > 0.f)) v[q * 4 + 3] = 0.f;
             }
+          }
+          if (p.round_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -660,31 +652,34 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
           ++boxes_issued;
         }
       } else if (!TF && p.out_bf16) {
-        // 16-bit activations: one 32 x 64 box (32 rows of 128 bytes) per step.  As above, everything that does not need the warp's
-        // single staging buffer is done before the wait for the previous store: the mask rows are requested, and without a mask both
-        // halves of the box are read from TMEM, finished and packed in registers first
         for (int c0 = parity * 64; c0 < bn_tile; c0 += 128) {
-          const int n_half = (c0 + 32 < bn_tile) ? 2 : 1;      // columns >= bn_tile >= ldc are clipped by the TMA store
-          uint4 mreg[8];
+          if (boxes_issued >= 1) {                 // this warp's previous store has finished reading the staging box
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
           if (p.mask) {
-            // the 32 x 64 mask box of this warp goes through the staging buffer: 8 fully coalesced 512-byte warp loads (4 rows x
-            // 128 B each) instead of 32-sector row-per-thread loads; same XOR swizzle, and each thread later overwrites only the
-            // chunks of its own row that it has already consumed
+            // the 32 x 64 mask box of this warp goes through the staging buffer first: 8 fully coalesced 512-byte
+            // warp loads (4 rows x 128 B each) instead of 32-sector row-per-thread loads; same XOR swizzle, and each
+            // thread later overwrites only the chunks of its own row that it has already consumed
             const int rbase = mb * BM + quarter * 32, cbase = nb * BN_MAX + c0 + (lane & 7) * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + (lane >> 3);
-              mreg[i] = make_uint4(0u, 0u, 0u, 0u);
+              uint4 mraw = make_uint4(0u, 0u, 0u, 0u);
               if (rbase + r < m_dyn && cbase < p.ldmask)
-                mreg[i] = __ldg(reinterpret_cast<const uint4*>((const uint16_t*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
+                mraw = __ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.mask + (int64_t)(rbase + r) * p.ldmask + cbase));
+              *reinterpret_cast<uint4*>(buf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = mraw;
             }
+            __syncwarp();
           }
-          // one half (32 columns) of the box: accumulator -> alpha, bias, ReLU -> v[]
-          auto half_values = [&](int half, float (&v)[32]) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
             const int cc = c0 + half * 32;
+            if (cc >= bn_tile) break;              // columns >= bn_tile >= ldc are clipped by the TMA store
             uint32_t r[32];
             tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX + cc), r);
             const int gn0 = nb * BN_MAX + cc;
+            float v[32];
             if (tile_live && gn0 + 32 <= p.n) {
               // interior chunk (every row live, every column < n): branch-free, bias through 16-byte shared loads
 #pragma unroll
@@ -703,66 +698,25 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
                 v[j] = x;
               }
             }
-          };
-          auto pack4 = [&](const float (&v)[32], int q) {
-            uint4 o;
-            o.x = pack16<KIND>(v[q * 8 + 0], v[q * 8 + 1]);
-            o.y = pack16<KIND>(v[q * 8 + 2], v[q * 8 + 3]);
-            o.z = pack16<KIND>(v[q * 8 + 4], v[q * 8 + 5]);
-            o.w = pack16<KIND>(v[q * 8 + 6], v[q * 8 + 7]);
-            return o;
-          };
-          // row `lane` of the box, 16-byte chunk (half*4 + q) XOR-swizzled like TMA's SWIZZLE_128B
-          if (!p.mask) {
-            uint4 o[8];
+            if (p.mask) {                          // mask box staged in `buf` (coalesced loads, see above)
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              if (half < n_half) {
-                float v[32];
-                half_values(half, v);
+              for (int q = 0; q < 4; ++q) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4));
+                const uint16_t* mv = reinterpret_cast<const uint16_t*>(&raw);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) o[half * 4 + q] = pack4(v, q);
+                for (int j = 0; j < 8; ++j)
+                  if (!positive16<KIND>(mv[j])) v[q * 8 + j] = 0.f;
               }
             }
-            if (boxes_issued >= 1) {               // this warp's previous store has finished reading the staging box
-              if (lane == 0) tma_store_wait_read<0>();
-              __syncwarp();
-            }
+            // row `lane` of the box, 16-byte chunk (half*4 + q) XOR-swizzled like TMA's SWIZZLE_128B
 #pragma unroll
-            for (int half = 0; half < 2; ++half)
-              if (half < n_half) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = o[half * 4 + q];
-              }
-          } else {
-            if (boxes_issued >= 1) {
-              if (lane == 0) tma_store_wait_read<0>();
-              __syncwarp();
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r_ = i * 4 + (lane >> 3);
-              *reinterpret_cast<uint4*>(buf + r_ * 128 + (((lane & 7) ^ (r_ & 7)) << 4)) = mreg[i];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              if (half < n_half) {
-                float v[32];
-                half_values(half, v);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint4 raw = *reinterpret_cast<const uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4));
-                  const uint16_t* mv = reinterpret_cast<const uint16_t*>(&raw);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (!positive16<KIND>(mv[j])) v[q * 8 + j] = 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = pack4(v, q);
-              }
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack16<KIND>(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack16<KIND>(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack16<KIND>(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack16<KIND>(v[q * 8 + 6], v[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(buf + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4)) = o;
             }
           }
           fence_async_smem();

@@ -163,6 +163,12 @@ struct ogl_plan {
   int use_side = 1;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int fuse_head = 0;                     // train steps run the last layer's segmax + output GEMM + loss + dneigh GEMM as ONE kernel
+                                         // (k_head_fused; option "fuse_head" / OGL_FUSE_HEAD=1).  OFF by default: 36 us against 58 us for
+                                         // the five launches it replaces when timed alone, but the graph-replayed, overlapped step does
+                                         // not get shorter (0.535 vs 0.534 ms) and the end-to-end loop gets slower -- DESIGN.md section 3
+  int head_active = 0;                   // ... set by step_body around forward / loss / backward of a step
+  uint32_t* head_counter = nullptr;      // the fused head's "CTAs done" word (zero between launches)
   float head_loss_scale = 0.f;           // loss scale of the last ogl_plan_step_finish_head (its tail must unscale by the same)
   float grad_scale = 1.f;                // mode OGL_FP16: the loss scale the stored activation gradients of the current backward pass carry
   int skip_gather = 0;                   // step_finish: the input rows were already gathered by step_begin
@@ -380,6 +386,8 @@ extern "C" int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg) {
   OGL_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   DM0(p->per_loss, sizeof(float) * cfg->max_seeds);
   DM0(p->loss_sum, sizeof(float) * 4);
+  DM0(p->head_counter, sizeof(uint32_t) * 4);
+  if (const char* e = getenv("OGL_FUSE_HEAD")) p->fuse_head = atoi(e) != 0;
   DM0(p->adam_m, sizeof(float) * p->n_params);
   DM0(p->adam_v, sizeof(float) * p->n_params);
   *out = p;
@@ -405,7 +413,7 @@ extern "C" int ogl_plan_destroy(ogl_plan* p) {
     for (auto x : *v) cudaFree(x);
   cudaFree(p->alt.counts); cudaFree(p->alt.x); cudaFree(p->alt.seeds_stage);
   void* ptrs[] = {p->counts, p->ctl, p->seeds_stage, p->tn_partial, p->colsum_partial, p->per_loss,
-                  p->loss_sum, p->adam_m, p->adam_v, p->shadow_segs};
+                  p->loss_sum, p->adam_m, p->adam_v, p->shadow_segs, p->head_counter};
   for (void* q : ptrs) cudaFree(q);
   for (auto& r : p->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   cudaDeviceSynchronize();
@@ -527,6 +535,7 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
     g1.c = lb.hp; g1.ldc = lb.pin; g1.m_max = p->nmax[sl]; g1.m_dev = p->counts + sl; g1.n = lb.in;
     g1.in_bf16 = p->bf16; g1.out_bf16 = p->bf16; g1.f16 = p->fp16; g1.tf32 = p->tf32; g1.out_tf32 = p->tf32;
     STAGE(nm("l%d.pool_gemm", l).c_str(), gemm_nt(p, g1, s));
+    if (p->head_active && l == L - 1) break;       // the fused head (plan_loss) does the rest of the last layer
     STAGE(nm("l%d.segmax", l).c_str(),
           segmax_fwd(p->mode, lb.hp, lb.pin, p->edge_lid[h], p->cfg.fanouts[h], p->counts + dl, p->nmax[dl], lb.neigh, lb.arg, s));
     GemmNT g2;
@@ -559,9 +568,18 @@ static float grad_scale_for(const ogl_plan* p, float loss_scale) {
 
 static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
   const int L = p->L;
+  LayerBuf& last = p->layer[L - 1];
   p->grad_scale = want_grad ? grad_scale_for(p, scale) : 1.f;
   scale *= p->grad_scale;
-  LayerBuf& last = p->layer[L - 1];
+  if (p->head_active) {
+    // last layer on the seed rows: segment max + [x_self | neigh] x [W_self | W_neigh]^T + cross entropy + loss sum + dneigh GEMM
+    float* per_h = per_vertex_loss_dev ? per_vertex_loss_dev : p->per_loss;
+    STAGE(nm("l%d.head", L - 1).c_str(),
+          head_fused(p->mode, last.hp, p->act[1], last.pin, last.in, p->edge_lid[0], p->cfg.fanouts[0], last.ws, last.wn, p->params + last.o_bs,
+                     p->params + last.o_bn, last.out, f->labels, p->nodes[0], p->counts, p->nmax[0], round_up(p->nmax[0], 128), scale, want_grad,
+                     last.neigh, last.arg, (float*)p->act[0], last.pout, per_h, last.dpre, last.pout, last.dng, loss_sum_dev, p->head_counter, s));
+    return OGL_OK;
+  }
   float* per = per_vertex_loss_dev ? per_vertex_loss_dev : p->per_loss;
   STAGE("xent", xent(p->mode, (const float*)p->act[0], last.pout, p->cfg.dims[L], f->labels, p->nodes[0], p->counts, p->nmax[0],
                      round_up(p->nmax[0], 128), scale, per, last.dpre, last.pout, want_grad, s));
@@ -645,7 +663,7 @@ static int plan_backward_layers(ogl_plan* p, cudaStream_t s) {
     n1.c = lb.dng; n1.ldc = lb.pin; n1.m_max = p->nmax[dl]; n1.m_dev = p->counts + dl; n1.n = lb.in;
     n1.in_bf16 = p->bf16; n1.out_bf16 = p->bf16; n1.f16 = p->fp16; n1.tf32 = p->tf32; n1.out_tf32 = p->tf32; n1.zero_tail = 0;
     n1.mask = lb.neigh; n1.ldmask = lb.pin;        // relu'(hp) at the argmax: neigh[d, f] == hp[src(arg), f]
-    STAGE(nm("l%d.dneigh_gemm", l).c_str(), gemm_nt(p, n1, s));
+    if (!(p->head_active && l == L - 1)) STAGE(nm("l%d.dneigh_gemm", l).c_str(), gemm_nt(p, n1, s));      // (else: done by the fused head)
     // fc_pool bias gradient: every dng[d, f] lands in exactly one source row, so colsum(dhp) == colsum(dng).  Side stream too (behind the
     // weight-gradient group): only Adam reads it
     if (ov) {
@@ -770,6 +788,11 @@ static int join_side(ogl_plan* p, cudaStream_t s) {
   return OGL_OK;
 }
 
+static int head_usable(const ogl_plan* p) {
+  const LayerBuf& last = p->layer[p->L - 1];
+  return p->fuse_head && head_fused_supported(p->mode, last.pin, last.out) ? 1 : 0;
+}
+
 static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n_seeds, float loss_scale, int do_step,
                      float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
   if (kind == 0 || kind == 1) {
@@ -804,6 +827,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
     p->skip_gather = 1;
     const int keep_mode = p->train_mode;
     p->train_mode = 1;
+    p->head_active = head_usable(p);
     int r = ogl_plan_forward(p, f, nullptr, s);
     p->skip_gather = 0;
     if (r == OGL_OK) {
@@ -811,6 +835,7 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
       r = ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s);
       p->tail_mode = 0;
     }
+    p->head_active = 0;
     p->train_mode = keep_mode;
     OGL_TRY(r);
     const int64_t n0 = p->layer[0].o_bp;            // = in * in: layer 0's fc_pool.weight leads the flat buffers
@@ -829,12 +854,14 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
   p->skip_gather = (kind == 2 || kind == 3);
   const int keep_mode = p->train_mode;
   p->train_mode = 1;                             // a train step: feat_drop on (the reference calls model.train() first, pytorch/model.py:120)
+  p->head_active = head_usable(p);
   const int rf = ogl_plan_forward(p, f, nullptr, s);
   p->skip_gather = 0;
-  if (rf != OGL_OK) { p->train_mode = keep_mode; return rf; }
+  if (rf != OGL_OK) { p->train_mode = keep_mode; p->head_active = 0; return rf; }
   p->tail_mode = (kind == 3) ? 1 : 0;
   p->adam_in_backward = (do_step && kind != 3) ? 1 : 0;
   const int rl = ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s);
+  p->head_active = 0;
   p->train_mode = keep_mode;
   p->tail_mode = 0;
   p->adam_in_backward = 0;
@@ -1163,6 +1190,15 @@ extern "C" int ogl_plan_set_option(ogl_plan* p, const char* name, int value) {
   if (strcmp(name, "side_stream") == 0) { p->use_side = value ? 1 : 0; return OGL_OK; }
   if (strcmp(name, "pipeline") == 0) { p->use_pipeline = value ? 1 : 0; return OGL_OK; }
   if (strcmp(name, "train_mode") == 0) { p->train_mode = value ? 1 : 0; return OGL_OK; }
+  if (strcmp(name, "fuse_head") == 0) {            // (captured step graphs hold the old launch sequence)
+    if ((value ? 1 : 0) != p->fuse_head) {
+      OGL_CUDA(cudaDeviceSynchronize());
+      for (auto& sg : p->step_graphs) cudaGraphExecDestroy(sg.exec);
+      p->step_graphs.clear();
+    }
+    p->fuse_head = value ? 1 : 0;
+    return OGL_OK;
+  }
   set_error("ogl_plan_set_option: unknown option '%s'", name);
   return OGL_ERR_ARG;
 }

@@ -98,6 +98,7 @@ def test_step_vs_unquantised_oracle_at_bench_shape(mode):
         per2 = torch.empty(B, device="cuda")
         plan.train_step(w["g"], fs, seeds_dev, loss_scale=1.0 / B, do_step=False, per_vertex_out=per2)
         torch.cuda.synchronize()
-        assert torch.allclose(per2, per, rtol=1e-5, atol=1e-6)
+        # (the step runs the last layer on the seed rows through the fused head kernel: same operands, another fp32 summation order)
+        assert torch.allclose(per2, per, rtol=1e-4, atol=1e-5)
         d = (grad - direct).abs().max().item()
         assert d <= 1e-4 * direct.abs().max().item(), "fused step differs from the direct launches by %g" % d

@@ -8,10 +8,10 @@ if [ "${1:-}" != "quick" ]; then
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err; cut -c1-200 gpurun_out/final_ref.json
 fi
 B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-aux --no-parity --no-alt"
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r2.csv $B > gpurun_out/ncu_l.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tn_tc -s 10 -c 2 -f -o gpurun_out/prof_tn_r2 $B > gpurun_out/ncu_tn.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gemm_nt_tc -s 21 -c 2 -f -o gpurun_out/prof_nt_r2 $B > gpurun_out/ncu_nt.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r2b.csv $B > gpurun_out/ncu_l.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tn_tc -s 10 -c 2 -f -o gpurun_out/prof_tn_r2b $B > gpurun_out/ncu_tn.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gemm_nt_tc -s 21 -c 2 -f -o gpurun_out/prof_nt_r2b $B > gpurun_out/ncu_nt.log 2>&1
 if [ "${1:-}" != "quick" ]; then
-timeout 300 ncu --set full --clock-control none --import-source on -k "regex:k_pool_bwd|k_segmax_fwd|k_gather_rows|k_sample" -s 21 -c 7 -f -o gpurun_out/prof_mem_r2 $B > gpurun_out/ncu_mem.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k "regex:k_pool_bwd|k_segmax_fwd|k_gather_rows" -s 6 -c 5 -f -o gpurun_out/prof_mem_r2b $B > gpurun_out/ncu_mem.log 2>&1
 fi
-ls -la gpurun_out/*r2*
+ls -la gpurun_out/*r2b*
