@@ -120,7 +120,7 @@ def test_nt_persistent_loop_many_tiles_per_cta():
 # result differs from the fp64 product of the same operands only by the fp32 accumulation
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("m,n,k", [(128, 16, 16), (128, 256, 512), (100, 24, 50), (1000, 602, 602), (2500, 600, 1204), (26000, 41, 600),
-                                   (1, 8, 8), (129, 257, 65), (40000, 602, 602)])
+                                   (1, 8, 8), (129, 257, 65), (40000, 602, 602), (77000, 300, 640), (60001, 1000, 90)])
 def test_gemm_nt_tcgen05_fp16(m, n, k, cg):
     from ogl_b200 import native
     torch.manual_seed(m + n + k)
@@ -143,6 +143,11 @@ def test_gemm_nt_tcgen05_fp16(m, n, k, cg):
     ref2 = torch.relu(ref + bias.double()) * (mask[:, :n].float() > 0)
     err = (got2.double() - ref2).abs()
     assert bool((err <= 2 ** -11 * ref2.abs() + 1e-6 * (k ** 0.5 + 8) * ref.abs().max() + 2 ** -25).all()), "fp16 activation epilogue: max err %.3e" % err.max().item()
+    # the same without a mask (the forward fc_pool epilogue: bias + ReLU, 16-bit TMA stores)
+    got3 = native.gemm_f16_nt_ex(a, b, k=k, out_f16=True, bias=bias, relu=True, cg=cg)
+    ref3 = torch.relu(ref + bias.double())
+    err = (got3.double() - ref3).abs()
+    assert bool((err <= 2 ** -11 * ref3.abs() + 1e-6 * (k ** 0.5 + 8) * ref.abs().max() + 2 ** -25).all()), "fp16 bias + ReLU epilogue: max err %.3e" % err.max().item()
 
 
 @pytest.mark.parametrize("m,n,k,ws", [(64, 64, 64, 1 << 22), (1000, 602, 602, 1 << 24), (100, 41, 600, 1 << 22), (5000, 600, 41, 1 << 22),
