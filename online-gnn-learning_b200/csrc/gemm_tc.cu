@@ -4,9 +4,9 @@
 // inside the kernels): a 128-byte swizzle row then holds 32 contraction elements instead of 64 and one MMA contracts 8 instead of
 // 16, so stages, descriptors and barriers are byte-identical.
 //
-// Two warp-specialised kernels, both with 128 x <=256 output tiles, 64-deep contraction stages moved by TMA
-// (SWIZZLE_128B) into a 4-stage shared-memory ring, one elected thread issuing tcgen05.mma (UMMA 128 x N x 16,
-// cta_group::1), accumulators in TMEM, and four epilogue warps reading them back with tcgen05.ld:
+// Two warp-specialised kernels: 128-byte-wide contraction stages moved by TMA (SWIZZLE_128B) into a shared-memory ring, producer and
+// MMA warps that run warp-uniform loops and issue through elect.sync (see elect_one), tcgen05.mma with accumulators in TMEM
+// (cta_group::2 CTA pairs for the large NT shapes), epilogue warps reading them back with tcgen05.ld and leaving through TMA stores:
 //
 //   k_gemm_nt_tc   C[m, n] = act(sum_seg A_seg[m, :] . B_seg[n, :] + bias)    both operands K-major.  Persistent CTAs
 //                  (one per SM), two 256-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of
@@ -410,15 +410,13 @@ __global__ void __launch_bounds__(THREADS_NT, 1) k_gemm_nt_tc(const __grid_const
                                          // kernel's CTA leaves it, instead of waiting for the whole grid
 
   // ===== TMA producers (in pair mode: in both CTAs, each for its own shared memory) =====
-  // One thread's TMA copies are served at ~30 B/clk however many are in flight; copies issued by threads of DIFFERENT warps are
-  // served in parallel (tools/exp/ingest_probe.cu: 30.4 B/clk from one issuing thread, 60.7 from two).  The kernel needs ~64 B/clk
-  // to keep the tensor pipe fed, so the A and the B boxes of a stage are issued by two producers (warp 0 and warp 10), each with
-  // its own expect_tx arrival on the stage's full barrier.  which: 0 = A and B (single producer), 1 = A only, 2 = B only.
-  // which: 0 = A and B (single producer), 1 = A only, 2 = B only, 3 = no loads at all: L2 PREFETCHES of the A boxes p.prefetch
-  // k-blocks ahead of the loads (warp 11).  The A operand streams from DRAM; a miss costs 2-3 us under load, and the ring's 160 KB
-  // then sustain only ~32 B/clk per SM (Little's law) -- a box that is already in L2 when its load is issued comes back in ~0.7 us.
-  // The prefetcher paces itself on a progress counter in shared memory that the A producer advances once per stage: it stays at
-  // most p.prefetch k-blocks ahead and ends with its cursor (no barrier wait that could outlive the producers).
+  // The A and the B boxes of a stage are issued by two producer warps (0 and 10), each with its own expect_tx arrival on the stage's
+  // full barrier (loader 3; loader 0 = one producer for both).  That split dates from the thread-divergent issue path, where every
+  // TMA instruction cost ~500 clocks of waterfall (the "30 B/clk per issuing thread" of tools/exp/ingest_probe.cu); with elect_one()
+  // one producer does as well (tools/nt_exp.py), the second is kept because it costs nothing.  which: 0 = A and B, 1 = A only,
+  // 2 = B only.  Warp 11 can run L2 PREFETCHES of the A boxes p.prefetch k-blocks ahead (OGL_GEMM_PF_NT; off: measured slower before
+  // and after the issue fix -- the kernel is bound by L2 -> SM bytes, not by the latency of its misses).  The prefetcher paces itself
+  // on a progress counter in shared memory that the A producer advances once per stage.
   // (run by ONE lane of warp 11) the L2 prefetcher of the A boxes: paces itself on the A producer's progress counter
   auto l2_prefetcher = [&]() {
     // prefetch cursor: (tile, segment, k-block) of the position p.prefetch k-blocks ahead, across segment and tile boundaries
@@ -861,9 +859,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const __grid_constant
   auto a_stage = [&](int i) { return smem_raw + i * TN_A_STAGE_BYTES; };
   pdl_wait();
 
-  // FOUR TMA producers (see k_gemm_nt_tc: copies issued by ONE thread are served at ~30 B/clk -- and, for the 4 KB boxes of the
-  // tf32 flavour, at a fixed cost per box -- while those of different warps are served in parallel): warps 0 / 6 load the first /
-  // second half of the A chunks of a stage, warps 7 / 8 of the B chunks; each makes its own expect_tx arrival on the full barrier
+  // FOUR TMA producers: warps 0 / 6 load the first / second half of the A chunks of a stage, warps 7 / 8 of the B chunks; each makes
+  // its own expect_tx arrival on the full barrier (the split paid under the thread-divergent issue path, see k_gemm_nt_tc; kept)
   auto tma_producer = [&](int which, int part) {    // which: 1 = A chunks, 2 = B chunks; part: 0 / 1 = first / second half of them
     int stage = 0;
     uint32_t phase = 0;
