@@ -278,7 +278,7 @@ def test_autograd_bridge_matches_fused_path():
         close(logits, lref, 1e-5, "autograd logits")
         for (k, _), ga in zip(model.named_parameters(), g_auto):
             close(ga, gref[k], 1e-5, "autograd grad " + k)
-    ogl_b200.config.set_precision("bf16")
+    ogl_b200.config.set_precision("tf32")
 
 
 def test_cuda_graph_replay_equals_direct_launches():

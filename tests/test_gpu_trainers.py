@@ -177,4 +177,4 @@ def test_train_step_honours_the_blocks_it_is_given():
         next(it)
         assert t.train_step(dg, blocks, input_nodes, seeds, None) == "resampled"
     finally:
-        ogl_b200.config.set_precision("bf16")
+        ogl_b200.config.set_precision("tf32")
