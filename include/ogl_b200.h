@@ -146,7 +146,9 @@ int ogl_plan_sample(ogl_plan* p, ogl_graph* g, const int64_t* seeds_dev, int n_s
 int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev, void* stream);
 /* loss + backward; grads land in the bound gradient buffer (overwritten).
  * loss_scale multiplies dlogits (1/global_batch for the 'mean' reduction);
- * per_vertex_loss_dev (fp32 [n_seeds]) may be NULL */
+ * per_vertex_loss_dev (fp32 [n_seeds]) may be NULL; loss_sum_dev (fp32 [1], may be NULL; here and in every step entry point
+ * below) receives the sum of the per-vertex losses -- any device-ACCESSIBLE address: device memory, or pinned host memory, in
+ * which case the loss kernel stores the 4 bytes over PCIe itself and no D2H copy is needed (valid once the stream has passed) */
 int ogl_plan_loss_backward(ogl_plan* p, ogl_features* f, float loss_scale, float* per_vertex_loss_dev,
                            float* loss_sum_dev, void* stream);
 /* autograd-compat path (GraphSAGE.forward(blocks, x) + loss.backward() driven from Python):
