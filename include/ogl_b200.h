@@ -122,6 +122,10 @@ typedef struct {
                             (train steps; ogl_plan_forward after ogl_plan_set_option("train_mode", 1)); 0 = off */
 } ogl_plan_config;
 
+/* mode OGL_FP16: the power of two the stored activation gradients of a backward pass carry for a given loss scale (1 / global batch):
+ * 2^floor(log2(64 / loss_scale)), i.e. the largest |dlogits| element is stored in (32, 64].  Pure host function (no device needed);
+ * oracle/sage.py: grad_scale_for is its twin */
+float ogl_fp16_grad_scale(float loss_scale);
 int ogl_plan_create(ogl_plan** out, const ogl_plan_config* cfg);
 int ogl_plan_destroy(ogl_plan* p);
 /* flat fp32 parameter / gradient buffers (caller-owned device memory, e.g. a torch

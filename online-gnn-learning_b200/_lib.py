@@ -120,6 +120,7 @@ SIGNATURES = {
     "ogl_gemm_bf16_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "ogl_gemm_tf32_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "ogl_gemm_tf32_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "ogl_fp16_grad_scale": (_f, [_f]),
     "ogl_gemm_f16_nt_ex": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "ogl_gemm_f16_tn": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i64, _vp]),
 }

@@ -557,14 +557,14 @@ extern "C" int ogl_plan_forward(ogl_plan* p, ogl_features* f, float* logits_dev,
 // result that leaves the backward pass -- the weight gradients (the TN GEMMs' reduce) and the bias gradients (column sums) -- is
 // multiplied by 1 / gs where it is written; a power of two, so the unscaling is exact and Adam, the peer exchange and the
 // gradient readers see true gradients.
-static float grad_scale_for(const ogl_plan* p, float loss_scale) {
-  if (!p->fp16) return 1.f;
+extern "C" float ogl_fp16_grad_scale(float loss_scale) {
   const float a = fabsf(loss_scale);
   if (!(a > 0.f) || !std::isfinite(a)) return 1.f;
   int e = 0;
   frexpf(64.f / a, &e);                 // 64 / a = m * 2^e, m in [0.5, 1)
   return ldexpf(1.f, e - 1);            // 2^floor(log2(64 / a)):  a * gs in (32, 64]
 }
+static float grad_scale_for(const ogl_plan* p, float loss_scale) { return p->fp16 ? ogl_fp16_grad_scale(loss_scale) : 1.f; }
 
 static int plan_loss(ogl_plan* p, ogl_features* f, float scale, int want_grad, float* per_vertex_loss_dev, float* loss_sum_dev, cudaStream_t s) {
   const int L = p->L;

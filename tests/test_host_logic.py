@@ -239,3 +239,19 @@ def test_oracle_tf32_rounding_matches_cvt_rna():
     assert r[0] == 1.0 and r[1] == 1.0 + 2 ** -10 and r[2] == 1.0 and r[3] == -1.0 - 2 ** -10      # ties away from zero
     assert bool(((r.view(torch.int32) & 0x1FFF) == 0).all())
     assert float(((r - x).abs() / x.abs()).max()) <= 2 ** -11
+
+
+def test_fp16_loss_scale_matches_the_oracle_model():
+    """mode OGL_FP16 stores activation gradients times a power of two derived from the loss scale (csrc/plan.cu); oracle/sage.py rounds
+    its gradients on the same grid: the two formulas must agree for every loss scale a trainer can pass (no device needed)"""
+    from ogl_b200._lib import lib
+    from oracle import sage as osage
+    import random
+    rng = random.Random(0)
+    cases = [1.0, 0.5, 1.0 / 3, 1.0 / 96, 1.0 / 1024, 1.0 / 8192, 64.0, 65.0, 1e-7, 3e4] + [2.0 ** rng.uniform(-20, 10) for _ in range(500)]
+    for a in cases:
+        a = float(np.float32(a))
+        gs = float(lib.ogl_fp16_grad_scale(a))
+        assert gs == osage.grad_scale_for(a), (a, gs, osage.grad_scale_for(a))
+        assert 32.0 < a * gs <= 64.0 and np.log2(gs) == int(np.log2(gs)), (a, gs)
+    assert float(lib.ogl_fp16_grad_scale(0.0)) == 1.0 and float(lib.ogl_fp16_grad_scale(float("inf"))) == 1.0
