@@ -818,18 +818,21 @@ static int step_body(ogl_plan* p, int kind, ogl_graph* g, ogl_features* f, int n
     // the whole data-parallel finish as ONE launch sequence (one CUDA graph per step): the split form (head graph | exchange kernel
     // | tail graph | exchange kernel on a communication stream, with events between them) costs ~80 us of launch / dependency latency
     // per step even on a single rank; here the exchanges are nodes of the same graph as the GEMMs they overlap.
-    //   peers have read my previous gradients -> forward -> loss -> backward without the last weight-gradient GEMM
+    //   forward -> peers have read my previous gradients -> loss -> backward without the last weight-gradient GEMM
     //   -> [side: exchange + Adam of everything but layer 0's fc_pool.weight]  ||  [main: that GEMM]
     //   -> exchange + Adam of fc_pool.weight -> optimiser step counter
     ogl_peer* peer = p->dp_peer;
     OGL_ARG(peer && p->use_side, "ogl_plan_step_finish_dp: needs a peer group and the side stream");
-    OGL_TRY(peer_wait_readers(peer, s));
     p->skip_gather = 1;
     const int keep_mode = p->train_mode;
     p->train_mode = 1;
     p->head_active = head_usable(p);
     int r = ogl_plan_forward(p, f, nullptr, s);
     p->skip_gather = 0;
+    // the peers must have finished reading my previous gradients before this step's backward pass overwrites them: checked HERE,
+    // after the forward pass (a quarter of a millisecond after they started reading), not at the start of the step where it is a
+    // third box-wide synchronisation on the critical path
+    if (r == OGL_OK) r = peer_wait_readers(peer, s);
     if (r == OGL_OK) {
       p->tail_mode = 1;
       r = ogl_plan_loss_backward(p, f, loss_scale, per_vertex_loss_dev, loss_sum_dev, s);
